@@ -1,0 +1,147 @@
+/*
+ * madtp_b200 -- C ABI of the B200 (sm_100a) kernels behind MADTP's pruned vision-language forward path.
+ *
+ * The reference (double125/MADTP) is pure PyTorch and has no native interface; every entry point below replaces a
+ * group of library calls on its hot path. The citation on each function is the reference code it stands in for
+ * (paths under the reference tree). Python binds these with ctypes (madtp_b200/_lib.py); see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (1 invalid argument, 2 CUDA error, 3 workspace,
+ *     4 unsupported); madtp_last_error_string() describes the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless stated otherwise; the library never allocates, frees or retains them.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work.
+ *   - leading dimensions (ld*) and batch strides (bs*) are in ELEMENTS.
+ *   - fp16 buffers are IEEE binary16 (`__half`), passed as void*.
+ */
+#ifndef MADTP_B200_H_
+#define MADTP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MADTP_B200_ABI_VERSION 1
+
+/* GEMM operand precision */
+#define MADTP_GEMM_F16 0     /* fp16 operands, fp32 accumulate, tcgen05 kind::f16 */
+#define MADTP_GEMM_TF32X3 1  /* fp32 operands pre-split into tf32 hi/lo, 3 tcgen05 kind::tf32 MMAs per k-step */
+#define MADTP_GEMM_SIMT 2    /* fp32 FFMA on CUDA cores (device-side checker, tiny shapes) */
+
+/* GEMM epilogue activation */
+#define MADTP_ACT_NONE 0
+#define MADTP_ACT_GELU 1       /* erf GELU: nn.GELU (vit.py:18) / ACT2FN["gelu"] (med.py:308) */
+#define MADTP_ACT_RELU 2       /* cls_head ReLU (blip_nlvr.py:58) */
+#define MADTP_ACT_QUICKGELU 3  /* clip/model.py QuickGELU */
+
+int madtp_abi_version(void);
+const char* madtp_last_error_string(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+long long madtp_launch_count(void);
+
+/*
+ * C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias[N]) + residual[M,N]
+ * Replaces every nn.Linear on the path: vit.py:48-49,77,92 (qkv, proj), vit.py:24-26 (fc1, fc2),
+ * nlvr_encoder.py:103-109 (query/key/value), :247-263 (dense0/dense1/merge_layer), :371,385 (intermediate, output),
+ * models/utils.py:170 (token . codebook^T), blip_nlvr.py:56-60 (cls_head), timm PatchEmbed conv (vit.py:241).
+ * a_lo / b_lo: tf32 residual halves, only for MADTP_GEMM_TF32X3 (see madtp_split_tf32 / madtp_layernorm).
+ * c_f16 != 0 writes fp16 output. bias, residual may be NULL. MADTP_GEMM_F16 reads fp16 a, b; the others fp32.
+ */
+int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, const void* b, const void* b_lo,
+               int64_t ldb, void* c, int64_t ldc, int c_f16, const float* bias, const float* residual, int64_t ldr,
+               int act, float alpha, int M, int N, int K, void* stream);
+
+/*
+ * Row LayerNorm with fused GEMM-operand preparation. Replaces nn.LayerNorm at vit.py:111,115,239 (eps 1e-6) and
+ * nlvr_encoder.py:54,243,381 / med.py:54,242,324 (eps 1e-12).
+ * Outputs are optional (NULL to skip), each [rows, d] contiguous: y_f32; y_hi/y_lo (tf32 split of y); y_f16;
+ * x_hi/x_lo (tf32 split of the un-normalised input row, operand of the Query_model product).
+ * gamma == beta == NULL: only x_hi/x_lo are produced. d must be a multiple of 128, <= 1024.
+ */
+int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
+                    float* y_f32, float* y_hi, float* y_lo, void* y_f16, float* x_hi, float* x_lo, void* stream);
+
+/* hi = round_to_tf32(x), lo = x - hi (exact). Used once per weight at load time. */
+int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* y = (fp16) x */
+int madtp_cast_f16(const float* x, void* y_f16, int64_t n, void* stream);
+
+/*
+ * ViT stem (timm PatchEmbed = Conv2d(C, D, P, stride P), vit.py:241-242,284): non-overlapping patches of
+ * img[B,C,H,W] as GEMM rows [B*(H/P)*(W/P), C*P*P] in Conv2d weight order, written as tf32 hi/lo.
+ */
+int madtp_patchify(const float* img, float* rows_hi, float* rows_lo, int B, int C, int H, int W, int P, void* stream);
+/* x[b,0,:] = cls + pos[0]; x[b,1+p,:] = patches[b,p,:] + pos[1+p]   (vit.py:286-289) */
+int madtp_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
+                          void* stream);
+/* out[b,l,:] = word[ids[b,l]] + position[l]   (nlvr_encoder.py:61-85; the LayerNorm is a madtp_layernorm call) */
+int madtp_bert_embed(const int64_t* ids, const float* word, const float* position, float* out, int B, int L, int d,
+                     int vocab, void* stream);
+
+/*
+ * Multi-head attention, head dim 64: context = softmax(q.k^T * scale + key_mask) v, heads merged into
+ * out_f16[b, i, h*64 + :]. Replaces vit.py:79-91, nlvr_encoder.py:174-219 / med.py:175-217 (self and cross
+ * attention) without materialising the [B,H,N,N] probabilities.
+ * key_mask: additive [B, Nk] (0 / -10000, nlvr_encoder.py:870-871) or NULL.
+ * row_max/row_sum/out_norm ([B,H,Nq] each, all three or none): softmax row statistics and ||context[b,h,i,:]||_2,
+ * the un-normalised "head importance" of vit.py:97 / nlvr_encoder.py:231.
+ */
+int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, const float* v,
+                   int64_t ldv, int64_t bsv, int B, int H, int Nq, int Nk, float scale, const float* key_mask,
+                   void* out_f16, int64_t ldo, int64_t bso, float* row_max, float* row_sum, float* out_norm,
+                   void* stream);
+
+/*
+ * Pruning statistics of a self-attention (Nq == Nk == N), from the row statistics of madtp_attn_fwd:
+ *   col_part[b, it, j] = sum_{i in query tile it, i >= 1} max_h P[b,h,i,j]      (vit.py:126-127; sum `it` in order)
+ *   cls_attn[b, j]     = sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)   (vit.py:96-100)
+ * col_part is [B, ceil(N/64), N], cls_attn is [B, N]; index j = 0 (CLS) is not meaningful.
+ */
+int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, int B, int H,
+                     int N, float scale, const float* key_mask, const float* row_max, const float* row_sum,
+                     const float* out_norm, float* col_part, float* cls_attn, void* stream);
+
+/*
+ * Query_model (models/utils.py:147-183), given token_att = ft . sd^T from madtp_gemm:
+ *   colstats: col_max[b,t], col_sum[b,t] of softmax over tokens of token_att / divisor   (divisor = sqrt(sd_dim))
+ *   sdft:     sd_ft[b,t,:] (+)= sum_j softmax_j(token_att[b,j,t] / divisor) * ft[b,j,:]
+ * token_att row j of batch b is at token_att + b*bs_ta + j*ld_ta; ft row j at ft + b*bs_ft + j*ld_ft.
+ */
+int madtp_token_colstats(const float* token_att, int64_t ld_ta, int64_t bs_ta, int B, int n, int T, float divisor,
+                         float* col_max, float* col_sum, void* stream);
+int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
+                     const float* ft, int64_t ld_ft, int64_t bs_ft, int B, int n, int T, int d, float divisor,
+                     float* sd_ft, int accumulate, void* stream);
+
+/*
+ * DTP scoring (vit.py:123-145 / nlvr_encoder.py:400-432 / med.py:345-369): Importance_score, threshold,
+ * per-row count and topk = max_b count (atomicMax into *topk, which the caller zeroes first).
+ * n = number of prunable tokens (positions 1..n); col_part/cls_attn as produced by madtp_attn_stats with N = n+1.
+ */
+int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
+                    const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
+                    float* threshold, int32_t* count, int32_t* topk, void* stream);
+
+/*
+ * DTP selection (vit.py:153-158): exact top-k of score per row (k read from *topk on the device), survivors keep
+ * ascending token order. keep[B,n] (1 = survivor), dst[B,n] (slot among survivors or -1), tail_w[B,n] (merge weight
+ * score_j / (sum_tail + 1e-8) of pruned tokens), tail_idx[B,n] (pruned token indices, first n-k valid).
+ * If k < 1 or n - k <= 1 nothing is pruned (vit.py:148-149) and dst is the identity.
+ * mask_mode 1 (nlvr_encoder.py:451-452) / 2 (med.py:377-390) additionally gathers the additive key mask
+ * mask_in[B,n+1] -> mask_out[B, 0..k+1]; mask_mode 0 ignores both.
+ */
+int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
+                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, void* stream);
+
+/*
+ * DTP gather + merge (vit.py:154-161,202; models/utils.py:13-33 vector_gather): out[b] = [x[b,0], survivors in
+ * ascending token order, sum_j tail_w[j] x[b,1+j]] -- shape [B, k+2, d] with batch stride bso.
+ */
+int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADTP_B200_H_ */

@@ -1,0 +1,298 @@
+"""ctypes binding of libmadtp_b200.so (C ABI declared in include/madtp_b200.h).
+
+The wrappers take torch CUDA tensors, pass raw device pointers + sizes + the current CUDA stream, and raise
+RuntimeError on any non-zero status. There is deliberately no CPU or PyTorch fallback: if the shared library is
+missing or a tensor is not on a CUDA device the call fails loudly (the reference raises Python exceptions /
+asserts on bad input too, e.g. models/utils.py:28, models/med.py:443).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
+_lib = None
+
+GEMM_F16, GEMM_TF32X3, GEMM_SIMT = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
+
+_i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+# name -> argtypes; must list every function include/madtp_b200.h declares (tests/test_abi.py checks this).
+SIGNATURES = {
+    "madtp_abi_version": [],
+    "madtp_last_error_string": [],
+    "madtp_launch_count": [],
+    "madtp_gemm": [_i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _i32,
+                   _i32, _vp],
+    "madtp_layernorm": [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
+    "madtp_cast_f16": [_vp, _vp, _i64, _vp],
+    "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "madtp_assemble_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "madtp_bert_embed": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "madtp_attn_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
+                       _i64, _i64, _vp, _vp, _vp, _vp],
+    "madtp_attn_stats": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
+    "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
+    "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
+    "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (building nothing: run `python -m madtp_b200.csrc.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -m madtp_b200.csrc.build`). madtp_b200 has no CPU fallback.")
+    lib = C.CDLL(os.fspath(_LIB_PATH))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.madtp_last_error_string.restype = C.c_char_p
+    lib.madtp_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load().madtp_launch_count())
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = load().madtp_last_error_string().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"madtp_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"madtp_b200: {name} must have dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rowmajor(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"madtp_b200: {name} must be a 2-D tensor with unit inner stride")
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin functional wrappers
+# ------------------------------------------------------------------------------------------------------------------
+def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None, act=ACT_NONE, alpha=1.0):
+    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual. out may be a column slice of a wider buffer."""
+    lda, ldb, ldc = _rowmajor(a, "a"), _rowmajor(b, "b"), _rowmajor(out, "out")
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
+        raise RuntimeError(f"madtp_b200.gemm: shape mismatch a{tuple(a.shape)} b{tuple(b.shape)} out{tuple(out.shape)}")
+    op_dtype = torch.float16 if precision == GEMM_F16 else torch.float32
+    if out.dtype not in (torch.float32, torch.float16):
+        raise RuntimeError("madtp_b200.gemm: out must be fp32 or fp16")
+    ldr = 0
+    if residual is not None:
+        ldr = _rowmajor(residual, "residual")
+        if residual.shape != out.shape:
+            raise RuntimeError("madtp_b200.gemm: residual shape mismatch")
+    if a_lo is not None and (a_lo.shape != a.shape or a_lo.stride(0) != lda):
+        raise RuntimeError("madtp_b200.gemm: a_lo layout must match a")
+    if b_lo is not None and (b_lo.shape != b.shape or b_lo.stride(0) != ldb):
+        raise RuntimeError("madtp_b200.gemm: b_lo layout must match b")
+    st = load().madtp_gemm(precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, torch.float32, "a_lo"), lda,
+                           _ptr(b, op_dtype, "b"), _ptr(b_lo, torch.float32, "b_lo"), ldb, _ptr(out, None, "out"),
+                           ldc, 1 if out.dtype == torch.float16 else 0, _ptr(bias, torch.float32, "bias"),
+                           _ptr(residual, torch.float32, "residual"), ldr, act, float(alpha), M, N, K, _stream())
+    _check(st, "madtp_gemm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=None, x_hi=None, x_lo=None):
+    """x: [rows, d] fp32 (row stride free). Every output is optional and contiguous [rows, d]."""
+    ldx = _rowmajor(x, "x")
+    rows, d = x.shape
+    for nm, t, dt in (("y_f32", y_f32, torch.float32), ("y_hi", y_hi, torch.float32), ("y_lo", y_lo, torch.float32),
+                      ("y_f16", y_f16, torch.float16), ("x_hi", x_hi, torch.float32), ("x_lo", x_lo, torch.float32)):
+        if t is not None and (t.dtype != dt or not t.is_contiguous() or t.numel() != rows * d):
+            raise RuntimeError(f"madtp_b200.layernorm: bad output {nm}")
+    st = load().madtp_layernorm(_ptr(x, torch.float32, "x"), ldx, rows, d, _ptr(gamma, torch.float32, "gamma"),
+                                _ptr(beta, torch.float32, "beta"), float(eps), _ptr(y_f32), _ptr(y_hi), _ptr(y_lo),
+                                _ptr(y_f16), _ptr(x_hi), _ptr(x_lo), _stream())
+    _check(st, "madtp_layernorm")
+
+
+def split_tf32(x):
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _check(load().madtp_split_tf32(_ptr(x, torch.float32, "x"), _ptr(hi), _ptr(lo), x.numel(), _stream()),
+           "madtp_split_tf32")
+    return hi, lo
+
+
+def cast_f16(x):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _check(load().madtp_cast_f16(_ptr(x, torch.float32, "x"), _ptr(y), x.numel(), _stream()), "madtp_cast_f16")
+    return y
+
+
+def patchify(img, P):
+    B, Cc, H, W = img.shape
+    img = img.contiguous()
+    rows = B * (H // P) * (W // P)
+    hi = torch.empty(rows, Cc * P * P, dtype=torch.float32, device=img.device)
+    lo = torch.empty_like(hi)
+    _check(load().madtp_patchify(_ptr(img, torch.float32, "img"), _ptr(hi), _ptr(lo), B, Cc, H, W, P, _stream()),
+           "madtp_patchify")
+    return hi, lo
+
+
+def assemble_tokens(patches, cls, pos, B, n, d):
+    x = torch.empty(B, n + 1, d, dtype=torch.float32, device=patches.device)
+    _check(load().madtp_assemble_tokens(_ptr(patches, torch.float32, "patches"), _ptr(cls, torch.float32, "cls"),
+                                        _ptr(pos, torch.float32, "pos"), _ptr(x), B, n, d, _stream()),
+           "madtp_assemble_tokens")
+    return x
+
+
+def bert_embed(ids, word, position):
+    B, L = ids.shape
+    ids = ids.contiguous()
+    d = word.shape[1]
+    out = torch.empty(B, L, d, dtype=torch.float32, device=word.device)
+    _check(load().madtp_bert_embed(_ptr(ids, torch.int64, "ids"), _ptr(word, torch.float32, "word"),
+                                   _ptr(position, torch.float32, "position"), _ptr(out), B, L, d, word.shape[0],
+                                   _stream()), "madtp_bert_embed")
+    return out
+
+
+def _qkv_strides(t, name):
+    """t: [B, N, H*64] view (row stride / batch stride arbitrary, unit inner stride)."""
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise RuntimeError(f"madtp_b200: {name} must be [B, N, H*64] with unit inner stride")
+    return t.stride(1), t.stride(0)
+
+
+def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None):
+    """q [B,Nq,H*64], k/v [B,Nk,H*64] fp32 views; out_f16 [B,Nq,H*64] fp16 view. stats = (row_max,row_sum,out_norm)."""
+    B, Nq, _ = q.shape
+    Nk = k.shape[1]
+    ldq, bsq = _qkv_strides(q, "q")
+    ldk, bsk = _qkv_strides(k, "k")
+    ldv, bsv = _qkv_strides(v, "v")
+    ldo, bso = _qkv_strides(out_f16, "out_f16")
+    rm = rs = on = None
+    if stats is not None:
+        rm, rs, on = stats
+    if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Nk):
+        raise RuntimeError("madtp_b200.attn_fwd: key_mask must be contiguous [B, Nk]")
+    st = load().madtp_attn_fwd(_ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
+                               _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Nq, Nk, float(scale),
+                               _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
+                               bso, _ptr(rm), _ptr(rs), _ptr(on), _stream())
+    _check(st, "madtp_attn_fwd")
+
+
+def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None):
+    B, N, _ = q.shape
+    ldq, bsq = _qkv_strides(q, "q")
+    ldk, bsk = _qkv_strides(k, "k")
+    rm, rs, on = stats
+    st = load().madtp_attn_stats(_ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk, B, H, N,
+                                 float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(rm), _ptr(rs), _ptr(on),
+                                 _ptr(col_part, torch.float32, "col_part"), _ptr(cls_attn, torch.float32, "cls_attn"),
+                                 _stream())
+    _check(st, "madtp_attn_stats")
+
+
+def token_colstats(token_att, n, T, divisor):
+    """token_att: [B, rows>=n, ld] fp32 view whose row j is prunable token j. Returns (col_max, col_sum) [B, T]."""
+    B = token_att.shape[0]
+    ld, bs = token_att.stride(1), token_att.stride(0)
+    cm = torch.empty(B, T, dtype=torch.float32, device=token_att.device)
+    cs = torch.empty_like(cm)
+    _check(load().madtp_token_colstats(_ptr(token_att, torch.float32, "token_att"), ld, bs, B, n, T, float(divisor),
+                                       _ptr(cm), _ptr(cs), _stream()), "madtp_token_colstats")
+    return cm, cs
+
+
+def query_sdft(token_att, col_max, col_sum, ft, n, T, divisor, sd_ft, accumulate):
+    B = token_att.shape[0]
+    d = ft.shape[-1]
+    st = load().madtp_query_sdft(_ptr(token_att, torch.float32, "token_att"), token_att.stride(1), token_att.stride(0),
+                                 _ptr(col_max), _ptr(col_sum), _ptr(ft, torch.float32, "ft"), ft.stride(1),
+                                 ft.stride(0), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
+                                 1 if accumulate else 0, _stream())
+    _check(st, "madtp_query_sdft")
+
+
+def dtp_score(col_part, cls_attn, token_att, n, T, temperature):
+    """Returns (score [B,n], threshold [B], count [B] int32, topk [1] int32)."""
+    B, n_parts, N = col_part.shape
+    assert N == n + 1
+    dev = col_part.device
+    score = torch.empty(B, n, dtype=torch.float32, device=dev)
+    thr = torch.empty(B, dtype=torch.float32, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    topk = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = load().madtp_dtp_score(B, n, T, _ptr(col_part, torch.float32, "col_part"), n_parts,
+                                _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(token_att, torch.float32, "token_att"),
+                                token_att.stride(1), token_att.stride(0), float(temperature), _ptr(score), _ptr(thr),
+                                _ptr(cnt), _ptr(topk), _stream())
+    _check(st, "madtp_dtp_score")
+    return score, thr, cnt, topk
+
+
+def dtp_select(score, topk, *, mask_mode=0, mask_in=None):
+    B, n = score.shape
+    dev = score.device
+    keep = torch.empty(B, n, dtype=torch.uint8, device=dev)
+    dst = torch.empty(B, n, dtype=torch.int32, device=dev)
+    tail_w = torch.empty(B, n, dtype=torch.float32, device=dev)
+    tail_idx = torch.empty(B, n, dtype=torch.int32, device=dev)
+    mask_out = None
+    if mask_mode:
+        if mask_in is None or not mask_in.is_contiguous() or mask_in.numel() != B * (n + 1):
+            raise RuntimeError("madtp_b200.dtp_select: mask_in must be contiguous [B, n+1]")
+        mask_out = torch.empty(B, n + 1, dtype=torch.float32, device=dev)
+    st = load().madtp_dtp_select(B, n, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"), _ptr(keep),
+                                 _ptr(dst), _ptr(tail_w), _ptr(tail_idx), mask_mode,
+                                 _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), _stream())
+    _check(st, "madtp_dtp_select")
+    return keep, dst, tail_w, tail_idx, mask_out
+
+
+def dtp_gather(x, topk, dst, tail_w, tail_idx, k):
+    """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d]."""
+    B, N, d = x.shape
+    if x.stride(2) != 1 or x.stride(1) != d:
+        raise RuntimeError("madtp_b200.dtp_gather: x rows must be dense")
+    out = torch.empty(B, k + 2, d, dtype=torch.float32, device=x.device)
+    st = load().madtp_dtp_gather(B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
+                                 _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
+                                 _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _stream())
+    _check(st, "madtp_dtp_gather")
+    return out

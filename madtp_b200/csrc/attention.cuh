@@ -1,0 +1,29 @@
+// Internal interface of the attention kernels (see attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace madtp {
+
+// q, k, v are fp32 with head h at column offset h*64 of each token row. Row strides (ld*) and batch strides (bs*)
+// are in elements, so fused QKV buffers ([B, N, 3*H*64]) and separate projections are both expressible.
+struct AttnArgs {
+  const float* q; long long ldq, bsq;
+  const float* k; long long ldk, bsk;
+  const float* v; long long ldv, bsv;
+  int B, H, Nq, Nk;
+  float scale;              // logits = q.k * scale + key_mask
+  const float* key_mask;    // additive, [B, Nk] or nullptr (BERT padding mask: 0 / -10000)
+  // ---- outputs of the forward pass ----
+  __half* out_f16; long long ldo, bso;   // context, heads merged: out[b, i, h*64 + :]  (ldo/bso in elements)
+  float* row_max;           // [B, H, Nq]  max_j logits           (nullptr when statistics are not needed)
+  float* row_sum;           // [B, H, Nq]  sum_j exp(logit - max)
+  float* out_norm;          // [B, H, Nq]  || context[b, h, i, :] ||_2   ("head importance" before normalisation)
+  // ---- outputs of the statistics pass (self-attention only, Nq == Nk) ----
+  float* col_part;          // [B, ceil(Nq/64), Nk]  partial column sums over query tiles of max_h P[b,h,i,j], i,j >= 1
+  float* cls_attn;          // [B, Nk]  sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8); entry 0 unused
+};
+
+int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream);
+int launch_attn_stats(const AttnArgs& a, cudaStream_t stream);
+
+}  // namespace madtp

@@ -1,0 +1,190 @@
+// extern "C" boundary of libmadtp_b200.so -- see include/madtp_b200.h for the contract of every entry point.
+#include "../../include/madtp_b200.h"
+
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "dtp.cuh"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+namespace madtp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int counted(int status, int launches = 1) {
+  if (status == kOk) g_launches.fetch_add(launches, std::memory_order_relaxed);
+  return status;
+}
+
+}  // namespace madtp
+
+using namespace madtp;
+
+extern "C" {
+
+int madtp_abi_version(void) { return MADTP_B200_ABI_VERSION; }
+const char* madtp_last_error_string(void) { return last_error(); }
+long long madtp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, const void* b, const void* b_lo,
+               int64_t ldb, void* c, int64_t ldc, int c_f16, const float* bias, const float* residual, int64_t ldr,
+               int act, float alpha, int M, int N, int K, void* stream) {
+  GemmEpilogue ep;
+  ep.c = c;
+  ep.ldc = ldc;
+  ep.c_f16 = c_f16;
+  ep.bias = bias;
+  ep.residual = residual;
+  ep.ldr = ldr;
+  ep.act = act;
+  ep.alpha = alpha;
+  MADTP_CHECK_ARG(act >= 0 && act <= 3, "gemm: unknown activation %d", act);
+  return counted(launch_gemm(precision, a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, as_stream(stream)), M > 0 ? 1 : 0);
+}
+
+int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
+                    float* y_f32, float* y_hi, float* y_lo, void* y_f16, float* x_hi, float* x_lo, void* stream) {
+  LayerNormArgs a;
+  a.x = x;
+  a.ldx = ldx;
+  a.rows = rows;
+  a.d = d;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.eps = eps;
+  a.y_f32 = y_f32;
+  a.y_hi = y_hi;
+  a.y_lo = y_lo;
+  a.y_f16 = static_cast<__half*>(y_f16);
+  a.x_hi = x_hi;
+  a.x_lo = x_lo;
+  return counted(launch_layernorm(a, as_stream(stream)), rows > 0 ? 1 : 0);
+}
+
+int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  return counted(launch_split_tf32(x, hi, lo, n, as_stream(stream)), n > 0 ? 1 : 0);
+}
+int madtp_cast_f16(const float* x, void* y_f16, int64_t n, void* stream) {
+  return counted(launch_cast_f16(x, y_f16, n, as_stream(stream)), n > 0 ? 1 : 0);
+}
+
+int madtp_patchify(const float* img, float* rows_hi, float* rows_lo, int B, int C, int H, int W, int P, void* stream) {
+  return counted(launch_patchify(img, rows_hi, rows_lo, B, C, H, W, P, as_stream(stream)), B > 0 ? 1 : 0);
+}
+int madtp_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
+                          void* stream) {
+  return counted(launch_assemble_tokens(patches, cls, pos, x, B, n, d, as_stream(stream)), B > 0 ? 1 : 0);
+}
+int madtp_bert_embed(const int64_t* ids, const float* word, const float* position, float* out, int B, int L, int d,
+                     int vocab, void* stream) {
+  return counted(launch_bert_embed(reinterpret_cast<const long long*>(ids), word, position, out, B, L, d, vocab,
+                                   as_stream(stream)),
+                 B > 0 ? 1 : 0);
+}
+
+int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, const float* v,
+                   int64_t ldv, int64_t bsv, int B, int H, int Nq, int Nk, float scale, const float* key_mask,
+                   void* out_f16, int64_t ldo, int64_t bso, float* row_max, float* row_sum, float* out_norm,
+                   void* stream) {
+  AttnArgs a = {};
+  a.q = q; a.ldq = ldq; a.bsq = bsq;
+  a.k = k; a.ldk = ldk; a.bsk = bsk;
+  a.v = v; a.ldv = ldv; a.bsv = bsv;
+  a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk;
+  a.scale = scale;
+  a.key_mask = key_mask;
+  a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
+  a.row_max = row_max; a.row_sum = row_sum; a.out_norm = out_norm;
+  return counted(launch_attn_fwd(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
+int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, int B, int H,
+                     int N, float scale, const float* key_mask, const float* row_max, const float* row_sum,
+                     const float* out_norm, float* col_part, float* cls_attn, void* stream) {
+  AttnArgs a = {};
+  a.q = q; a.ldq = ldq; a.bsq = bsq;
+  a.k = k; a.ldk = ldk; a.bsk = bsk;
+  a.v = k; a.ldv = ldk; a.bsv = bsk;  // unused by the statistics pass
+  a.B = B; a.H = H; a.Nq = N; a.Nk = N;
+  a.scale = scale;
+  a.key_mask = key_mask;
+  a.row_max = const_cast<float*>(row_max);
+  a.row_sum = const_cast<float*>(row_sum);
+  a.out_norm = const_cast<float*>(out_norm);
+  a.col_part = col_part;
+  a.cls_attn = cls_attn;
+  return counted(launch_attn_stats(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
+int madtp_token_colstats(const float* token_att, int64_t ld_ta, int64_t bs_ta, int B, int n, int T, float divisor,
+                         float* col_max, float* col_sum, void* stream) {
+  return counted(launch_token_colstats(token_att, ld_ta, bs_ta, B, n, T, divisor, col_max, col_sum, as_stream(stream)),
+                 B > 0 ? 1 : 0);
+}
+int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
+                     const float* ft, int64_t ld_ft, int64_t bs_ft, int B, int n, int T, int d, float divisor,
+                     float* sd_ft, int accumulate, void* stream) {
+  return counted(launch_query_sdft(token_att, ld_ta, bs_ta, col_max, col_sum, ft, ld_ft, bs_ft, B, n, T, d, divisor,
+                                   sd_ft, accumulate, as_stream(stream)),
+                 B > 0 ? 1 : 0);
+}
+
+int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
+                    const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
+                    float* threshold, int32_t* count, int32_t* topk, void* stream) {
+  DtpScoreArgs a;
+  a.B = B; a.n = n; a.T = T;
+  a.col_part = col_part; a.n_parts = n_parts;
+  a.cls_attn = cls_attn;
+  a.token_att = token_att; a.ld_ta = ld_ta; a.bs_ta = bs_ta;
+  a.temperature = temperature;
+  a.score = score; a.threshold = threshold; a.count = count; a.topk = topk;
+  return counted(launch_dtp_score(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
+int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
+                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, void* stream) {
+  DtpSelectArgs a;
+  a.B = B; a.n = n;
+  a.score = score; a.topk = topk;
+  a.keep = keep; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
+  a.mask_mode = mask_mode; a.mask_in = mask_in; a.mask_out = mask_out;
+  return counted(launch_dtp_select(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
+int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream) {
+  DtpGatherArgs a;
+  a.B = B; a.n = n; a.d = d;
+  a.x = x; a.bsx = bsx;
+  a.topk = topk; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
+  a.out = out; a.bso = bso;
+  return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Internal interface of the Dynamic Token Pruning kernels (see dtp.cu).
+#pragma once
+#include "common.cuh"
+
+namespace madtp {
+
+constexpr int kDtpMaxTokens = 1024;  // n = N-1 prunable tokens per sequence handled by one CTA
+
+// Column (over-token) softmax statistics of token_att / divisor, per codebook entry t:
+//   col_max[b,t] = max_j x[b,j,t],  col_sum[b,t] = sum_j exp(x[b,j,t] - col_max[b,t]),  x = token_att / divisor
+int launch_token_colstats(const float* token_att, long long ld_ta, long long bs_ta, int B, int n, int T, float divisor,
+                          float* col_max, float* col_sum, cudaStream_t stream);
+
+// Query_model's aggregated feature (reference models/utils.py:174-178):
+//   sd_ft[b,t,:] (+)= sum_j softmax_j(token_att[b,j,t] / divisor) * x[b,j,:]
+int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
+                      const float* col_sum, const float* x, long long ldx, long long bsx, int B, int n, int T, int d,
+                      float divisor, float* sd_ft, int accumulate, cudaStream_t stream);
+
+struct DtpScoreArgs {
+  int B, n, T;                // n prunable tokens (sequence position 1..n), T codebook entries
+  const float* col_part;      // [B, n_parts, n+1] partial column sums from attn_stats (index 0 = CLS, unused)
+  int n_parts;
+  const float* cls_attn;      // [B, n+1] (index 0 unused)
+  const float* token_att;     // [B, *, ld_ta]; row j (0-based over prunable tokens) at token_att + b*bs_ta + j*ld_ta
+  long long ld_ta, bs_ta;
+  float temperature;
+  float* score;               // [B, n]  Importance_score
+  float* threshold;           // [B]
+  int* count;                 // [B]     #(score > threshold)
+  int* topk;                  // [1]     max_b count, must be zeroed before the launch (atomicMax)
+};
+int launch_dtp_score(const DtpScoreArgs& a, cudaStream_t stream);
+
+struct DtpSelectArgs {
+  int B, n;
+  const float* score;         // [B, n]
+  const int* topk;            // device scalar k (batch max count)
+  unsigned char* keep;        // [B, n]  1 = survivor
+  int* dst;                   // [B, n]  slot of survivor j among the survivors (ascending token index), -1 if pruned
+  float* tail_w;              // [B, n]  merge weight of pruned token j (0 for survivors)
+  int* tail_idx;              // [B, n]  pruned token indices, ascending; the first n-k entries are valid
+  // optional additive key-mask bookkeeping for text (mask_mode 0: none)
+  int mask_mode;              // 1: nlvr_encoder semantics (mask of the r-th ranked token at slot r, r <= k)
+                              // 2: med.py semantics (mask travels with its token; merged slot = mask of rank k)
+  const float* mask_in;       // [B, n+1] additive mask incl. position 0
+  float* mask_out;            // [B, n+1] worst case; entries [0, k+2) are written
+};
+int launch_dtp_select(const DtpSelectArgs& a, cudaStream_t stream);
+
+struct DtpGatherArgs {
+  int B, n, d;
+  const float* x;             // [B, n+1, d] tokens incl. position 0 (CLS / [ENC]) which always survives
+  long long bsx;              // batch stride of x (elements)
+  const int* topk;
+  const int* dst;             // from dtp_select
+  const float* tail_w;
+  const int* tail_idx;
+  float* out;                 // [B, k+2, d] packed survivors: [cls, survivors ascending, merged]
+  long long bso;              // batch stride of out (elements) -- the caller sizes it with the k it read back
+};
+int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);
+
+}  // namespace madtp

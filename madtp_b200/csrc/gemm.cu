@@ -1,0 +1,647 @@
+// GEMM kernels for the packed token stream: C[M,N] = epilogue(A[M,K] * B[N,K]^T).
+//
+// gemm_tcgen05_kernel — persistent, warp-specialised Blackwell kernel:
+//   warp 0 (one lane)  : TMA producer   (cp.async.bulk.tensor 2-D tiles, 128-byte swizzle, mbarrier tx-count)
+//   warp 1 (one lane)  : MMA issuer     (tcgen05.mma, accumulators in TMEM, tcgen05.commit -> mbarriers)
+//   warps 2..5         : epilogue       (tcgen05.ld TMEM -> registers, bias / activation / residual, global stores)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Precision modes:
+//   kGemmF16    fp16 operands, fp32 accumulation, one kind::f16 MMA per 16-element k-step.
+//   kGemmTF32x3 error-compensated fp32: operands are pre-split into tf32 "hi" (low 13 mantissa bits zero) and the
+//               exact residual "lo"; every k-step issues lo*hi + hi*lo + hi*hi (kind::tf32, fp32 accumulation).
+//               This is the "scoring lane" precision: keep-masks are decided on score gaps of ~1e-7, which plain
+//               tf32/fp16 products do not resolve (hard part 1).
+//
+// gemm_simt_kernel — plain fp32 FFMA tiling; device-side cross-check for the tensor-core path and tiny shapes.
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace madtp {
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool TF32X3>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int ROW_BYTES = 128;                       // one 128B swizzle atom of K per stage
+  static constexpr int K_ELEMS = TF32X3 ? 32 : 64;            // K elements per stage
+  static constexpr int UMMA_K_BYTES = 32;                     // K bytes per tcgen05.mma
+  static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = (TF32X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;               // double-buffered fp32 accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 192;
+};
+
+
+// Epilogue for 32 consecutive accumulator columns [col0, col0+32) of one output row held by one thread:
+// out = act(alpha * acc + bias) + residual, written as fp32 or fp16 with 128-bit stores when the layout allows.
+__device__ __forceinline__ void store_row_chunk32(const GemmEpilogue& ep, const float (&acc)[32], long long row,
+                                                  int col0, int N, bool vec_ok) {
+  if (vec_ok && col0 + 32 <= N) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.residual) rv = __ldg(reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col0 + j));
+      o[j + 0] = apply_act(ep.alpha * acc[j + 0] + bv.x, ep.act) + rv.x;
+      o[j + 1] = apply_act(ep.alpha * acc[j + 1] + bv.y, ep.act) + rv.y;
+      o[j + 2] = apply_act(ep.alpha * acc[j + 2] + bv.z, ep.act) + rv.z;
+      o[j + 3] = apply_act(ep.alpha * acc[j + 3] + bv.w, ep.act) + rv.w;
+    }
+    if (ep.c_f16) {
+      __half* dst = reinterpret_cast<__half*>(ep.c) + row * ep.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __half2 h0 = __floats2half2_rn(o[j + 0], o[j + 1]);
+        __half2 h1 = __floats2half2_rn(o[j + 2], o[j + 3]);
+        __half2 h2 = __floats2half2_rn(o[j + 4], o[j + 5]);
+        __half2 h3 = __floats2half2_rn(o[j + 6], o[j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + j) = pk;
+      }
+    } else {
+      float* dst = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < N) {
+        float x = ep.alpha * acc[j];
+        if (ep.bias) x += __ldg(ep.bias + col);
+        x = apply_act(x, ep.act);
+        if (ep.residual) x += __ldg(ep.residual + row * ep.ldr + col);
+        if (ep.c_f16)
+          reinterpret_cast<__half*>(ep.c)[row * ep.ldc + col] = __float2half_rn(x);
+        else
+          reinterpret_cast<float*>(ep.c)[row * ep.ldc + col] = x;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool epilogue_vec_ok(const GemmEpilogue& ep, int N) {
+  const bool al = (reinterpret_cast<uintptr_t>(ep.c) & 15) == 0 &&
+                  (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+                  (ep.residual == nullptr || (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
+  return al && ((ep.ldc & 7) == 0) && ((N & 3) == 0) && (ep.residual == nullptr || (ep.ldr & 3) == 0);
+}
+
+template <int BLOCK_N, bool TF32X3>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
+                    GemmEpilogue ep, int M, int N, int K) {
+  using Cfg = GemmCfg<BLOCK_N, TF32X3>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + Cfg::K_ELEMS - 1) / Cfg::K_ELEMS;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    if (TF32X3) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+        const int n0 = (tile % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * Cfg::K_ELEMS;
+          tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
+          tma_load_2d(&tm_b, &full_bar[stage], s + Cfg::A_BYTES, k0, n0);
+          if (TF32X3) {
+            tma_load_2d(&tm_a_lo, &full_bar[stage], s + Cfg::A_BYTES + Cfg::B_BYTES, k0, m0);
+            tma_load_2d(&tm_b_lo, &full_bar[stage], s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TF32X3 ? 2u : 0u, Cfg::BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_kmajor_desc(s);
+          const uint64_t b_hi = make_sw128_kmajor_desc(s + Cfg::A_BYTES);
+          const uint64_t a_lo = make_sw128_kmajor_desc(s + Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint64_t b_lo = make_sw128_kmajor_desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::ROW_BYTES / Cfg::UMMA_K_BYTES; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * Cfg::UMMA_K_BYTES) >> 4);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (TF32X3) {
+              // small terms first, then the dominant hi*hi product
+              umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
+              umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+      const int n0 = (tile % n_tiles) * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const bool vec_ok = epilogue_vec_ok(ep, N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;
+        uint32_t v[32];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + c * 32);
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float acc32[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(v[j]);
+        store_row_chunk32(ep, acc32, row, col0, N, vec_ok);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TF32x3 kernel with chunk-drained accumulation.
+//
+// Measured on B200: the tensor core's fp32 accumulator truncates on every accumulate, so a K=768 TF32x3 GEMM that
+// accumulates all of K in TMEM comes out ~5e-6 relative (and ~2e-5 at K=3072), 50x worse than an fp32 FFMA GEMM --
+// too coarse for the scoring lane. Here every 32-element K chunk (one pipeline stage: 4 k-steps x 3 MMAs) is
+// accumulated into its own TMEM buffer (two buffers, ping-pong) and the eight epilogue warps drain each chunk with
+// tcgen05.ld and add it into fp32 registers with round-to-nearest. The tensor core therefore only ever sums 32
+// products plus the small cross terms; the long K reduction is IEEE fp32.
+//   warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: drain + epilogue (warp%4 = TMEM lane quadrant,
+//   (warp-2)/4 = column half of the tile).
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Tf32Cfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int K_ELEMS = 32;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int THREADS = 320;
+  static constexpr int COLS_PER_WARP = BLOCK_N / 2;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(320, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
+                   GemmEpilogue ep, int M, int N, int K) {
+  using Cfg = Tf32Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CW = Cfg::COLS_PER_WARP;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + Cfg::K_ELEMS - 1) / Cfg::K_ELEMS;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+        const int n0 = (tile % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * Cfg::K_ELEMS;
+          tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
+          tma_load_2d(&tm_b, &full_bar[stage], s + Cfg::A_BYTES, k0, n0);
+          tma_load_2d(&tm_a_lo, &full_bar[stage], s + Cfg::A_BYTES + Cfg::B_BYTES, k0, m0);
+          tma_load_2d(&tm_b_lo, &full_bar[stage], s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2u, Cfg::BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&tmem_empty[buf], buf_phase ^ 1u);
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BLOCK_N);
+          const uint32_t s = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_kmajor_desc(s);
+          const uint64_t b_hi = make_sw128_kmajor_desc(s + Cfg::A_BYTES);
+          const uint64_t a_lo = make_sw128_kmajor_desc(s + Cfg::A_BYTES + Cfg::B_BYTES);
+          const uint64_t b_lo = make_sw128_kmajor_desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+          // cross terms first (tiny partial sums), then the dominant hi*hi products: only the last four
+          // accumulates truncate at the full partial-sum magnitude
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[buf]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          buf ^= 1;
+          if (buf == 0) buf_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    const bool vec_ok = epilogue_vec_ok(ep, N);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+      const int n0 = (tile % n_tiles) * BLOCK_N;
+      float sum[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) sum[j] = 0.f;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&tmem_full[buf], buf_phase);
+        tcgen05_fence_after();
+        const uint32_t tbase =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * BLOCK_N + half * CW);
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tbase + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(v[j]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        buf ^= 1;
+        if (buf == 0) buf_phase ^= 1u;
+      }
+      const long long row = m0 + quad * 32 + lane;
+      if (row < M) {
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) {
+          const int col0 = n0 + half * CW + c * 32;
+          if (col0 < N) {
+            float acc32[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc32[j] = sum[c * 32 + j];
+            store_row_chunk32(ep, acc32, row, col0, N, vec_ok);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT fp32 kernel: 64x64 tile, 16-deep k slices, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
+                 GemmEpilogue ep, int M, int N, int K) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? A[gm * lda + gk] : 0.f;
+      Bs[kk][r] = (gn < N && gk < K) ? B[gn * ldb + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      float x = ep.alpha * acc[i][j];
+      if (ep.bias) x += ep.bias[col];
+      x = apply_act(x, ep.act);
+      if (ep.residual) x += ep.residual[row * ep.ldr + col];
+      if (ep.c_f16)
+        reinterpret_cast<__half*>(ep.c)[row * ep.ldc + col] = __float2half_rn(x);
+      else
+        reinterpret_cast<float*>(ep.c)[row * ep.ldc + col] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps + dispatch
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// Row-major [rows, cols] matrix with leading dimension ld (elements); box = box_rows x (128 bytes of columns).
+static int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld,
+                     int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return kCudaError;
+  }
+  const int es = f32 ? 4 : 2;
+  MADTP_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+  MADTP_CHECK_ARG((ld * es) % 16 == 0, "GEMM operand row pitch must be a multiple of 16 bytes (ld=%lld)", ld);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+    return kCudaError;
+  }
+  return kOk;
+}
+
+template <int BLOCK_N, bool TF32X3>
+static int launch_tc(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
+                     const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, TF32X3>;
+  CUtensorMap ta, tal, tb, tbl;
+  int st;
+  if ((st = make_tmap(&ta, a, TF32X3, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+  if ((st = make_tmap(&tb, b, TF32X3, N, K, ldb, BLOCK_N)) != kOk) return st;
+  if (TF32X3) {
+    if ((st = make_tmap(&tal, a_lo, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+    if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N)) != kOk) return st;
+  } else {
+    tal = ta;
+    tbl = tb;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tcgen05_kernel<BLOCK_N, TF32X3><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, ep, M, N, K);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+
+template <int BLOCK_N>
+static int launch_tf32(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
+                       const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+  using Cfg = Tf32Cfg<BLOCK_N>;
+  CUtensorMap ta, tal, tb, tbl;
+  int st;
+  if ((st = make_tmap(&ta, a, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+  if ((st = make_tmap(&tb, b, true, N, K, ldb, BLOCK_N)) != kOk) return st;
+  if ((st = make_tmap(&tal, a_lo, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+  if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N)) != kOk) return st;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tf32x3_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, ep, M, N, K);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// Pick the N tile that wastes the fewest SM-waves (persistent grid of num_sms CTAs).
+static int pick_block_n(int M, int N) {
+  const int sms = num_sms();
+  const int m_tiles = (M + 127) / 128;
+  auto cost = [&](int bn) {
+    const long long tiles = 1LL * m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    return waves * bn;  // time ~ waves x tile width
+  };
+  return cost(256) <= cost(128) ? 256 : 128;
+}
+
+int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
+                long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+  MADTP_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
+  MADTP_CHECK_ARG(a && b && ep.c, "null GEMM operand");
+  if (M == 0) return kOk;
+  if (precision == kGemmSimtF32) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(a), lda, static_cast<const float*>(b), ldb,
+                                               ep, M, N, K);
+    MADTP_LAUNCH_CHECK();
+    return kOk;
+  }
+  const int bn = pick_block_n(M, N);
+  if (precision == kGemmTF32x3) {
+    MADTP_CHECK_ARG(a_lo && b_lo, "TF32x3 GEMM needs the lo halves of both operands");
+    return bn == 256 ? launch_tf32<256>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream)
+                     : launch_tf32<128>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+  }
+  if (precision == kGemmF16) {
+    return bn == 256 ? launch_tc<256, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream)
+                     : launch_tc<128, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
+  }
+  set_error("unknown GEMM precision %d", precision);
+  return kInvalidArgument;
+}
+
+}  // namespace madtp

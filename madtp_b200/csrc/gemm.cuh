@@ -1,0 +1,44 @@
+// Internal interface of the GEMM kernels (not part of the C ABI; see include/madtp_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace madtp {
+
+// Epilogue applied to every accumulator element:  out = act(alpha * acc + bias[col]) + residual[row, col]
+struct GemmEpilogue {
+  void* c;                // output [M, ldc] (fp32 or fp16)
+  long long ldc;          // elements
+  int c_f16;              // 0: fp32 output, 1: fp16 output
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // fp32 [M, ldr] or nullptr
+  long long ldr;
+  int act;                // 0 none, 1 GELU(erf), 2 ReLU, 3 QuickGELU (x * sigmoid(1.702 x))
+  float alpha;
+};
+
+enum GemmPrecision : int {
+  kGemmF16 = 0,      // fp16 operands, fp32 accumulate (kind::f16), one MMA per k-step
+  kGemmTF32x3 = 1,   // fp32 operands pre-split into tf32 hi/lo; hi*hi + hi*lo + lo*hi (kind::tf32)
+  kGemmSimtF32 = 2,  // CUDA-core fp32 FFMA (device-side checker and tiny shapes)
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case 1:
+      return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case 2:
+      return fmaxf(x, 0.0f);
+    case 3:
+      return x / (1.0f + __expf(-1.702f * x));
+    default:
+      return x;
+  }
+}
+
+// C[M,N] = epilogue(A[M,K] * B[N,K]^T). A and B are row-major with the reduction dimension contiguous
+// (activations [tokens, features] and nn.Linear weights [out, in]).
+// a_lo/b_lo are only read for kGemmTF32x3. Returns a Status.
+int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
+                long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream);
+
+}  // namespace madtp

@@ -1,0 +1,240 @@
+// Row-wise HBM-bound kernels around the GEMMs: LayerNorm with fused operand preparation (tf32 hi/lo split, fp16
+// copy), the tf32 split itself, patch extraction for the ViT stem, token assembly and the BERT embedding lookup.
+// One warp owns one row; rows are d <= 1024 floats held in registers, accessed with 128-bit loads/stores.
+#include "rowops.cuh"
+
+namespace madtp {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (two-pass in registers: mean, then centred variance) + optional operand preparation.
+// ------------------------------------------------------------------------------------------------
+template <int V>  // V float4 per lane: d == 128 * V
+__global__ void __launch_bounds__(256)
+layernorm_kernel(LayerNormArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.rows) return;
+  const long long row = warp;
+  const float4* xin = reinterpret_cast<const float4*>(a.x + row * a.ldx);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xin[lane + 32 * i];
+
+  if (a.x_hi) {  // tf32 split of the *input* row (operand of the token/codebook product)
+    float4* hi = reinterpret_cast<float4*>(a.x_hi + row * a.d);
+    float4* lo = reinterpret_cast<float4*>(a.x_lo + row * a.d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+      hi[lane + 32 * i] = h;
+      lo[lane + 32 * i] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+    }
+  }
+  if (a.gamma == nullptr) return;  // split-only call
+
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(a.d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float var = warp_sum(q) / static_cast<float>(a.d);
+  const float rstd = 1.0f / sqrtf(var + a.eps);
+
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    const int c = lane + 32 * i;
+    if (a.y_f32) reinterpret_cast<float4*>(a.y_f32 + row * a.d)[c] = y;
+    if (a.y_hi) {
+      float4 h = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
+      reinterpret_cast<float4*>(a.y_hi + row * a.d)[c] = h;
+      reinterpret_cast<float4*>(a.y_lo + row * a.d)[c] = make_float4(y.x - h.x, y.y - h.y, y.z - h.z, y.w - h.w);
+    }
+    if (a.y_f16) {
+      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(a.y_f16 + row * a.d)[c] = pk;
+    }
+  }
+}
+
+int launch_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
+  MADTP_CHECK_ARG(a.rows >= 0 && a.d > 0 && a.d % 128 == 0 && a.d <= 1024,
+                  "layernorm: d must be a multiple of 128 and <= 1024 (d=%d)", a.d);
+  MADTP_CHECK_ARG(a.x != nullptr && a.ldx % 4 == 0, "layernorm: bad input");
+  MADTP_CHECK_ARG((a.x_hi == nullptr) == (a.x_lo == nullptr) && (a.y_hi == nullptr) == (a.y_lo == nullptr),
+                  "layernorm: hi/lo outputs come in pairs");
+  MADTP_CHECK_ARG((a.gamma == nullptr) == (a.beta == nullptr), "layernorm: gamma/beta come in pairs");
+  if (a.rows == 0) return kOk;
+  const int blocks = (a.rows + 7) / 8;
+  switch (a.d / 128) {
+#define MADTP_LN_CASE(V)                                  \
+  case V:                                                 \
+    layernorm_kernel<V><<<blocks, 256, 0, stream>>>(a);   \
+    break;
+    MADTP_LN_CASE(1) MADTP_LN_CASE(2) MADTP_LN_CASE(3) MADTP_LN_CASE(4) MADTP_LN_CASE(5) MADTP_LN_CASE(6)
+    MADTP_LN_CASE(7) MADTP_LN_CASE(8)
+#undef MADTP_LN_CASE
+  }
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise tf32 split / fp16 cast (weights at load time, small activations)
+// ------------------------------------------------------------------------------------------------
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                  long long n) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = x[i];
+    const float h = tf32_hi(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+__global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) y[i] = __float2half_rn(x[i]);
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream) {
+  MADTP_CHECK_ARG(x && hi && lo && n >= 0, "split_tf32: bad arguments");
+  if (n == 0) return kOk;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  split_tf32_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, hi, lo, n);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t stream) {
+  MADTP_CHECK_ARG(x && y && n >= 0, "cast_f16: bad arguments");
+  if (n == 0) return kOk;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  cast_f16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, static_cast<__half*>(y), n);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT stem: non-overlapping PxP patches of [B,C,H,W] -> rows [B*gh*gw, C*P*P] (Conv2d weight order c,py,px),
+// written as tf32 hi/lo so the projection runs on the error-compensated tensor-core path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, float* __restrict__ hi, float* __restrict__ lo, int B, int C, int H,
+                int W, int P) {
+  const int gh = H / P, gw = W / P;
+  const int kdim = C * P * P;
+  const long long total4 = static_cast<long long>(B) * gh * gw * kdim / 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long e = i * 4;
+    const int kk = static_cast<int>(e % kdim);
+    const long long prow = e / kdim;
+    const int px = kk % P, py = (kk / P) % P, c = kk / (P * P);
+    const int gx = static_cast<int>(prow % gw), gy = static_cast<int>((prow / gw) % gh);
+    const int b = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
+    const float4 v = *reinterpret_cast<const float4*>(
+        img + ((static_cast<long long>(b) * C + c) * H + (gy * P + py)) * W + gx * P + px);
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+int launch_patchify(const float* img, float* hi, float* lo, int B, int C, int H, int W, int P, cudaStream_t stream) {
+  MADTP_CHECK_ARG(img && hi && lo, "patchify: null pointer");
+  MADTP_CHECK_ARG(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "patchify: H,W must be multiples of P, P of 4");
+  const long long total4 = static_cast<long long>(B) * (H / P) * (W / P) * C * P * P / 4;
+  if (total4 == 0) return kOk;
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  patchify_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(img, hi, lo, B, C, H, W, P);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// x[b,0,:] = cls + pos[0];  x[b,1+p,:] = patches[b,p,:] + pos[1+p]
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const float* __restrict__ patches, const float* __restrict__ cls,
+                       const float* __restrict__ pos, float* __restrict__ x, int B, int n, int d) {
+  const int d4 = d / 4;
+  const long long total = static_cast<long long>(B) * (n + 1) * d4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>(i % d4);
+    const long long r = i / d4;
+    const int t = static_cast<int>(r % (n + 1));
+    const long long b = r / (n + 1);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<long long>(t) * d4 + c);
+    float4 v;
+    if (t == 0)
+      v = __ldg(reinterpret_cast<const float4*>(cls) + c);
+    else
+      v = reinterpret_cast<const float4*>(patches)[(b * n + (t - 1)) * d4 + c];
+    reinterpret_cast<float4*>(x)[i] = make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+  }
+}
+
+int launch_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
+                           cudaStream_t stream) {
+  MADTP_CHECK_ARG(patches && cls && pos && x && d % 4 == 0, "assemble_tokens: bad arguments");
+  const long long total = static_cast<long long>(B) * (n + 1) * (d / 4);
+  if (total == 0) return kOk;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  assemble_tokens_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(patches, cls, pos, x, B, n, d);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// BERT embeddings: out[b,l,:] = word[ids[b,l]] + position[l]  (LayerNorm follows as a separate launch)
+__global__ void __launch_bounds__(256)
+bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ posemb,
+                  float* __restrict__ out, int B, int L, int d, int vocab) {
+  const int d4 = d / 4;
+  const long long total = static_cast<long long>(B) * L * d4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>(i % d4);
+    const long long r = i / d4;
+    const int l = static_cast<int>(r % L);
+    long long id = ids[r];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(word) + id * d4 + c);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(posemb) + static_cast<long long>(l) * d4 + c);
+    reinterpret_cast<float4*>(out)[i] = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, w.w + p.w);
+  }
+}
+
+int launch_bert_embed(const long long* ids, const float* word, const float* posemb, float* out, int B, int L, int d,
+                      int vocab, cudaStream_t stream) {
+  MADTP_CHECK_ARG(ids && word && posemb && out && d % 4 == 0 && vocab > 0, "bert_embed: bad arguments");
+  const long long total = static_cast<long long>(B) * L * (d / 4);
+  if (total == 0) return kOk;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  bert_embed_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(ids, word, posemb, out, B, L, d, vocab);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // namespace madtp

@@ -1,0 +1,285 @@
+"""Kernel-level checks of the C-ABI entry points on a real GPU, each against a straightforward fp64 PyTorch statement
+of the same arithmetic (this file checks kernels in isolation; parity with the reference algorithm is in
+test_parity_gpu.py, which goes through the oracle and the golden fixtures)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 256, 128), (256, 128, 32), (300, 200, 96), (1000, 768, 768), (77, 100, 768),
+    (4099, 2304, 768), (640, 3072, 768), (640, 768, 3072), (2, 8, 8), (36928, 128, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_simt(lib, dev, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    out = torch.empty(M, N, device=dev)
+    lib.gemm(lib.GEMM_SIMT, a, b, out, bias=bias)
+    ref = a.double() @ b.double().T + bias.double()
+    assert _rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tf32x3(lib, dev, M, N, K):
+    if K % 4:
+        pytest.skip("row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + 1)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    a_hi, a_lo = lib.split_tf32(a)
+    b_hi, b_lo = lib.split_tf32(b)
+    assert torch.equal(a_hi + a_lo, a), "tf32 split must be exact"
+    assert int((a_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0, "hi must have the low 13 mantissa bits clear"
+    out = torch.full((M, N), float("nan"), device=dev)
+    lib.gemm(lib.GEMM_TF32X3, a_hi, b_hi, out, a_lo=a_lo, b_lo=b_lo, bias=bias)
+    ref = a.double() @ b.double().T + bias.double()
+    err = _rel(out, ref)
+    # an fp32 FFMA GEMM of this depth sits around 1e-7; plain TF32 would be ~5e-4, and TF32x3 accumulated over the
+    # whole K inside the tensor core measured 5e-6 (K=768) .. 2e-5 (K=3072) because its accumulator truncates
+    simt = torch.empty(M, N, device=dev)
+    lib.gemm(lib.GEMM_SIMT, a, b, simt, bias=bias)
+    print(f"tf32x3 M={M} N={N} K={K}: rel err {err:.3e} (simt fp32 {_rel(simt, ref):.3e})")
+    assert err < 6e-7, f"TF32x3 relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_f16(lib, dev, M, N, K):
+    if K % 8:
+        pytest.skip("row pitch must be a multiple of 16 bytes")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + 2)
+    a = torch.randn(M, K, generator=g).to(dev).half()
+    b = torch.randn(N, K, generator=g).to(dev).half()
+    out = torch.full((M, N), float("nan"), device=dev)
+    lib.gemm(lib.GEMM_F16, a, b, out)
+    ref = a.double() @ b.double().T
+    # operands are exactly representable; the error is the tensor core's truncating fp32 accumulation (grows ~K)
+    assert _rel(out, ref) < 1e-5
+
+
+def test_gemm_epilogues(lib, dev):
+    M, N, K = 333, 768, 256
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(dev).half()
+    b = (torch.randn(N, K, generator=g) * 0.05).to(dev).half()
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    acc = a.double() @ b.double().T
+    for act, fn in ((lib.ACT_NONE, lambda x: x), (lib.ACT_GELU, lambda x: torch.nn.functional.gelu(x)),
+                    (lib.ACT_RELU, torch.relu), (lib.ACT_QUICKGELU, lambda x: x * torch.sigmoid(1.702 * x))):
+        out = torch.empty(M, N, device=dev)
+        lib.gemm(lib.GEMM_F16, a, b, out, bias=bias, residual=res, act=act, alpha=0.5)
+        ref = fn(0.5 * acc + bias.double()) + res.double()
+        assert _rel(out, ref) < 5e-6, f"act {act}"
+    # fp16 output into a column slice of a wider buffer (ldc != N)
+    wide = torch.zeros(M, 2 * N, device=dev, dtype=torch.float16)
+    lib.gemm(lib.GEMM_F16, a, b, wide[:, N:], bias=bias)
+    ref = (acc + bias.double())
+    assert _rel(wide[:, N:], ref) < 1e-3
+    assert float(wide[:, :N].abs().max()) == 0.0
+
+
+def test_gemm_rejects_cpu_tensors(lib):
+    a = torch.randn(8, 8)
+    with pytest.raises(RuntimeError):
+        lib.gemm(lib.GEMM_SIMT, a, a, torch.empty(8, 8))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LayerNorm / row ops
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,d,eps", [(1154, 768, 1e-6), (37, 768, 1e-12), (64, 1024, 1e-6)])
+def test_layernorm(lib, dev, rows, d, eps):
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    x = (torch.randn(rows, d, generator=g) * 3 + 0.5).to(dev)
+    gamma = torch.randn(d, generator=g).to(dev)
+    beta = torch.randn(d, generator=g).to(dev)
+    outs = {k: torch.empty(rows, d, device=dev) for k in ("y_f32", "y_hi", "y_lo", "x_hi", "x_lo")}
+    y16 = torch.empty(rows, d, device=dev, dtype=torch.float16)
+    lib.layernorm(x, gamma, beta, eps, y_f16=y16, **outs)
+    ref = torch.nn.functional.layer_norm(x.double(), (d,), gamma.double(), beta.double(), eps)
+    assert (outs["y_f32"].double() - ref).abs().max().item() < 5e-6
+    assert torch.equal(outs["y_hi"] + outs["y_lo"], outs["y_f32"])
+    assert torch.equal(outs["x_hi"] + outs["x_lo"], x)
+    assert torch.equal(y16, outs["y_f32"].half())
+
+
+def test_patchify_matches_conv(lib, dev):
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, C, H, W, P, D = 3, 3, 64, 48, 16, 768
+    img = torch.randn(B, C, H, W, generator=g).to(dev)
+    w = (torch.randn(D, C, P, P, generator=g) * 0.02).to(dev)
+    bias = torch.randn(D, generator=g).to(dev)
+    hi, lo = lib.patchify(img, P)
+    assert torch.equal((hi + lo).view(B, H // P, W // P, C, P, P),
+                       img.view(B, C, H // P, P, W // P, P).permute(0, 2, 4, 1, 3, 5))
+    w_hi, w_lo = lib.split_tf32(w.view(D, -1))
+    out = torch.empty(hi.shape[0], D, device=dev)
+    lib.gemm(lib.GEMM_TF32X3, hi, w_hi, out, a_lo=lo, b_lo=w_lo, bias=bias)
+    ref = torch.nn.functional.conv2d(img.double(), w.double(), bias.double(), stride=P).flatten(2).transpose(1, 2)
+    assert _rel(out.view(B, -1, D), ref) < 6e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# attention + statistics
+# ---------------------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, scale, mask):
+    s = q @ k.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + mask[:, None, None, :]
+    p = torch.softmax(s, dim=-1)
+    o = p @ v
+    return p, o
+
+
+@pytest.mark.parametrize("B,H,N,masked", [(2, 12, 197, False), (3, 12, 20, True), (2, 12, 577, False), (1, 4, 64, False),
+                                          (2, 3, 65, True)])
+def test_attention_and_stats(lib, dev, B, H, N, masked):
+    g = torch.Generator(device="cpu").manual_seed(N + B)
+    qkv = torch.randn(B, N, 3 * H * 64, generator=g).to(dev)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    mask = None
+    if masked:
+        lens = torch.randint(N // 2, N + 1, (B,), generator=g)
+        mask = torch.zeros(B, N)
+        for b in range(B):
+            mask[b, lens[b]:] = -10000.0
+        mask = mask.to(dev)
+    scale = 0.125
+    out = torch.empty(B, N, H * 64, device=dev, dtype=torch.float16)
+    stats = tuple(torch.empty(B, H, N, device=dev) for _ in range(3))
+    lib.attn_fwd(q, k, v, H, scale, out, key_mask=mask, stats=stats)
+    n_parts = (N + 63) // 64
+    col_part = torch.zeros(B, n_parts, N, device=dev)
+    cls_attn = torch.zeros(B, N, device=dev)
+    lib.attn_stats(q, k, H, scale, stats, col_part, cls_attn, key_mask=mask)
+
+    def heads(t):
+        return t.reshape(B, N, H, 64).permute(0, 2, 1, 3).double()
+
+    p, o = _attn_ref(heads(q), heads(k), heads(v), scale, None if mask is None else mask.double())
+    o_merged = o.permute(0, 2, 1, 3).reshape(B, N, H * 64)
+    assert _rel(out, o_merged) < 6e-4  # fp16 output rounding
+    assert (stats[2].double() - o.norm(dim=-1)).abs().max().item() < 1e-5
+    hi = o[..., 1:, :].norm(dim=-1)
+    hi = hi / (hi.sum(dim=1, keepdim=True) + 1e-8)
+    cls_ref = (p[:, :, 0, 1:] * hi).sum(dim=1)
+    a_ref = p[:, :, 1:, 1:].max(dim=1)[0].sum(dim=1)
+    assert (cls_attn[:, 1:].double() - cls_ref).abs().max().item() < 1e-6
+    a = col_part.double().sum(dim=1)[:, 1:]
+    assert ((a - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 2e-6
+
+
+def test_cross_attention(lib, dev):
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, H, Lq, Nk = 4, 12, 19, 283
+    q = torch.randn(B, Lq, H * 64, generator=g).to(dev)
+    kv = torch.randn(B, Nk, 2 * H * 64, generator=g).to(dev)
+    k, v = kv[..., :H * 64], kv[..., H * 64:]
+    wide = torch.zeros(B, Lq, 2 * H * 64, device=dev, dtype=torch.float16)
+    lib.attn_fwd(q, k, v, H, 0.125, wide[..., H * 64:])
+
+    def heads(t, n):
+        return t.reshape(B, n, H, 64).permute(0, 2, 1, 3).double()
+
+    _, o = _attn_ref(heads(q, Lq), heads(k, Nk), heads(v, Nk), 0.125, None)
+    assert _rel(wide[..., H * 64:], o.permute(0, 2, 1, 3).reshape(B, Lq, H * 64)) < 6e-4
+    assert float(wide[..., :H * 64].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Query_model pieces and DTP kernels
+# ---------------------------------------------------------------------------------------------------------------
+def test_query_model_kernels(lib, dev):
+    g = torch.Generator(device="cpu").manual_seed(21)
+    B, n, T, d = 3, 196, 100, 768
+    x = torch.randn(B, n + 1, d, generator=g).to(dev)
+    ta = (torch.randn(B, n + 1, 128, generator=g) * 20).to(dev)
+    ta_p = ta[:, 1:, :]
+    div = math.sqrt(768)
+    cm, cs = lib.token_colstats(ta_p, n, T, div)
+    xs = ta_p[..., :T].double() / div
+    assert (cm.double() - xs.max(dim=1)[0]).abs().max().item() < 1e-6
+    w = torch.softmax(xs, dim=1)
+    sd = torch.zeros(B, T, d, device=dev)
+    lib.query_sdft(ta_p, cm, cs, x[:, 1:, :], n, T, div, sd, False)
+    ref = w.transpose(1, 2) @ x[:, 1:, :].double()
+    assert _rel(sd, ref) < 2e-6
+    lib.query_sdft(ta_p, cm, cs, x[:, 1:, :], n, T, div, sd, True)
+    assert _rel(sd, 2 * ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,n,temp", [(4, 196, 1.0), (2, 576, 5.0), (5, 19, 2.0), (3, 900, 50.0)])
+def test_dtp_score_select_gather(lib, dev, B, n, temp):
+    g = torch.Generator(device="cpu").manual_seed(n)
+    T, d, N = 100, 768, n + 1
+    n_parts = (N + 63) // 64
+    col_part = torch.rand(B, n_parts, N, generator=g).to(dev)
+    cls_attn = (torch.rand(B, N, generator=g) / n).to(dev)
+    ta = (torch.randn(B, N, 128, generator=g) * 10).to(dev)
+    x = torch.randn(B, N, d, generator=g).to(dev)
+    score, thr, cnt, topk = lib.dtp_score(col_part, cls_attn, ta[:, 1:, :], n, T, temp)
+
+    a = col_part.double().sum(1)[:, 1:]
+    a = a / (a.sum(1, keepdim=True) + 1e-8)
+    tb = ta[:, 1:, :T].double()
+    bm = tb.max(2)[0]
+    bm = bm / (bm.sum(1, keepdim=True) + 1e-8)
+    s_ref = (a + bm + cls_attn[:, 1:].double()) / 3.0
+    assert (score.double() - s_ref).abs().max().item() < 1e-8
+    w = torch.softmax(tb / temp, dim=1)
+    thr_ref = (w * score.double()[..., None]).sum(1).min(1)[0]
+    assert (thr.double() - thr_ref).abs().max().item() < 1e-9
+    cnt_ref = (score > thr[:, None]).sum(1)
+    assert torch.equal(cnt.long(), cnt_ref)
+    k = int(topk.item())
+    assert k == int(cnt_ref.max())
+
+    mask_in = torch.where(torch.rand(B, N, generator=g) < 0.3, -10000.0, 0.0).to(dev)
+    for mode in (0, 1, 2):
+        keep, dst, tail_w, tail_idx, mask_out = lib.dtp_select(score, topk, mask_mode=mode,
+                                                               mask_in=mask_in if mode else None)
+        if k < 1 or n - k <= 1:
+            assert bool(keep.all())
+            continue
+        order = torch.sort(score, dim=1, descending=True, stable=True)[1]
+        keep_ref = torch.zeros(B, n, dtype=torch.bool, device=dev)
+        keep_ref.scatter_(1, order[:, :k], True)
+        assert torch.equal(keep.bool(), keep_ref)
+        out = lib.dtp_gather(x, topk, dst, tail_w, tail_idx, k)
+        for b in range(B):
+            idx = keep_ref[b].nonzero().flatten()
+            assert torch.equal(out[b, 0], x[b, 0])
+            assert torch.equal(out[b, 1:1 + k], x[b, 1 + idx])
+            tail = (~keep_ref[b]).nonzero().flatten()
+            wts = score[b, tail].double()
+            wts = wts / (wts.sum() + 1e-8)
+            merged = (wts[:, None] * x[b, 1 + tail].double()).sum(0)
+            assert (out[b, 1 + k].double() - merged).abs().max().item() < 1e-5
+            if mode == 1:
+                exp = torch.cat([mask_in[b, :1], mask_in[b, 1 + order[b, :k + 1]]])
+                assert torch.equal(mask_out[b, :k + 2], exp)
+            if mode == 2:
+                exp = torch.cat([mask_in[b, :1], mask_in[b, 1 + idx], mask_in[b, 1 + order[b, k:k + 1]]])
+                assert torch.equal(mask_out[b, :k + 2], exp)

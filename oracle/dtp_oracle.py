@@ -336,3 +336,33 @@ def vit_macs_from_traces(traces: List[PruneTrace], n0: int, d: int = 768, patch_
         total += vit_layer_macs(n_in, n_out, d)
         n_in = n_out
     return total
+
+
+def text_layer_macs(L_in: int, L_out: int, n_img: int, layer_num: int, d: int = 768, dff: int = 3072,
+                    T: int = 100) -> int:
+    """MACs of one NLVR text layer per sample: L_in tokens through self-attention, L_out
+    through the twin cross-attention (keys/values = n_img image tokens, two images) and the FFN."""
+    macs = 4 * L_in * d * d + 2 * L_in * L_in * d + 2 * (L_in - 1) * d * T
+    macs += 2 * (2 * L_out * d * d + 2 * n_img * d * d + 2 * L_out * n_img * d)
+    if layer_num >= 6:
+        macs += 2 * L_out * d * d
+    return macs + 2 * L_out * d * dff
+
+
+def nlvr_macs_from_trace(trace: "NlvrTrace", n0: int, text_len: int, d: int = 768) -> int:
+    """MACs of one BLIP-NLVR sample (two images + one sentence) along the oracle's pruning trajectory."""
+    total = 2 * vit_macs_from_traces(trace.vit, n0, d)
+    n_img = trace.image_embeds.shape[1]
+    L = text_len
+    for i, tr in enumerate(trace.text):
+        L_out = (tr.k + 2) if tr.pruned else L
+        total += text_layer_macs(L, L_out, n_img, i, d)
+        L = L_out
+    return total + d * d + 2 * d
+
+
+def nlvr_macs_unpruned(n0: int, text_len: int, d: int = 768, depth: int = 12) -> int:
+    total = 2 * ((n0 - 1) * 768 * d + depth * vit_layer_macs(n0, n0, d))
+    for i in range(depth):
+        total += text_layer_macs(text_len, text_len, n0, i, d)
+    return total + d * d + 2 * d

@@ -141,6 +141,11 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
                      const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream);
 
+/* vector_gather (models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :], x [B,L,d] with batch stride bsx, idx [B,K]
+ * (indices are clamped to [0, L)), out [B,K,d] contiguous. */
+int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ SIGNATURES = {
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
 }
 
 
@@ -295,4 +296,16 @@ def dtp_gather(x, topk, dst, tail_w, tail_idx, k):
                                  _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
                                  _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _stream())
     _check(st, "madtp_dtp_gather")
+    return out
+
+
+def gather_rows(x, idx):
+    """x [B,L,d] fp32 (dense rows), idx [B,K] int32 -> [B,K,d]."""
+    B, Ltok, d = x.shape
+    K = idx.shape[1]
+    if x.stride(2) != 1 or x.stride(1) != d:
+        raise RuntimeError("madtp_b200.gather_rows: x rows must be dense")
+    out = torch.empty(B, K, d, dtype=torch.float32, device=x.device)
+    _check(load().madtp_gather_rows(_ptr(x, torch.float32, "x"), x.stride(0), _ptr(idx, torch.int32, "idx"), _ptr(out),
+                                    B, Ltok, K, d, _stream()), "madtp_gather_rows")
     return out

@@ -187,4 +187,9 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
   return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
+int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,
+                      void* stream) {
+  return counted(launch_gather_rows(x, bsx, idx, out, B, L, K, d, as_stream(stream)), (B > 0 && K > 0) ? 1 : 0);
+}
+
 }  // extern "C"

@@ -494,4 +494,32 @@ int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream) {
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// vector_gather: one warp per output row, 128-bit copies. grid = ceil(B*K/8), block = 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ x, long long bsx, const int* __restrict__ idx, float* __restrict__ out,
+                   int B, int L, int K, int d4) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<long long>(B) * K) return;
+  const int b = static_cast<int>(row / K);
+  int j = idx[row];
+  j = j < 0 ? 0 : (j >= L ? L - 1 : j);
+  const float4* src = reinterpret_cast<const float4*>(x + b * bsx) + static_cast<long long>(j) * d4;
+  float4* dst = reinterpret_cast<float4*>(out) + row * d4;
+  for (int c = lane; c < d4; c += 32) dst[c] = src[c];
+}
+
+int launch_gather_rows(const float* x, long long bsx, const int* idx, float* out, int B, int L, int K, int d,
+                       cudaStream_t stream) {
+  MADTP_CHECK_ARG(x && idx && out, "gather_rows: null pointer");
+  MADTP_CHECK_ARG(B >= 0 && L > 0 && K >= 0 && d > 0 && d % 4 == 0 && bsx % 4 == 0, "gather_rows: bad shape");
+  const long long rows = static_cast<long long>(B) * K;
+  if (rows == 0) return kOk;
+  gather_rows_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, stream>>>(x, bsx, idx, out, B, L, K, d / 4);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
 }  // namespace madtp

@@ -61,4 +61,8 @@ struct DtpGatherArgs {
 };
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);
 
+// vector_gather (reference models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :]; one warp per output row.
+int launch_gather_rows(const float* x, long long bsx, const int* idx, float* out, int B, int L, int K, int d,
+                       cudaStream_t stream);
+
 }  // namespace madtp

@@ -1,0 +1,216 @@
+"""Compositions of the C-ABI kernels (madtp_b200/_lib.py) that the module mirrors in vit.py / nlvr_encoder.py /
+med.py / utils.py share. Everything here runs on the GPU through libmadtp_b200.so; there is no CPU path.
+
+Precision lanes (hard part 1):
+  scoring lane  LayerNorm -> q/k/v projection -> attention statistics, and token . codebook^T: fp32-accurate
+                (TF32x3 tensor-core GEMMs with chunk-drained fp32 accumulation, fp32 CUDA-core attention)
+  value lane    attention output projection, FFN, cross-attention: fp16 operands, fp32 accumulation
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+TA_LD = 128  # row pitch of token_att buffers (T = 100 codebook entries padded to a 16-byte multiple of columns)
+
+
+def require_cuda(t: Tensor, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"madtp_b200: {name} must be a CUDA tensor -- this package has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"madtp_b200: {name} must be float32 (the reference's evaluation dtype), got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# prepared weights
+# ------------------------------------------------------------------------------------------------------------------
+class PreparedLinear:
+    """GEMM-ready copies of an nn.Linear: tf32 hi/lo split (scoring lane) and/or fp16 (value lane)."""
+    __slots__ = ("hi", "lo", "w16", "w32", "bias", "out_features", "in_features")
+
+    def __init__(self, weight: Tensor, bias: Optional[Tensor], tf32: bool = False, f16: bool = False,
+                 f32: bool = False, bias_scale: float = 1.0):
+        w = weight.detach().to(torch.float32).contiguous()
+        self.out_features, self.in_features = w.shape
+        self.hi = self.lo = self.w16 = self.w32 = None
+        if tf32:
+            self.hi, self.lo = L.split_tf32(w)
+        if f16:
+            self.w16 = L.cast_f16(w)
+        if f32:
+            self.w32 = w
+        self.bias = None if bias is None else (bias.detach().to(torch.float32) * bias_scale).contiguous()
+
+
+class WeightCache:
+    """Per-module cache of PreparedLinear objects, invalidated when any source parameter is modified or replaced."""
+
+    def __init__(self):
+        self._store = {}
+
+    @staticmethod
+    def _stamp(params):
+        return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params if p is not None)
+
+    def get(self, key, params, build):
+        stamp = self._stamp(params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        val = build()
+        self._store[key] = (stamp, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# row operations
+# ------------------------------------------------------------------------------------------------------------------
+def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float, *, f32=False, tf32=False,
+                   f16=False, split_x=False):
+    """LayerNorm over the rows of x2d [rows, d] with the requested operand copies.
+    Returns dict with any of y, y_hi, y_lo, y16, x_hi, x_lo."""
+    rows, d = x2d.shape
+    dev = x2d.device
+    out = {}
+
+    def new(dt=torch.float32):
+        return torch.empty(rows, d, dtype=dt, device=dev)
+    if f32:
+        out["y"] = new()
+    if tf32:
+        out["y_hi"], out["y_lo"] = new(), new()
+    if f16:
+        out["y16"] = new(torch.float16)
+    if split_x:
+        out["x_hi"], out["x_lo"] = new(), new()
+    L.layernorm(x2d, gamma, beta, eps, y_f32=out.get("y"), y_hi=out.get("y_hi"), y_lo=out.get("y_lo"),
+                y_f16=out.get("y16"), x_hi=out.get("x_hi"), x_lo=out.get("x_lo"))
+    return out
+
+
+def split_rows(x2d: Tensor) -> Tuple[Tensor, Tensor]:
+    """tf32 hi/lo split of fp32 rows (the operand format of the TF32x3 GEMM)."""
+    o = layernorm_rows(x2d, None, None, 0.0, split_x=True)
+    return o["x_hi"], o["x_lo"]
+
+
+def linear_tf32(a_hi: Tensor, a_lo: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, residual=None,
+                act=L.ACT_NONE, alpha=1.0) -> Tensor:
+    if out is None:
+        out = torch.empty(a_hi.shape[0], lin.out_features, dtype=torch.float32, device=a_hi.device)
+    return L.gemm(L.GEMM_TF32X3, a_hi, lin.hi, out, a_lo=a_lo, b_lo=lin.lo, bias=lin.bias, residual=residual, act=act,
+                  alpha=alpha)
+
+
+def linear_f16(a16: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, out_dtype=torch.float32,
+               residual=None, act=L.ACT_NONE, alpha=1.0) -> Tensor:
+    if out is None:
+        out = torch.empty(a16.shape[0], lin.out_features, dtype=out_dtype, device=a16.device)
+    return L.gemm(L.GEMM_F16, a16, lin.w16, out, bias=lin.bias, residual=residual, act=act, alpha=alpha)
+
+
+def linear_f32(a: Tensor, lin: PreparedLinear, *, act=L.ACT_NONE) -> Tensor:
+    """fp32 CUDA-core GEMM for tiny heads (cls_head)."""
+    out = torch.empty(a.shape[0], lin.out_features, dtype=torch.float32, device=a.device)
+    return L.gemm(L.GEMM_SIMT, a, lin.w32, out, bias=lin.bias, act=act)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Query_model  (reference models/utils.py:147-183)
+# ------------------------------------------------------------------------------------------------------------------
+def prepare_codebook(space_dict: Tensor):
+    """space_dict [T, sd_dim] -> tf32 hi/lo, rows padded to TA_LD so token_att rows are 16-byte aligned."""
+    T, d = space_dict.shape
+    if T > TA_LD:
+        raise RuntimeError(f"madtp_b200: codebook size {T} exceeds the supported {TA_LD}")
+    pad = torch.zeros(TA_LD, d, dtype=torch.float32, device=space_dict.device)
+    pad[:T] = space_dict.detach()
+    hi, lo = L.split_tf32(pad)
+    return hi, lo, T
+
+
+def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int, sd_ft: Optional[Tensor],
+                     first_token: int = 1):
+    """token_att for EVERY row of x3d [B,N,d] (one GEMM over the flat rows), then the over-token softmax
+    aggregation over tokens first_token..N-1.  Returns (token_att view [B, N-first_token, T], sd_ft [B,T,d])."""
+    B, N, d = x3d.shape
+    hi, lo, T = book
+    ta = torch.empty(B * N, TA_LD, dtype=torch.float32, device=x3d.device)
+    L.gemm(L.GEMM_TF32X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo)
+    ta3 = ta.view(B, N, TA_LD)[:, first_token:, :]
+    n = N - first_token
+    div = math.sqrt(sd_dim)
+    cm, cs = L.token_colstats(ta3, n, T, div)
+    accumulate = sd_ft is not None
+    if sd_ft is None:
+        sd_ft = torch.empty(B, T, d, dtype=torch.float32, device=x3d.device)
+    L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate)
+    return ta3[:, :, :T], sd_ft
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# attention + pruning statistics
+# ------------------------------------------------------------------------------------------------------------------
+@dataclass
+class AttnStats:
+    """What Reduce_token needs from the self-attention instead of the materialised [B,H,N,N] map
+    (reference models/vit.py:83,101): per-query-tile partial column sums of max_h P, and cls_attn."""
+    col_part: Tensor   # [B, n_parts, N]
+    cls_attn: Tensor   # [B, N]  (entry 0 unused)
+
+
+def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_mask: Optional[Tensor],
+                   want_stats: bool, ctx16: Optional[Tensor] = None):
+    """q,k,v: [B,N,H*64] fp32 views. Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
+    B, N, C = q.shape
+    dev = q.device
+    if ctx16 is None:
+        ctx16 = torch.empty(B, N, C, dtype=torch.float16, device=dev)
+    if not want_stats:
+        L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask)
+        return ctx16, None
+    rows = torch.empty(3, B, H, N, dtype=torch.float32, device=dev)
+    stats = (rows[0], rows[1], rows[2])
+    L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, stats=stats)
+    n_parts = (N + 63) // 64
+    col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
+    cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
+    L.attn_stats(q, k, H, scale, stats, col_part, cls_attn, key_mask=key_mask)
+    return ctx16, AttnStats(col_part, cls_attn)
+
+
+@dataclass
+class PruneResult:
+    x: Tensor                       # [B, k+2, d] (or the input when nothing was pruned)
+    pruned: bool
+    k: int
+    score: Tensor                   # [B, n]
+    threshold: Tensor               # [B]
+    count: Tensor                   # [B] int32
+    keep: Optional[Tensor] = None   # [B, n] uint8
+    mask: Optional[Tensor] = None   # [B, k+2] additive mask (text)
+
+
+def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,
+              mask_in: Optional[Tensor] = None) -> PruneResult:
+    """Reduce_token on x [B, n+1, d] (position 0 always survives). reference models/vit.py:123-163,
+    models/nlvr_encoder.py:400-454 (mask_mode 1), models/med.py:345-391 (mask_mode 2)."""
+    B, N, d = x.shape
+    n = N - 1
+    T = token_att.shape[2]
+    score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature)
+    k = int(topk.item())            # the reference's one host sync per pruned layer (models/vit.py:145)
+    if k < 1 or n - k <= 1:         # models/vit.py:148-149
+        return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
+    keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in)
+    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k)
+    return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2])

@@ -1,0 +1,563 @@
+"""Mirror of the reference's models/nlvr_encoder.py hot path -- the BERT text encoder with twin cross-attention used
+by BLIP-NLVR: BertEmbeddings (:43-85), BertSelfAttention (:88-237), BertSelfOutput (:240-271), BertAttention
+(:274-349), BertIntermediate/BertOutput (:352-385), BertLayer (:388-559), BertEncoder (:562-687), BertModel
+(:760-1015). Same constructor arguments, forward signatures (including nlvr_encoder's positional order, which differs
+from med.py), return arity and state-dict keys; executed by the sm_100a kernels of libmadtp_b200.so.
+
+Contract differences: evaluation forward only; `past_key_value`, `head_mask`, `output_attentions`,
+relative position embeddings and the decoder (`is_decoder=True`) are not on the pruned encoder path and raise;
+attention maps are AttnStats handles; survivors keep ascending token order; the key/value cache slot of the returned
+tuples is None.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import functional as Fn
+from .utils import Query_model, vector_gather  # noqa: F401
+from .vit import _eval_only
+
+
+class EncoderOutput:
+    """Stand-in for transformers' BaseModelOutputWithPoolingAndCrossAttentions: attribute and [0] access."""
+
+    def __init__(self, last_hidden_state, pooler_output=None):
+        self.last_hidden_state = last_hidden_state
+        self.pooler_output = pooler_output
+        self.past_key_values = None
+        self.hidden_states = None
+        self.attentions = None
+        self.cross_attentions = None
+
+    def __getitem__(self, i):
+        return (self.last_hidden_state, self.pooler_output)[i]
+
+
+def _unsupported(**kw):
+    for name, val in kw.items():
+        if val is not None and val is not False:
+            raise NotImplementedError(f"madtp_b200: `{name}` is not part of the pruned encoder forward path")
+
+
+def _key_mask(ext_mask: Optional[torch.Tensor], B: int, N: int) -> Optional[torch.Tensor]:
+    """additive extended mask [B,1,1,N] (or [B,N]) -> contiguous [B,N] fp32."""
+    if ext_mask is None:
+        return None
+    m = ext_mask.reshape(B, -1)
+    if m.shape[1] != N:
+        raise RuntimeError("madtp_b200: attention mask must broadcast as [B,1,1,N] over keys")
+    return m.to(torch.float32).contiguous()
+
+
+class BertEmbeddings(nn.Module):
+    """word + position embeddings -> LayerNorm (models/nlvr_encoder.py:43-85)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
+        self.position_embedding_type = getattr(config, "position_embedding_type", "absolute")
+        self.config = config
+
+    def forward(self, input_ids=None, position_ids=None, inputs_embeds=None, past_key_values_length=0):
+        _unsupported(position_ids=position_ids, inputs_embeds=inputs_embeds)
+        if past_key_values_length != 0 or self.position_embedding_type != "absolute":
+            raise NotImplementedError("madtp_b200: only absolute positions without a key/value cache")
+        if not input_ids.is_cuda:
+            raise RuntimeError("madtp_b200: input_ids must be a CUDA tensor -- this package has no CPU fallback")
+        B, Ltok = input_ids.shape
+        e = L.bert_embed(input_ids.to(torch.int64), self.word_embeddings.weight.detach(),
+                         self.position_embeddings.weight.detach())
+        d = e.shape[-1]
+        y = Fn.layernorm_rows(e.view(B * Ltok, d), self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps,
+                              f32=True)["y"]
+        return y.view(B, Ltok, d)
+
+
+class BertSelfAttention(nn.Module):
+    def __init__(self, config, is_cross_attention):
+        super().__init__()
+        self.config = config
+        if config.hidden_size % config.num_attention_heads != 0 and not hasattr(config, "embedding_size"):
+            raise ValueError("The hidden size (%d) is not a multiple of the number of attention heads (%d)" %
+                             (config.hidden_size, config.num_attention_heads))
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = int(config.hidden_size / config.num_attention_heads)
+        if self.attention_head_size != 64:
+            raise RuntimeError("madtp_b200: the attention kernels are built for head_dim 64")
+        self.all_head_size = self.num_attention_heads * self.attention_head_size
+        self.query = nn.Linear(config.hidden_size, self.all_head_size)
+        kv_in = config.encoder_width if is_cross_attention else config.hidden_size
+        self.key = nn.Linear(kv_in, self.all_head_size)
+        self.value = nn.Linear(kv_in, self.all_head_size)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+        self.position_embedding_type = getattr(config, "position_embedding_type", "absolute")
+        if self.position_embedding_type != "absolute":
+            raise NotImplementedError("madtp_b200: relative position embeddings are not on the pruned path")
+        self.save_attention = False
+        self.attention_map = None
+        self.cls_attn = None
+        self.is_cross_attention = bool(is_cross_attention)
+        self._cache = Fn.WeightCache()
+
+    def save_attn_gradients(self, attn_gradients):
+        self.attn_gradients = attn_gradients
+
+    def get_attn_gradients(self):
+        return self.attn_gradients
+
+    def save_attention_map(self, attention_map):
+        self.attention_map = attention_map
+
+    def get_attention_map(self):
+        return self.attention_map
+
+    def save_cls_attn(self, cls_attn):
+        self.cls_attn = cls_attn
+
+    def get_cls_attn(self):
+        return self.cls_attn
+
+    # -- prepared operands ------------------------------------------------------------------------------------
+    def _qkv_tf32(self):
+        ps = [self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight, self.value.bias]
+        return self._cache.get("qkv", ps, lambda: Fn.PreparedLinear(
+            torch.cat([self.query.weight, self.key.weight, self.value.weight], 0),
+            torch.cat([self.query.bias, self.key.bias, self.value.bias], 0), tf32=True))
+
+    def _q_f16(self):
+        return self._cache.get("q16", [self.query.weight, self.query.bias],
+                               lambda: Fn.PreparedLinear(self.query.weight, self.query.bias, f16=True))
+
+    def _kv_f16(self):
+        ps = [self.key.weight, self.key.bias, self.value.weight, self.value.bias]
+        return self._cache.get("kv16", ps, lambda: Fn.PreparedLinear(
+            torch.cat([self.key.weight, self.value.weight], 0), torch.cat([self.key.bias, self.value.bias], 0),
+            f16=True))
+
+    # -- kernels ----------------------------------------------------------------------------------------------
+    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True):
+        """Self-attention on the scoring lane. Returns ctx16 [B,L,C]; stores AttnStats + cls_attn (:213-235)."""
+        C = self.all_head_size
+        qkv = Fn.linear_tf32(h_hi, h_lo, self._qkv_tf32()).view(B, Ltok, 3 * C)
+        ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_attention_heads,
+                                         1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats)
+        self.save_attention_map(stats)
+        self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
+        return ctx16
+
+    def project_kv(self, enc16_rows):
+        """enc16_rows [B*Nk, width] fp16 -> fp32 [B*Nk, 2C] = [key | value] projections of the encoder states."""
+        return Fn.linear_f16(enc16_rows, self._kv_f16())
+
+    def cross_rows(self, q, k, v, key_mask, out16):
+        """q [B,Lq,C], k/v [B,Nk,C] fp32 views -> context written into out16 [B,Lq,C] (fp16 view)."""
+        L.attn_fwd(q, k, v, self.num_attention_heads, 1.0 / math.sqrt(self.attention_head_size), out16,
+                   key_mask=key_mask)
+        return out16
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_value=None, output_attentions=False):
+        Fn.require_cuda(hidden_states, "hidden_states")
+        _eval_only(self)
+        _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
+        B, Ltok, d = hidden_states.shape
+        C = self.all_head_size
+        if encoder_hidden_states is None:
+            h = hidden_states.contiguous()
+            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+            ctx16 = self.self_rows(h_hi, h_lo, B, Ltok, _key_mask(attention_mask, B, Ltok))
+        else:
+            enc = encoder_hidden_states.contiguous()
+            Nk = enc.shape[1]
+            kv = self.project_kv(L.cast_f16(enc.view(B * Nk, -1))).view(B, Nk, 2 * C)
+            q = Fn.linear_f16(L.cast_f16(hidden_states.reshape(B * Ltok, d)), self._q_f16()).view(B, Ltok, C)
+            ctx16 = torch.empty(B, Ltok, C, dtype=torch.float16, device=q.device)
+            self.cross_rows(q, kv[..., :C], kv[..., C:], _key_mask(encoder_attention_mask, B, Nk), ctx16)
+        return (ctx16.float(), None)
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, config, twin=False, merge=False):
+        super().__init__()
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        if twin:
+            self.dense0 = nn.Linear(config.hidden_size, config.hidden_size)
+            self.dense1 = nn.Linear(config.hidden_size, config.hidden_size)
+        else:
+            self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.twin = twin
+        if merge:
+            self.act = nn.GELU()
+            self.merge_layer = nn.Linear(config.hidden_size * 2, config.hidden_size)
+            self.merge = True
+        else:
+            self.merge = False
+        self._cache = Fn.WeightCache()
+
+    def _dense(self):
+        return self._cache.get("dense", [self.dense.weight, self.dense.bias],
+                               lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
+
+    def _twin_avg(self):
+        """(dense0(c0) + dense1(c1)) / 2 as ONE GEMM over K = 2C: 0.5 * [c0|c1] . [W0|W1]^T + 0.5 (b0 + b1)."""
+        ps = [self.dense0.weight, self.dense0.bias, self.dense1.weight, self.dense1.bias]
+        return self._cache.get("avg", ps, lambda: Fn.PreparedLinear(
+            torch.cat([self.dense0.weight, self.dense1.weight], 1), self.dense0.bias + self.dense1.bias, f16=True,
+            bias_scale=0.5))
+
+    def _twin_sep(self):
+        d0 = self._cache.get("d0", [self.dense0.weight, self.dense0.bias],
+                             lambda: Fn.PreparedLinear(self.dense0.weight, self.dense0.bias, f16=True))
+        d1 = self._cache.get("d1", [self.dense1.weight, self.dense1.bias],
+                             lambda: Fn.PreparedLinear(self.dense1.weight, self.dense1.bias, f16=True))
+        mg = self._cache.get("mg", [self.merge_layer.weight, self.merge_layer.bias],
+                             lambda: Fn.PreparedLinear(self.merge_layer.weight, self.merge_layer.bias, f16=True))
+        return d0, d1, mg
+
+    def rows(self, ctx16, residual, *, f16=False, tf32=False):
+        """ctx16 [rows, C] (or [rows, 2C] = [ctx0|ctx1] for the twin); residual fp32 [rows, C].
+        Returns the layernorm_rows dict of LayerNorm(dense(ctx) + residual) (always with 'y')."""
+        if not self.twin:
+            pre = Fn.linear_f16(ctx16, self._dense(), residual=residual)
+        elif not self.merge:
+            pre = Fn.linear_f16(ctx16, self._twin_avg(), residual=residual, alpha=0.5)
+        else:
+            d0, d1, mg = self._twin_sep()
+            C = d0.out_features
+            d01 = torch.empty(ctx16.shape[0], 2 * C, dtype=torch.float16, device=ctx16.device)
+            Fn.linear_f16(ctx16[:, :C], d0, out=d01[:, :C])
+            Fn.linear_f16(ctx16[:, C:], d1, out=d01[:, C:])
+            pre = Fn.linear_f16(d01, mg, residual=residual)
+        return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
+                                 f16=f16, tf32=tf32)
+
+    def forward(self, hidden_states, input_tensor):
+        _eval_only(self)
+        shape = input_tensor.shape
+        C = shape[-1]
+        res = input_tensor.reshape(-1, C).contiguous()
+        if type(hidden_states) == list:
+            ctx16 = torch.cat([L.cast_f16(hidden_states[0].reshape(-1, C)), L.cast_f16(hidden_states[1].reshape(-1, C))],
+                              dim=1)
+        else:
+            ctx16 = L.cast_f16(hidden_states.reshape(-1, C))
+        return self.rows(ctx16, res)["y"].view(shape)
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config, is_cross_attention=False, layer_num=-1):
+        super().__init__()
+        if is_cross_attention:
+            self.self0 = BertSelfAttention(config, is_cross_attention)
+            self.self1 = BertSelfAttention(config, is_cross_attention)
+        else:
+            self.self = BertSelfAttention(config, is_cross_attention)
+        self.output = BertSelfOutput(config, twin=is_cross_attention, merge=(is_cross_attention and layer_num >= 6))
+        self.is_cross_attention = bool(is_cross_attention)
+        self.pruned_heads = set()
+
+    def prune_heads(self, heads):
+        if len(heads):
+            raise NotImplementedError("madtp_b200: head pruning is not supported")
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_value=None, output_attentions=False, space_dict=None):
+        if type(encoder_hidden_states) == list:
+            o0 = self.self0(hidden_states, attention_mask, head_mask, encoder_hidden_states[0],
+                            encoder_attention_mask[0], past_key_value, output_attentions)
+            o1 = self.self1(hidden_states, attention_mask, head_mask, encoder_hidden_states[1],
+                            encoder_attention_mask[1], past_key_value, output_attentions)
+            attention_output = self.output([o0[0], o1[0]], hidden_states)
+            return (attention_output,) + o0[1:]
+        o = self.self(hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
+                      past_key_value, output_attentions)
+        return (self.output(o[0], hidden_states),) + o[1:]
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        act = config.hidden_act
+        if act not in ("gelu", "relu"):
+            raise NotImplementedError(f"madtp_b200: hidden_act {act!r}")
+        self.act_code = L.ACT_GELU if act == "gelu" else L.ACT_RELU
+        self.intermediate_act_fn = nn.GELU() if act == "gelu" else nn.ReLU()
+        self._cache = Fn.WeightCache()
+
+    def rows(self, y16):
+        w = self._cache.get("dense", [self.dense.weight, self.dense.bias],
+                            lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
+        return Fn.linear_f16(y16, w, out_dtype=torch.float16, act=self.act_code)
+
+    def forward(self, hidden_states):
+        _eval_only(self)
+        shape = hidden_states.shape
+        return self.rows(L.cast_f16(hidden_states.reshape(-1, shape[-1]))).float().view(*shape[:-1], -1)
+
+
+class BertOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self._cache = Fn.WeightCache()
+
+    def rows(self, inter16, residual):
+        w = self._cache.get("dense", [self.dense.weight, self.dense.bias],
+                            lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
+        pre = Fn.linear_f16(inter16, w, residual=residual)
+        return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True)["y"]
+
+    def forward(self, hidden_states, input_tensor):
+        _eval_only(self)
+        shape = input_tensor.shape
+        return self.rows(L.cast_f16(hidden_states.reshape(-1, hidden_states.shape[-1])),
+                         input_tensor.reshape(-1, shape[-1]).contiguous()).view(shape)
+
+
+class BertLayer(nn.Module):
+    MASK_MODE = 1   # nlvr_encoder.py:451-452: slot r of the pruned mask <- mask of the r-th ranked token
+
+    def __init__(self, config, layer_num):
+        super().__init__()
+        self.config = config
+        self.chunk_size_feed_forward = getattr(config, "chunk_size_feed_forward", 0)
+        self.seq_len_dim = 1
+        self.attention = BertAttention(config)
+        self.layer_num = layer_num
+        if self.config.add_cross_attention:
+            self.crossattention = BertAttention(config, is_cross_attention=self.config.add_cross_attention,
+                                                layer_num=layer_num)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+        self.last_prune = None
+
+    def Reduce_token(self, x, reduce_num, temperature=0, self_attn=None, cls_attn=None, token_attn=None, mask=None):
+        """x [B,n,d] prunable tokens, mask [B,n] additive -> (x' [B,k+1,d], mask' [B,k+1]) or the inputs unchanged."""
+        Fn.require_cuda(x, "x")
+        if not isinstance(self_attn, Fn.AttnStats):
+            raise RuntimeError("madtp_b200: Reduce_token expects the AttnStats handle of get_attention_map()")
+        B, n, d = x.shape
+        xin = torch.cat([x[:, :1, :], x], dim=1).contiguous()
+        min_ = None
+        if mask is not None:
+            min_ = torch.cat([mask[:, :1], mask], dim=1).to(torch.float32).contiguous()
+        res = Fn.dtp_prune(xin, self_attn, token_attn, float(temperature),
+                           mask_mode=self.MASK_MODE if mask is not None else 0, mask_in=min_)
+        self.last_prune = res
+        if not res.pruned:
+            return x, mask
+        return res.x[:, 1:, :], (None if mask is None else res.mask[:, 1:])
+
+    def forward(self, hidden_states, attention_mask=None, space_dict=None, head_mask=None,
+                encoder_hidden_states=None, encoder_attention_mask=None, past_key_value=None,
+                output_attentions=False, mode=None, token_attn=None, reduce_num=0, temperature=0, _kv=None):
+        """Returns (layer_output, None, attention_mask') -- the last element is the pruned extended mask
+        (models/nlvr_encoder.py:551-553), consumed by BertEncoder."""
+        Fn.require_cuda(hidden_states, "hidden_states")
+        _eval_only(self)
+        _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
+        h = hidden_states.contiguous()
+        B, Ltok, d = h.shape
+        key_mask = _key_mask(attention_mask, B, Ltok)
+        prune = temperature > 0
+        if prune and token_attn is None:
+            raise RuntimeError("madtp_b200: temperature > 0 needs token_attn")
+
+        # self-attention + output LayerNorm (:501-509)
+        h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+        sa = self.attention.self
+        ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune)
+        att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=not prune)
+        att_f32, att16 = att["y"].view(B, Ltok, d), att.get("y16")
+
+        # dynamic token pruning between self- and cross-attention (:519-533)
+        self.last_prune = None
+        if prune:
+            if key_mask is None:
+                key_mask = torch.zeros(B, Ltok, dtype=torch.float32, device=h.device)
+            res = Fn.dtp_prune(att_f32, sa.get_attention_map(), token_attn, float(temperature),
+                               mask_mode=self.MASK_MODE, mask_in=key_mask)
+            self.last_prune = res
+            att_f32 = res.x
+            if res.pruned:
+                key_mask = res.mask.contiguous()
+                Ltok = att_f32.shape[1]
+            attention_mask = key_mask.view(B, 1, 1, Ltok)
+            att16 = L.cast_f16(att_f32.reshape(B * Ltok, d))
+        att_rows = att_f32.reshape(B * Ltok, d)
+
+        if mode == 'multimodal':
+            assert encoder_hidden_states is not None, "encoder_hidden_states must be given for cross-attention layers"
+            att_rows, att16 = self._cross(att_rows, att16, B, Ltok, encoder_hidden_states, encoder_attention_mask, _kv)
+
+        inter16 = self.intermediate.rows(att16)
+        out = self.output.rows(inter16, att_rows).view(B, Ltok, d)
+        return (out, None, attention_mask)
+
+    def _cross(self, att_rows, att16, B, Ltok, enc, enc_mask, kv):
+        """Twin (list-valued encoder states, :312-335) or single cross-attention + output LayerNorm."""
+        ca = self.crossattention
+        d = att_rows.shape[1]
+        if type(enc) == list:
+            selfs = [ca.self0, ca.self1]
+            masks = enc_mask if type(enc_mask) == list else [enc_mask, enc_mask]
+        else:
+            selfs, enc, masks = [ca.self], [enc], [enc_mask]
+        C = selfs[0].all_head_size
+        nb = len(selfs)
+        ctx = torch.empty(B, Ltok, nb * C, dtype=torch.float16, device=att_rows.device)
+        for i, s in enumerate(selfs):
+            q = Fn.linear_f16(att16, s._q_f16()).view(B, Ltok, C)
+            Nk = enc[i].shape[1]
+            if kv is not None:
+                k, v = kv[i]
+            else:
+                e16 = L.cast_f16(enc[i].contiguous().view(B * Nk, -1))
+                kvp = s.project_kv(e16).view(B, Nk, 2 * C)
+                k, v = kvp[..., :C], kvp[..., C:]
+            s.cross_rows(q, k, v, _key_mask(masks[i], B, Nk), ctx[..., i * C:(i + 1) * C])
+        o = ca.output.rows(ctx.view(B * Ltok, nb * C), att_rows, f16=True)
+        return o["y"], o["y16"]
+
+    def feed_forward_chunk(self, attention_output):
+        return self.output(self.intermediate(attention_output), attention_output)
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config, sd_dim=768):
+        super().__init__()
+        self.config = config
+        self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.gradient_checkpointing = False
+        self.txt_query_model = Query_model(ft_dim=config.hidden_size, sd_dim=sd_dim, temperature=1,
+                                           att_func_type='sparsemax', pool_type='max')
+        self._cache = Fn.WeightCache()
+
+    def _all_kv_weights(self, which: str):
+        """[key; value] weights of crossattention.<which> of every layer stacked along N: one GEMM projects the image
+        tokens for all layers at once (they do not depend on the text stream)."""
+        selfs = [getattr(l.crossattention, which) for l in self.layer]
+        ps = [p for s in selfs for p in (s.key.weight, s.key.bias, s.value.weight, s.value.bias)]
+        return self._cache.get("kv_" + which, ps, lambda: Fn.PreparedLinear(
+            torch.cat([torch.cat([s.key.weight, s.value.weight], 0) for s in selfs], 0),
+            torch.cat([torch.cat([s.key.bias, s.value.bias], 0) for s in selfs], 0), f16=True))
+
+    def _project_encoder_states(self, enc):
+        """Returns per-layer [(k0, v0), (k1, v1)] (or [(k, v)]) fp32 views [B, Nk, C] for every layer."""
+        names = ["self0", "self1"] if type(enc) == list else ["self"]
+        encs = enc if type(enc) == list else [enc]
+        C = self.config.hidden_size
+        per_layer = [[] for _ in self.layer]
+        for name, e in zip(names, encs):
+            Fn.require_cuda(e, "encoder_hidden_states")
+            B, Nk, w = e.shape
+            e16 = L.cast_f16(e.contiguous().view(B * Nk, w))
+            allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(B, Nk, -1)
+            for i in range(len(self.layer)):
+                o = i * 2 * C
+                per_layer[i].append((allkv[..., o:o + C], allkv[..., o + C:o + 2 * C]))
+        return per_layer
+
+    def forward(self, hidden_states, attention_mask=None, space_dict=None, temperature=0, head_mask=None,
+                encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None, use_cache=None,
+                output_attentions=False, output_hidden_states=False, return_dict=True, mode='multimodal'):
+        _unsupported(past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
+                     output_hidden_states=output_hidden_states)
+        Fn.require_cuda(hidden_states, "hidden_states")
+        if space_dict is None:
+            raise RuntimeError("madtp_b200: nlvr_encoder.BertEncoder always queries the codebook (:605-608)")
+        B = hidden_states.shape[0]
+        token_num = hidden_states.shape[-2]
+        reduce_num = int((token_num - 1) // self.config.num_hidden_layers)
+        kv = None
+        if mode == 'multimodal' and encoder_hidden_states is not None:
+            kv = self._project_encoder_states(encoder_hidden_states)
+        sd_txt_ft_all = None
+        for i, layer_module in enumerate(self.layer):
+            h = hidden_states.contiguous()
+            Ltok, d = h.shape[1], h.shape[2]
+            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+            token_attn, sd_txt_ft_all = self.txt_query_model.forward_rows(h, h_hi, h_lo, space_dict, sd_txt_ft_all)
+            layer_outputs = layer_module(h, attention_mask, space_dict, None, encoder_hidden_states,
+                                         encoder_attention_mask, None, False, mode=mode, token_attn=token_attn,
+                                         reduce_num=reduce_num, temperature=temperature,
+                                         _kv=None if kv is None else kv[i])
+            hidden_states = layer_outputs[0]
+            attention_mask = layer_outputs[-1]
+        if not return_dict:
+            return (hidden_states,), sd_txt_ft_all
+        return EncoderOutput(hidden_states), sd_txt_ft_all
+
+
+class BertModel(nn.Module):
+    """models/nlvr_encoder.py:760-1015 without the HuggingFace PreTrainedModel machinery (no pooler on this path)."""
+
+    def __init__(self, config, add_pooling_layer=True, sd_dim=768):
+        super().__init__()
+        if add_pooling_layer:
+            raise NotImplementedError("madtp_b200: the pooler is not used by BLIP (add_pooling_layer=False)")
+        self.config = config
+        self.embeddings = BertEmbeddings(config)
+        self.encoder = BertEncoder(config, sd_dim)
+        self.pooler = None
+
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    @staticmethod
+    def get_extended_attention_mask(attention_mask, input_shape=None, device=None, is_decoder=False):
+        """(1 - mask) * -10000 broadcastable over heads and queries (:826-871)."""
+        if is_decoder:
+            raise NotImplementedError("madtp_b200: decoder (causal) masks are not on the pruned encoder path")
+        if attention_mask.dim() != 2:
+            raise NotImplementedError("madtp_b200: only [batch, seq] attention masks")
+        return (1.0 - attention_mask[:, None, None, :].to(torch.float32)) * -10000.0
+
+    invert_attention_mask = get_extended_attention_mask
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, space_dict=None, temperature=0, position_ids=None,
+                head_mask=None, inputs_embeds=None, encoder_embeds=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_values=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, is_decoder=False, mode='multimodal'):
+        _eval_only(self)
+        _unsupported(position_ids=position_ids, head_mask=head_mask, inputs_embeds=inputs_embeds,
+                     past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
+                     output_hidden_states=output_hidden_states, is_decoder=is_decoder)
+        if input_ids is not None:
+            B, Ltok = input_ids.shape
+            device = input_ids.device
+        elif encoder_embeds is not None:
+            B, Ltok = encoder_embeds.shape[:2]
+            device = encoder_embeds.device
+        else:
+            raise ValueError("You have to specify either input_ids or encoder_embeds")
+        if attention_mask is None:
+            attention_mask = torch.ones((B, Ltok), device=device)
+        ext = self.get_extended_attention_mask(attention_mask)
+        enc_ext = None
+        if encoder_hidden_states is not None:
+            if type(encoder_attention_mask) == list:
+                enc_ext = [self.invert_attention_mask(m) for m in encoder_attention_mask]
+            elif encoder_attention_mask is not None:
+                enc_ext = self.invert_attention_mask(encoder_attention_mask)
+            if enc_ext is not None and type(encoder_hidden_states) == list and type(enc_ext) != list:
+                enc_ext = [enc_ext] * len(encoder_hidden_states)
+        emb = self.embeddings(input_ids=input_ids) if encoder_embeds is None else encoder_embeds
+        out, sd_txt_ft = self.encoder(emb, attention_mask=ext, space_dict=space_dict, temperature=temperature,
+                                      encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=enc_ext,
+                                      mode=mode)
+        return out, sd_txt_ft

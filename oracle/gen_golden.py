@@ -64,9 +64,7 @@ class GatherRecorder:
 # ---------------------------------------------------------------------------------------------------------------
 # BASELINE config 1: one vit.Block + Query_model, B=2, N=197
 # ---------------------------------------------------------------------------------------------------------------
-def block_inputs(seed: int = 0, B: int = 2, N: int = 197, d: int = 768, T: int = 100):
-    g = torch.Generator().manual_seed(seed)
-    return torch.randn(B, N, d, generator=g), torch.randn(T, d, generator=g)
+block_inputs = weights.block_inputs
 
 
 def gen_block():

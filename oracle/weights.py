@@ -125,3 +125,18 @@ def nlvr_inputs(pairs: int, img_size: int = 384, text_len: int = 20, seed: int =
             full_mask[b, :lens[b]] = 1
         ids, mask = full_ids, full_mask
     return images, ids, mask
+
+
+def block_inputs(seed: int = 0, B: int = 2, N: int = 197, d: int = 768, T: int = 100):
+    """BASELINE config 1 inputs: layer input x [B,N,d] and codebook [T,d], both ~ N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, N, d, generator=g), torch.randn(T, d, generator=g)
+
+
+def tensor_digest(*tensors) -> str:
+    """sha256 prefix of the raw bytes -- fixtures store it so a drifting RNG is detected instead of mis-compared."""
+    import hashlib
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(t.detach().contiguous().cpu().numpy().tobytes())
+    return h.hexdigest()[:16]

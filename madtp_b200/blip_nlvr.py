@@ -1,0 +1,128 @@
+"""Mirror of the reference's models/blip_nlvr.py evaluation forward (BLIP_NLVR.forward(train=False), :63-81,99-100):
+pruned ViT on cat(image0, image1) -> split -> twin cross-attention text encoder -> cls_head. Same constructor
+arguments, attribute names and state-dict keys (`space_dict`, `visual_encoder.*`, `text_encoder.*`, `cls_head.*`).
+
+The HuggingFace tokenizer is host-side I/O outside the hot path: pass `tokenizer=` (any callable with the
+BertTokenizer call signature and an `enc_token_id`), or hand `forward` pre-tokenised text (an object with
+`input_ids` / `attention_mask`, as the reference's own forward_throughput does, :103-120).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from .configuration import BertConfig
+from .nlvr_encoder import BertModel
+from .vit import VisionTransformer, interpolate_pos_embed
+
+ENC_TOKEN_ID = 30523    # id of '[ENC]' after models/blip.py:222-224 extends bert-base-uncased (30522 + [DEC] + [ENC])
+
+
+def create_vit(vit, image_size, use_grad_checkpointing=False, ckpt_layer=0, drop_path_rate=0, evaluate=False,
+               sd_dim=768, map_func=False):
+    """models/blip.py:228-247."""
+    if vit == 'base':
+        vision_width = 768
+        enc = VisionTransformer(img_size=image_size, patch_size=16, embed_dim=vision_width, depth=12, num_heads=12,
+                                evaluate=evaluate, sd_dim=sd_dim, map_func=map_func)
+    elif vit == 'large':
+        vision_width = 1024
+        enc = VisionTransformer(img_size=image_size, patch_size=16, embed_dim=vision_width, depth=24, num_heads=16,
+                                evaluate=evaluate, sd_dim=sd_dim, map_func=map_func)
+    else:
+        raise ValueError(vit)
+    return enc, vision_width
+
+
+class TokenizedText:
+    def __init__(self, input_ids, attention_mask):
+        self.input_ids, self.attention_mask = input_ids, attention_mask
+
+    def to(self, device):
+        return TokenizedText(self.input_ids.to(device), self.attention_mask.to(device))
+
+
+class BLIP_NLVR(nn.Module):
+    def __init__(self, med_config='configs/med_config.json', image_size=480, vit='base', vit_grad_ckpt=False,
+                 vit_ckpt_layer=0, evaluate=False, config=None, tokenizer=None):
+        super().__init__()
+        self.layers = 12 if vit == 'base' else 24
+        if config is None:
+            self.sd_num, self.sd_dim, self.batch_size = 100, 768, 16
+        else:
+            self.sd_num, self.sd_dim, self.batch_size = config['sd_num'], config['sd_dim'], config['batch_size_train']
+        self.space_dict = nn.Parameter(torch.randn(self.sd_num, self.sd_dim))
+        self.world_size = int(os.environ.get('WORLD_SIZE', 1))
+        self.visual_encoder, vision_width = create_vit(vit, image_size, vit_grad_ckpt, vit_ckpt_layer,
+                                                       drop_path_rate=0.1, evaluate=evaluate, sd_dim=self.sd_dim)
+        self.tokenizer = tokenizer
+        cfg = BertConfig.from_json_file(med_config) if (isinstance(med_config, str) and os.path.isfile(med_config)) \
+            else (med_config if isinstance(med_config, BertConfig) else BertConfig())
+        cfg.encoder_width = vision_width
+        cfg.evaluate = evaluate
+        self.text_encoder = BertModel(config=cfg, add_pooling_layer=False, sd_dim=self.sd_dim)
+        hs = cfg.hidden_size
+        self.cls_head = nn.Sequential(nn.Linear(hs, hs), nn.ReLU(), nn.Linear(hs, 2))
+        self._cache = Fn.WeightCache()
+
+    def _tokenize(self, text, device):
+        if hasattr(text, "input_ids"):
+            return text.input_ids.to(device).clone(), text.attention_mask.to(device)
+        if isinstance(text, (tuple, list)) and len(text) == 2 and torch.is_tensor(text[0]):
+            return text[0].to(device).clone(), text[1].to(device)
+        if self.tokenizer is None:
+            raise RuntimeError("madtp_b200.BLIP_NLVR: pass tokenizer= or pre-tokenised text (input_ids, attention_mask)")
+        t = self.tokenizer(text, padding='longest', return_tensors="pt").to(device)
+        return t.input_ids.clone(), t.attention_mask
+
+    @torch.no_grad()
+    def forward(self, image, text, targets, temperature=0, train=True):
+        if train:
+            raise NotImplementedError("madtp_b200 implements the evaluation forward (train=False) only")
+        image_embeds, sd_img_ft = self.visual_encoder(image, space_dict=self.space_dict, temperature=temperature)
+        P = targets.size(0) if torch.is_tensor(targets) else int(targets)
+        image0_embeds, image1_embeds = image_embeds[:P], image_embeds[P:]                   # blip_nlvr.py:67
+        input_ids, attention_mask = self._tokenize(text, image.device)
+        enc_id = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        input_ids[:, 0] = enc_id                                                            # blip_nlvr.py:69
+        # image_atts is all ones (blip_nlvr.py:66) -> the additive encoder mask is identically zero: pass None
+        output, sd_txt_ft = self.text_encoder(input_ids, attention_mask=attention_mask,
+                                              encoder_hidden_states=[image0_embeds, image1_embeds],
+                                              encoder_attention_mask=None, return_dict=True,
+                                              space_dict=self.space_dict, temperature=temperature)
+        hidden_state = output.last_hidden_state[:, 0, :].contiguous()
+        l0, l2 = self.cls_head[0], self.cls_head[2]
+        w0 = self._cache.get("c0", [l0.weight, l0.bias], lambda: Fn.PreparedLinear(l0.weight, l0.bias, f32=True))
+        w2 = self._cache.get("c2", [l2.weight, l2.bias], lambda: Fn.PreparedLinear(l2.weight, l2.bias, f32=True))
+        from . import _lib as L
+        self.last = {"image_embeds": image_embeds, "last_hidden_state": output.last_hidden_state,
+                     "sd_img_ft": sd_img_ft, "sd_txt_ft": sd_txt_ft}
+        return Fn.linear_f32(Fn.linear_f32(hidden_state, w0, act=L.ACT_RELU), w2)
+
+
+def load_state_dict_from_checkpoint(model: BLIP_NLVR, state_dict):
+    """models/blip_nlvr.py:143-158: pos-embed interpolation and self -> self0/self1, dense -> dense0/dense1 fan-out."""
+    state_dict = dict(state_dict)
+    state_dict['visual_encoder.pos_embed'] = interpolate_pos_embed(state_dict['visual_encoder.pos_embed'],
+                                                                   model.visual_encoder)
+    for key in list(state_dict.keys()):
+        if 'crossattention.self.' in key:
+            state_dict[key.replace('self', 'self0')] = state_dict[key]
+            state_dict[key.replace('self', 'self1')] = state_dict[key]
+        elif 'crossattention.output.dense.' in key:
+            state_dict[key.replace('dense', 'dense0')] = state_dict[key]
+            state_dict[key.replace('dense', 'dense1')] = state_dict[key]
+    return model.load_state_dict(state_dict, strict=False)
+
+
+def blip_nlvr(pretrained='', **kwargs):
+    model = BLIP_NLVR(**kwargs)
+    if pretrained:
+        ckpt = torch.load(pretrained, map_location='cpu')
+        msg = load_state_dict_from_checkpoint(model, ckpt['model'])
+        print("missing keys:")
+        print(msg.missing_keys)
+    return model

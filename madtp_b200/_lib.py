@@ -75,6 +75,53 @@ def launch_count() -> int:
     return int(load().madtp_launch_count())
 
 
+class LaunchTimer:
+    """Optional per-entry-point device timing with CUDA events on the launching stream (bench.py's roofline leg).
+    `only` restricts the instrumentation to the named entry points so that a timed region is not perturbed."""
+
+    def __init__(self, only=None):
+        self.only = set(only) if only else None
+        self.records = []          # (name, start_event, end_event, shape arguments)
+
+    def summary(self):
+        out = {}
+        for name, e0, e1, meta in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "meta": []})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["meta"].append(meta)
+        return out
+
+
+_timer = None
+# positions of the shape arguments recorded with each timed launch
+_META_ARGS = {"madtp_gemm": (0, 15, 16, 17), "madtp_attn_fwd": (9, 10, 11, 12), "madtp_attn_stats": (6, 7, 8),
+              "madtp_layernorm": (2, 3), "madtp_dtp_gather": (0, 1, 2), "madtp_dtp_score": (0, 1, 2),
+              "madtp_dtp_select": (0, 1)}
+
+
+def set_launch_timer(timer):
+    global _timer
+    _timer = timer
+
+
+def _call(name, *args):
+    """Invoke one C-ABI entry point (optionally bracketed by CUDA events on the current stream)."""
+    fn = getattr(load(), name)
+    t = _timer
+    if t is None:
+        return fn(*args)
+    key = name if name != "madtp_gemm" else "madtp_gemm:" + ("f16", "tf32x3", "simt")[args[0]]
+    if t.only is not None and key not in t.only:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = fn(*args)
+    e1.record()
+    t.records.append((key, e0, e1, tuple(args[i] for i in _META_ARGS.get(name, ()))))
+    return st
+
+
 def _check(status: int, what: str):
     if status != 0:
         msg = load().madtp_last_error_string().decode(errors="replace")
@@ -123,7 +170,7 @@ def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None
         raise RuntimeError("madtp_b200.gemm: a_lo layout must match a")
     if b_lo is not None and (b_lo.shape != b.shape or b_lo.stride(0) != ldb):
         raise RuntimeError("madtp_b200.gemm: b_lo layout must match b")
-    st = load().madtp_gemm(precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, torch.float32, "a_lo"), lda,
+    st = _call("madtp_gemm", precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, torch.float32, "a_lo"), lda,
                            _ptr(b, op_dtype, "b"), _ptr(b_lo, torch.float32, "b_lo"), ldb, _ptr(out, None, "out"),
                            ldc, 1 if out.dtype == torch.float16 else 0, _ptr(bias, torch.float32, "bias"),
                            _ptr(residual, torch.float32, "residual"), ldr, act, float(alpha), M, N, K, _stream())
@@ -139,7 +186,7 @@ def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=No
                       ("y_f16", y_f16, torch.float16), ("x_hi", x_hi, torch.float32), ("x_lo", x_lo, torch.float32)):
         if t is not None and (t.dtype != dt or not t.is_contiguous() or t.numel() != rows * d):
             raise RuntimeError(f"madtp_b200.layernorm: bad output {nm}")
-    st = load().madtp_layernorm(_ptr(x, torch.float32, "x"), ldx, rows, d, _ptr(gamma, torch.float32, "gamma"),
+    st = _call("madtp_layernorm", _ptr(x, torch.float32, "x"), ldx, rows, d, _ptr(gamma, torch.float32, "gamma"),
                                 _ptr(beta, torch.float32, "beta"), float(eps), _ptr(y_f32), _ptr(y_hi), _ptr(y_lo),
                                 _ptr(y_f16), _ptr(x_hi), _ptr(x_lo), _stream())
     _check(st, "madtp_layernorm")
@@ -148,7 +195,7 @@ def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=No
 def split_tf32(x):
     x = x.contiguous()
     hi, lo = torch.empty_like(x), torch.empty_like(x)
-    _check(load().madtp_split_tf32(_ptr(x, torch.float32, "x"), _ptr(hi), _ptr(lo), x.numel(), _stream()),
+    _check(_call("madtp_split_tf32", _ptr(x, torch.float32, "x"), _ptr(hi), _ptr(lo), x.numel(), _stream()),
            "madtp_split_tf32")
     return hi, lo
 
@@ -156,7 +203,7 @@ def split_tf32(x):
 def cast_f16(x):
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    _check(load().madtp_cast_f16(_ptr(x, torch.float32, "x"), _ptr(y), x.numel(), _stream()), "madtp_cast_f16")
+    _check(_call("madtp_cast_f16", _ptr(x, torch.float32, "x"), _ptr(y), x.numel(), _stream()), "madtp_cast_f16")
     return y
 
 
@@ -166,14 +213,14 @@ def patchify(img, P):
     rows = B * (H // P) * (W // P)
     hi = torch.empty(rows, Cc * P * P, dtype=torch.float32, device=img.device)
     lo = torch.empty_like(hi)
-    _check(load().madtp_patchify(_ptr(img, torch.float32, "img"), _ptr(hi), _ptr(lo), B, Cc, H, W, P, _stream()),
+    _check(_call("madtp_patchify", _ptr(img, torch.float32, "img"), _ptr(hi), _ptr(lo), B, Cc, H, W, P, _stream()),
            "madtp_patchify")
     return hi, lo
 
 
 def assemble_tokens(patches, cls, pos, B, n, d):
     x = torch.empty(B, n + 1, d, dtype=torch.float32, device=patches.device)
-    _check(load().madtp_assemble_tokens(_ptr(patches, torch.float32, "patches"), _ptr(cls, torch.float32, "cls"),
+    _check(_call("madtp_assemble_tokens", _ptr(patches, torch.float32, "patches"), _ptr(cls, torch.float32, "cls"),
                                         _ptr(pos, torch.float32, "pos"), _ptr(x), B, n, d, _stream()),
            "madtp_assemble_tokens")
     return x
@@ -184,7 +231,7 @@ def bert_embed(ids, word, position):
     ids = ids.contiguous()
     d = word.shape[1]
     out = torch.empty(B, L, d, dtype=torch.float32, device=word.device)
-    _check(load().madtp_bert_embed(_ptr(ids, torch.int64, "ids"), _ptr(word, torch.float32, "word"),
+    _check(_call("madtp_bert_embed", _ptr(ids, torch.int64, "ids"), _ptr(word, torch.float32, "word"),
                                    _ptr(position, torch.float32, "position"), _ptr(out), B, L, d, word.shape[0],
                                    _stream()), "madtp_bert_embed")
     return out
@@ -210,7 +257,7 @@ def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None):
         rm, rs, on = stats
     if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Nk):
         raise RuntimeError("madtp_b200.attn_fwd: key_mask must be contiguous [B, Nk]")
-    st = load().madtp_attn_fwd(_ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
+    st = _call("madtp_attn_fwd", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
                                _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Nq, Nk, float(scale),
                                _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
                                bso, _ptr(rm), _ptr(rs), _ptr(on), _stream())
@@ -222,7 +269,7 @@ def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None):
     ldq, bsq = _qkv_strides(q, "q")
     ldk, bsk = _qkv_strides(k, "k")
     rm, rs, on = stats
-    st = load().madtp_attn_stats(_ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk, B, H, N,
+    st = _call("madtp_attn_stats", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk, B, H, N,
                                  float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(rm), _ptr(rs), _ptr(on),
                                  _ptr(col_part, torch.float32, "col_part"), _ptr(cls_attn, torch.float32, "cls_attn"),
                                  _stream())
@@ -235,7 +282,7 @@ def token_colstats(token_att, n, T, divisor):
     ld, bs = token_att.stride(1), token_att.stride(0)
     cm = torch.empty(B, T, dtype=torch.float32, device=token_att.device)
     cs = torch.empty_like(cm)
-    _check(load().madtp_token_colstats(_ptr(token_att, torch.float32, "token_att"), ld, bs, B, n, T, float(divisor),
+    _check(_call("madtp_token_colstats", _ptr(token_att, torch.float32, "token_att"), ld, bs, B, n, T, float(divisor),
                                        _ptr(cm), _ptr(cs), _stream()), "madtp_token_colstats")
     return cm, cs
 
@@ -243,7 +290,7 @@ def token_colstats(token_att, n, T, divisor):
 def query_sdft(token_att, col_max, col_sum, ft, n, T, divisor, sd_ft, accumulate):
     B = token_att.shape[0]
     d = ft.shape[-1]
-    st = load().madtp_query_sdft(_ptr(token_att, torch.float32, "token_att"), token_att.stride(1), token_att.stride(0),
+    st = _call("madtp_query_sdft", _ptr(token_att, torch.float32, "token_att"), token_att.stride(1), token_att.stride(0),
                                  _ptr(col_max), _ptr(col_sum), _ptr(ft, torch.float32, "ft"), ft.stride(1),
                                  ft.stride(0), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
                                  1 if accumulate else 0, _stream())
@@ -259,7 +306,7 @@ def dtp_score(col_part, cls_attn, token_att, n, T, temperature):
     thr = torch.empty(B, dtype=torch.float32, device=dev)
     cnt = torch.empty(B, dtype=torch.int32, device=dev)
     topk = torch.zeros(1, dtype=torch.int32, device=dev)
-    st = load().madtp_dtp_score(B, n, T, _ptr(col_part, torch.float32, "col_part"), n_parts,
+    st = _call("madtp_dtp_score", B, n, T, _ptr(col_part, torch.float32, "col_part"), n_parts,
                                 _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(token_att, torch.float32, "token_att"),
                                 token_att.stride(1), token_att.stride(0), float(temperature), _ptr(score), _ptr(thr),
                                 _ptr(cnt), _ptr(topk), _stream())
@@ -279,7 +326,7 @@ def dtp_select(score, topk, *, mask_mode=0, mask_in=None):
         if mask_in is None or not mask_in.is_contiguous() or mask_in.numel() != B * (n + 1):
             raise RuntimeError("madtp_b200.dtp_select: mask_in must be contiguous [B, n+1]")
         mask_out = torch.empty(B, n + 1, dtype=torch.float32, device=dev)
-    st = load().madtp_dtp_select(B, n, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"), _ptr(keep),
+    st = _call("madtp_dtp_select", B, n, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"), _ptr(keep),
                                  _ptr(dst), _ptr(tail_w), _ptr(tail_idx), mask_mode,
                                  _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), _stream())
     _check(st, "madtp_dtp_select")
@@ -292,7 +339,7 @@ def dtp_gather(x, topk, dst, tail_w, tail_idx, k):
     if x.stride(2) != 1 or x.stride(1) != d:
         raise RuntimeError("madtp_b200.dtp_gather: x rows must be dense")
     out = torch.empty(B, k + 2, d, dtype=torch.float32, device=x.device)
-    st = load().madtp_dtp_gather(B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
+    st = _call("madtp_dtp_gather", B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
                                  _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
                                  _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _stream())
     _check(st, "madtp_dtp_gather")
@@ -306,6 +353,7 @@ def gather_rows(x, idx):
     if x.stride(2) != 1 or x.stride(1) != d:
         raise RuntimeError("madtp_b200.gather_rows: x rows must be dense")
     out = torch.empty(B, K, d, dtype=torch.float32, device=x.device)
-    _check(load().madtp_gather_rows(_ptr(x, torch.float32, "x"), x.stride(0), _ptr(idx, torch.int32, "idx"), _ptr(out),
+    _check(_call("madtp_gather_rows", _ptr(x, torch.float32, "x"), x.stride(0), _ptr(idx, torch.int32, "idx"), _ptr(out),
                                     B, Ltok, K, d, _stream()), "madtp_gather_rows")
     return out
+

@@ -1,0 +1,77 @@
+"""Batch-only sharding of the pruned forward over the GPUs of one node (one process per GPU, torch.distributed).
+
+The path shards over samples only: weights are replicated with ONE broadcast of a flat blob
+from rank 0, every rank runs the forward on its own pairs (topk_num is the max over the LOCAL batch, which is the
+reference's own multi-GPU evaluation semantics, compress_nlvr_dtp.py:131,210-211), and the logits are all-gathered.
+There is no collective on the data path between those two points.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def env_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1-process defaults)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def init(backend: str = "nccl"):
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of `total` samples owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0):
+    """Replicates rank `src`'s parameters and buffers with a single broadcast of one flat fp32 blob."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    tensors: List[torch.Tensor] = [p.data for p in module.parameters()] + \
+        [b.data for b in module.buffers() if b.is_floating_point()]
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+    dist.broadcast(flat, src=src)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+    return flat.numel() * 4
+
+
+def all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    """Concatenates every rank's [B_local, ...] tensor along dim 0 (equal B_local on all ranks)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    out = torch.empty((dist.get_world_size() * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous())
+    return out
+
+
+def max_over_ranks(value: float, device) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

@@ -1,142 +1,4 @@
-"""Deterministic synthetic weights and inputs -- TEST INFRASTRUCTURE (see oracle/dtp_oracle.py header).
-
-There is no network, so neither released checkpoints nor datasets exist here or on the GPU box. Both the oracle and
-the CUDA path are driven from a state dict generated on the CPU from a fixed seed, with the reference's key names
-and shapes (SURVEY.md section 8b "State-dict keys") and the distributions the reference modules get by default
-construction with evaluate=True (nn.Linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias; LayerNorm 1/0;
-nn.Embedding N(0,1); space_dict = randn, models/blip_nlvr.py:46). cls_token / pos_embed are zeros in the reference
-under evaluate=True (models/vit.py:244-245,257-260); a small N(0, 0.02) is used here so positions are not degenerate.
-"""
-from __future__ import annotations
-
-import math
-from typing import Dict
-
-import torch
-
-Tensor = torch.Tensor
-
-
-def _linear(sd: Dict[str, Tensor], g: torch.Generator, name: str, out_f: int, in_f: int, bias: bool = True):
-    bound = 1.0 / math.sqrt(in_f)
-    sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
-    if bias:
-        sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
-
-
-def _ln(sd: Dict[str, Tensor], name: str, d: int):
-    sd[name + ".weight"] = torch.ones(d)
-    sd[name + ".bias"] = torch.zeros(d)
-
-
-def vit_state_dict(g: torch.Generator, prefix: str = "", img_size: int = 384, patch: int = 16, d: int = 768,
-                   depth: int = 12, mlp_ratio: int = 4) -> Dict[str, Tensor]:
-    """Keys of models/vit.py:VisionTransformer (timm naming)."""
-    sd: Dict[str, Tensor] = {}
-    n = (img_size // patch) ** 2
-    sd[prefix + "cls_token"] = torch.randn(1, 1, d, generator=g) * 0.02
-    sd[prefix + "pos_embed"] = torch.randn(1, n + 1, d, generator=g) * 0.02
-    bound = 1.0 / math.sqrt(3 * patch * patch)
-    sd[prefix + "patch_embed.proj.weight"] = (torch.rand(d, 3, patch, patch, generator=g) * 2 - 1) * bound
-    sd[prefix + "patch_embed.proj.bias"] = (torch.rand(d, generator=g) * 2 - 1) * bound
-    for i in range(depth):
-        p = f"{prefix}blocks.{i}"
-        _ln(sd, p + ".norm1", d)
-        _linear(sd, g, p + ".attn.qkv", 3 * d, d)
-        _linear(sd, g, p + ".attn.proj", d, d)
-        _ln(sd, p + ".norm2", d)
-        _linear(sd, g, p + ".mlp.fc1", mlp_ratio * d, d)
-        _linear(sd, g, p + ".mlp.fc2", d, mlp_ratio * d)
-    _ln(sd, prefix + "norm", d)
-    return sd
-
-
-def block_state_dict(seed: int = 1234, d: int = 768, mlp_ratio: int = 4) -> Dict[str, Tensor]:
-    """One models/vit.py:Block (BASELINE config 1)."""
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, Tensor] = {}
-    _ln(sd, "norm1", d)
-    _linear(sd, g, "attn.qkv", 3 * d, d)
-    _linear(sd, g, "attn.proj", d, d)
-    _ln(sd, "norm2", d)
-    _linear(sd, g, "mlp.fc1", mlp_ratio * d, d)
-    _linear(sd, g, "mlp.fc2", d, mlp_ratio * d)
-    return sd
-
-
-def nlvr_text_state_dict(g: torch.Generator, prefix: str = "", d: int = 768, depth: int = 12, dff: int = 3072,
-                         vocab: int = 30524, max_pos: int = 512) -> Dict[str, Tensor]:
-    """Keys of models/nlvr_encoder.py:BertModel(add_pooling_layer=False)."""
-    sd: Dict[str, Tensor] = {}
-    e = prefix + "embeddings."
-    sd[e + "word_embeddings.weight"] = torch.randn(vocab, d, generator=g)
-    sd[e + "word_embeddings.weight"][0].zero_()        # padding_idx = 0
-    sd[e + "position_embeddings.weight"] = torch.randn(max_pos, d, generator=g)
-    sd[e + "position_ids"] = torch.arange(max_pos).unsqueeze(0)
-    _ln(sd, e + "LayerNorm", d)
-    for i in range(depth):
-        p = f"{prefix}encoder.layer.{i}"
-        for nm in ("query", "key", "value"):
-            _linear(sd, g, f"{p}.attention.self.{nm}", d, d)
-        _linear(sd, g, p + ".attention.output.dense", d, d)
-        _ln(sd, p + ".attention.output.LayerNorm", d)
-        for s in ("self0", "self1"):
-            for nm in ("query", "key", "value"):
-                _linear(sd, g, f"{p}.crossattention.{s}.{nm}", d, d)
-        _linear(sd, g, p + ".crossattention.output.dense0", d, d)
-        _linear(sd, g, p + ".crossattention.output.dense1", d, d)
-        if i >= 6:
-            _linear(sd, g, p + ".crossattention.output.merge_layer", d, 2 * d)
-        _ln(sd, p + ".crossattention.output.LayerNorm", d)
-        _linear(sd, g, p + ".intermediate.dense", dff, d)
-        _linear(sd, g, p + ".output.dense", d, dff)
-        _ln(sd, p + ".output.LayerNorm", d)
-    return sd
-
-
-def blip_nlvr_state_dict(seed: int = 1234, img_size: int = 384, sd_num: int = 100, sd_dim: int = 768,
-                         depth: int = 12) -> Dict[str, Tensor]:
-    """Keys of models/blip_nlvr.py:BLIP_NLVR."""
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, Tensor] = {"space_dict": torch.randn(sd_num, sd_dim, generator=g)}
-    sd.update(vit_state_dict(g, "visual_encoder.", img_size=img_size, depth=depth))
-    sd.update(nlvr_text_state_dict(g, "text_encoder.", depth=depth))
-    _linear(sd, g, "cls_head.0", 768, 768)
-    _linear(sd, g, "cls_head.2", 2, 768)
-    return sd
-
-
-def nlvr_inputs(pairs: int, img_size: int = 384, text_len: int = 20, seed: int = 0, pad_to: int = 0):
-    """Synthetic batch: images = cat(image0, image1) ~ N(0,1); ids ~ U[1000, 30000), ids[:,0]=101.
-
-    pad_to > text_len appends pad tokens (id 0, mask 0) with per-row true lengths in [text_len//2, text_len]."""
-    g = torch.Generator().manual_seed(seed)
-    images = torch.randn(2 * pairs, 3, img_size, img_size, generator=g)
-    ids = torch.randint(1000, 30000, (pairs, text_len), generator=g)
-    ids[:, 0] = 101
-    mask = torch.ones(pairs, text_len, dtype=torch.long)
-    if pad_to > text_len:
-        lens = torch.randint(max(2, text_len // 2), text_len + 1, (pairs,), generator=g)
-        lens[0] = text_len
-        full_ids = torch.zeros(pairs, pad_to, dtype=torch.long)
-        full_mask = torch.zeros(pairs, pad_to, dtype=torch.long)
-        for b in range(pairs):
-            full_ids[b, :lens[b]] = ids[b, :lens[b]]
-            full_mask[b, :lens[b]] = 1
-        ids, mask = full_ids, full_mask
-    return images, ids, mask
-
-
-def block_inputs(seed: int = 0, B: int = 2, N: int = 197, d: int = 768, T: int = 100):
-    """BASELINE config 1 inputs: layer input x [B,N,d] and codebook [T,d], both ~ N(0,1)."""
-    g = torch.Generator().manual_seed(seed)
-    return torch.randn(B, N, d, generator=g), torch.randn(T, d, generator=g)
-
-
-def tensor_digest(*tensors) -> str:
-    """sha256 prefix of the raw bytes -- fixtures store it so a drifting RNG is detected instead of mis-compared."""
-    import hashlib
-    h = hashlib.sha256()
-    for t in tensors:
-        h.update(t.detach().contiguous().cpu().numpy().tobytes())
-    return h.hexdigest()[:16]
+"""Seeded synthetic weights / inputs shared by the oracle, the tests and bench.py (they live in the package so that
+bench.py's product arm does not import anything from oracle/)."""
+from madtp_b200.synthetic import *  # noqa: F401,F403
+from madtp_b200.synthetic import block_inputs, block_state_dict, blip_nlvr_state_dict, nlvr_inputs, tensor_digest  # noqa: F401

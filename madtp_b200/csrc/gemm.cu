@@ -34,7 +34,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = (TF32X3 ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;               // double-buffered fp32 accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 4096;                   // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;
 };
 
@@ -102,6 +103,55 @@ __device__ __forceinline__ bool epilogue_vec_ok(const GemmEpilogue& ep, int N) {
   return al && ((ep.ldc & 7) == 0) && ((N & 3) == 0) && (ep.residual == nullptr || (ep.ldr & 3) == 0);
 }
 
+
+// Coalesced epilogue for one 32 x 32 accumulator chunk owned by one warp. After tcgen05.ld every lane holds one ROW
+// (32 consecutive columns); storing that directly makes each warp-wide access touch 32 different 128-byte lines.
+// The chunk is therefore transposed through a 4 KB per-warp shared-memory tile (float4 granules, XOR-swizzled by
+// row so both the row-wise writes and the column-wise reads are bank-conflict free) and then written -- and the
+// residual read -- with 8 lanes covering one 128-byte row segment, 4 rows per instruction.
+//   out = act(alpha * acc + bias[col]) + residual[row, col]
+__device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, const float (&acc)[32], float* stage,
+                                                      long long row_base, int col0, int M, int N, int lane) {
+  float4* st4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st4[lane * 8 + (j ^ (lane & 7))] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  __syncwarp();
+  const int jj = lane & 7;
+  const int col = col0 + jj * 4;
+  if (col < N) {  // N % 4 == 0 on this path, so the whole float4 is in range
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3);
+      const long long row = row_base + r;
+      if (row < M) {
+        const float4 a = st4[r * 8 + (jj ^ (r & 7))];
+        float4 o;
+        o.x = apply_act(ep.alpha * a.x + bv.x, ep.act);
+        o.y = apply_act(ep.alpha * a.y + bv.y, ep.act);
+        o.z = apply_act(ep.alpha * a.z + bv.z, ep.act);
+        o.w = apply_act(ep.alpha * a.w + bv.w, ep.act);
+        if (ep.residual) {
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col));
+          o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+        }
+        if (ep.c_f16) {
+          __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.c) + row * ep.ldc + col) = pk;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.c) + row * ep.ldc + col) = o;
+        }
+      }
+    }
+  }
+  __syncwarp();  // the tile is reused by the next chunk
+}
+
 template <int BLOCK_N, bool TF32X3>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -112,7 +162,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -245,11 +296,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + c * 32);
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (!row_ok) continue;
         float acc32[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(v[j]);
-        store_row_chunk32(ep, acc32, row, col0, N, vec_ok);
+        if (vec_ok)
+          store_chunk_coalesced(ep, acc32, epi_stage + (warp - 2) * 1024, m0 + quad * 32, col0, M, N, lane);
+        else if (row_ok)
+          store_row_chunk32(ep, acc32, row, col0, N, false);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -289,7 +342,8 @@ struct Tf32Cfg {
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int EPI_BYTES = 8 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int THREADS = 320;
   static constexpr int COLS_PER_WARP = BLOCK_N / 2;
 };
@@ -305,7 +359,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -436,16 +491,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         if (buf == 0) buf_phase ^= 1u;
       }
       const long long row = m0 + quad * 32 + lane;
-      if (row < M) {
 #pragma unroll
-        for (int c = 0; c < CW / 32; ++c) {
-          const int col0 = n0 + half * CW + c * 32;
-          if (col0 < N) {
-            float acc32[32];
+      for (int c = 0; c < CW / 32; ++c) {
+        const int col0 = n0 + half * CW + c * 32;
+        if (col0 < N) {
+          float acc32[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc32[j] = sum[c * 32 + j];
-            store_row_chunk32(ep, acc32, row, col0, N, vec_ok);
-          }
+          for (int j = 0; j < 32; ++j) acc32[j] = sum[c * 32 + j];
+          if (vec_ok)
+            store_chunk_coalesced(ep, acc32, epi_stage + (warp - 2) * 1024, m0 + quad * 32, col0, M, N, lane);
+          else if (row < M)
+            store_row_chunk32(ep, acc32, row, col0, N, false);
         }
       }
     }

@@ -34,9 +34,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = (TF32X3 ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;               // double-buffered fp32 accumulator
-  static constexpr int EPI_BYTES = 4 * 4096;                   // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int EPI_BYTES = 8 * 4096;                   // one 32x32 fp32 transpose tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 320;
 };
 
 
@@ -107,36 +107,80 @@ __device__ __forceinline__ bool epilogue_vec_ok(const GemmEpilogue& ep, int N) {
 // Coalesced epilogue for one 32 x 32 accumulator chunk owned by one warp. After tcgen05.ld every lane holds one ROW
 // (32 consecutive columns); storing that directly makes each warp-wide access touch 32 different 128-byte lines.
 // The chunk is therefore transposed through a 4 KB per-warp shared-memory tile (float4 granules, XOR-swizzled by
-// row so both the row-wise writes and the column-wise reads are bank-conflict free) and then written -- and the
-// residual read -- with 8 lanes covering one 128-byte row segment, 4 rows per instruction.
+// row so both the row-wise writes and the column-wise reads are bank-conflict free) and then written with 8 lanes
+// covering one 128-byte row segment, 4 rows per instruction.
 //   out = act(alpha * acc + bias[col]) + residual[row, col]
-__device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, const float (&acc)[32], float* stage,
-                                                      long long row_base, int col0, int M, int N, int lane) {
-  float4* st4 = reinterpret_cast<float4*>(stage);
+// The residual sub-tile is prefetched into L2 while the warp waits for the accumulator (prefetch_residual): with only
+// 8 epilogue warps per SM the memory-level parallelism of a load-then-use epilogue is far too low to cover the DRAM
+// latency of the fp32 residual stream, and a register prefetch one chunk ahead spills.
+__device__ __forceinline__ void load_residual(const GemmEpilogue& ep, long long row_base, int col0, int M, int N,
+                                              int lane, float4 (&rv)[8]) {
+  const int col = col0 + (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const long long row = row_base + it * 4 + (lane >> 3);
+    rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.residual != nullptr && row < M && col < N)
+      rv[it] = __ldg(reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col));
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if (ACT == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (ACT == 2) return fmaxf(x, 0.0f);
+  if (ACT == 3) return x / (1.0f + __expf(-1.702f * x));
+  return x;
+}
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+
+template <int ACT, bool RES = true, int GROUP = 8>
+__device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, const float* acc, float* stage,
+                                                      long long row_base, int col0, int M, int N, int lane,
+                                                      const float4 (&rv)[8]) {
+  const uint32_t sbase = smem_u32(stage);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
-    st4[lane * 8 + (j ^ (lane & 7))] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    sts_v4(sbase + static_cast<uint32_t>((lane * 8 + (j ^ (lane & 7))) * 16), acc[4 * j], acc[4 * j + 1],
+           acc[4 * j + 2], acc[4 * j + 3]);
   __syncwarp();
   const int jj = lane & 7;
+  const int rq = lane >> 3;
   const int col = col0 + jj * 4;
-  if (col < N) {  // N % 4 == 0 on this path, so the whole float4 is in range
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+  const bool col_ok = col < N;  // N % 4 == 0 on this path, so the whole float4 is in range
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.bias != nullptr && col_ok) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+  // GROUP rows-of-four are fetched from the tile at a time (8 = whole chunk in flight; 4 halves the live registers)
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3);
-      const long long row = row_base + r;
-      if (row < M) {
-        const float4 a = st4[r * 8 + (jj ^ (r & 7))];
-        float4 o;
-        o.x = apply_act(ep.alpha * a.x + bv.x, ep.act);
-        o.y = apply_act(ep.alpha * a.y + bv.y, ep.act);
-        o.z = apply_act(ep.alpha * a.z + bv.z, ep.act);
-        o.w = apply_act(ep.alpha * a.w + bv.w, ep.act);
-        if (ep.residual) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.residual + row * ep.ldr + col));
-          o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-        }
+  for (int g = 0; g < 8; g += GROUP) {
+    float4 a[GROUP];
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      const int r = (g + i) * 4 + rq;
+      a[i] = lds_v4(sbase + static_cast<uint32_t>((r * 8 + (jj ^ (r & 7))) * 16));
+    }
+#pragma unroll
+    for (int i = 0; i < GROUP; ++i) {
+      const int it = g + i;
+      const long long row = row_base + it * 4 + rq;
+      float4 o;
+      o.x = act_fn<ACT>(ep.alpha * a[i].x + bv.x);
+      o.y = act_fn<ACT>(ep.alpha * a[i].y + bv.y);
+      o.z = act_fn<ACT>(ep.alpha * a[i].z + bv.z);
+      o.w = act_fn<ACT>(ep.alpha * a[i].w + bv.w);
+      if (RES) {
+        o.x += rv[it].x; o.y += rv[it].y; o.z += rv[it].z; o.w += rv[it].w;
+      }
+      if (col_ok && row < M) {
         if (ep.c_f16) {
           __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
           uint2 pk;
@@ -152,8 +196,44 @@ __device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, co
   __syncwarp();  // the tile is reused by the next chunk
 }
 
+// L2 prefetch of the residual sub-tile a warp is about to need (32 rows x NCH 128-byte lines; lane = row). Issued
+// while the warp would otherwise idle on the accumulator barrier; needs no registers, unlike a register prefetch.
+template <int NCH>
+__device__ __forceinline__ void prefetch_residual(const GemmEpilogue& ep, long long row_base, int col_begin, int M,
+                                                  int N, int lane) {
+  if (ep.residual == nullptr) return;
+  const long long row = row_base + lane;
+  if (row >= M) return;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = col_begin + c * 32;
+    if (col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.residual + row * ep.ldr + col));
+  }
+}
+
+// Epilogue of NCH consecutive 32-column chunks starting at TMEM address taddr / output column col_begin, for the 32
+// rows [row_base, row_base+32) owned by this warp.
+template <int ACT, int NCH>
+__device__ __forceinline__ void epilogue_chunks_tmem(const GemmEpilogue& ep, uint32_t taddr, float* stage,
+                                                     long long row_base, int col_begin, int M, int N, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = col_begin + c * 32;
+    if (col0 >= N) break;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, v);
+    float4 rv[8];
+    load_residual(ep, row_base, col0, M, N, lane, rv);   // L2 hits (prefetched); overlaps the TMEM load + transpose
+    tmem_ld_wait();
+    float acc32[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(v[j]);
+    store_chunk_coalesced<ACT>(ep, acc32, stage, row_base, col0, M, N, lane, rv);
+  }
+}
+
 template <int BLOCK_N, bool TF32X3>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
                     GemmEpilogue ep, int M, int N, int K) {
@@ -191,7 +271,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_mbar_init();
   }
@@ -275,34 +355,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
+    // warp % 4 = TMEM lane quadrant (a warp may only touch lanes [32*(warp%4), +32)); (warp-2)/4 = column half.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NCH = BLOCK_N / 64;   // 32-column chunks per warp
+    float* stage = epi_stage + (warp - 2) * 1024;
+    const bool vec_ok = epilogue_vec_ok(ep, N);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
       const int n0 = (tile % n_tiles) * BLOCK_N;
+      const long long row_base = m0 + quad * 32;
+      const int col_begin = n0 + half * (BLOCK_N / 2);
+      if (vec_ok) prefetch_residual<NCH>(ep, row_base, col_begin, M, N, lane);   // lands in L2 while the MMAs finish
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < M;
-      const bool vec_ok = epilogue_vec_ok(ep, N);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(acc * BLOCK_N + half * (BLOCK_N / 2));
+      if (vec_ok) {
+        switch (ep.act) {
+          case 1: epilogue_chunks_tmem<1, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
+          case 2: epilogue_chunks_tmem<2, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
+          case 3: epilogue_chunks_tmem<3, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
+          default: epilogue_chunks_tmem<0, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
+        }
+      } else {
+        const long long row = row_base + lane;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;
-        uint32_t v[32];
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N + c * 32);
-        tmem_ld_32x32b_x32(taddr, v);
-        tmem_ld_wait();
-        float acc32[32];
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = col_begin + c * 32;
+          if (col0 >= N) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (row < M) {
+            float acc32[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(v[j]);
-        if (vec_ok)
-          store_chunk_coalesced(ep, acc32, epi_stage + (warp - 2) * 1024, m0 + quad * 32, col0, M, N, lane);
-        else if (row_ok)
-          store_row_chunk32(ep, acc32, row, col0, N, false);
+            for (int j = 0; j < 32; ++j) acc32[j] = __uint_as_float(v[j]);
+            store_row_chunk32(ep, acc32, row, col0, N, false);
+          }
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -495,13 +589,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int c = 0; c < CW / 32; ++c) {
         const int col0 = n0 + half * CW + c * 32;
         if (col0 < N) {
-          float acc32[32];
+          if (vec_ok && ep.act == 0) {
+            float* stg = epi_stage + (warp - 2) * 1024;
+            float4 rv[8];
+            if (ep.residual != nullptr) {
+              load_residual(ep, m0 + quad * 32, col0, M, N, lane, rv);
+              store_chunk_coalesced<0, true, (CW > 64 ? 4 : 8)>(ep, &sum[c * 32], stg, m0 + quad * 32, col0, M, N, lane, rv);
+            } else {
+              store_chunk_coalesced<0, false, (CW > 64 ? 4 : 8)>(ep, &sum[c * 32], stg, m0 + quad * 32, col0, M, N, lane, rv);
+            }
+          } else if (row < M) {
+            float acc32[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc32[j] = sum[c * 32 + j];
-          if (vec_ok)
-            store_chunk_coalesced(ep, acc32, epi_stage + (warp - 2) * 1024, m0 + quad * 32, col0, M, N, lane);
-          else if (row < M)
+            for (int j = 0; j < 32; ++j) acc32[j] = sum[c * 32 + j];
             store_row_chunk32(ep, acc32, row, col0, N, false);
+          }
         }
       }
     }

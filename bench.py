@@ -151,6 +151,15 @@ def algorithmic_flops(name, meta):
     if name == "madtp_attn_fwd":
         B, H, Nq, Nk = meta
         return 4.0 * B * H * Nq * Nk * 64            # QK^T and PV, 2 FLOPs per MAC
+    if name == "madtp_attn_tc_fwd":
+        B, H, N = meta
+        return 4.0 * B * H * N * N * 64
+    if name == "madtp_attn_tc_stats":
+        B, H, N = meta
+        return 2.0 * B * H * N * N                   # max over heads + column sum; the QK^T recompute is not credited
+    if name == "madtp_gemm_qkv":
+        M, K, heads = meta
+        return 2.0 * M * (3 * heads * 64) * K
     if name.startswith("madtp_gemm"):
         _, M, N, K = meta
         return 2.0 * M * N * K
@@ -266,8 +275,8 @@ def main():
                 "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
                 "launches_per_step": rec["launches"] // args.steps, "ms_per_step": rec["ms"] / args.steps,
                 "share_of_step": share,
-                "note": "fp32 CUDA-core attention this round (scoring lane must be fp32-accurate for bit-exact "
-                        "keep-masks); algorithmic FLOPs = 4*B*H*Nq*Nk*64 per launch"}
+                "note": "algorithmic FLOPs per launch as in DESIGN.md section 5 (error-compensation passes and the "
+                        "second QK^T pass are not credited)"}
     step_flops = 2.0 * cal["macs_pruned"] * PAIRS          # oracle trajectory, per rank
     step_roofline = {"algorithmic_tflop_per_step": step_flops / 1e12,
                      "achieved": step_flops / (ms / args.steps / 1e3) / 1e12, "peak": peaks["tflops_sustained"],

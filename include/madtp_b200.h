@@ -141,6 +141,25 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
                      const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream);
 
+/*
+ * Tensor-core self-attention for the scoring lane (vit.py:75-103 without materialising P). madtp_gemm_qkv is the
+ * fused q|k|v projection (vit.py:77) with an epilogue that writes q and k as tf32 hi/lo planes [M, ld_qk] (q of head
+ * h at column h*64, k at heads*64 + h*64) and v transposed per (sequence, head) as hi/lo planes
+ * vt[((b*heads + h)*64 + d) * ld_vt + token] (keys contiguous). M = B * n_tok rows, K = model width.
+ * madtp_attn_tc_fwd: context (fp16, heads merged), row_lse[b,h,i] = log sum_j exp(logit) and out_norm[b,h,i].
+ * madtp_attn_tc_stats: col_part[b, it, j] = sum_{i in 128-query tile it, i >= 1} max_h P[b,h,i,j]  (n_parts =
+ * ceil(N/128)) and cls_attn[b, j] as in madtp_attn_stats. Head dim 64.
+ */
+int madtp_gemm_qkv(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo, int64_t ldb,
+                   const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo, int64_t ld_qk,
+                   float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream);
+int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, const float* vt_hi, const float* vt_lo,
+                      int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
+                      int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream);
+int madtp_attn_tc_stats(const float* qk_hi, const float* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
+                        const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
+                        int n_parts, float* cls_attn, void* stream);
+
 /* vector_gather (models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :], x [B,L,d] with batch stride bsx, idx [B,K]
  * (indices are clamped to [0, L)), out [B,K,d] contiguous. */
 int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,

@@ -44,6 +44,9 @@ SIGNATURES = {
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
+    "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
+    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
 }
 
 
@@ -95,7 +98,8 @@ class LaunchTimer:
 
 _timer = None
 # positions of the shape arguments recorded with each timed launch
-_META_ARGS = {"madtp_gemm": (0, 15, 16, 17), "madtp_attn_fwd": (9, 10, 11, 12), "madtp_attn_stats": (6, 7, 8),
+_META_ARGS = {"madtp_gemm": (0, 15, 16, 17), "madtp_gemm_qkv": (7, 8, 10), "madtp_attn_tc_fwd": (6, 7, 8),
+              "madtp_attn_tc_stats": (3, 4, 5), "madtp_attn_fwd": (9, 10, 11, 12), "madtp_attn_stats": (6, 7, 8),
               "madtp_layernorm": (2, 3), "madtp_dtp_gather": (0, 1, 2), "madtp_dtp_score": (0, 1, 2),
               "madtp_dtp_select": (0, 1)}
 
@@ -357,3 +361,40 @@ def gather_rows(x, idx):
                                     B, Ltok, K, d, _stream()), "madtp_gather_rows")
     return out
 
+
+
+def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads):
+    """Fused q|k|v projection for the tensor-core attention: returns (qk_hi, qk_lo [M, 2*heads*64], vt_hi, vt_lo
+    [B*heads*64, n_pad]) -- see madtp_gemm_qkv in include/madtp_b200.h."""
+    M, K = a_hi.shape
+    B = M // n_tok
+    n_pad = (n_tok + 3) // 4 * 4
+    dev = a_hi.device
+    qk_hi = torch.empty(M, 2 * heads * 64, dtype=torch.float32, device=dev)
+    qk_lo = torch.empty_like(qk_hi)
+    vt_hi = torch.empty(B * heads * 64, n_pad, dtype=torch.float32, device=dev)
+    vt_lo = torch.empty_like(vt_hi)
+    st = _call("madtp_gemm_qkv", _ptr(a_hi, torch.float32, "a_hi"), _ptr(a_lo, torch.float32, "a_lo"),
+               _rowmajor(a_hi, "a_hi"), _ptr(w_hi, torch.float32, "w_hi"), _ptr(w_lo, torch.float32, "w_lo"),
+               _rowmajor(w_hi, "w_hi"), _ptr(bias, torch.float32, "bias"), M, K, n_tok, heads, _ptr(qk_hi),
+               _ptr(qk_lo), qk_hi.stride(0), _ptr(vt_hi), _ptr(vt_lo), n_pad, _stream())
+    _check(st, "madtp_gemm_qkv")
+    return qk_hi, qk_lo, vt_hi, vt_lo
+
+
+def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None):
+    ldo, bso = _qkv_strides(out_f16, "out_f16")
+    st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float32, "qk_hi"), _ptr(qk_lo, torch.float32, "qk_lo"),
+               qk_hi.stride(0), _ptr(vt_hi, torch.float32, "vt_hi"), _ptr(vt_lo, torch.float32, "vt_lo"),
+               vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
+               _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
+               _ptr(out_norm, torch.float32, "out_norm"), _stream())
+    _check(st, "madtp_attn_tc_fwd")
+
+
+def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, *, key_mask=None):
+    st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float32, "qk_hi"), _ptr(qk_lo, torch.float32, "qk_lo"),
+               qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
+               _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
+               _ptr(cls_attn, torch.float32, "cls_attn"), _stream())
+    _check(st, "madtp_attn_tc_stats")

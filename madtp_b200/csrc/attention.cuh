@@ -23,6 +23,24 @@ struct AttnArgs {
   float* cls_attn;          // [B, Nk]  sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8); entry 0 unused
 };
 
+// Tensor-core path (attn_tc.cu). q and k are tf32 hi/lo planes [B*N, ld_qk] (q of head h at column h*64, k at
+// H*64 + h*64); v is stored transposed per (sequence, head): vt[((b*H + h)*64 + d) * ld_vt + token]. Both are written
+// by launch_gemm_qkv.
+struct AttnTcArgs {
+  const float* qk_hi; const float* qk_lo; long long ld_qk;
+  const float* vt_hi; const float* vt_lo; long long ld_vt;
+  int B, H, N;
+  float scale;
+  const float* key_mask;                 // additive [B, N] or nullptr
+  __half* out_f16; long long ldo, bso;   // context, heads merged
+  float* row_lse;                        // [B, H, N]  log sum_j exp(logit_j)   (max + log of the row sum)
+  float* out_norm;                       // [B, H, N]  || context[b, h, i, :] ||_2
+  float* col_part; int n_parts;          // [B, ceil(N/128), N]
+  float* cls_attn;                       // [B, N]
+};
+int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
+int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);
+
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream);
 int launch_attn_stats(const AttnArgs& a, cudaStream_t stream);
 

@@ -1,0 +1,584 @@
+// Tensor-core self-attention with fused token-pruning statistics (head dim 64) for the scoring lane.
+//
+// Same three outputs as attention.cu (context, ||context|| per head and token, column sums of max_h P, the
+// head-importance-weighted CLS row) but the two big contractions run on tcgen05 with error-compensated tf32
+// operands (hi/lo planes written by the fused q|k|v projection, gemm.cu launch_gemm_qkv):
+//
+//   attn_fwd_tc_kernel    one CTA per (128-query tile, head, sequence); 64-key tiles.
+//       S   = Q K^T           2 x 12 MMAs per key tile: each 32-wide slice of the head dim accumulates in its own
+//                             TMEM buffer and the two partials are added in fp32 registers (the tensor core's
+//                             accumulator truncates, so long in-TMEM accumulations lose accuracy -- DESIGN.md section 3)
+//       P   = online softmax   4 warps, one query row per thread, fp32, expf
+//       O_t = P V              P goes back to TMEM as tf32 hi/lo (tcgen05.st) and is the A operand of 24 MMAs against
+//                             V^T tiles (keys contiguous, written transposed by the projection epilogue); every key
+//                             tile's partial product is drained and accumulated in fp32 registers with the usual
+//                             running-max correction.
+//   attn_stats_tc_kernel  one CTA per (128-query tile, 128-key tile, sequence), looping over the heads.
+//       log P_h(i,j) = S_h(i,j) * scale + mask_j - lse_h(i) is formed for every head, the running max over heads is
+//       kept in registers (exp is monotone, so ONE expf per (i,j) after the head loop replaces one per head), then
+//       the tile is column-summed over its query rows in a fixed order.
+//   attn_cls_kernel       the CLS query row of every head (tiny, fp32 FFMA) weighted by the per-head context norms.
+//
+// Warp roles in both tensor-core kernels: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
+// warps 2..5 = consumers (TMEM lane quadrant = warp % 4, thread = query row).
+#include "attention.cuh"
+#include "gemm.cuh"
+
+namespace madtp {
+
+namespace {
+
+constexpr int BM = 128;        // query rows per CTA
+constexpr int BOX = 32;        // floats per 128-byte swizzled row
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ void ld2_add(uint32_t ta, uint32_t tb, float (&out)[32]) {
+  uint32_t a[32], b[32];
+  tmem_ld_32x32b_x32(ta, a);
+  tmem_ld_32x32b_x32(tb, b);
+  tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 32; ++k) out[k] = __uint_as_float(a[k]) + __uint_as_float(b[k]);
+}
+
+// 12 tf32 MMAs = one 32-wide K slice of an error-compensated product (lo*hi, hi*lo, hi*hi per 8-element k-step)
+__device__ __forceinline__ void issue_slice_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                               uint32_t b_lo, uint32_t idesc) {
+  const uint64_t dah = make_sw128_kmajor_desc(a_hi), dal = make_sw128_kmajor_desc(a_lo);
+  const uint64_t dbh = make_sw128_kmajor_desc(b_hi), dbl = make_sw128_kmajor_desc(b_lo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, k != 0 ? 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1u);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1
+// ------------------------------------------------------------------------------------------------
+struct FwdSmem {
+  static constexpr int Q_BYTES = 4 * BM * 128;              // (slice 0/1) x (hi/lo) boxes of [128 x 32]
+  static constexpr int KBOX = 64 * 128;                     // [64 keys x 32] or [64 dims x 32 keys]
+  static constexpr int STAGE_BYTES = 8 * KBOX;              // K: 4 boxes, V^T: 4 boxes
+  static constexpr int BAR_OFF = Q_BYTES + 2 * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+                   const __grid_constant__ CUtensorMap tm_k_hi, const __grid_constant__ CUtensorMap tm_k_lo,
+                   const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
+                   AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* kv_s = smem + FwdSmem::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR_OFF);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2]
+  uint64_t* s_empty = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int N = a.N, HD = a.H * 64;
+  const int T = (N + 63) / 64;   // key tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q_hi);
+    tma_prefetch_desc(&tm_q_lo);
+    tma_prefetch_desc(&tm_k_hi);
+    tma_prefetch_desc(&tm_k_lo);
+    tma_prefetch_desc(&tm_v_hi);
+    tma_prefetch_desc(&tm_v_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S buffers (slice A | slice B) at 0 and 128, P hi at 256, P lo at 320, O partial at 384
+  constexpr uint32_t kP_HI = 256, kP_LO = 320, kO = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qrow = b * N + i0;
+      mbar_arrive_expect_tx(q_full, FwdSmem::Q_BYTES);
+      for (int c = 0; c < 2; ++c) {
+        tma_load_2d(&tm_q_hi, q_full, q_s + (c * 2 + 0) * BM * 128, h * 64 + c * BOX, qrow);
+        tma_load_2d(&tm_q_lo, q_full, q_s + (c * 2 + 1) * BM * 128, h * 64 + c * BOX, qrow);
+      }
+      for (int t = 0; t < T; ++t) {
+        const int st = t & 1;
+        mbar_wait(&kv_empty[st], ((t >> 1) & 1) ^ 1);
+        uint8_t* s = kv_s + st * FwdSmem::STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[st], FwdSmem::STAGE_BYTES);
+        const int krow = b * N + t * 64;
+        const int vrow = (b * a.H + h) * 64;
+        for (int c = 0; c < 2; ++c) {
+          tma_load_2d(&tm_k_hi, &kv_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+          tma_load_2d(&tm_k_lo, &kv_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+          tma_load_2d(&tm_v_hi, &kv_full[st], s + (4 + c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+          tma_load_2d(&tm_v_lo, &kv_full[st], s + (4 + c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2u, BM, 64);
+      const uint32_t q_u = smem_u32(q_s);
+      auto issue_qk = [&](int t) {
+        const int st = t & 1, sb = t & 1;
+        mbar_wait(&kv_full[st], (t >> 1) & 1);
+        mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t k_u = smem_u32(kv_s + st * FwdSmem::STAGE_BYTES);
+        for (int c = 0; c < 2; ++c)
+          issue_slice_ss(tmem_base + sb * 128 + c * 64, q_u + (c * 2 + 0) * BM * 128, q_u + (c * 2 + 1) * BM * 128,
+                         k_u + (c * 2 + 0) * FwdSmem::KBOX, k_u + (c * 2 + 1) * FwdSmem::KBOX, idesc);
+        umma_commit(&s_full[sb]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_qk(t + 1);
+        mbar_wait(p_full, t & 1);
+        tcgen05_fence_after();
+        const uint32_t v_u = smem_u32(kv_s + (t & 1) * FwdSmem::STAGE_BYTES) + 4 * FwdSmem::KBOX;
+        // O_t = P_lo V_hi + P_hi V_lo + P_hi V_hi over 8 k-steps of 8 keys
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t pa = tmem_base + (pass == 0 ? kP_LO : kP_HI);
+          const int vplane = (pass == 1) ? 1 : 0;  // pass 1 multiplies by V_lo
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bd =
+                make_sw128_kmajor_desc(v_u + ((ks >> 2) * 2 + vplane) * FwdSmem::KBOX) + 2 * (ks & 3);
+            umma_tf32_ts(tmem_base + kO, pa + ks * 8, bd, idesc, (pass | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[t & 1]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int i = i0 + quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+
+    for (int t = 0; t < T; ++t) {
+      const int sb = t & 1;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      tcgen05_fence_after();
+      float s[64];
+      {
+        float tmp[32];
+        ld2_add(tmem_base + lane_off + sb * 128, tmem_base + lane_off + sb * 128 + 64, tmp);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[k] = tmp[k];
+        ld2_add(tmem_base + lane_off + sb * 128 + 32, tmem_base + lane_off + sb * 128 + 96, tmp);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s[32 + k] = tmp[k];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+
+      const int j0 = t * 64;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        const int j = j0 + k;
+        const float mk = (mask != nullptr && j < N) ? __ldg(mask + j) : 0.f;
+        s[k] = (j < N) ? fmaf(s[k], a.scale, mk) : -INFINITY;
+        mx = fmaxf(mx, s[k]);
+      }
+      const float m_new = fmaxf(m, mx);
+      const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
+      float ps = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        s[k] = expf(s[k] - m_new);
+        ps += s[k];
+      }
+      l = l * corr + ps;
+      m = m_new;
+
+      if (t > 0) {  // drain the previous tile's P V partial (it is relative to the previous running max)
+        mbar_wait(o_full, (t - 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + kO + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[c * 32 + k] += __uint_as_float(v[k]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] *= corr;
+
+      // P -> TMEM as tf32 hi / lo (A operand of the P V MMAs)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float p = s[c * 32 + k];
+          const float ph = tf32_hi(p);
+          hi[k] = __float_as_uint(ph);
+          lo[k] = __float_as_uint(p - ph);
+        }
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + c * 32, hi);
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + c * 32, lo);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (T - 1) & 1);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) o[c * 32 + k] += __uint_as_float(v[k]);
+    }
+    if (i < N) {
+      const float inv = 1.0f / l;
+      float nsq = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) {
+        o[d] *= inv;
+        nsq = fmaf(o[d], o[d], nsq);
+      }
+      __half* dst = a.out_f16 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64;
+#pragma unroll
+      for (int d = 0; d < 64; d += 8) {
+        __half2 h0 = __floats2half2_rn(o[d], o[d + 1]), h1 = __floats2half2_rn(o[d + 2], o[d + 3]);
+        __half2 h2 = __floats2half2_rn(o[d + 4], o[d + 5]), h3 = __floats2half2_rn(o[d + 6], o[d + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + d) = pk;
+      }
+      const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
+      a.row_lse[sidx] = m + logf(l);
+      a.out_norm[sidx] = sqrtf(nsq);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2
+// ------------------------------------------------------------------------------------------------
+struct StatsSmem {
+  static constexpr int BOX_BYTES = BM * 128;                // [128 rows x 32 floats]
+  static constexpr int STAGE_BYTES = 4 * BOX_BYTES;         // Q hi, Q lo, K hi, K lo of one (head, 32-wide slice)
+  static constexpr int STAGES = 3;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 1024 + 1024;
+  static constexpr int RED_LD = 129;                        // column-sum staging pitch (floats), reuses the stages
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                     AttnTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + StatsSmem::BAR_OFF);
+  uint64_t* full = bars;           // [3]
+  uint64_t* empty = bars + 3;      // [3]
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* s_empty = bars + 8;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* colmask = reinterpret_cast<float*>(bars + 12);  // [128] additive mask of this key tile (-inf past N)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * BM, it = blockIdx.y, i0 = it * BM, b = blockIdx.z;
+  const int N = a.N, H = a.H, HD = a.H * 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < StatsSmem::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  if (warp >= 2) {
+    const int c = threadIdx.x - 64;
+    const int j = j0 + c;
+    colmask[c] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f) : -INFINITY;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int u = 0; u < 2 * H; ++u) {
+        const int st = u % StatsSmem::STAGES, hh = u >> 1, c = u & 1;
+        mbar_wait(&empty[st], ((u / StatsSmem::STAGES) & 1) ^ 1);
+        uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[st], StatsSmem::STAGE_BYTES);
+        tma_load_2d(&tm_hi, &full[st], s, hh * 64 + c * BOX, b * N + i0);
+        tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64 + c * BOX, b * N + i0);
+        tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
+        tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2u, BM, BM);
+      for (int hh = 0; hh < H; ++hh) {
+        const int hb = hh & 1;
+        mbar_wait(&s_empty[hb], ((hh >> 1) & 1) ^ 1);
+        for (int c = 0; c < 2; ++c) {
+          const int u = hh * 2 + c, st = u % StatsSmem::STAGES;
+          mbar_wait(&full[st], (u / StatsSmem::STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
+          issue_slice_ss(tmem_base + hb * 256 + c * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
+                         s + 3 * StatsSmem::BOX_BYTES, idesc);
+          umma_commit(&empty[st]);
+        }
+        umma_commit(&s_full[hb]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;          // row within the tile
+    const int i = i0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const bool row_ok = (i >= 1) && (i < N);  // the CLS query row is excluded (reference vit.py:126)
+    float mx[BM];
+#pragma unroll
+    for (int c = 0; c < BM; ++c) mx[c] = -INFINITY;
+    for (int hh = 0; hh < H; ++hh) {
+      const int hb = hh & 1;
+      const float lse = (i < N) ? a.row_lse[(static_cast<long long>(b) * H + hh) * N + i] : 0.f;
+      mbar_wait(&s_full[hb], (hh >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float s[32];
+        ld2_add(tmem_base + lane_off + hb * 256 + cc * 32, tmem_base + lane_off + hb * 256 + 128 + cc * 32, s);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float t = fmaf(s[k], a.scale, colmask[cc * 32 + k]) - lse;
+          mx[cc * 32 + k] = fmaxf(mx[cc * 32 + k], t);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[hb]);
+    }
+    // every MMA has retired (the last s_full fired), so the operand stages can be reused as the reduction tile
+    float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int c = 0; c < BM; ++c) red[r * StatsSmem::RED_LD + c] = row_ok ? expf(mx[c]) : 0.f;
+    named_bar_sync(1, 128);
+    const int c = threadIdx.x - 64;
+    const int j = j0 + c;
+    float sum = 0.f;
+    for (int rr = 0; rr < BM; ++rr) sum += red[rr * StatsSmem::RED_LD + c];   // fixed order: deterministic
+    if (j < N) a.col_part[(static_cast<long long>(b) * a.n_parts + it) * N + j] = sum;
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CLS row: cls_attn[b,j] = sum_h softmax_j(q_0 . k_j)_h * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)
+// grid = B, block = 256, dynamic smem = (H*64 + H*N + 64) floats
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_cls_kernel(AttnTcArgs a) {
+  extern __shared__ float sm[];
+  const int N = a.N, H = a.H, HD = H * 64;
+  float* q0 = sm;                 // [H*64]
+  float* P = q0 + HD;             // [H][N]
+  float* red = P + H * N;         // [64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const float* row0_hi = a.qk_hi + static_cast<long long>(b) * N * a.ld_qk;
+  const float* row0_lo = a.qk_lo + static_cast<long long>(b) * N * a.ld_qk;
+  for (int x = tid; x < HD; x += 256) q0[x] = row0_hi[x] + row0_lo[x];
+  __syncthreads();
+  for (int hh = 0; hh < H; ++hh) {
+    for (int j = tid; j < N; j += 256) {
+      const float4* kh = reinterpret_cast<const float4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+      const float4* kl = reinterpret_cast<const float4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+      float s = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < 16; ++d4) {
+        const float4 x = kh[d4], y = kl[d4];
+        const float4 q = *reinterpret_cast<const float4*>(q0 + hh * 64 + d4 * 4);
+        s = fmaf(q.x, x.x + y.x, s);
+        s = fmaf(q.y, x.y + y.y, s);
+        s = fmaf(q.z, x.z + y.z, s);
+        s = fmaf(q.w, x.w + y.w, s);
+      }
+      const float mk = a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f;
+      P[hh * N + j] = fmaf(s, a.scale, mk);
+    }
+  }
+  __syncthreads();
+  for (int hh = 0; hh < H; ++hh) {
+    float mx = -INFINITY;
+    for (int j = tid; j < N; j += 256) mx = fmaxf(mx, P[hh * N + j]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    float sum = 0.f;
+    for (int j = tid; j < N; j += 256) {
+      const float e = expf(P[hh * N + j] - mx);
+      P[hh * N + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[8 + warp] = sum;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[8 + w];
+    const float inv = 1.0f / tot;
+    for (int j = tid; j < N; j += 256) P[hh * N + j] *= inv;
+    __syncthreads();
+  }
+  for (int j = tid; j < N; j += 256) {
+    float hs = 0.f;
+    for (int hh = 0; hh < H; ++hh) hs += a.out_norm[(static_cast<long long>(b) * H + hh) * N + j];
+    hs += 1e-8f;
+    float acc = 0.f;
+    for (int hh = 0; hh < H; ++hh)
+      acc += P[hh * N + j] * (a.out_norm[(static_cast<long long>(b) * H + hh) * N + j] / hs);
+    a.cls_attn[static_cast<long long>(b) * N + j] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int check_tc(const AttnTcArgs& a) {
+  MADTP_CHECK_ARG(a.qk_hi && a.qk_lo, "attn_tc: null q/k planes");
+  MADTP_CHECK_ARG(a.B >= 0 && a.H > 0 && a.N > 0, "attn_tc: bad shape B=%d H=%d N=%d", a.B, a.H, a.N);
+  MADTP_CHECK_ARG(a.ld_qk >= 2LL * a.H * 64 && a.ld_qk % 4 == 0, "attn_tc: bad q/k leading dimension");
+  MADTP_CHECK_ARG(a.B <= 65535 && a.H <= 65535, "attn_tc: B and H must fit the grid limits");
+  return kOk;
+}
+
+int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
+  int st = check_tc(a);
+  if (st != kOk) return st;
+  MADTP_CHECK_ARG(a.vt_hi && a.vt_lo && a.ld_vt >= a.N && a.ld_vt % 4 == 0, "attn_fwd_tc: bad V^T planes");
+  MADTP_CHECK_ARG(a.out_f16 && a.ldo % 8 == 0 && a.bso % 8 == 0 && a.row_lse && a.out_norm, "attn_fwd_tc: bad outputs");
+  if (a.B == 0) return kOk;
+  const long long rows = static_cast<long long>(a.B) * a.N;
+  CUtensorMap tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo;
+  if ((st = make_tmap(&tq_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&tq_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&tk_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
+  if ((st = make_tmap(&tk_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
+  const long long vrows = static_cast<long long>(a.B) * a.H * 64;
+  if ((st = make_tmap(&tv_hi, a.vt_hi, true, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
+  if ((st = make_tmap(&tv_lo, a.vt_lo, true, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    attr_done = true;
+  }
+  dim3 grid((a.N + BM - 1) / BM, a.H, a.B);
+  attn_fwd_tc_kernel<<<grid, TC_THREADS, FwdSmem::TOTAL, stream>>>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
+  int st = check_tc(a);
+  if (st != kOk) return st;
+  MADTP_CHECK_ARG(a.row_lse && a.out_norm && a.col_part && a.cls_attn, "attn_stats_tc: null statistics buffer");
+  MADTP_CHECK_ARG(a.n_parts == (a.N + BM - 1) / BM, "attn_stats_tc: n_parts must be ceil(N/128)");
+  MADTP_CHECK_ARG(a.N <= 4096, "attn_stats_tc: sequence too long for the CLS-row kernel");
+  if (a.B == 0) return kOk;
+  const long long rows = static_cast<long long>(a.B) * a.N;
+  CUtensorMap t_hi, t_lo;
+  if ((st = make_tmap(&t_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&t_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MADTP_CUDA(cudaFuncSetAttribute(attn_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    StatsSmem::TOTAL));
+    MADTP_CUDA(cudaFuncSetAttribute(attn_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  dim3 grid(a.n_parts, a.n_parts, a.B);
+  attn_stats_tc_kernel<<<grid, TC_THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
+  MADTP_LAUNCH_CHECK();
+  const size_t cls_smem = (static_cast<size_t>(a.H) * 64 + static_cast<size_t>(a.H) * a.N + 64) * sizeof(float);
+  MADTP_CHECK_ARG(cls_smem <= 200 * 1024, "attn_stats_tc: H*N too large for the CLS-row kernel");
+  attn_cls_kernel<<<a.B, 256, cls_smem, stream>>>(a);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+}  // namespace madtp

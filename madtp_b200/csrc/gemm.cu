@@ -143,7 +143,7 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
-template <int ACT, bool RES = true, int GROUP = 8>
+template <int ACT, bool RES = true, int GROUP = 8, bool SPLIT = false>
 __device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, const float* acc, float* stage,
                                                       long long row_base, int col0, int M, int N, int lane,
                                                       const float4 (&rv)[8]) {
@@ -180,7 +180,14 @@ __device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, co
       if (RES) {
         o.x += rv[it].x; o.y += rv[it].y; o.z += rv[it].z; o.w += rv[it].w;
       }
-      if (col_ok && row < M) {
+      if (SPLIT) {
+        if (col_ok && row < M) {
+          const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.c) + row * ep.ldc + col) = h;
+          *reinterpret_cast<float4*>(ep.c_lo + row * ep.ldc + col) =
+              make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+        }
+      } else if (col_ok && row < M) {
         if (ep.c_f16) {
           __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
           uint2 pk;
@@ -589,7 +596,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int c = 0; c < CW / 32; ++c) {
         const int col0 = n0 + half * CW + c * 32;
         if (col0 < N) {
-          if (vec_ok && ep.act == 0) {
+          if (ep.mode == 1) {
+            if (col0 < ep.qk_cols) {
+              float4 rv[8];
+              store_chunk_coalesced<0, false, (CW > 64 ? 4 : 8), true>(ep, &sum[c * 32], epi_stage + (warp - 2) * 1024,
+                                                                       m0 + quad * 32, col0, M, N, lane, rv);
+            } else if (row < M) {
+              // value projection: lane = token, so consecutive lanes write consecutive keys of one V^T row
+              const int b = static_cast<int>(row / ep.n_tok);
+              const int i = static_cast<int>(row - static_cast<long long>(b) * ep.n_tok);
+              const int vc = col0 - ep.qk_cols;
+              const long long off =
+                  (static_cast<long long>(b * ep.heads + (vc >> 6)) * 64 + (vc & 63)) * ep.ld_vt + i;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float o = sum[c * 32 + j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
+                const float h = tf32_hi(o);
+                ep.vt_hi[off + j * ep.ld_vt] = h;
+                ep.vt_lo[off + j * ep.ld_vt] = o - h;
+              }
+            }
+          } else if (vec_ok && ep.act == 0) {
             float* stg = epi_stage + (warp - 2) * 1024;
             float4 rv[8];
             if (ep.residual != nullptr) {
@@ -686,7 +713,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // Row-major [rows, cols] matrix with leading dimension ld (elements); box = box_rows x (128 bytes of columns).
-static int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld,
+int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld,
                      int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) {
@@ -762,6 +789,33 @@ static int launch_tf32(const void* a, const void* a_lo, long long lda, const voi
   gemm_tf32x3_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, ep, M, N, K);
   MADTP_LAUNCH_CHECK();
   return kOk;
+}
+
+int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
+                    long long ldb, const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+                    long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream) {
+  MADTP_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && qk_hi && qk_lo && vt_hi && vt_lo, "gemm_qkv: null pointer");
+  MADTP_CHECK_ARG(M >= 0 && K > 0 && n_tok > 0 && heads > 0 && M % n_tok == 0, "gemm_qkv: bad shape M=%d n_tok=%d", M,
+                  n_tok);
+  MADTP_CHECK_ARG(ld_qk % 4 == 0 && ld_qk >= 2LL * heads * 64 && ld_vt >= n_tok, "gemm_qkv: bad leading dimensions");
+  MADTP_CHECK_ARG((reinterpret_cast<uintptr_t>(qk_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qk_lo) & 15) == 0 &&
+                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                  "gemm_qkv: outputs and bias must be 16-byte aligned");
+  if (M == 0) return kOk;
+  GemmEpilogue ep = {};
+  ep.c = qk_hi;
+  ep.c_lo = qk_lo;
+  ep.ldc = ld_qk;
+  ep.bias = bias;
+  ep.alpha = 1.0f;
+  ep.mode = 1;
+  ep.vt_hi = vt_hi;
+  ep.vt_lo = vt_lo;
+  ep.ld_vt = ld_vt;
+  ep.n_tok = n_tok;
+  ep.heads = heads;
+  ep.qk_cols = 2 * heads * 64;
+  return launch_tf32<256>(a_hi, a_lo, lda, w_hi, w_lo, ldb, ep, M, 3 * heads * 64, K, stream);
 }
 
 // Pick the N tile that wastes the fewest SM-waves (persistent grid of num_sms CTAs).

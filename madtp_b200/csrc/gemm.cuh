@@ -14,6 +14,18 @@ struct GemmEpilogue {
   long long ldr;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU, 3 QuickGELU (x * sigmoid(1.702 x))
   float alpha;
+  // ---- mode 1 (TF32x3 kernel only): fused q|k|v projection feeding the tensor-core attention kernels ----
+  // columns [0, qk_cols) are written as tf32 hi/lo planes into c / c_lo ([M, ldc] each); columns [qk_cols, N) (the
+  // value projection, head h = (col - qk_cols) / 64) are written TRANSPOSED per sequence as hi/lo planes
+  // vt[((b * heads + h) * 64 + d) * ld_vt + i] for token i of sequence b = row / n_tok, so that keys are contiguous.
+  int mode;
+  float* c_lo;
+  float* vt_hi;
+  float* vt_lo;
+  long long ld_vt;
+  int n_tok;
+  int heads;
+  int qk_cols;
 };
 
 enum GemmPrecision : int {
@@ -38,6 +50,15 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // C[M,N] = epilogue(A[M,K] * B[N,K]^T). A and B are row-major with the reduction dimension contiguous
 // (activations [tokens, features] and nn.Linear weights [out, in]).
 // a_lo/b_lo are only read for kGemmTF32x3. Returns a Status.
+// 2-D TMA descriptor of a row-major [rows, cols] matrix (leading dimension ld elements, fp32 or fp16) with a
+// box of box_rows x 128 bytes and the 128-byte swizzle; out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld, int box_rows);
+
+// Fused q|k|v projection (TF32x3) with the split / transposed epilogue described at GemmEpilogue::mode.
+int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
+                    long long ldb, const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+                    long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream);
+
 int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
                 long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream);
 

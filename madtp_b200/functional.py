@@ -188,6 +188,25 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
     return ctx16, AttnStats(col_part, cls_attn)
 
 
+def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N: int, H: int, scale: float,
+                      want_stats: bool):
+    """Tensor-core scoring-lane self-attention from the tf32 split of the normalised rows [B*N, C]:
+    fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
+    Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
+    dev = y_hi.device
+    qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H)
+    ctx16 = torch.empty(B, N, H * 64, dtype=torch.float16, device=dev)
+    rows = torch.empty(2, B, H, N, dtype=torch.float32, device=dev)
+    L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1])
+    if not want_stats:
+        return ctx16, None
+    n_parts = (N + 127) // 128
+    col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
+    cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
+    L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn)
+    return ctx16, AttnStats(col_part, cls_attn)
+
+
 @dataclass
 class PruneResult:
     x: Tensor                       # [B, k+2, d] (or the input when nothing was pruned)

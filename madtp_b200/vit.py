@@ -122,9 +122,7 @@ class Attention(nn.Module):
         and stores the pruning statistics (models/vit.py:83,96-101)."""
         qkv_w, proj_w = self._prepared()
         C = self.dim
-        qkv = Fn.linear_tf32(y_hi, y_lo, qkv_w).view(B, N, 3 * C)
-        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-        ctx16, stats = Fn.self_attention(q, k, v, self.num_heads, self.scale, None, want_stats)
+        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, self.scale, want_stats)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return Fn.linear_f16(ctx16.view(B * N, C), proj_w, residual=residual)

@@ -283,3 +283,64 @@ def test_dtp_score_select_gather(lib, dev, B, n, temp):
             if mode == 2:
                 exp = torch.cat([mask_in[b, :1], mask_in[b, 1 + idx], mask_in[b, 1 + order[b, k:k + 1]]])
                 assert torch.equal(mask_out[b, :k + 2], exp)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core attention path: fused q|k|v projection with split / transposed epilogue, fwd + statistics
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,N,masked", [(2, 12, 197, False), (2, 12, 577, False), (1, 2, 128, False), (3, 4, 65, True),
+                                          (2, 12, 346, False), (1, 12, 901, False)])
+def test_attention_tensor_core_path(lib, dev, B, H, N, masked):
+    g = torch.Generator(device="cpu").manual_seed(N * 3 + B)
+    K = 256
+    HD = H * 64
+    x = torch.randn(B * N, K, generator=g).to(dev)
+    w = (torch.randn(3 * HD, K, generator=g) * 0.08).to(dev)
+    bias = (torch.randn(3 * HD, generator=g) * 0.1).to(dev)
+    x_hi, x_lo = lib.split_tf32(x)
+    w_hi, w_lo = lib.split_tf32(w)
+    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(x_hi, x_lo, w_hi, w_lo, bias, N, H)
+    ref = x.double() @ w.double().T + bias.double()
+    qk = qk_hi + qk_lo
+    assert int((qk_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert _rel(qk, ref[:, :2 * HD]) < 6e-7
+    vt = (vt_hi + vt_lo)[:, :N].reshape(B, H, 64, N)
+    v_ref = ref[:, 2 * HD:].reshape(B, N, H, 64).permute(0, 2, 3, 1)
+    assert _rel(vt, v_ref) < 6e-7
+
+    mask = None
+    if masked:
+        lens = torch.randint(N // 2, N + 1, (B,), generator=g)
+        mask = torch.zeros(B, N)
+        for b in range(B):
+            mask[b, lens[b]:] = -10000.0
+        mask = mask.to(dev)
+    scale = 0.125
+    out = torch.empty(B, N, HD, device=dev, dtype=torch.float16)
+    lse = torch.empty(B, H, N, device=dev)
+    norm = torch.empty(B, H, N, device=dev)
+    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out, lse, norm, key_mask=mask)
+    n_parts = (N + 127) // 128
+    col_part = torch.zeros(B, n_parts, N, device=dev)
+    cls_attn = torch.zeros(B, N, device=dev)
+    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, lse, norm, col_part, cls_attn, key_mask=mask)
+
+    # fp64 reference from the very operands the kernels consumed (so projection rounding does not enter)
+    q = qk[:, :HD].reshape(B, N, H, 64).permute(0, 2, 1, 3).double()
+    k = qk[:, HD:].reshape(B, N, H, 64).permute(0, 2, 1, 3).double()
+    v = vt.permute(0, 1, 3, 2).double()
+    p, o = _attn_ref(q, k, v, scale, None if mask is None else mask.double())
+    o_merged = o.permute(0, 2, 1, 3).reshape(B, N, HD)
+    assert _rel(out, o_merged) < 6e-4
+    assert (norm.double() - o.norm(dim=-1)).abs().max().item() < 1e-5 * max(1.0, o.norm(dim=-1).max().item())
+    s = q @ k.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + mask.double()[:, None, None, :]
+    assert (lse.double() - torch.logsumexp(s, dim=-1)).abs().max().item() < 2e-5
+    hi = o[..., 1:, :].norm(dim=-1)
+    hi = hi / (hi.sum(dim=1, keepdim=True) + 1e-8)
+    cls_ref = (p[:, :, 0, 1:] * hi).sum(dim=1)
+    a_ref = p[:, :, 1:, 1:].max(dim=1)[0].sum(dim=1)
+    assert (cls_attn[:, 1:].double() - cls_ref).abs().max().item() < 1e-6
+    a = col_part.double().sum(dim=1)[:, 1:]
+    assert ((a - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 3e-6

@@ -158,7 +158,7 @@ int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, con
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream);
 int madtp_attn_tc_stats(const float* qk_hi, const float* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, void* stream);
+                        int n_parts, float* cls_attn, float* cls_scratch /* [B,H,N] workspace */, void* stream);
 
 /* vector_gather (models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :], x [B,L,d] with batch stride bsx, idx [B,K]
  * (indices are clamped to [0, L)), out [B,K,d] contiguous. */

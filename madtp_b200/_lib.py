@@ -46,7 +46,7 @@ SIGNATURES = {
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
-    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
 }
 
 
@@ -142,7 +142,14 @@ def _ptr(t, dtype=None, name="tensor"):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Raw cudaStream_t of torch's current stream on the current device (the fast C accessor: the Python
+    torch.cuda.current_stream() wrapper costs ~15 us per call, more than a small kernel)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -396,5 +403,6 @@ def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls
     st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float32, "qk_hi"), _ptr(qk_lo, torch.float32, "qk_lo"),
                qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
                _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
-               _ptr(cls_attn, torch.float32, "cls_attn"), _stream())
+               _ptr(cls_attn, torch.float32, "cls_attn"),
+               _ptr(torch.empty(B, H, N, dtype=torch.float32, device=qk_hi.device)), _stream())
     _check(st, "madtp_attn_tc_stats")

@@ -37,6 +37,7 @@ struct AttnTcArgs {
   float* out_norm;                       // [B, H, N]  || context[b, h, i, :] ||_2
   float* col_part; int n_parts;          // [B, ceil(N/128), N]
   float* cls_attn;                       // [B, N]
+  float* cls_scratch;                    // [B, H, N] workspace: the CLS query row of every head
 };
 int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);

@@ -448,72 +448,75 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 
 // ------------------------------------------------------------------------------------------------
 // CLS row: cls_attn[b,j] = sum_h softmax_j(q_0 . k_j)_h * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)
-// grid = B, block = 256, dynamic smem = (H*64 + H*N + 64) floats
+//   attn_cls_head_kernel     grid (H, B), block 256: the CLS query row of one head (fp32 FFMA, own softmax) -> scratch
+//   attn_cls_combine_kernel  grid (ceil(N/256), B): head-importance weighting and the sum over heads (h ascending)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-attn_cls_kernel(AttnTcArgs a) {
+attn_cls_head_kernel(AttnTcArgs a) {
   extern __shared__ float sm[];
   const int N = a.N, H = a.H, HD = H * 64;
-  float* q0 = sm;                 // [H*64]
-  float* P = q0 + HD;             // [H][N]
-  float* red = P + H * N;         // [64]
+  float* q0 = sm;        // [64]
+  float* red = sm + 64;  // [16]
+  float* P = sm + 80;    // [N]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x;
+  const int hh = blockIdx.x, b = blockIdx.y;
   const float* row0_hi = a.qk_hi + static_cast<long long>(b) * N * a.ld_qk;
   const float* row0_lo = a.qk_lo + static_cast<long long>(b) * N * a.ld_qk;
-  for (int x = tid; x < HD; x += 256) q0[x] = row0_hi[x] + row0_lo[x];
+  if (tid < 64) q0[tid] = row0_hi[hh * 64 + tid] + row0_lo[hh * 64 + tid];
   __syncthreads();
-  for (int hh = 0; hh < H; ++hh) {
-    for (int j = tid; j < N; j += 256) {
-      const float4* kh = reinterpret_cast<const float4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
-      const float4* kl = reinterpret_cast<const float4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
-      float s = 0.f;
-#pragma unroll
-      for (int d4 = 0; d4 < 16; ++d4) {
-        const float4 x = kh[d4], y = kl[d4];
-        const float4 q = *reinterpret_cast<const float4*>(q0 + hh * 64 + d4 * 4);
-        s = fmaf(q.x, x.x + y.x, s);
-        s = fmaf(q.y, x.y + y.y, s);
-        s = fmaf(q.z, x.z + y.z, s);
-        s = fmaf(q.w, x.w + y.w, s);
-      }
-      const float mk = a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f;
-      P[hh * N + j] = fmaf(s, a.scale, mk);
-    }
-  }
-  __syncthreads();
-  for (int hh = 0; hh < H; ++hh) {
-    float mx = -INFINITY;
-    for (int j = tid; j < N; j += 256) mx = fmaxf(mx, P[hh * N + j]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-    float sum = 0.f;
-    for (int j = tid; j < N; j += 256) {
-      const float e = expf(P[hh * N + j] - mx);
-      P[hh * N + j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) red[8 + warp] = sum;
-    __syncthreads();
-    float tot = 0.f;
-    for (int w = 0; w < 8; ++w) tot += red[8 + w];
-    const float inv = 1.0f / tot;
-    for (int j = tid; j < N; j += 256) P[hh * N + j] *= inv;
-    __syncthreads();
-  }
+  float mx = -INFINITY;
   for (int j = tid; j < N; j += 256) {
-    float hs = 0.f;
-    for (int hh = 0; hh < H; ++hh) hs += a.out_norm[(static_cast<long long>(b) * H + hh) * N + j];
-    hs += 1e-8f;
-    float acc = 0.f;
-    for (int hh = 0; hh < H; ++hh)
-      acc += P[hh * N + j] * (a.out_norm[(static_cast<long long>(b) * H + hh) * N + j] / hs);
-    a.cls_attn[static_cast<long long>(b) * N + j] = acc;
+    const float4* kh = reinterpret_cast<const float4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+    const float4* kl = reinterpret_cast<const float4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+    float s = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < 16; ++d4) {
+      const float4 x = kh[d4], y = kl[d4];
+      const float4 q = *reinterpret_cast<const float4*>(q0 + d4 * 4);
+      s = fmaf(q.x, x.x + y.x, s);
+      s = fmaf(q.y, x.y + y.y, s);
+      s = fmaf(q.z, x.z + y.z, s);
+      s = fmaf(q.w, x.w + y.w, s);
+    }
+    const float mk = a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f;
+    const float lg = fmaf(s, a.scale, mk);
+    P[j] = lg;
+    mx = fmaxf(mx, lg);
   }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  float sum = 0.f;
+  for (int j = tid; j < N; j += 256) {
+    const float e = expf(P[j] - mx);
+    P[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[8 + warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[8 + w];
+  const float inv = 1.0f / tot;
+  float* out = a.cls_scratch + (static_cast<long long>(b) * H + hh) * N;
+  for (int j = tid; j < N; j += 256) out[j] = P[j] * inv;
+}
+
+__global__ void __launch_bounds__(256)
+attn_cls_combine_kernel(AttnTcArgs a) {
+  const int N = a.N, H = a.H;
+  const int j = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (j >= N) return;
+  const long long base = static_cast<long long>(b) * H * N + j;
+  float hs = 0.f;
+  for (int hh = 0; hh < H; ++hh) hs += a.out_norm[base + static_cast<long long>(hh) * N];
+  hs += 1e-8f;
+  float acc = 0.f;
+  for (int hh = 0; hh < H; ++hh)
+    acc += a.cls_scratch[base + static_cast<long long>(hh) * N] * (a.out_norm[base + static_cast<long long>(hh) * N] / hs);
+  a.cls_attn[static_cast<long long>(b) * N + j] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,9 +559,10 @@ int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   int st = check_tc(a);
   if (st != kOk) return st;
-  MADTP_CHECK_ARG(a.row_lse && a.out_norm && a.col_part && a.cls_attn, "attn_stats_tc: null statistics buffer");
+  MADTP_CHECK_ARG(a.row_lse && a.out_norm && a.col_part && a.cls_attn && a.cls_scratch,
+                  "attn_stats_tc: null statistics buffer");
   MADTP_CHECK_ARG(a.n_parts == (a.N + BM - 1) / BM, "attn_stats_tc: n_parts must be ceil(N/128)");
-  MADTP_CHECK_ARG(a.N <= 4096, "attn_stats_tc: sequence too long for the CLS-row kernel");
+  MADTP_CHECK_ARG(a.N <= 8192, "attn_stats_tc: sequence too long for the CLS-row kernel");
   if (a.B == 0) return kOk;
   const long long rows = static_cast<long long>(a.B) * a.N;
   CUtensorMap t_hi, t_lo;
@@ -568,15 +572,15 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   if (!attr_done) {
     MADTP_CUDA(cudaFuncSetAttribute(attn_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     StatsSmem::TOTAL));
-    MADTP_CUDA(cudaFuncSetAttribute(attn_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   dim3 grid(a.n_parts, a.n_parts, a.B);
   attn_stats_tc_kernel<<<grid, TC_THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
   MADTP_LAUNCH_CHECK();
-  const size_t cls_smem = (static_cast<size_t>(a.H) * 64 + static_cast<size_t>(a.H) * a.N + 64) * sizeof(float);
-  MADTP_CHECK_ARG(cls_smem <= 200 * 1024, "attn_stats_tc: H*N too large for the CLS-row kernel");
-  attn_cls_kernel<<<a.B, 256, cls_smem, stream>>>(a);
+  const size_t cls_smem = (80 + static_cast<size_t>(a.N)) * sizeof(float);
+  attn_cls_head_kernel<<<dim3(a.H, a.B), 256, cls_smem, stream>>>(a);
+  MADTP_LAUNCH_CHECK();
+  attn_cls_combine_kernel<<<dim3((a.N + 255) / 256, a.B), 256, 0, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

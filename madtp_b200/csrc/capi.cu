@@ -209,13 +209,13 @@ int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, con
 
 int madtp_attn_tc_stats(const float* qk_hi, const float* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, void* stream) {
+                        int n_parts, float* cls_attn, float* cls_scratch, void* stream) {
   AttnTcArgs a = {};
   a.qk_hi = qk_hi; a.qk_lo = qk_lo; a.ld_qk = ld_qk;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.row_lse = const_cast<float*>(row_lse); a.out_norm = const_cast<float*>(out_norm);
-  a.col_part = col_part; a.n_parts = n_parts; a.cls_attn = cls_attn;
-  return counted(launch_attn_stats_tc(a, as_stream(stream)), B > 0 ? 2 : 0);
+  a.col_part = col_part; a.n_parts = n_parts; a.cls_attn = cls_attn; a.cls_scratch = cls_scratch;
+  return counted(launch_attn_stats_tc(a, as_stream(stream)), B > 0 ? 3 : 0);
 }
 
 int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,

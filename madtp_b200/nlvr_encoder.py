@@ -83,6 +83,8 @@ class BertEmbeddings(nn.Module):
 
 
 class BertSelfAttention(nn.Module):
+    CROSS_ATTENTION_MASK = True     # nlvr_encoder adds the encoder mask in cross-attention (:196); med.py does not (:197)
+
     def __init__(self, config, is_cross_attention):
         super().__init__()
         self.config = config
@@ -181,7 +183,8 @@ class BertSelfAttention(nn.Module):
             kv = self.project_kv(L.cast_f16(enc.view(B * Nk, -1))).view(B, Nk, 2 * C)
             q = Fn.linear_f16(L.cast_f16(hidden_states.reshape(B * Ltok, d)), self._q_f16()).view(B, Ltok, C)
             ctx16 = torch.empty(B, Ltok, C, dtype=torch.float16, device=q.device)
-            self.cross_rows(q, kv[..., :C], kv[..., C:], _key_mask(encoder_attention_mask, B, Nk), ctx16)
+            em = encoder_attention_mask if self.CROSS_ATTENTION_MASK else None
+            self.cross_rows(q, kv[..., :C], kv[..., C:], _key_mask(em, B, Nk), ctx16)
         return (ctx16.float(), None)
 
 
@@ -366,6 +369,12 @@ class BertLayer(nn.Module):
                 output_attentions=False, mode=None, token_attn=None, reduce_num=0, temperature=0, _kv=None):
         """Returns (layer_output, None, attention_mask') -- the last element is the pruned extended mask
         (models/nlvr_encoder.py:551-553), consumed by BertEncoder."""
+        return self._forward_impl(hidden_states, attention_mask, head_mask, encoder_hidden_states,
+                                  encoder_attention_mask, past_key_value, output_attentions, mode, token_attn,
+                                  temperature, _kv)
+
+    def _forward_impl(self, hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
+                      past_key_value, output_attentions, mode, token_attn, temperature, _kv):
         Fn.require_cuda(hidden_states, "hidden_states")
         _eval_only(self)
         _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
@@ -428,7 +437,8 @@ class BertLayer(nn.Module):
                 e16 = L.cast_f16(enc[i].contiguous().view(B * Nk, -1))
                 kvp = s.project_kv(e16).view(B, Nk, 2 * C)
                 k, v = kvp[..., :C], kvp[..., C:]
-            s.cross_rows(q, k, v, _key_mask(masks[i], B, Nk), ctx[..., i * C:(i + 1) * C])
+            em = masks[i] if s.CROSS_ATTENTION_MASK else None
+            s.cross_rows(q, k, v, _key_mask(em, B, Nk), ctx[..., i * C:(i + 1) * C])
         o = ca.output.rows(ctx.view(B * Ltok, nb * C), att_rows, f16=True)
         return o["y"], o["y16"]
 
@@ -437,13 +447,17 @@ class BertLayer(nn.Module):
 
 
 class BertEncoder(nn.Module):
-    def __init__(self, config, sd_dim=768):
+    REQUIRE_SPACE_DICT = True
+    LAYER_CLS = None    # set below (BertLayer); med.py overrides
+
+    def __init__(self, config, sd_dim=768, map_func=False):
         super().__init__()
         self.config = config
-        self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
+        layer_cls = self.LAYER_CLS or BertLayer
+        self.layer = nn.ModuleList([layer_cls(config, i) for i in range(config.num_hidden_layers)])
         self.gradient_checkpointing = False
         self.txt_query_model = Query_model(ft_dim=config.hidden_size, sd_dim=sd_dim, temperature=1,
-                                           att_func_type='sparsemax', pool_type='max')
+                                           att_func_type='sparsemax', pool_type='max', map_func=map_func)
         self._cache = Fn.WeightCache()
 
     def _all_kv_weights(self, which: str):
@@ -477,7 +491,7 @@ class BertEncoder(nn.Module):
         _unsupported(past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
                      output_hidden_states=output_hidden_states)
         Fn.require_cuda(hidden_states, "hidden_states")
-        if space_dict is None:
+        if space_dict is None and self.REQUIRE_SPACE_DICT:
             raise RuntimeError("madtp_b200: nlvr_encoder.BertEncoder always queries the codebook (:605-608)")
         B = hidden_states.shape[0]
         token_num = hidden_states.shape[-2]
@@ -489,12 +503,14 @@ class BertEncoder(nn.Module):
         for i, layer_module in enumerate(self.layer):
             h = hidden_states.contiguous()
             Ltok, d = h.shape[1], h.shape[2]
-            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
-            token_attn, sd_txt_ft_all = self.txt_query_model.forward_rows(h, h_hi, h_lo, space_dict, sd_txt_ft_all)
-            layer_outputs = layer_module(h, attention_mask, space_dict, None, encoder_hidden_states,
-                                         encoder_attention_mask, None, False, mode=mode, token_attn=token_attn,
-                                         reduce_num=reduce_num, temperature=temperature,
-                                         _kv=None if kv is None else kv[i])
+            token_attn = None
+            if space_dict is not None:
+                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+                token_attn, sd_txt_ft_all = self.txt_query_model.forward_rows(h, h_hi, h_lo, space_dict,
+                                                                              sd_txt_ft_all)
+            layer_outputs = layer_module._forward_impl(h, attention_mask, None, encoder_hidden_states,
+                                                       encoder_attention_mask, None, False, mode, token_attn,
+                                                       temperature, None if kv is None else kv[i])
             hidden_states = layer_outputs[0]
             attention_mask = layer_outputs[-1]
         if not return_dict:

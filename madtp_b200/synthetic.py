@@ -94,6 +94,56 @@ def nlvr_text_state_dict(g: torch.Generator, prefix: str = "", d: int = 768, dep
     return sd
 
 
+def med_text_state_dict(g: torch.Generator, prefix: str = "", d: int = 768, depth: int = 12, dff: int = 3072,
+                        vocab: int = 30524, max_pos: int = 512) -> Dict[str, Tensor]:
+    """Keys of models/med.py:BertModel(add_pooling_layer=False) with add_cross_attention=True."""
+    sd: Dict[str, Tensor] = {}
+    e = prefix + "embeddings."
+    sd[e + "word_embeddings.weight"] = torch.randn(vocab, d, generator=g)
+    sd[e + "word_embeddings.weight"][0].zero_()
+    sd[e + "position_embeddings.weight"] = torch.randn(max_pos, d, generator=g)
+    sd[e + "position_ids"] = torch.arange(max_pos).unsqueeze(0)
+    _ln(sd, e + "LayerNorm", d)
+    for i in range(depth):
+        p = f"{prefix}encoder.layer.{i}"
+        for blk in ("attention", "crossattention"):
+            for nm in ("query", "key", "value"):
+                _linear(sd, g, f"{p}.{blk}.self.{nm}", d, d)
+            _linear(sd, g, f"{p}.{blk}.output.dense", d, d)
+            _ln(sd, f"{p}.{blk}.output.LayerNorm", d)
+        _linear(sd, g, p + ".intermediate.dense", dff, d)
+        _linear(sd, g, p + ".output.dense", d, dff)
+        _ln(sd, p + ".output.LayerNorm", d)
+    return sd
+
+
+def retrieval_state_dict(seed: int = 4321, img_size: int = 384, sd_num: int = 100, sd_dim: int = 768,
+                         depth: int = 12) -> Dict[str, Tensor]:
+    """The encoder part of models/blip_retrieval.py:BLIP_Retrieval: space_dict, visual_encoder.*, text_encoder.*,
+    itm_head.* (the projections / momentum twins / queues are training-only and not generated)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {"space_dict": torch.randn(sd_num, sd_dim, generator=g)}
+    sd.update(vit_state_dict(g, "visual_encoder.", img_size=img_size, depth=depth))
+    sd.update(med_text_state_dict(g, "text_encoder.", depth=depth))
+    _linear(sd, g, "itm_head", 2, 768)
+    return sd
+
+
+def retrieval_inputs(batch: int, img_size: int = 384, max_len: int = 35, seed: int = 0):
+    """BASELINE config 3 inputs: images ~ N(0,1); text padded to max_len (`padding='max_length'`,
+    models/blip_retrieval.py:107) with true lengths ~ U[8, 20)."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, 3, img_size, img_size, generator=g)
+    lens = torch.randint(8, 20, (batch,), generator=g)
+    ids = torch.zeros(batch, max_len, dtype=torch.long)
+    mask = torch.zeros(batch, max_len, dtype=torch.long)
+    for b in range(batch):
+        ids[b, :lens[b]] = torch.randint(1000, 30000, (int(lens[b]),), generator=g)
+        ids[b, 0] = 101
+        mask[b, :lens[b]] = 1
+    return images, ids, mask
+
+
 def blip_nlvr_state_dict(seed: int = 1234, img_size: int = 384, sd_num: int = 100, sd_dim: int = 768,
                          depth: int = 12) -> Dict[str, Tensor]:
     """Keys of models/blip_nlvr.py:BLIP_NLVR."""

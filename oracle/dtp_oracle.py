@@ -366,3 +366,57 @@ def nlvr_macs_unpruned(n0: int, text_len: int, d: int = 768, depth: int = 12) ->
     for i in range(depth):
         total += text_layer_macs(text_len, text_len, n0, i, d)
     return total + d * d + 2 * d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# med.py text encoder (BLIP retrieval / VQA): single cross-attention, mode 'text' | 'multimodal'
+# ---------------------------------------------------------------------------------------------------------------
+def med_layer(h: Tensor, ext_mask: Tensor, sd: SD, prefix: str, enc: Optional[Tensor], temperature: float,
+              token_attn: Optional[Tensor], mode: str, H: int = 12, eps: float = 1e-12,
+              trace: Optional[PruneTrace] = None):
+    """models/med.py:393-467. Returns (layer_output, pruned ext_mask)."""
+    if trace is not None:
+        trace.layer_input, trace.mask_in = h, ext_mask
+    ctx, probs, cls_attn = bert_self_attention(h, ext_mask, sd, prefix + ".attention.self", H)
+    att = layer_norm(linear(ctx, sd, prefix + ".attention.output.dense") + h, sd,
+                     prefix + ".attention.output.LayerNorm", eps)
+    if temperature > 0:                                                                  # :427-441
+        tokens, pm = reduce_token(att[:, 1:, :], probs, cls_attn, token_attn, temperature,
+                                  mask=ext_mask[:, 0, 0, 1:], variant="med", trace=trace)
+        att = torch.cat([att[:, :1, :], tokens], dim=1)
+        ext_mask = torch.cat([ext_mask[:, :, :, :1], pm[:, None, None, :]], dim=-1)
+    if mode == "multimodal":                                                             # :443-455; no mask (:197)
+        c, _, _ = bert_self_attention(att, None, sd, prefix + ".crossattention.self", H, enc=enc, enc_mask=None)
+        att = layer_norm(linear(c, sd, prefix + ".crossattention.output.dense") + att, sd,
+                         prefix + ".crossattention.output.LayerNorm", eps)
+    inter = F.gelu(linear(att, sd, prefix + ".intermediate.dense"))
+    out = layer_norm(linear(inter, sd, prefix + ".output.dense") + att, sd, prefix + ".output.LayerNorm", eps)
+    if trace is not None:
+        trace.layer_output, trace.mask_out = out, ext_mask
+    return out, ext_mask
+
+
+def med_text_encoder(ids: Tensor, attn_mask: Tensor, sd: SD, prefix: str, enc: Optional[Tensor],
+                     space_dict: Optional[Tensor], temperature: float, mode: str, depth: int = 12,
+                     traces: Optional[List[PruneTrace]] = None):
+    """models/med.py:788-929 + :478-598. Returns (last_hidden_state, sd_txt_ft)."""
+    ext_mask = (1.0 - attn_mask[:, None, None, :].to(torch.float32)) * -10000.0          # :784-785
+    h = bert_embeddings(ids, sd, prefix + "embeddings.")
+    sd_ft_all = None
+    for i in range(depth):
+        token_attn = None
+        if space_dict is not None:                                                       # :513-524
+            token_attn, sd_ft = query_model(h[:, 1:, :], space_dict, space_dict.shape[1])
+            if sd_ft_all is None:
+                sd_ft_all = sd_ft
+            elif sd_ft_all.shape == sd_ft.shape:
+                sd_ft_all = sd_ft_all + sd_ft
+            else:
+                sd_ft_all = None
+        tr = None
+        if traces is not None:
+            tr = PruneTrace()
+            traces.append(tr)
+        h, ext_mask = med_layer(h, ext_mask, sd, f"{prefix}encoder.layer.{i}", enc, temperature, token_attn, mode,
+                                trace=tr)
+    return h, sd_ft_all

@@ -270,6 +270,109 @@ def gen_nlvr(image_size: int, pairs: int, text_len: int, temps, name: str, pad_t
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# models/med.py text encoder (BLIP retrieval / VQA): mode 'text' with padded text and mode 'multimodal'
+# ---------------------------------------------------------------------------------------------------------------
+def gen_med():
+    ref_shims.install()
+    import models.med as rmed
+    from transformers.models.bert.configuration_bert import BertConfig as HFBertConfig
+    cfg = HFBertConfig.from_json_file(os.path.join(ref_shims.REFERENCE_ROOT, "configs/med_config.json"))
+    cfg.encoder_width = 768
+    cfg.evaluate = True
+    model = rmed.BertModel(config=cfg, add_pooling_layer=False, sd_dim=768)
+    g = torch.Generator().manual_seed(4321)
+    sd = weights.med_text_state_dict(g, "")
+    space = torch.randn(100, 768, generator=g)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys and all("position_ids" in k for k in msg.missing_keys), msg
+    model.eval()
+    _, ids, mask = weights.retrieval_inputs(4, img_size=32, max_len=35, seed=0)
+    enc = torch.randn(4, 60, 768, generator=g)
+    out = {"input_digest": np.array(digest(ids, mask, enc, space))}
+    cases = [("text", 3.0), ("text", 10.0), ("multimodal", 10.0)]
+    out["modes"] = np.array([c[0] for c in cases])
+    out["temps"] = np.array([c[1] for c in cases])
+    for ci, (mode, temp) in enumerate(cases):
+        cap = []
+        hooks = []
+
+        def pre(mod, args, kwargs):
+            cap.append({"h": args[0].detach().clone(), "mask": args[1].detach().clone(),
+                        "token_attn": kwargs["token_attn"].detach().clone(), "gather": None})
+
+        def post(mod, args, kwargs, o):
+            cap[-1]["out"], cap[-1]["mask_out"] = o[0].detach().clone(), o[-1].detach().clone()
+        for layer in model.encoder.layer:
+            hooks.append(layer.register_forward_pre_hook(pre, with_kwargs=True))
+            hooks.append(layer.register_forward_hook(post, with_kwargs=True))
+
+        class Rec(GatherRecorder):
+            def __enter__(s):
+                def rec(vectors, indices):
+                    if cap[-1]["gather"] is None and vectors.shape[-1] == 768:
+                        cap[-1]["gather"] = indices.detach().clone()
+                    return s.orig(vectors, indices)
+                s.module.vector_gather = rec
+                return s
+        with torch.no_grad(), Rec(rmed):
+            o, sd_txt = model(ids, attention_mask=mask, encoder_hidden_states=enc if mode == "multimodal" else None,
+                              return_dict=True, mode=mode, space_dict=space, temperature=temp)
+        for h in hooks:
+            h.remove()
+        # canonical order bookkeeping; med keeps the first k of topk(k+1) and gathers masks with the same indices
+        B, n0 = ids.shape[0], ids.shape[1] - 1
+        pos = torch.arange(n0).unsqueeze(0).expand(B, n0).clone()
+        ks, n_pruned = [], 0
+        for i, L in enumerate(cap):
+            x, ta, m = L["h"], L["token_attn"], L["mask"]
+            n = x.shape[1] - 1
+            inv = torch.argsort(pos, dim=1)
+            cx = torch.cat([x[:, :1], torch.gather(x[:, 1:], 1, inv[..., None].expand(-1, -1, 768))], dim=1)
+            cta = torch.gather(ta, 1, inv[..., None].expand(-1, -1, ta.shape[-1]))
+            cm = torch.cat([m[..., :1], torch.gather(m[:, 0, 0, 1:], 1, inv)[:, None, None, :]], dim=-1)
+            tr = O.PruneTrace()
+            y, mo = O.med_layer(cx, cm, sd, f"encoder.layer.{i}", enc if mode == "multimodal" else None, temp,
+                                cta.clone(), mode, trace=tr)
+            o_ref, mo_ref = L["out"], L["mask_out"]
+            if L["gather"] is None or o_ref.shape[1] == x.shape[1]:
+                assert not tr.pruned, i
+                c_out = torch.cat([o_ref[:, :1], torch.gather(o_ref[:, 1:], 1, inv[..., None].expand(-1, -1, 768))], 1)
+                c_mo = torch.cat([mo_ref[..., :1], torch.gather(mo_ref[:, 0, 0, 1:], 1, inv)[:, None, None, :]], -1)
+                ks.append(-1)
+            else:
+                idx = L["gather"]
+                k = idx.shape[1] - 1
+                cpos = torch.gather(pos, 1, idx[:, :k])
+                ckeep = torch.zeros(B, n, dtype=torch.bool).scatter_(1, cpos, True)
+                assert tr.pruned and tr.k == k and torch.equal(tr.keep, ckeep), f"med layer {i}: keep-mask differs"
+                perm = torch.argsort(cpos, dim=1)
+                c_out = torch.cat([o_ref[:, :1], torch.gather(o_ref[:, 1:1 + k], 1, perm[..., None].expand(-1, -1, 768)),
+                                   o_ref[:, 1 + k:]], dim=1)
+                mrow = mo_ref[:, 0, 0, :]
+                c_mo = torch.cat([mrow[:, :1], torch.gather(mrow[:, 1:1 + k], 1, perm), mrow[:, 1 + k:]], 1)[:, None, None, :]
+                rank = torch.argsort(torch.argsort(cpos, dim=1), dim=1)
+                pos = torch.cat([rank, torch.full((B, 1), k, dtype=torch.long)], dim=1)
+                ks.append(k)
+                n_pruned += 1
+                out[f"c{ci}_l{i}_keep"] = np.packbits(ckeep.numpy(), axis=1)
+                out[f"c{ci}_l{i}_score"] = tr.score.numpy()
+            err = (y - c_out).abs().max().item()
+            assert err < 2e-4, (i, err)
+            assert torch.equal(mo, c_mo), f"med layer {i}: pruned mask differs"
+        h_or, sd_or = O.med_text_encoder(ids, mask, sd, "", enc if mode == "multimodal" else None, space, temp, mode)
+        a = h_or.sum(-1).sort(dim=1)[0]
+        b = o.last_hidden_state.sum(-1).sort(dim=1)[0]
+        print(f"med {mode} T={temp}: k per layer {ks}; free-running |row-sum diff| {(a - b).abs().max():.2e}")
+        assert n_pruned > 0
+        out[f"c{ci}_k"] = np.array(ks)
+        out[f"c{ci}_cls"] = o.last_hidden_state[:, 0, :].numpy()
+        out[f"c{ci}_sd_txt_s4"] = sd_txt[:, :, ::4].contiguous().numpy()
+        assert (h_or[:, 0] - o.last_hidden_state[:, 0]).abs().max() < 1e-3
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / "med_text.npz", **out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Temperature calibration for "p = 0.5" on the bench batch (BASELINE config 2), on the oracle
 # ---------------------------------------------------------------------------------------------------------------
 def gen_calibration(pairs: int, image_size: int = 384, text_len: int = 20, p: float = 0.5):
@@ -326,6 +429,8 @@ if __name__ == "__main__":
         gen_block()
     if a.only in ("all", "nlvr"):
         gen_nlvr(224, 2, 20, (1.0, 8.0), "nlvr_small224")
+    if a.only in ("all", "med"):
+        gen_med()
     if a.only in ("all", "nlvr384"):
         gen_nlvr(384, 2, 20, (1.5,), "nlvr_small384")
     if a.only in ("all", "calib"):

@@ -131,3 +131,22 @@ def test_mac_model_matches_survey_numbers():
     # unpruned ViT-B/16 @ 384 = 12 x 4.59 GMAC = 55.1 GMAC per image
     per_layer = O.vit_layer_macs(577, 577) - 2 * 576 * 768 * 100
     assert abs(per_layer / 1e9 - 4.595) < 0.01
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_oracle_med_matches_reference_fixture(ci):
+    gold = np.load(GOLDEN / "med_text.npz")
+    mode, temp = str(gold["modes"][ci]), float(gold["temps"][ci])
+    g = torch.Generator().manual_seed(4321)
+    sd = weights.med_text_state_dict(g, "")
+    space = torch.randn(100, 768, generator=g)
+    _, ids, mask = weights.retrieval_inputs(4, img_size=32, max_len=35, seed=0)
+    enc = torch.randn(4, 60, 768, generator=g)
+    assert weights.tensor_digest(ids, mask, enc, space) == str(gold["input_digest"])
+    traces = []
+    with torch.no_grad():
+        h, sd_txt = O.med_text_encoder(ids, mask, sd, "", enc if mode == "multimodal" else None, space, temp, mode,
+                                       traces=traces)
+    assert [t.k if t.pruned else -1 for t in traces] == gold[f"c{ci}_k"].tolist()
+    assert (h[:, 0, :] - torch.from_numpy(gold[f"c{ci}_cls"])).abs().max().item() < 1e-3
+    assert (sd_txt[:, :, ::4] - torch.from_numpy(gold[f"c{ci}_sd_txt_s4"])).abs().max().item() < 1e-3

@@ -230,3 +230,59 @@ def test_nlvr_small_end_to_end_against_golden(dev, ti):
     assert tks == gold[f"t{ti}_text_k"].tolist()
     assert rel(model.last["image_embeds"][:, :, ::8], torch.from_numpy(gold[f"t{ti}_image_embeds_s8"])) < 2e-3
     assert rel(model.last["last_hidden_state"], torch.from_numpy(gold[f"t{ti}_last_hidden"])) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# models/med.py text encoder (BLIP retrieval / VQA): padded text in mode 'text', and mode 'multimodal'
+# ---------------------------------------------------------------------------------------------------------------
+def med_setup(dev):
+    if "med" in _NLVR_CACHE:
+        return _NLVR_CACHE["med"]
+    from madtp_b200.configuration import BertConfig
+    from madtp_b200.med import BertModel
+    g = torch.Generator().manual_seed(4321)
+    sd = weights.med_text_state_dict(g, "")
+    space = torch.randn(100, 768, generator=g)
+    model = BertModel(BertConfig(evaluate=True, encoder_width=768), add_pooling_layer=False, sd_dim=768)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.missing_keys and not msg.unexpected_keys
+    _, ids, mask = weights.retrieval_inputs(4, img_size=32, max_len=35, seed=0)
+    enc = torch.randn(4, 60, 768, generator=g)
+    _NLVR_CACHE["med"] = (model.to(dev).eval(), sd, space, ids, mask, enc)
+    return _NLVR_CACHE["med"]
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_med_layers_teacher_forced_and_golden(dev, ci):
+    gold = np.load(GOLDEN / "med_text.npz")
+    mode, temp = str(gold["modes"][ci]), float(gold["temps"][ci])
+    model, sd, space, ids, mask, enc = med_setup(dev)
+    assert weights.tensor_digest(ids, mask, enc, space) == str(gold["input_digest"])
+    enc_or = enc if mode == "multimodal" else None
+    traces = []
+    with torch.no_grad():
+        h_or, sd_or = O.med_text_encoder(ids, mask, sd, "", enc_or, space, temp, mode, traces=traces)
+    assert [t.k if t.pruned else -1 for t in traces] == gold[f"c{ci}_k"].tolist()
+    sg, eg = space.to(dev), (enc.to(dev) if mode == "multimodal" else None)
+    worst = 0.0
+    for i, (layer, t) in enumerate(zip(model.encoder.layer, traces)):
+        h, ext = t.layer_input.to(dev), t.mask_in.to(dev)
+        with torch.no_grad():
+            token_attn, _, _ = model.encoder.txt_query_model(h[:, 1:, :], sg, return_token_att=True)
+            out = layer(h, ext, None, eg, None, None, False, mode, sg, token_attn, 0, temp)
+        res = layer.last_prune
+        assert res.pruned == t.pruned and res.k == t.k, f"med layer {i}: k {res.k} vs oracle {t.k}"
+        assert torch.equal(res.count.cpu().long(), t.count.long())
+        if t.pruned:
+            assert_masks_equal(res.keep, t.keep, t.score, t.k, f"med layer {i} ({mode}, T={temp})")
+            assert_masks_equal(res.keep, unpack(gold[f"c{ci}_l{i}_keep"], t.score.shape[1]),
+                               torch.from_numpy(gold[f"c{ci}_l{i}_score"]), t.k, f"med layer {i} vs reference fixture")
+        assert torch.equal(out[-1].cpu(), t.mask_out), f"med layer {i}: pruned attention mask differs"
+        worst = max(worst, rel(out[0], t.layer_output))
+    assert worst < REL_TOL
+    # free-running forward through BertModel with med.py's signature
+    with torch.no_grad():
+        o, sd_txt = model(ids.to(dev), attention_mask=mask.to(dev), encoder_hidden_states=eg, return_dict=True,
+                          mode=mode, space_dict=sg, temperature=temp)
+    assert rel(o.last_hidden_state[:, 0, :], torch.from_numpy(gold[f"c{ci}_cls"])) < 2e-3
+    assert rel(sd_txt[:, :, ::4], torch.from_numpy(gold[f"c{ci}_sd_txt_s4"])) < 2e-3

@@ -1,0 +1,127 @@
+"""Mirror of the evaluation-path surface of the reference's models/blip_retrieval.py (BLIP_Retrieval) and
+models/blip_vqa.py (BLIP_VQA): the attributes and encoder calls that compress_retrieval_dtp.py:85-207 and
+blip_vqa.py:58-125 use -- `space_dict`, `visual_encoder`, `text_encoder` (models/med.py), `vision_proj`,
+`text_proj`, `itm_head`, `tokenizer`. The training forward (ITC/ITM losses, momentum encoders, queues,
+blip_retrieval.py:99-282) and the answer decoder (blip_vqa.py:156-203) are out of scope;
+their parameters are simply absent, so released checkpoints load with strict=False.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import functional as Fn
+from .blip_nlvr import ENC_TOKEN_ID, create_vit
+from .configuration import BertConfig
+from .med import BertModel
+
+
+def _med_config(med_config, vision_width, evaluate):
+    cfg = BertConfig.from_json_file(med_config) if (isinstance(med_config, str) and os.path.isfile(med_config)) \
+        else (med_config if isinstance(med_config, BertConfig) else BertConfig())
+    cfg.encoder_width = vision_width
+    cfg.evaluate = evaluate
+    return cfg
+
+
+class BLIP_Retrieval(nn.Module):
+    def __init__(self, med_config='configs/med_config.json', image_size=384, vit='base', vit_grad_ckpt=False,
+                 vit_ckpt_layer=0, embed_dim=256, queue_size=57600, momentum=0.995, negative_all_rank=False,
+                 evaluate=False, config=None, tokenizer=None):
+        super().__init__()
+        self.sd_num, self.sd_dim = (100, 768) if config is None else (config['sd_num'], config['sd_dim'])
+        self.space_dict = nn.Parameter(torch.randn(self.sd_num, self.sd_dim))
+        self.layers = 12
+        self.visual_encoder, vision_width = create_vit(vit, image_size, vit_grad_ckpt, vit_ckpt_layer, 0,
+                                                       evaluate=evaluate, sd_dim=self.sd_dim)
+        self.tokenizer = tokenizer
+        cfg = _med_config(med_config, vision_width, evaluate)
+        self.text_encoder = BertModel(config=cfg, add_pooling_layer=False, sd_dim=self.sd_dim)
+        text_width = cfg.hidden_size
+        self.vision_proj = nn.Linear(vision_width, embed_dim)
+        self.text_proj = nn.Linear(text_width, embed_dim)
+        self.itm_head = nn.Linear(text_width, 2)
+        self.temp = nn.Parameter(0.07 * torch.ones([]))
+        self._cache = Fn.WeightCache()
+
+    def _lin(self, name):
+        m = getattr(self, name)
+        return self._cache.get(name, [m.weight, m.bias], lambda: Fn.PreparedLinear(m.weight, m.bias, f32=True))
+
+    @torch.no_grad()
+    def encode_text(self, input_ids, attention_mask, temperature=0):
+        """compress_retrieval_dtp.py:104-105: text-only encoder pass -> L2-normalised text embedding [B, embed_dim]."""
+        out, _ = self.text_encoder(input_ids, attention_mask=attention_mask, mode='text', space_dict=self.space_dict,
+                                   temperature=temperature)
+        e = Fn.linear_f32(out.last_hidden_state[:, 0, :].contiguous(), self._lin("text_proj"))
+        return torch.nn.functional.normalize(e, dim=-1)
+
+    @torch.no_grad()
+    def encode_image(self, image, temperature=0):
+        """compress_retrieval_dtp.py:120-122 -> (image_feat [B, N', d], L2-normalised image embedding)."""
+        feat, _ = self.visual_encoder(image, space_dict=self.space_dict, temperature=temperature)
+        e = Fn.linear_f32(feat[:, 0, :].contiguous(), self._lin("vision_proj"))
+        return feat, torch.nn.functional.normalize(e, dim=-1)
+
+    @torch.no_grad()
+    def itm_score(self, input_ids, attention_mask, image_feats, temperature=0):
+        """compress_retrieval_dtp.py:166-176: multimodal pass + itm_head -> logits [B, 2]. input_ids[:,0] is
+        replaced by [ENC] as the driver does (:112)."""
+        ids = input_ids.clone()
+        ids[:, 0] = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        out, _ = self.text_encoder(ids, attention_mask=attention_mask, encoder_hidden_states=image_feats,
+                                   encoder_attention_mask=None, return_dict=True, space_dict=self.space_dict,
+                                   temperature=temperature)
+        return Fn.linear_f32(out.last_hidden_state[:, 0, :].contiguous(), self._lin("itm_head"))
+
+    @torch.no_grad()
+    def forward(self, image, caption, alpha=0.0, idx=None, temperature=0, train=True):
+        """Evaluation-path forward (BASELINE config 3): image encoder + text-only encoder + one multimodal ITM pass
+        over the matched pairs. `caption` is pre-tokenised (input_ids, attention_mask) or text for `tokenizer`."""
+        if train:
+            raise NotImplementedError("madtp_b200 implements the evaluation path only (train=False)")
+        if hasattr(caption, "input_ids"):
+            ids, mask = caption.input_ids, caption.attention_mask
+        elif isinstance(caption, (tuple, list)) and torch.is_tensor(caption[0]):
+            ids, mask = caption
+        else:
+            t = self.tokenizer(caption, padding='max_length', truncation=True, max_length=35,
+                               return_tensors="pt").to(image.device)
+            ids, mask = t.input_ids, t.attention_mask
+        image_feat, image_embed = self.encode_image(image, temperature)
+        text_embed = self.encode_text(ids, mask, temperature)
+        itm = self.itm_score(ids, mask, image_feat, temperature)
+        return image_embed @ text_embed.t(), itm
+
+
+class BLIP_VQA(nn.Module):
+    def __init__(self, med_config='configs/med_config.json', image_size=480, vit='base', vit_grad_ckpt=False,
+                 vit_ckpt_layer=0, evaluate=False, config=None, tokenizer=None):
+        super().__init__()
+        self.sd_num, self.sd_dim = (100, 768) if config is None else (config['sd_num'], config['sd_dim'])
+        self.space_dict = nn.Parameter(torch.randn(self.sd_num, self.sd_dim))
+        self.visual_encoder, vision_width = create_vit(vit, image_size, vit_grad_ckpt, vit_ckpt_layer,
+                                                       drop_path_rate=0.1, evaluate=evaluate, sd_dim=self.sd_dim)
+        self.tokenizer = tokenizer
+        cfg = _med_config(med_config, vision_width, evaluate)
+        self.text_encoder = BertModel(config=cfg, add_pooling_layer=False, sd_dim=self.sd_dim)
+
+    @torch.no_grad()
+    def encode_question(self, image, input_ids, attention_mask, temperature=0):
+        """blip_vqa.py:60,119-125: pruned image encoder, then the question encoder cross-attending to the pruned image
+        tokens. Returns (question_states [B, L', d], pruned additive question mask is internal, image_embeds)."""
+        image_embeds, _ = self.visual_encoder(image, space_dict=self.space_dict, temperature=temperature)
+        ids = input_ids.clone()
+        ids[:, 0] = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        out, _ = self.text_encoder(ids, attention_mask=attention_mask, encoder_hidden_states=image_embeds,
+                                   encoder_attention_mask=None, return_dict=True, space_dict=self.space_dict,
+                                   temperature=temperature)
+        return out.last_hidden_state, image_embeds
+
+    def forward(self, image, question, answer=None, n=None, weights=None, temperature=0, train=True,
+                inference='rank', k_test=128):
+        raise NotImplementedError("madtp_b200: the VQA answer decoder (blip_vqa.py:156-203) is out of scope; "
+                                  "use encode_question for the pruned encoder path")

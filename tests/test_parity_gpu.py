@@ -286,3 +286,68 @@ def test_med_layers_teacher_forced_and_golden(dev, ci):
                           mode=mode, space_dict=sg, temperature=temp)
     assert rel(o.last_hidden_state[:, 0, :], torch.from_numpy(gold[f"c{ci}_cls"])) < 2e-3
     assert rel(sd_txt[:, :, ::4], torch.from_numpy(gold[f"c{ci}_sd_txt_s4"])) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 5 (shapes): BLIP retrieval evaluation path and the VQA question encoder over pruned image tokens
+# ---------------------------------------------------------------------------------------------------------------
+def _retrieval_oracle(sd, images, ids, mask, temp):
+    space = sd["space_dict"]
+    feat, _ = O.vit_forward(images, sd, "visual_encoder.", space, temp)
+    txt, _ = O.med_text_encoder(ids, mask, sd, "text_encoder.", None, space, temp, "text")
+    ids2 = ids.clone()
+    ids2[:, 0] = 30523
+    mm, _ = O.med_text_encoder(ids2, mask, sd, "text_encoder.", feat, space, temp, "multimodal")
+    itm = O.linear(mm[:, 0, :], sd, "itm_head")
+    return feat, txt, mm, itm
+
+
+@pytest.mark.parametrize("image_size,temp", [(224, 8.0), (384, 12.0)])
+def test_blip_retrieval_eval_path(dev, image_size, temp):
+    from madtp_b200.blip_retrieval import BLIP_Retrieval
+    sd = weights.retrieval_state_dict(4321, img_size=image_size)
+    model = BLIP_Retrieval(image_size=image_size, evaluate=True)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys
+    assert set(msg.missing_keys) <= {"vision_proj.weight", "vision_proj.bias", "text_proj.weight", "text_proj.bias", "temp"}
+    model = model.to(dev).eval()
+    images, ids, mask = weights.retrieval_inputs(3, image_size, 35, seed=1)
+    with torch.no_grad():
+        feat_o, txt_o, mm_o, itm_o = _retrieval_oracle(sd, images, ids, mask, temp)
+        feat, _ = model.encode_image(images.to(dev), temp)
+        itm = model.itm_score(ids.to(dev), mask.to(dev), feat, temp)
+        sim, itm2 = model(images.to(dev), (ids.to(dev), mask.to(dev)), 0.0, None, temp, train=False)
+    # free-running (not teacher-forced): a boundary decision within fp16 drift of a tie may move k by a token or two
+    assert abs(feat.shape[1] - feat_o.shape[1]) <= 2, f"pruned tokens {tuple(feat.shape)} vs oracle {tuple(feat_o.shape)}"
+    assert feat.shape[1] < (image_size // 16) ** 2 // 2, "deep prune expected at this temperature"
+    if feat.shape == feat_o.shape:
+        assert rel(feat, feat_o) < 3e-3
+    assert rel(feat[:, 0, :], feat_o[:, 0, :]) < 5e-3
+    assert (itm.cpu() - itm_o).abs().max().item() < 2e-2
+    assert torch.equal(itm, itm2) and sim.shape == (3, 3)
+
+
+def test_blip_vqa_question_encoder_480(dev):
+    """Config 5 shapes: 480x480 images -> 901 tokens through the tensor-core attention path, question encoder with
+    cross-attention over the pruned image tokens."""
+    from madtp_b200.blip_retrieval import BLIP_VQA
+    sd = weights.retrieval_state_dict(99, img_size=480)
+    model = BLIP_VQA(image_size=480, evaluate=True)
+    msg = model.load_state_dict(sd, strict=False)
+    assert set(msg.unexpected_keys) <= {"itm_head.weight", "itm_head.bias"} and not msg.missing_keys
+    model = model.to(dev).eval()
+    images, ids, mask = weights.retrieval_inputs(2, 480, 20, seed=2)
+    temp = 6.0
+    space = sd["space_dict"]
+    with torch.no_grad():
+        q, img = model.encode_question(images.to(dev), ids.to(dev), mask.to(dev), temp)
+        feat_o, _ = O.vit_forward(images, sd, "visual_encoder.", space, temp)
+        ids2 = ids.clone()
+        ids2[:, 0] = 30523
+        q_o, _ = O.med_text_encoder(ids2, mask, sd, "text_encoder.", feat_o, space, temp, "multimodal")
+    assert abs(img.shape[1] - feat_o.shape[1]) <= 2 and img.shape[1] < 901
+    if img.shape == feat_o.shape:
+        assert rel(img, feat_o) < 3e-3
+    assert rel(img[:, 0, :], feat_o[:, 0, :]) < 5e-3
+    assert abs(q.shape[1] - q_o.shape[1]) <= 1
+    assert rel(q[:, 0, :], q_o[:, 0, :]) < 5e-3

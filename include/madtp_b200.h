@@ -83,14 +83,15 @@ int madtp_bert_embed(const int64_t* ids, const float* word, const float* positio
  * Multi-head attention, head dim 64: context = softmax(q.k^T * scale + key_mask) v, heads merged into
  * out_f16[b, i, h*64 + :]. Replaces vit.py:79-91, nlvr_encoder.py:174-219 / med.py:175-217 (self and cross
  * attention) without materialising the [B,H,N,N] probabilities.
- * key_mask: additive [B, Nk] (0 / -10000, nlvr_encoder.py:870-871) or NULL.
+ * key_mask: additive [B, Nk] (0 / -10000, nlvr_encoder.py:870-871) or NULL. causal != 0 additionally hides keys
+ * j > i from query i (the CLIP text transformer's mask, clip/model.py:452-457 cropped by clip/mock.py:309-310).
  * row_max/row_sum/out_norm ([B,H,Nq] each, all three or none): softmax row statistics and ||context[b,h,i,:]||_2,
  * the un-normalised "head importance" of vit.py:97 / nlvr_encoder.py:231.
  */
 int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, const float* v,
                    int64_t ldv, int64_t bsv, int B, int H, int Nq, int Nk, float scale, const float* key_mask,
                    void* out_f16, int64_t ldo, int64_t bso, float* row_max, float* row_sum, float* out_norm,
-                   void* stream);
+                   int causal, void* stream);
 
 /*
  * Pruning statistics of a self-attention (Nq == Nk == N), from the row statistics of madtp_attn_fwd:
@@ -100,7 +101,7 @@ int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int
  */
 int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, int B, int H,
                      int N, float scale, const float* key_mask, const float* row_max, const float* row_sum,
-                     const float* out_norm, float* col_part, float* cls_attn, void* stream);
+                     const float* out_norm, float* col_part, float* cls_attn, int causal, void* stream);
 
 /*
  * Query_model (models/utils.py:147-183), given token_att = ft . sd^T from madtp_gemm:
@@ -127,19 +128,22 @@ int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, con
  * DTP selection (vit.py:153-158): exact top-k of score per row (k read from *topk on the device), survivors keep
  * ascending token order. keep[B,n] (1 = survivor), dst[B,n] (slot among survivors or -1), tail_w[B,n] (merge weight
  * score_j / (sum_tail + 1e-8) of pruned tokens), tail_idx[B,n] (pruned token indices, first n-k valid).
- * If k < 1 or n - k <= 1 nothing is pruned (vit.py:148-149) and dst is the identity.
+ * If k <= max_keep or n - k <= 1 nothing is pruned and dst is the identity: max_keep = 0 is vit.py:148-149 /
+ * nlvr_encoder.py:434 / med.py:371; CLIP passes its EOT guard (clip/model.py:220,492).
  * mask_mode 1 (nlvr_encoder.py:451-452) / 2 (med.py:377-390) additionally gathers the additive key mask
  * mask_in[B,n+1] -> mask_out[B, 0..k+1]; mask_mode 0 ignores both.
  */
 int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
-                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, void* stream);
+                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
+                     void* stream);
 
 /*
  * DTP gather + merge (vit.py:154-161,202; models/utils.py:13-33 vector_gather): out[b] = [x[b,0], survivors in
  * ascending token order, sum_j tail_w[j] x[b,1+j]] -- shape [B, k+2, d] with batch stride bso.
  */
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
-                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream);
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, int max_keep,
+                     void* stream);
 
 /*
  * Tensor-core self-attention for the scoring lane (vit.py:75-103 without materialising P). madtp_gemm_qkv is the

@@ -36,13 +36,14 @@ SIGNATURES = {
     "madtp_assemble_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "madtp_bert_embed": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_attn_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
-                       _i64, _i64, _vp, _vp, _vp, _vp],
-    "madtp_attn_stats": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                       _i64, _i64, _vp, _vp, _vp, _i32, _vp],
+    "madtp_attn_stats": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                         _vp],
     "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
-    "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
-    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
+    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
@@ -255,7 +256,7 @@ def _qkv_strides(t, name):
     return t.stride(1), t.stride(0)
 
 
-def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None):
+def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None, causal=False):
     """q [B,Nq,H*64], k/v [B,Nk,H*64] fp32 views; out_f16 [B,Nq,H*64] fp16 view. stats = (row_max,row_sum,out_norm)."""
     B, Nq, _ = q.shape
     Nk = k.shape[1]
@@ -271,11 +272,11 @@ def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None):
     st = _call("madtp_attn_fwd", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
                                _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Nq, Nk, float(scale),
                                _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
-                               bso, _ptr(rm), _ptr(rs), _ptr(on), _stream())
+                               bso, _ptr(rm), _ptr(rs), _ptr(on), 1 if causal else 0, _stream())
     _check(st, "madtp_attn_fwd")
 
 
-def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None):
+def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None, causal=False):
     B, N, _ = q.shape
     ldq, bsq = _qkv_strides(q, "q")
     ldk, bsk = _qkv_strides(k, "k")
@@ -283,7 +284,7 @@ def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None):
     st = _call("madtp_attn_stats", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk, B, H, N,
                                  float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(rm), _ptr(rs), _ptr(on),
                                  _ptr(col_part, torch.float32, "col_part"), _ptr(cls_attn, torch.float32, "cls_attn"),
-                                 _stream())
+                                 1 if causal else 0, _stream())
     _check(st, "madtp_attn_stats")
 
 
@@ -325,7 +326,7 @@ def dtp_score(col_part, cls_attn, token_att, n, T, temperature):
     return score, thr, cnt, topk
 
 
-def dtp_select(score, topk, *, mask_mode=0, mask_in=None):
+def dtp_select(score, topk, *, mask_mode=0, mask_in=None, max_keep=0):
     B, n = score.shape
     dev = score.device
     keep = torch.empty(B, n, dtype=torch.uint8, device=dev)
@@ -339,12 +340,12 @@ def dtp_select(score, topk, *, mask_mode=0, mask_in=None):
         mask_out = torch.empty(B, n + 1, dtype=torch.float32, device=dev)
     st = _call("madtp_dtp_select", B, n, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"), _ptr(keep),
                                  _ptr(dst), _ptr(tail_w), _ptr(tail_idx), mask_mode,
-                                 _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), _stream())
+                                 _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), int(max_keep), _stream())
     _check(st, "madtp_dtp_select")
     return keep, dst, tail_w, tail_idx, mask_out
 
 
-def dtp_gather(x, topk, dst, tail_w, tail_idx, k):
+def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0):
     """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d]."""
     B, N, d = x.shape
     if x.stride(2) != 1 or x.stride(1) != d:
@@ -352,7 +353,8 @@ def dtp_gather(x, topk, dst, tail_w, tail_idx, k):
     out = torch.empty(B, k + 2, d, dtype=torch.float32, device=x.device)
     st = _call("madtp_dtp_gather", B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
                                  _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
-                                 _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _stream())
+                                 _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), int(max_keep),
+                                 _stream())
     _check(st, "madtp_dtp_gather")
     return out
 

@@ -1,0 +1,259 @@
+"""Mirror of the pruned encoder path of the reference's clip/model.py (+ the patched nn.MultiheadAttention of
+clip/mock.py): LayerNorm (:160-166), QuickGELU (:169-171), ResidualAttentionBlock (:174-261), Transformer (:264-272),
+VisionTransformer (:275-313) and CLIP.encode_image / encode_text (:482-503), with the reference's constructor
+arguments, tuple-in / tuple-out block protocol, [N, B, C] tensor layout at the module boundary and state-dict keys
+(`attn.in_proj_weight`, `attn.out_proj.*`, `ln_1`, `mlp.c_fc`, `mlp.c_proj`, `ln_2`, `query_model.q_map.0.*`).
+The ResNet towers, momentum twins, queues and losses of that file are out of scope.
+
+Per block (clip/model.py:236-261): the block's own Query_model with the learned q_map scores the tokens BEFORE
+attention; pre-LN multi-head attention (q pre-scaled by 1/sqrt(head_dim), additive causal mask cropped to the current
+length for text, clip/mock.py:309-310); Reduce_token with the `topk_num <= max_keep` guard (:220); QuickGELU MLP.
+The vision tower runs the tensor-core attention path; the 77-token causal text tower the fp32 CUDA-core one.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import functional as Fn
+from .utils import Query_model, vector_gather  # noqa: F401
+from .vit import _eval_only
+
+
+class LayerNorm(nn.LayerNorm):
+    """clip/model.py:160-166 (fp32 LayerNorm); evaluated by the row kernel."""
+
+    def forward(self, x: torch.Tensor):
+        Fn.require_cuda(x, "x")
+        shape = x.shape
+        return Fn.layernorm_rows(x.reshape(-1, shape[-1]).contiguous(), self.weight, self.bias, self.eps,
+                                 f32=True)["y"].view(shape)
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x: torch.Tensor):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class MultiheadAttention(nn.Module):
+    """Parameter layout and accessors of the patched nn.MultiheadAttention (clip/mock.py:252-358)."""
+
+    def __init__(self, embed_dim, num_heads):
+        super().__init__()
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim != 64:
+            raise RuntimeError("madtp_b200: the attention kernels are built for head_dim 64")
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        self.attention_map = None
+        self.cls_attn = None
+        self._cache = Fn.WeightCache()
+
+    def save_attention_map(self, attention_map):
+        self.attention_map = attention_map
+
+    def get_attention_map(self):
+        return self.attention_map
+
+    def save_cls_attn(self, cls_attn):
+        self.cls_attn = cls_attn
+
+    def get_cls_attn(self):
+        return self.cls_attn
+
+    def _prepared(self):
+        qkv = self._cache.get("in", [self.in_proj_weight, self.in_proj_bias],
+                              lambda: Fn.PreparedLinear(self.in_proj_weight, self.in_proj_bias, tf32=True))
+        out = self._cache.get("out", [self.out_proj.weight, self.out_proj.bias],
+                              lambda: Fn.PreparedLinear(self.out_proj.weight, self.out_proj.bias, f16=True))
+        return qkv, out
+
+    def rows(self, y_hi, y_lo, B, N, residual, want_stats, causal):
+        qkv_w, out_w = self._prepared()
+        C = self.embed_dim
+        scale = self.head_dim ** -0.5        # q / sqrt(E) then q.k: exact for head_dim 64 (a power of two)
+        if causal:
+            qkv = Fn.linear_tf32(y_hi, y_lo, qkv_w).view(B, N, 3 * C)
+            ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_heads, scale,
+                                             None, want_stats, causal=True)
+        else:
+            ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, scale, want_stats)
+        self.save_attention_map(stats)
+        self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
+        return Fn.linear_f16(ctx16.view(B * N, C), out_w, residual=residual)
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None, sd_dim=768):
+        super().__init__()
+        self.attn = MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = attn_mask           # only its presence matters: the text tower's mask is causal (:452-457)
+        self.query_model = Query_model(ft_dim=d_model, sd_dim=sd_dim, temperature=1, att_func_type='sparsemax',
+                                       pool_type='max', map_func=True)
+        self.last_prune = None
+        self._cache = Fn.WeightCache()
+
+    def _mlp(self):
+        fc, pj = self.mlp.c_fc, self.mlp.c_proj
+        a = self._cache.get("fc", [fc.weight, fc.bias], lambda: Fn.PreparedLinear(fc.weight, fc.bias, f16=True))
+        b = self._cache.get("pj", [pj.weight, pj.bias], lambda: Fn.PreparedLinear(pj.weight, pj.bias, f16=True))
+        return a, b
+
+    def forward_bnc(self, x, space_dict, temperature, sd_ft_all, max_keep):
+        """x [B, N, C] contiguous fp32 -> (x', sd_ft_all)."""
+        B, N, C = x.shape
+        with_dict = space_dict is not None
+        prune = with_dict and temperature > 0
+        ln1 = Fn.layernorm_rows(x.view(B * N, C), self.ln_1.weight, self.ln_1.bias, self.ln_1.eps, tf32=True,
+                                split_x=with_dict)
+        token_attn = None
+        if with_dict:                                                                    # :239-245
+            token_attn, sd_ft_all = self.query_model.forward_rows(x, ln1["x_hi"], ln1["x_lo"], space_dict, sd_ft_all)
+        x1 = self.attn.rows(ln1["y_hi"], ln1["y_lo"], B, N, x.view(B * N, C), prune, self.attn_mask is not None)
+        x1 = x1.view(B, N, C)
+        self.last_prune = None
+        if prune:                                                                        # :254-258
+            res = Fn.dtp_prune(x1, self.attn.get_attention_map(), token_attn, float(temperature),
+                               max_keep=int(max_keep))
+            self.last_prune = res
+            x1 = res.x
+        N2 = x1.shape[1]
+        x2d = x1.view(B * N2, C)
+        fc, pj = self._mlp()
+        y16 = Fn.layernorm_rows(x2d, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, f16=True)["y16"]
+        h = Fn.linear_f16(y16, fc, out_dtype=torch.float16, act=L.ACT_QUICKGELU)
+        return Fn.linear_f16(h, pj, residual=x2d).view(B, N2, C), sd_ft_all
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        # x: (N, B, C)
+        x, space_dict, temperature, sd_ft_all, max_keep = inputs
+        Fn.require_cuda(x, "x")
+        _eval_only(self)
+        y, sd_ft_all = self.forward_bnc(x.permute(1, 0, 2).contiguous(), space_dict, temperature, sd_ft_all, max_keep)
+        return y.permute(1, 0, 2), space_dict, temperature, sd_ft_all, max_keep
+
+
+class Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int, attn_mask: torch.Tensor = None, sd_dim=768):
+        super().__init__()
+        self.width = width
+        self.layers = layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask, sd_dim=sd_dim)
+                                         for _ in range(layers)])
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, space_dict=None, temperature=0, sd_ft_all=None, max_keep=1):
+        """x [N, B, C] -> the reference's 5-tuple (:271-272); one layout change in, one out."""
+        Fn.require_cuda(x, "x")
+        _eval_only(self)
+        y = x.permute(1, 0, 2).contiguous()
+        for blk in self.resblocks:
+            y, sd_ft_all = blk.forward_bnc(y, space_dict, temperature, sd_ft_all, max_keep)
+        return y.permute(1, 0, 2), space_dict, temperature, sd_ft_all, max_keep
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int, output_dim: int,
+                 sd_dim=768):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.patch_size = patch_size
+        self.conv1 = nn.Conv2d(in_channels=3, out_channels=width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads, sd_dim=sd_dim)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._cache = Fn.WeightCache()
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, space_dict=None, temperature=0, max_keep=1):
+        Fn.require_cuda(x, "image")
+        _eval_only(self)
+        B, _, Hh, Ww = x.shape
+        P = self.patch_size
+        conv = self._cache.get("conv1", [self.conv1.weight], lambda: Fn.PreparedLinear(
+            self.conv1.weight.reshape(self.conv1.weight.shape[0], -1), None, tf32=True))
+        hi, lo = L.patchify(x.contiguous(), P)
+        n = (Hh // P) * (Ww // P)
+        patches = Fn.linear_tf32(hi, lo, conv)
+        C = patches.shape[1]
+        tok = L.assemble_tokens(patches, self.class_embedding.detach(), self.positional_embedding.detach(), B, n, C)
+        y = self.ln_pre(tok)
+        sd_img_ft_all = None
+        for blk in self.transformer.resblocks:
+            y, sd_img_ft_all = blk.forward_bnc(y, space_dict, temperature if space_dict is not None else 0,
+                                               sd_img_ft_all, max_keep)
+        cls = self.ln_post(y[:, 0, :].contiguous())
+        proj = self._cache.get("proj", [self.proj], lambda: Fn.PreparedLinear(self.proj.t(), None, f32=True))
+        return Fn.linear_f32(cls, proj), sd_img_ft_all
+
+
+class CLIP(nn.Module):
+    """The two encoders of clip/model.py:CLIP (ViT towers only) with `encode_image` / `encode_text` (:482-503)."""
+
+    def __init__(self, embed_dim: int, image_resolution: int, vision_layers: int, vision_width: int,
+                 vision_patch_size: int, context_length: int, vocab_size: int, transformer_width: int,
+                 transformer_heads: int, transformer_layers: int, config=None):
+        super().__init__()
+        self.sd_num, self.sd_dim = (100, 768) if config is None else (config['sd_num'], config['sd_dim'])
+        self.space_dict = nn.Parameter(torch.randn(self.sd_num, self.sd_dim))
+        self.context_length = context_length
+        self.visual = VisionTransformer(input_resolution=image_resolution, patch_size=vision_patch_size,
+                                        width=vision_width, layers=vision_layers, heads=vision_width // 64,
+                                        output_dim=embed_dim, sd_dim=self.sd_dim)
+        self.transformer = Transformer(width=transformer_width, layers=transformer_layers, heads=transformer_heads,
+                                       attn_mask=self.build_attention_mask(), sd_dim=self.sd_dim)
+        self.vocab_size = vocab_size
+        self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width).normal_(std=0.01))
+        self.ln_final = LayerNorm(transformer_width)
+        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim).normal_(
+            std=transformer_width ** -0.5))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
+        self._cache = Fn.WeightCache()
+
+    def build_attention_mask(self):
+        mask = torch.empty(self.context_length, self.context_length)
+        mask.fill_(float("-inf"))
+        mask.triu_(1)
+        return mask
+
+    @property
+    def dtype(self):
+        return self.visual.conv1.weight.dtype
+
+    def encode_image(self, image, space_dict=None, temperature=0):
+        return self.visual(image.type(self.dtype), space_dict=space_dict, temperature=temperature)
+
+    @torch.no_grad()
+    def encode_text(self, text, space_dict=None, temperature=0):
+        if not text.is_cuda:
+            raise RuntimeError("madtp_b200: text ids must be a CUDA tensor -- this package has no CPU fallback")
+        x = L.bert_embed(text.to(torch.int64), self.token_embedding.weight.detach(),
+                         self.positional_embedding.detach())                               # :490-492
+        max_keep = int(text.argmax(dim=-1).max()) + 2                                      # :495
+        y = x
+        sd_txt_ft_all = None
+        for blk in self.transformer.resblocks:
+            y, sd_txt_ft_all = blk.forward_bnc(y, space_dict, temperature if space_dict is not None else 0,
+                                               sd_txt_ft_all, max_keep)
+        y = self.ln_final(y)
+        eot = y[torch.arange(y.shape[0], device=y.device), text.argmax(dim=-1)].contiguous()   # :501
+        proj = self._cache.get("tp", [self.text_projection],
+                               lambda: Fn.PreparedLinear(self.text_projection.t(), None, f32=True))
+        return Fn.linear_f32(eot, proj), sd_txt_ft_all

@@ -65,14 +65,18 @@ __device__ __forceinline__ void qk_tile(const float* Qs, const float* Ks, int ty
 }
 
 // logits = s * scale + mask[j];  keys past Nk get -inf
-__device__ __forceinline__ void finish_logits(float (&s)[4][8], float scale, const float* Ms, int j0, int Nk, int tx) {
+__device__ __forceinline__ void finish_logits(float (&s)[4][8], float scale, const float* Ms, int j0, int Nk, int tx,
+                                              int causal, int i_first) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int jl = tx + 8 * c;
     const bool valid = (j0 + jl) < Nk;
     const float mk = Ms[jl];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) s[r][c] = valid ? fmaf(s[r][c], scale, mk) : -INFINITY;
+    for (int r = 0; r < 4; ++r) {
+      const bool vis = valid && (!causal || (j0 + jl) <= (i_first + 16 * r));
+      s[r][c] = vis ? fmaf(s[r][c], scale, mk) : -INFINITY;
+    }
   }
 }
 
@@ -130,7 +134,7 @@ attn_fwd_kernel(AttnArgs a) {
 
     float s[4][8];
     qk_tile(Qs, Ks, ty, tx, s);
-    finish_logits(s, a.scale, Ms, j0, a.Nk, tx);
+    finish_logits(s, a.scale, Ms, j0, a.Nk, tx, a.causal, i0 + ty);
 
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -258,7 +262,7 @@ attn_stats_kernel(AttnArgs a) {
     __syncthreads();
     float s[4][8];
     qk_tile(Qs, Ks, ty, tx, s);
-    finish_logits(s, a.scale, Ms, j0, N, tx);
+    finish_logits(s, a.scale, Ms, j0, N, tx, a.causal, i0 + ty);
     const long long sbase = (static_cast<long long>(b) * a.H + h) * N;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

@@ -13,6 +13,7 @@ struct AttnArgs {
   int B, H, Nq, Nk;
   float scale;              // logits = q.k * scale + key_mask
   const float* key_mask;    // additive, [B, Nk] or nullptr (BERT padding mask: 0 / -10000)
+  int causal;               // 1: key j is visible to query i only if j <= i (CLIP text transformer, clip/model.py:452-457)
   // ---- outputs of the forward pass ----
   __half* out_f16; long long ldo, bso;   // context, heads merged: out[b, i, h*64 + :]  (ldo/bso in elements)
   float* row_max;           // [B, H, Nq]  max_j logits           (nullptr when statistics are not needed)

@@ -110,7 +110,7 @@ int madtp_bert_embed(const int64_t* ids, const float* word, const float* positio
 int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, const float* v,
                    int64_t ldv, int64_t bsv, int B, int H, int Nq, int Nk, float scale, const float* key_mask,
                    void* out_f16, int64_t ldo, int64_t bso, float* row_max, float* row_sum, float* out_norm,
-                   void* stream) {
+                   int causal, void* stream) {
   AttnArgs a = {};
   a.q = q; a.ldq = ldq; a.bsq = bsq;
   a.k = k; a.ldk = ldk; a.bsk = bsk;
@@ -120,12 +120,13 @@ int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int
   a.key_mask = key_mask;
   a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
   a.row_max = row_max; a.row_sum = row_sum; a.out_norm = out_norm;
+  a.causal = causal;
   return counted(launch_attn_fwd(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
 int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, int B, int H,
                      int N, float scale, const float* key_mask, const float* row_max, const float* row_sum,
-                     const float* out_norm, float* col_part, float* cls_attn, void* stream) {
+                     const float* out_norm, float* col_part, float* cls_attn, int causal, void* stream) {
   AttnArgs a = {};
   a.q = q; a.ldq = ldq; a.bsq = bsq;
   a.k = k; a.ldk = ldk; a.bsk = bsk;
@@ -138,6 +139,7 @@ int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, i
   a.out_norm = const_cast<float*>(out_norm);
   a.col_part = col_part;
   a.cls_attn = cls_attn;
+  a.causal = causal;
   return counted(launch_attn_stats(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
@@ -168,22 +170,26 @@ int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, con
 }
 
 int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
-                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, void* stream) {
+                     int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
+                     void* stream) {
   DtpSelectArgs a;
   a.B = B; a.n = n;
   a.score = score; a.topk = topk;
   a.keep = keep; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
   a.mask_mode = mask_mode; a.mask_in = mask_in; a.mask_out = mask_out;
+  a.max_keep = max_keep;
   return counted(launch_dtp_select(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
-                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* stream) {
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, int max_keep,
+                     void* stream) {
   DtpGatherArgs a;
   a.B = B; a.n = n; a.d = d;
   a.x = x; a.bsx = bsx;
   a.topk = topk; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
   a.out = out; a.bso = bso;
+  a.max_keep = max_keep;
   return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 

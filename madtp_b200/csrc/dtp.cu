@@ -303,7 +303,7 @@ dtp_select_kernel(DtpSelectArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x, n = a.n;
   const int k_in = *a.topk;
-  const bool identity = (k_in < 1) || (n - k_in <= 1);   // reference early-out: nothing is pruned
+  const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);   // reference early-out: nothing is pruned
   const int k = identity ? n : k_in;
 
   for (int j = tid; j < n; j += 256) S[j] = a.score[static_cast<long long>(b) * n + j];
@@ -411,7 +411,7 @@ dtp_gather_kernel(DtpGatherArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, n = a.n, d4 = a.d >> 2;
   const int k_in = *a.topk;
-  const bool identity = (k_in < 1) || (n - k_in <= 1);
+  const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);
   const int k = identity ? n : k_in;
   const float4* xb = reinterpret_cast<const float4*>(a.x + b * a.bsx);
   float4* ob = reinterpret_cast<float4*>(a.out + b * a.bso);

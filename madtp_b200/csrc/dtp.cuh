@@ -45,6 +45,7 @@ struct DtpSelectArgs {
                               // 2: med.py semantics (mask travels with its token; merged slot = mask of rank k)
   const float* mask_in;       // [B, n+1] additive mask incl. position 0
   float* mask_out;            // [B, n+1] worst case; entries [0, k+2) are written
+  int max_keep;               // nothing is pruned when k <= max_keep (0 everywhere but CLIP, clip/model.py:220)
 };
 int launch_dtp_select(const DtpSelectArgs& a, cudaStream_t stream);
 
@@ -58,6 +59,7 @@ struct DtpGatherArgs {
   const int* tail_idx;
   float* out;                 // [B, k+2, d] packed survivors: [cls, survivors ascending, merged]
   long long bso;              // batch stride of out (elements) -- the caller sizes it with the k it read back
+  int max_keep;
 };
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);
 

@@ -169,22 +169,22 @@ class AttnStats:
 
 
 def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_mask: Optional[Tensor],
-                   want_stats: bool, ctx16: Optional[Tensor] = None):
+                   want_stats: bool, ctx16: Optional[Tensor] = None, causal: bool = False):
     """q,k,v: [B,N,H*64] fp32 views. Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
     B, N, C = q.shape
     dev = q.device
     if ctx16 is None:
         ctx16 = torch.empty(B, N, C, dtype=torch.float16, device=dev)
     if not want_stats:
-        L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask)
+        L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal)
         return ctx16, None
     rows = torch.empty(3, B, H, N, dtype=torch.float32, device=dev)
     stats = (rows[0], rows[1], rows[2])
-    L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, stats=stats)
+    L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, stats=stats, causal=causal)
     n_parts = (N + 63) // 64
     col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
     cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
-    L.attn_stats(q, k, H, scale, stats, col_part, cls_attn, key_mask=key_mask)
+    L.attn_stats(q, k, H, scale, stats, col_part, cls_attn, key_mask=key_mask, causal=causal)
     return ctx16, AttnStats(col_part, cls_attn)
 
 
@@ -220,7 +220,7 @@ class PruneResult:
 
 
 def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,
-              mask_in: Optional[Tensor] = None) -> PruneResult:
+              mask_in: Optional[Tensor] = None, max_keep: int = 0) -> PruneResult:
     """Reduce_token on x [B, n+1, d] (position 0 always survives). reference models/vit.py:123-163,
     models/nlvr_encoder.py:400-454 (mask_mode 1), models/med.py:345-391 (mask_mode 2)."""
     B, N, d = x.shape
@@ -228,8 +228,9 @@ def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float
     T = token_att.shape[2]
     score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature)
     k = int(topk.item())            # the reference's one host sync per pruned layer (models/vit.py:145)
-    if k < 1 or n - k <= 1:         # models/vit.py:148-149
+    if k <= max_keep or n - k <= 1:         # models/vit.py:148-149 (max_keep = 0); clip/model.py:220
         return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
-    keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in)
-    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k)
+    keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
+                                                         max_keep=max_keep)
+    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep)
     return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2])

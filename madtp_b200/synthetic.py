@@ -144,6 +144,58 @@ def retrieval_inputs(batch: int, img_size: int = 384, max_len: int = 35, seed: i
     return images, ids, mask
 
 
+def clip_block_state_dict(sd: Dict[str, Tensor], g: torch.Generator, p: str, d: int, sd_dim: int):
+    """Keys of clip/model.py:ResidualAttentionBlock (patched nn.MultiheadAttention + per-block Query_model.q_map)."""
+    bound = 1.0 / math.sqrt(d)
+    sd[p + ".attn.in_proj_weight"] = (torch.rand(3 * d, d, generator=g) * 2 - 1) * bound
+    sd[p + ".attn.in_proj_bias"] = (torch.rand(3 * d, generator=g) * 2 - 1) * bound
+    _linear(sd, g, p + ".attn.out_proj", d, d)
+    _ln(sd, p + ".ln_1", d)
+    _linear(sd, g, p + ".mlp.c_fc", 4 * d, d)
+    _linear(sd, g, p + ".mlp.c_proj", d, 4 * d)
+    _ln(sd, p + ".ln_2", d)
+    _linear(sd, g, p + ".query_model.q_map.0", sd_dim, d)
+
+
+def clip_state_dict(seed: int = 777, img_size: int = 224, patch: int = 16, vision_width: int = 768,
+                    vision_layers: int = 12, text_width: int = 512, text_layers: int = 12, embed_dim: int = 512,
+                    context: int = 77, vocab: int = 49408, sd_num: int = 100, sd_dim: int = 768) -> Dict[str, Tensor]:
+    """The encoder part of clip/model.py:CLIP with ViT-B/16 shapes: space_dict, visual.*, transformer.*,
+    token_embedding, positional_embedding, ln_final, text_projection."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {"space_dict": torch.randn(sd_num, sd_dim, generator=g)}
+    scale = vision_width ** -0.5
+    n = (img_size // patch) ** 2
+    sd["visual.conv1.weight"] = (torch.rand(vision_width, 3, patch, patch, generator=g) * 2 - 1) / math.sqrt(3 * patch * patch)
+    sd["visual.class_embedding"] = scale * torch.randn(vision_width, generator=g)
+    sd["visual.positional_embedding"] = scale * torch.randn(n + 1, vision_width, generator=g)
+    _ln(sd, "visual.ln_pre", vision_width)
+    _ln(sd, "visual.ln_post", vision_width)
+    sd["visual.proj"] = scale * torch.randn(vision_width, embed_dim, generator=g)
+    for i in range(vision_layers):
+        clip_block_state_dict(sd, g, f"visual.transformer.resblocks.{i}", vision_width, sd_dim)
+    sd["token_embedding.weight"] = torch.randn(vocab, text_width, generator=g) * 0.02
+    sd["positional_embedding"] = torch.randn(context, text_width, generator=g) * 0.01
+    _ln(sd, "ln_final", text_width)
+    sd["text_projection"] = torch.randn(text_width, embed_dim, generator=g) * text_width ** -0.5
+    for i in range(text_layers):
+        clip_block_state_dict(sd, g, f"transformer.resblocks.{i}", text_width, sd_dim)
+    return sd
+
+
+def clip_inputs(batch: int, img_size: int = 224, context: int = 77, vocab: int = 49408, seed: int = 0):
+    """images ~ N(0,1); token ids: SOT (49406), random words, EOT (49407 = the arg-max id, clip/clip.py:235-239), zero pad."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(batch, 3, img_size, img_size, generator=g)
+    text = torch.zeros(batch, context, dtype=torch.long)
+    lens = torch.randint(6, 30, (batch,), generator=g)
+    for b in range(batch):
+        text[b, 0] = vocab - 2
+        text[b, 1:lens[b]] = torch.randint(1000, 40000, (int(lens[b]) - 1,), generator=g)
+        text[b, lens[b]] = vocab - 1
+    return images, text
+
+
 def blip_nlvr_state_dict(seed: int = 1234, img_size: int = 384, sd_num: int = 100, sd_dim: int = 768,
                          depth: int = 12) -> Dict[str, Tensor]:
     """Keys of models/blip_nlvr.py:BLIP_NLVR."""

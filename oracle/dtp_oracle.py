@@ -126,7 +126,8 @@ def select_and_merge(x: Tensor, score: Tensor, k: int):
 
 
 def reduce_token(x: Tensor, probs: Tensor, cls_attn: Tensor, token_attn: Tensor, temperature: float,
-                 mask: Optional[Tensor] = None, variant: str = "vit", trace: Optional[PruneTrace] = None):
+                 mask: Optional[Tensor] = None, variant: str = "vit", trace: Optional[PruneTrace] = None,
+                 max_keep: int = 0):
     """Reduce_token of vit.py:123-163 (variant 'vit'), nlvr_encoder.py:400-454 ('nlvr'), med.py:345-391 ('med').
 
     x [B,n,d] prunable tokens; mask [B,n] additive (text only). Returns (x', mask')."""
@@ -135,7 +136,7 @@ def reduce_token(x: Tensor, probs: Tensor, cls_attn: Tensor, token_attn: Tensor,
     threshold, count, k = prune_decision(score, token_attn, temperature)
     if trace is not None:
         trace.n_in, trace.k, trace.score, trace.threshold, trace.count = n, k, score, threshold, count
-    if k < 1 or n - k <= 1:                                                  # vit.py:148-149
+    if k <= max_keep or n - k <= 1:                                          # vit.py:148-149; clip/model.py:220
         if trace is not None:
             trace.keep = torch.ones(x.shape[0], n, dtype=torch.bool)
         return x, mask
@@ -318,6 +319,84 @@ def blip_nlvr_forward(images: Tensor, input_ids: Tensor, attn_mask: Tensor, sd: 
     if trace is not None:
         trace.image_embeds, trace.last_hidden, trace.sd_img_ft, trace.sd_txt_ft = emb, hidden, sd_img, sd_txt
     return pred
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLIP  (clip/model.py ResidualAttentionBlock / Transformer / VisionTransformer / encode_text, clip/mock.py MHA)
+# ---------------------------------------------------------------------------------------------------------------
+def clip_block(x: Tensor, sd: SD, prefix: str, H: int, space_dict: Optional[Tensor], temperature: float,
+               sd_ft_all: Optional[Tensor], max_keep: int = 1, causal: bool = False,
+               trace: Optional[PruneTrace] = None, eps: float = 1e-5):
+    """clip/model.py:236-261 on x [B,N,C] (the reference carries [N,B,C]; the math is layout-free).
+    Returns (x', sd_ft_all)."""
+    B, N, C = x.shape
+    dh = C // H
+    if trace is not None:
+        trace.layer_input = x
+    token_attn = None
+    if space_dict is not None:                                                           # :239-245
+        qm = {"q_map.0.weight": sd[prefix + ".query_model.q_map.0.weight"],
+              "q_map.0.bias": sd[prefix + ".query_model.q_map.0.bias"]}
+        token_attn, sd_ft = query_model(x[:, 1:, :], space_dict, space_dict.shape[1], q_map=qm)
+        sd_ft_all = sd_ft if sd_ft_all is None else sd_ft_all + sd_ft
+    y = layer_norm(x, sd, prefix + ".ln_1", eps)
+    qkv = F.linear(y, sd[prefix + ".attn.in_proj_weight"], sd[prefix + ".attn.in_proj_bias"])
+    q, k, v = (split_heads(t, H) for t in qkv.chunk(3, dim=-1))
+    q = q / math.sqrt(dh)                                                                # torch 1.11 _scaled_dot_product_attention
+    scores = q @ k.transpose(-1, -2)
+    if causal:                                                                           # :452-457, mock.py:309-310
+        scores = scores + torch.full((N, N), float("-inf")).triu_(1)
+    probs = torch.softmax(scores, dim=-1)
+    ctx = probs @ v
+    x = x + linear(merge_heads(ctx), sd, prefix + ".attn.out_proj")
+    if space_dict is not None and temperature > 0:                                       # :254-258
+        cls_attn = cls_attention(probs, ctx)                                             # mock.py:225-232
+        patches, _ = reduce_token(x[:, 1:, :], probs, cls_attn, token_attn, temperature, trace=trace,
+                                  max_keep=int(max_keep))
+        x = torch.cat([x[:, :1, :], patches], dim=1)
+    h = linear(layer_norm(x, sd, prefix + ".ln_2", eps), sd, prefix + ".mlp.c_fc")
+    x = x + linear(h * torch.sigmoid(1.702 * h), sd, prefix + ".mlp.c_proj")             # QuickGELU :168-170
+    if trace is not None:
+        trace.layer_output = x
+    return x, sd_ft_all
+
+
+def clip_vision_forward(img: Tensor, sd: SD, prefix: str, space_dict: Optional[Tensor], temperature: float,
+                        layers: int, H: int, patch: int = 16, traces: Optional[List[PruneTrace]] = None):
+    """clip/model.py:292-313. Returns (image embedding [B, output_dim], sd_img_ft)."""
+    x = F.conv2d(img, sd[prefix + "conv1.weight"], None, stride=patch).flatten(2).transpose(1, 2)
+    cls = sd[prefix + "class_embedding"] + torch.zeros(x.shape[0], 1, x.shape[-1])
+    x = torch.cat([cls, x], dim=1) + sd[prefix + "positional_embedding"]
+    x = layer_norm(x, sd, prefix + "ln_pre", 1e-5)
+    sd_ft_all = None
+    for i in range(layers):
+        tr = None
+        if traces is not None:
+            tr = PruneTrace()
+            traces.append(tr)
+        x, sd_ft_all = clip_block(x, sd, f"{prefix}transformer.resblocks.{i}", H, space_dict, temperature, sd_ft_all,
+                                  max_keep=1, causal=False, trace=tr)
+    x = layer_norm(x[:, 0, :], sd, prefix + "ln_post", 1e-5)
+    return x @ sd[prefix + "proj"], sd_ft_all
+
+
+def clip_text_forward(text: Tensor, sd: SD, space_dict: Optional[Tensor], temperature: float, layers: int, H: int,
+                      traces: Optional[List[PruneTrace]] = None):
+    """clip/model.py:489-503 (encode_text). Returns (text embedding, sd_txt_ft). After a prune the EOT token is read at
+    its ORIGINAL position in the pruned sequence, as the reference does (:501)."""
+    x = sd["token_embedding.weight"][text] + sd["positional_embedding"]
+    max_keep = int(text.argmax(dim=-1).max()) + 2                                        # :492
+    sd_ft_all = None
+    for i in range(layers):
+        tr = None
+        if traces is not None:
+            tr = PruneTrace()
+            traces.append(tr)
+        x, sd_ft_all = clip_block(x, sd, f"transformer.resblocks.{i}", H, space_dict, temperature, sd_ft_all,
+                                  max_keep=max_keep, causal=True, trace=tr)
+    x = layer_norm(x, sd, "ln_final", 1e-5)
+    x = x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ sd["text_projection"]
+    return x, sd_ft_all
 
 
 # ---------------------------------------------------------------------------------------------------------------

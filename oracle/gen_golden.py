@@ -373,6 +373,133 @@ def gen_med():
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# CLIP (clip/model.py + clip/mock.py): vision tower (free-running + per block) and causal text blocks (per block)
+# ---------------------------------------------------------------------------------------------------------------
+CLIP_LAYERS = 4   # fixture depth (every block has identical structure; full-depth shapes are covered on the GPU)
+
+
+def gen_clip():
+    ref_shims.install_clip()
+    import clip.model as cm
+    sd = weights.clip_state_dict(777, vision_layers=CLIP_LAYERS, text_layers=CLIP_LAYERS)
+    space = sd["space_dict"]
+    images, text = weights.clip_inputs(2)
+    out = {"input_digest": np.array(digest(images, text, space)), "layers": np.array(CLIP_LAYERS)}
+
+    def run_blocks(blocks, x_lnd, temp, max_keep):
+        cap = []
+        hooks = []
+
+        def pre(mod, args):
+            cap.append({"x": args[0][0].detach().permute(1, 0, 2).clone(), "gather": None})
+
+        def post(mod, args, o):
+            cap[-1]["out"] = o[0].detach().permute(1, 0, 2).clone()
+        for blk in blocks:
+            hooks.append(blk.register_forward_pre_hook(pre))
+            hooks.append(blk.register_forward_hook(post))
+
+        class Rec(GatherRecorder):
+            def __enter__(s):
+                def rec(vectors, indices):
+                    if cap[-1]["gather"] is None:
+                        cap[-1]["gather"] = indices.detach().clone()
+                    return s.orig(vectors, indices)
+                s.module.vector_gather = rec
+                return s
+        with torch.no_grad(), Rec(cm):
+            y = torch.nn.Sequential(*blocks)((x_lnd, space, temp, None, max_keep))
+        for h in hooks:
+            h.remove()
+        return cap, y
+
+    # ---- vision tower ----
+    vis = cm.VisionTransformer(input_resolution=224, patch_size=16, width=768, layers=CLIP_LAYERS, heads=12,
+                               output_dim=512, sd_dim=768)
+    msg = vis.load_state_dict({k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}, strict=True)
+    vis.eval()
+    temp_v = 5.0
+    with torch.no_grad():
+        emb_ref, sd_img_ref = vis(images, space_dict=space, temperature=temp_v)
+        x0 = vis.ln_pre(torch.cat([vis.class_embedding + torch.zeros(2, 1, 768),
+                                   vis.conv1(images).reshape(2, 768, -1).permute(0, 2, 1)], 1) + vis.positional_embedding)
+    cap, _ = run_blocks(list(vis.transformer.resblocks), x0.permute(1, 0, 2), temp_v, 1)
+    B, n0 = 2, x0.shape[1] - 1
+    pos = torch.arange(n0).unsqueeze(0).expand(B, n0).clone()
+    ks = []
+    for i, L in enumerate(cap):
+        x = L["x"]
+        n = x.shape[1] - 1
+        inv = torch.argsort(pos, dim=1)
+        cx = torch.cat([x[:, :1], torch.gather(x[:, 1:], 1, inv[..., None].expand(-1, -1, 768))], dim=1)
+        tr = O.PruneTrace()
+        y, _ = O.clip_block(cx, sd, f"visual.transformer.resblocks.{i}", 12, space, temp_v, None, 1, False, tr)
+        o_ref = L["out"]
+        assert L["gather"] is not None and o_ref.shape[1] != x.shape[1], "vision blocks are expected to prune"
+        idx = L["gather"]
+        k = idx.shape[1]
+        cpos = torch.gather(pos, 1, idx)
+        ckeep = torch.zeros(B, n, dtype=torch.bool).scatter_(1, cpos, True)
+        assert tr.pruned and tr.k == k and torch.equal(tr.keep, ckeep), f"CLIP vision block {i}: keep-mask differs"
+        perm = torch.argsort(cpos, dim=1)
+        c_out = torch.cat([o_ref[:, :1], torch.gather(o_ref[:, 1:1 + k], 1, perm[..., None].expand(-1, -1, 768)),
+                           o_ref[:, 1 + k:]], dim=1)
+        err = (y - c_out).abs().max().item()
+        assert err < 2e-4, (i, err)
+        rank = torch.argsort(torch.argsort(cpos, dim=1), dim=1)
+        pos = torch.cat([rank, torch.full((B, 1), k, dtype=torch.long)], dim=1)
+        ks.append(k)
+        out[f"v{i}_keep"] = np.packbits(ckeep.numpy(), axis=1)
+        out[f"v{i}_score"] = tr.score.numpy()
+    emb_or, sd_img_or = O.clip_vision_forward(images, sd, "visual.", space, temp_v, CLIP_LAYERS, 12)
+    print(f"clip vision T={temp_v}: k {ks}; |emb oracle - ref| {(emb_or - emb_ref).abs().max():.2e}")
+    assert (emb_or - emb_ref).abs().max() < 1e-4 and (sd_img_or - sd_img_ref).abs().max() < 1e-3
+    out["v_k"], out["v_temp"] = np.array(ks), np.array(temp_v)
+    out["v_emb"] = emb_ref.numpy()
+
+    # ---- text transformer blocks (causal, max_keep guard) ----
+    mask = torch.empty(77, 77).fill_(float("-inf")).triu_(1)
+    txt = cm.Transformer(width=512, layers=CLIP_LAYERS, heads=8, attn_mask=mask, sd_dim=768)
+    txt.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")},
+                        strict=True)
+    txt.eval()
+    temp_t = 50.0
+    max_keep = int(text.argmax(dim=-1).max()) + 2
+    x0 = sd["token_embedding.weight"][text] + sd["positional_embedding"]
+    cap, _ = run_blocks(list(txt.resblocks), x0.permute(1, 0, 2), temp_t, max_keep)
+    tks = []
+    for i, L in enumerate(cap):
+        x = L["x"]                                   # reference order: the causal mask makes order observable
+        tr = O.PruneTrace()
+        y, _ = O.clip_block(x, sd, f"transformer.resblocks.{i}", 8, space, temp_t, None, max_keep, True, tr)
+        o_ref = L["out"]
+        out[f"t{i}_x"] = x.numpy()
+        if L["gather"] is None or o_ref.shape[1] == x.shape[1]:
+            assert not tr.pruned, i
+            c_out = o_ref
+            tks.append(-1)
+        else:
+            idx = L["gather"]
+            k = idx.shape[1]
+            keep = torch.zeros(2, x.shape[1] - 1, dtype=torch.bool).scatter_(1, idx, True)
+            assert tr.pruned and tr.k == k and torch.equal(tr.keep, keep), f"CLIP text block {i}: keep-mask differs"
+            perm = torch.argsort(idx, dim=1)
+            c_out = torch.cat([o_ref[:, :1], torch.gather(o_ref[:, 1:1 + k], 1, perm[..., None].expand(-1, -1, 512)),
+                               o_ref[:, 1 + k:]], dim=1)
+            tks.append(k)
+            out[f"t{i}_keep"] = np.packbits(keep.numpy(), axis=1)
+            out[f"t{i}_score"] = tr.score.numpy()
+        err = (y - c_out).abs().max().item()
+        assert err < 2e-4, (i, err)
+        out[f"t{i}_out_s4"] = c_out[:, :, ::4].contiguous().numpy()
+    print(f"clip text T={temp_t} max_keep={max_keep}: k {tks}")
+    assert any(k > 0 for k in tks) and any(k < 0 for k in tks), "fixture must exercise both the prune and the guard"
+    out["t_k"], out["t_temp"], out["t_max_keep"] = np.array(tks), np.array(temp_t), np.array(max_keep)
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLDEN / "clip_blocks.npz", **out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Temperature calibration for "p = 0.5" on the bench batch (BASELINE config 2), on the oracle
 # ---------------------------------------------------------------------------------------------------------------
 def gen_calibration(pairs: int, image_size: int = 384, text_len: int = 20, p: float = 0.5):
@@ -429,6 +556,8 @@ if __name__ == "__main__":
         gen_block()
     if a.only in ("all", "nlvr"):
         gen_nlvr(224, 2, 20, (1.0, 8.0), "nlvr_small224")
+    if a.only in ("all", "clip"):
+        gen_clip()
     if a.only in ("all", "med"):
         gen_med()
     if a.only in ("all", "nlvr384"):

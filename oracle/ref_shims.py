@@ -157,3 +157,37 @@ def build_blip_nlvr(image_size: int = 384):
                          vit="base", evaluate=True)
     model.eval()
     return model, tok
+
+
+def install_clip():
+    """Extra stand-ins for clip/mock.py, which forks torch 1.11's nn.MultiheadAttention and imports 1.11 privates
+    (clip/mock.py:1-4). Only `_scaled_dot_product_attention(q, k, v, attn_mask, dropout_p) -> (out, attn)` is gone in
+    torch 2.x; it is restated here from torch 1.11 torch/nn/functional.py: q / sqrt(E), baddbmm with the additive mask,
+    softmax, dropout, bmm."""
+    install()
+    import math
+    import typing
+    import warnings
+
+    import torch.nn.functional as F
+    import torch.nn.modules.activation as act
+
+    for name, val in (("torch", torch), ("Optional", typing.Optional), ("Tuple", typing.Tuple)):
+        if not hasattr(act, name):
+            setattr(act, name, val)
+    if not hasattr(F, "_scaled_dot_product_attention"):
+        def _scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0):
+            B, Nt, E = q.shape
+            q = q / math.sqrt(E)
+            if attn_mask is not None:
+                attn = torch.baddbmm(attn_mask, q, k.transpose(-2, -1))
+            else:
+                attn = torch.bmm(q, k.transpose(-2, -1))
+            attn = F.softmax(attn, dim=-1)
+            if dropout_p > 0.0:
+                attn = F.dropout(attn, p=dropout_p)
+            return torch.bmm(attn, v), attn
+        F._scaled_dot_product_attention = _scaled_dot_product_attention
+    for name, val in (("math", math), ("warnings", warnings)):
+        if not hasattr(F, name):
+            setattr(F, name, val)

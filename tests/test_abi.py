@@ -34,7 +34,7 @@ def test_ctypes_signatures_cover_the_header(lib):
 def test_argument_errors_are_reported_without_a_gpu(lib):
     cdll = lib.load()
     # invalid shapes are rejected before any CUDA call, so this is safe on a CPU-only host
-    st = cdll.madtp_dtp_select(1, 0, None, None, None, None, None, None, 0, None, None, None)
+    st = cdll.madtp_dtp_select(1, 0, None, None, None, None, None, None, 0, None, None, 0, None)
     assert st == 1
     assert b"null pointer" in cdll.madtp_last_error_string() or b"out of range" in cdll.madtp_last_error_string()
     st = cdll.madtp_gemm(7, None, None, 0, None, None, 0, None, 0, 0, None, None, 0, 0, ctypes.c_float(1.0), 1, 1, 1,

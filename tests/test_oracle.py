@@ -150,3 +150,31 @@ def test_oracle_med_matches_reference_fixture(ci):
     assert [t.k if t.pruned else -1 for t in traces] == gold[f"c{ci}_k"].tolist()
     assert (h[:, 0, :] - torch.from_numpy(gold[f"c{ci}_cls"])).abs().max().item() < 1e-3
     assert (sd_txt[:, :, ::4] - torch.from_numpy(gold[f"c{ci}_sd_txt_s4"])).abs().max().item() < 1e-3
+
+
+def test_oracle_clip_matches_reference_fixture():
+    gold = np.load(GOLDEN / "clip_blocks.npz")
+    layers = int(gold["layers"])
+    sd = weights.clip_state_dict(777, vision_layers=layers, text_layers=layers)
+    images, text = weights.clip_inputs(2)
+    assert weights.tensor_digest(images, text, sd["space_dict"]) == str(gold["input_digest"])
+    traces = []
+    with torch.no_grad():
+        emb, _ = O.clip_vision_forward(images, sd, "visual.", sd["space_dict"], float(gold["v_temp"]), layers, 12,
+                                       traces=traces)
+    assert [t.k for t in traces] == gold["v_k"].tolist()
+    assert (emb - torch.from_numpy(gold["v_emb"])).abs().max().item() < 1e-4
+    for i, t in enumerate(traces):
+        score = torch.from_numpy(gold[f"v{i}_score"])
+        assert ambiguous_only(t.keep, unpack(gold[f"v{i}_keep"], score.shape[1]), score, t.k), i
+    max_keep, temp = int(gold["t_max_keep"]), float(gold["t_temp"])
+    for i in range(layers):                       # text blocks: teacher-forced on the reference's own block inputs
+        x = torch.from_numpy(gold[f"t{i}_x"])
+        tr = O.PruneTrace()
+        with torch.no_grad():
+            y, _ = O.clip_block(x, sd, f"transformer.resblocks.{i}", 8, sd["space_dict"], temp, None, max_keep, True, tr)
+        k_ref = int(gold["t_k"][i])
+        assert tr.pruned == (k_ref > 0)
+        if k_ref > 0:
+            assert tr.k == k_ref and torch.equal(tr.keep, unpack(gold[f"t{i}_keep"], x.shape[1] - 1))
+        assert (y[:, :, ::4] - torch.from_numpy(gold[f"t{i}_out_s4"])).abs().max().item() < 2e-4

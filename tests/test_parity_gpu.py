@@ -351,3 +351,102 @@ def test_blip_vqa_question_encoder_480(dev):
     assert rel(img[:, 0, :], feat_o[:, 0, :]) < 5e-3
     assert abs(q.shape[1] - q_o.shape[1]) <= 1
     assert rel(q[:, 0, :], q_o[:, 0, :]) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLIP (clip/model.py ResidualAttentionBlock + patched MHA): vision tower and causal text blocks with the EOT guard
+# ---------------------------------------------------------------------------------------------------------------
+def clip_setup(dev, layers):
+    key = ("clip", layers)
+    if key not in _NLVR_CACHE:
+        from madtp_b200.clip_model import CLIP
+        sd = weights.clip_state_dict(777, vision_layers=layers, text_layers=layers)
+        model = CLIP(512, 224, layers, 768, 16, 77, 49408, 512, 8, layers)
+        msg = model.load_state_dict(sd, strict=False)
+        assert not msg.unexpected_keys and msg.missing_keys == ["logit_scale"]
+        _NLVR_CACHE[key] = (model.to(dev).eval(), sd)
+    return _NLVR_CACHE[key]
+
+
+def test_clip_vision_blocks_teacher_forced_and_golden(dev):
+    gold = np.load(GOLDEN / "clip_blocks.npz")
+    layers, temp = int(gold["layers"]), float(gold["v_temp"])
+    model, sd = clip_setup(dev, layers)
+    images, text = weights.clip_inputs(2)
+    assert weights.tensor_digest(images, text, sd["space_dict"]) == str(gold["input_digest"])
+    space = sd["space_dict"]
+    traces = []
+    with torch.no_grad():
+        emb_o, _ = O.clip_vision_forward(images, sd, "visual.", space, temp, layers, 12, traces=traces)
+    assert [t.k for t in traces] == gold["v_k"].tolist()
+    sg = space.to(dev)
+    worst = 0.0
+    for i, (blk, t) in enumerate(zip(model.visual.transformer.resblocks, traces)):
+        x = t.layer_input.to(dev)
+        with torch.no_grad():    # the reference's tuple protocol and [N, B, C] layout (clip/model.py:236-261)
+            y, _, _, sd_ft, _ = blk((x.permute(1, 0, 2), sg, temp, None, 1))
+        y = y.permute(1, 0, 2)
+        res = blk.last_prune
+        assert res.pruned and res.k == t.k
+        assert torch.equal(res.count.cpu().long(), t.count.long())
+        assert score_err(res.score, t.score) < SCORE_RTOL
+        n = t.score.shape[1]
+        assert_masks_equal(res.keep, t.keep, t.score, t.k, f"CLIP vision block {i}")
+        assert_masks_equal(res.keep, unpack(gold[f"v{i}_keep"], n), torch.from_numpy(gold[f"v{i}_score"]), t.k,
+                           f"CLIP vision block {i} vs reference fixture")
+        worst = max(worst, rel(y, t.layer_output))
+    assert worst < REL_TOL
+    with torch.no_grad():
+        emb, _ = model.encode_image(images.to(dev), space_dict=sg, temperature=temp)
+    assert rel(emb, torch.from_numpy(gold["v_emb"])) < 5e-3
+
+
+def test_clip_text_blocks_against_golden(dev):
+    gold = np.load(GOLDEN / "clip_blocks.npz")
+    layers, temp, max_keep = int(gold["layers"]), float(gold["t_temp"]), int(gold["t_max_keep"])
+    model, sd = clip_setup(dev, layers)
+    sg = sd["space_dict"].to(dev)
+    n_pruned = 0
+    for i, blk in enumerate(model.transformer.resblocks):
+        x = torch.from_numpy(gold[f"t{i}_x"]).to(dev)       # the reference's own block input (order matters: causal)
+        with torch.no_grad():
+            y, _ = blk.forward_bnc(x.contiguous(), sg, temp, None, max_keep)
+            tr = O.PruneTrace()
+            y_o, _ = O.clip_block(x.cpu(), sd, f"transformer.resblocks.{i}", 8, sd["space_dict"], temp, None, max_keep,
+                                  True, tr)
+        k_ref = int(gold["t_k"][i])
+        res = blk.last_prune
+        assert res.pruned == (k_ref > 0), f"text block {i}: guard k <= max_keep ({res.k} vs {max_keep})"
+        assert torch.equal(res.count.cpu().long(), tr.count.long())
+        if k_ref > 0:
+            n_pruned += 1
+            assert res.k == k_ref
+            assert_masks_equal(res.keep, unpack(gold[f"t{i}_keep"], x.shape[1] - 1),
+                               torch.from_numpy(gold[f"t{i}_score"]), k_ref, f"CLIP text block {i}")
+        assert rel(y[:, :, ::4], torch.from_numpy(gold[f"t{i}_out_s4"])) < REL_TOL
+        assert rel(y, y_o) < REL_TOL
+    assert n_pruned > 0
+
+
+def test_clip_encode_text_unpruned_and_full_depth_shapes(dev):
+    """encode_text without pruning (the EOT read is order-independent there) against the oracle, and BASELINE config 4
+    shapes at full depth: ViT-B/16 vision tower at 336 px (442 tokens) through the pruned path."""
+    model, sd = clip_setup(dev, 4)
+    images, text = weights.clip_inputs(3, seed=5)
+    with torch.no_grad():
+        e, _ = model.encode_text(text.to(dev), space_dict=sd["space_dict"].to(dev), temperature=0)
+        e_o, _ = O.clip_text_forward(text, sd, sd["space_dict"], 0.0, 4, 8)
+    assert rel(e, e_o) < 2e-3
+    from madtp_b200.clip_model import CLIP
+    sd12 = weights.clip_state_dict(5, img_size=336, vision_layers=12, text_layers=1)
+    m = CLIP(512, 336, 12, 768, 16, 77, 49408, 512, 8, 1)
+    m.load_state_dict(sd12, strict=False)
+    m = m.to(dev).eval()
+    img = torch.randn(4, 3, 336, 336, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        emb, sd_ft = m.encode_image(img.to(dev), space_dict=sd12["space_dict"].to(dev), temperature=3.0)
+        emb_o, sd_ft_o = O.clip_vision_forward(img, sd12, "visual.", sd12["space_dict"], 3.0, 12, 12)
+    ks = [b.last_prune.k for b in m.visual.transformer.resblocks if b.last_prune is not None and b.last_prune.pruned]
+    assert emb.shape == (4, 512) and len(ks) > 0 and ks[-1] < 441
+    assert rel(emb, emb_o) < 2e-2        # free-running over 12 pruned layers
+    assert rel(sd_ft, sd_ft_o) < 2e-2

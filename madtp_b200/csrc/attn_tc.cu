@@ -58,33 +58,46 @@ __device__ __forceinline__ void issue_slice_ss(uint32_t d_tmem, uint32_t a_hi, u
 
 // ------------------------------------------------------------------------------------------------
 // Pass 1
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax: TMEM lane quadrant = warp % 4 (query rows), column
+//   half = (warp - 2) / 4 (32 of the tile's 64 keys, and 32 of the 64 output dims), so every query row is shared by
+//   two threads that exchange their tile maxima through shared memory.
+//   K tiles ride a 3-deep ring and V^T tiles a 2-deep ring: K(t+1) is requested two tiles ahead of its QK^T, V(t) is
+//   only needed after softmax(t), so neither TMA latency sits on the critical path.
 // ------------------------------------------------------------------------------------------------
 struct FwdSmem {
   static constexpr int Q_BYTES = 4 * BM * 128;              // (slice 0/1) x (hi/lo) boxes of [128 x 32]
   static constexpr int KBOX = 64 * 128;                     // [64 keys x 32] or [64 dims x 32 keys]
-  static constexpr int STAGE_BYTES = 8 * KBOX;              // K: 4 boxes, V^T: 4 boxes
-  static constexpr int BAR_OFF = Q_BYTES + 2 * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TILE_BYTES = 4 * KBOX;               // one K tile or one V^T tile: (slice 0/1) x (hi/lo)
+  static constexpr int K_STAGES = 3, V_STAGES = 2;
+  static constexpr int K_OFF = Q_BYTES;
+  static constexpr int V_OFF = K_OFF + K_STAGES * TILE_BYTES;
+  static constexpr int BAR_OFF = V_OFF + V_STAGES * TILE_BYTES;
+  static constexpr int XCH_OFF = BAR_OFF + 256;             // [2][2][128] floats: per-row exchange between column halves
+  static constexpr int TOTAL = XCH_OFF + 2 * 2 * BM * 4;
 };
+constexpr int FWD_THREADS = 320;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                    const __grid_constant__ CUtensorMap tm_k_hi, const __grid_constant__ CUtensorMap tm_k_lo,
                    const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
                    AttnTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* q_s = smem;
-  uint8_t* kv_s = smem + FwdSmem::Q_BYTES;
+  uint8_t* k_s = smem + FwdSmem::K_OFF;
+  uint8_t* v_s = smem + FwdSmem::V_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR_OFF);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* s_empty = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_full = bars + 1;     // [3]
+  uint64_t* k_empty = bars + 4;    // [3]
+  uint64_t* v_full = bars + 7;     // [2]
+  uint64_t* v_empty = bars + 9;    // [2]
+  uint64_t* s_full = bars + 11;    // [2]
+  uint64_t* s_empty = bars + 13;   // [2]
+  uint64_t* p_full = bars + 15;
+  uint64_t* o_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* xch = reinterpret_cast<float*>(smem + FwdSmem::XCH_OFF);   // [parity][half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
@@ -101,13 +114,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
+    for (int s = 0; s < FwdSmem::K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
     }
-    mbar_init(p_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 8);
+    }
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -130,19 +147,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         tma_load_2d(&tm_q_hi, q_full, q_s + (c * 2 + 0) * BM * 128, h * 64 + c * BOX, qrow);
         tma_load_2d(&tm_q_lo, q_full, q_s + (c * 2 + 1) * BM * 128, h * 64 + c * BOX, qrow);
       }
-      for (int t = 0; t < T; ++t) {
-        const int st = t & 1;
-        mbar_wait(&kv_empty[st], ((t >> 1) & 1) ^ 1);
-        uint8_t* s = kv_s + st * FwdSmem::STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[st], FwdSmem::STAGE_BYTES);
+      auto load_k = [&](int t) {
+        const int st = t % FwdSmem::K_STAGES;
+        mbar_wait(&k_empty[st], ((t / FwdSmem::K_STAGES) & 1) ^ 1);
+        uint8_t* s = k_s + st * FwdSmem::TILE_BYTES;
+        mbar_arrive_expect_tx(&k_full[st], FwdSmem::TILE_BYTES);
         const int krow = b * N + t * 64;
+        for (int c = 0; c < 2; ++c) {
+          tma_load_2d(&tm_k_hi, &k_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+          tma_load_2d(&tm_k_lo, &k_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+        }
+      };
+      auto load_v = [&](int t) {
+        const int st = t & 1;
+        mbar_wait(&v_empty[st], ((t >> 1) & 1) ^ 1);
+        uint8_t* s = v_s + st * FwdSmem::TILE_BYTES;
+        mbar_arrive_expect_tx(&v_full[st], FwdSmem::TILE_BYTES);
         const int vrow = (b * a.H + h) * 64;
         for (int c = 0; c < 2; ++c) {
-          tma_load_2d(&tm_k_hi, &kv_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
-          tma_load_2d(&tm_k_lo, &kv_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
-          tma_load_2d(&tm_v_hi, &kv_full[st], s + (4 + c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
-          tma_load_2d(&tm_v_lo, &kv_full[st], s + (4 + c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+          tma_load_2d(&tm_v_hi, &v_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+          tma_load_2d(&tm_v_lo, &v_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
         }
+      };
+      load_k(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) load_k(t + 1);
+        load_v(t);
       }
     }
   } else if (warp == 1) {
@@ -150,23 +180,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
       constexpr uint32_t idesc = make_idesc(2u, BM, 64);
       const uint32_t q_u = smem_u32(q_s);
       auto issue_qk = [&](int t) {
-        const int st = t & 1, sb = t & 1;
-        mbar_wait(&kv_full[st], (t >> 1) & 1);
+        const int st = t % FwdSmem::K_STAGES, sb = t & 1;
+        mbar_wait(&k_full[st], (t / FwdSmem::K_STAGES) & 1);
         mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t k_u = smem_u32(kv_s + st * FwdSmem::STAGE_BYTES);
+        const uint32_t k_u = smem_u32(k_s + st * FwdSmem::TILE_BYTES);
         for (int c = 0; c < 2; ++c)
           issue_slice_ss(tmem_base + sb * 128 + c * 64, q_u + (c * 2 + 0) * BM * 128, q_u + (c * 2 + 1) * BM * 128,
                          k_u + (c * 2 + 0) * FwdSmem::KBOX, k_u + (c * 2 + 1) * FwdSmem::KBOX, idesc);
         umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) issue_qk(t + 1);
+        mbar_wait(&v_full[t & 1], (t >> 1) & 1);
         mbar_wait(p_full, t & 1);
         tcgen05_fence_after();
-        const uint32_t v_u = smem_u32(kv_s + (t & 1) * FwdSmem::STAGE_BYTES) + 4 * FwdSmem::KBOX;
+        const uint32_t v_u = smem_u32(v_s + (t & 1) * FwdSmem::TILE_BYTES);
         // O_t = P_lo V_hi + P_hi V_lo + P_hi V_hi over 8 k-steps of 8 keys
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
@@ -180,51 +212,59 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
           }
         }
         umma_commit(o_full);
-        umma_commit(&kv_empty[t & 1]);
+        umma_commit(&v_empty[t & 1]);
       }
     }
   } else {
     const int quad = warp & 3;
-    const int i = i0 + quad * 32 + lane;
+    const int hf = (warp - 2) >> 2;                 // column half
+    const int r = quad * 32 + lane;                 // row within the tile
+    const int i = i0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
     float m = -INFINITY, l = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
 
     for (int t = 0; t < T; ++t) {
       const int sb = t & 1;
       mbar_wait(&s_full[sb], (t >> 1) & 1);
       tcgen05_fence_after();
-      float s[64];
-      {
-        float tmp[32];
-        ld2_add(tmem_base + lane_off + sb * 128, tmem_base + lane_off + sb * 128 + 64, tmp);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) s[k] = tmp[k];
-        ld2_add(tmem_base + lane_off + sb * 128 + 32, tmem_base + lane_off + sb * 128 + 96, tmp);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) s[32 + k] = tmp[k];
-      }
+      float s[32];
+      ld2_add(tmem_base + lane_off + sb * 128 + hf * 32, tmem_base + lane_off + sb * 128 + 64 + hf * 32, s);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
 
-      const int j0 = t * 64;
+      const int j0 = t * 64 + hf * 32;
       float mx = -INFINITY;
+      if (mask == nullptr && j0 + 32 <= N) {        // interior tile: no bounds or mask handling
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        const int j = j0 + k;
-        const float mk = (mask != nullptr && j < N) ? __ldg(mask + j) : 0.f;
-        s[k] = (j < N) ? fmaf(s[k], a.scale, mk) : -INFINITY;
-        mx = fmaxf(mx, s[k]);
+        for (int k = 0; k < 32; ++k) {
+          s[k] *= a.scale;
+          mx = fmaxf(mx, s[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int j = j0 + k;
+          const float mk = (mask != nullptr && j < N) ? __ldg(mask + j) : 0.f;
+          s[k] = (j < N) ? fmaf(s[k], a.scale, mk) : -INFINITY;
+          mx = fmaxf(mx, s[k]);
+        }
       }
+      // joint maximum of the row over both column halves
+      float* x = xch + (t & 1) * 2 * BM;
+      x[hf * BM + r] = mx;
+      named_bar_sync(1 + quad, 64);
+      mx = fmaxf(mx, x[(hf ^ 1) * BM + r]);
+
       const float m_new = fmaxf(m, mx);
       const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
       float ps = 0.f;
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
+      for (int k = 0; k < 32; ++k) {
         s[k] = expf(s[k] - m_new);
         ps += s[k];
       }
@@ -234,31 +274,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
       if (t > 0) {  // drain the previous tile's P V partial (it is relative to the previous running max)
         mbar_wait(o_full, (t - 1) & 1);
         tcgen05_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + kO + hf * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + kO + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[c * 32 + k] += __uint_as_float(v[k]);
-        }
+        for (int k = 0; k < 32; ++k) o[k] = (o[k] + __uint_as_float(v[k])) * corr;
       }
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o[d] *= corr;
 
       // P -> TMEM as tf32 hi / lo (A operand of the P V MMAs)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          const float p = s[c * 32 + k];
+          const float p = s[k];
           const float ph = tf32_hi(p);
           hi[k] = __float_as_uint(ph);
           lo[k] = __float_as_uint(p - ph);
         }
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + c * 32, hi);
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + c * 32, lo);
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + hf * 32, hi);
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + hf * 32, lo);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -267,25 +301,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
     }
     mbar_wait(o_full, (T - 1) & 1);
     tcgen05_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + c * 32, v);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + hf * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) o[c * 32 + k] += __uint_as_float(v[k]);
+      for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(v[k]);
     }
+    // row sum and squared norm: combine the two column halves (buffers of parity T&1 are free: their last readers
+    // passed the barrier of tile T-2 ... T-1 uses the other parity)
+    float* x = xch + (T & 1) * 2 * BM;
+    x[hf * BM + r] = l;
+    named_bar_sync(1 + quad, 64);
+    const float l_tot = l + x[(hf ^ 1) * BM + r];
+    const float inv = 1.0f / l_tot;
+    float nsq = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      o[d] *= inv;
+      nsq = fmaf(o[d], o[d], nsq);
+    }
+    named_bar_sync(1 + quad, 64);                    // both halves have read l before the buffer is reused
+    x[hf * BM + r] = nsq;
+    named_bar_sync(1 + quad, 64);
+    const float nsq_tot = (hf == 0) ? (nsq + x[BM + r]) : (x[r] + nsq);   // dims 0..31 first, then 32..63
     if (i < N) {
-      const float inv = 1.0f / l;
-      float nsq = 0.f;
+      __half* dst = a.out_f16 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64 + hf * 32;
 #pragma unroll
-      for (int d = 0; d < 64; ++d) {
-        o[d] *= inv;
-        nsq = fmaf(o[d], o[d], nsq);
-      }
-      __half* dst = a.out_f16 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64;
-#pragma unroll
-      for (int d = 0; d < 64; d += 8) {
+      for (int d = 0; d < 32; d += 8) {
         __half2 h0 = __floats2half2_rn(o[d], o[d + 1]), h1 = __floats2half2_rn(o[d + 2], o[d + 3]);
         __half2 h2 = __floats2half2_rn(o[d + 4], o[d + 5]), h3 = __floats2half2_rn(o[d + 6], o[d + 7]);
         uint4 pk;
@@ -295,9 +338,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         pk.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(dst + d) = pk;
       }
-      const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
-      a.row_lse[sidx] = m + logf(l);
-      a.out_norm[sidx] = sqrtf(nsq);
+      if (hf == 0) {
+        const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
+        a.row_lse[sidx] = m + logf(l_tot);
+        a.out_norm[sidx] = sqrtf(nsq_tot);
+      }
     }
   }
 
@@ -551,7 +596,7 @@ int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid((a.N + BM - 1) / BM, a.H, a.B);
-  attn_fwd_tc_kernel<<<grid, TC_THREADS, FwdSmem::TOTAL, stream>>>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a);
+  attn_fwd_tc_kernel<<<grid, FWD_THREADS, FwdSmem::TOTAL, stream>>>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

@@ -115,6 +115,12 @@ int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const
                      const float* ft, int64_t ld_ft, int64_t bs_ft, int B, int n, int T, int d, float divisor,
                      float* sd_ft, int accumulate, void* stream);
 
+/* madtp_query_sdft on the tensor cores: ft is the dense fp32 matrix x [x_rows, d] (token j of batch b at row
+ * b*row_stride + first_row + j); both operands are re-laid out K-major in shared memory, nothing transposed touches HBM. */
+int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
+                        const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
+                        float divisor, float* sd_ft, int accumulate, void* stream);
+
 /*
  * DTP scoring (vit.py:123-145 / nlvr_encoder.py:400-432 / med.py:345-369): Importance_score, threshold,
  * per-row count and topk = max_b count (atomicMax into *topk, which the caller zeroes first).

@@ -41,6 +41,7 @@ SIGNATURES = {
                          _vp],
     "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
+    "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
@@ -408,3 +409,17 @@ def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls
                _ptr(cls_attn, torch.float32, "cls_attn"),
                _ptr(torch.empty(B, H, N, dtype=torch.float32, device=qk_hi.device)), _stream())
     _check(st, "madtp_attn_tc_stats")
+
+
+def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T, divisor, sd_ft, accumulate):
+    """Tensor-core sd_ft: x2d is the dense fp32 matrix [rows, d] of ALL token rows (token j of batch b at row
+    b*row_stride + first_row + j)."""
+    B = token_att.shape[0]
+    d = x2d.shape[1]
+    if not x2d.is_contiguous():
+        raise RuntimeError("madtp_b200.query_sdft_tc: x2d must be dense")
+    st = _call("madtp_query_sdft_tc", _ptr(token_att, torch.float32, "token_att"), token_att.stride(1),
+               token_att.stride(0), _ptr(col_max), _ptr(col_sum), _ptr(x2d, torch.float32, "x"), x2d.shape[0],
+               int(row_stride), int(first_row), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
+               1 if accumulate else 0, _stream())
+    _check(st, "madtp_query_sdft_tc")

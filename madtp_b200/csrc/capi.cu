@@ -156,6 +156,14 @@ int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const
                  B > 0 ? 1 : 0);
 }
 
+int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
+                        const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
+                        float divisor, float* sd_ft, int accumulate, void* stream) {
+  return counted(launch_query_sdft_tc(token_att, ld_ta, bs_ta, col_max, col_sum, x, x_rows, row_stride,
+                                      first_row, B, n, T, d, divisor, sd_ft, accumulate, as_stream(stream)),
+                 B > 0 ? 1 : 0);
+}
+
 int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
                     const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
                     float* threshold, int32_t* count, int32_t* topk, void* stream) {

@@ -195,11 +195,29 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand (the M / N index is the contiguous one, as in a row-major
+// [K, MN] tile) with the 128-byte swizzle: atoms of [8 k-rows x 128 bytes of MN]; `lbo` = byte distance between
+// consecutive 128-byte MN groups, `sbo` = byte distance between consecutive groups of 8 k-rows. This is the layout a
+// TMA box of [k-rows x 32 floats] with CU_TENSOR_MAP_SWIZZLE_128B produces (boxes of successive MN groups back to back).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation, both operands K-major.
 //   [4,6) D format (1 = f32), [7,10) A format, [10,13) B format (0 = f16, 1 = bf16, 2 = tf32),
 //   [15] A major (0 = K), [16] B major (0 = K), [17,23) N >> 3, [24,29) M >> 4.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint32_t n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// Same with both operands MN-major ("transposed": bits 15 and 16).
+__host__ __device__ constexpr uint32_t make_idesc_mn(uint32_t fmt, uint32_t m, uint32_t n) {
+  return make_idesc(fmt, m, n) | (1u << 15) | (1u << 16);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -17,6 +17,12 @@ int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, 
                       const float* col_sum, const float* x, long long ldx, long long bsx, int B, int n, int T, int d,
                       float divisor, float* sd_ft, int accumulate, cudaStream_t stream);
 
+// Tensor-core variant (sdft_tc.cu): x is the dense fp32 matrix [x_rows, d]; token j of batch b sits at row
+// b*row_stride + first_row + j.
+int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
+                         const float* col_sum, const float* x, long long x_rows, int row_stride, int first_row, int B,
+                         int n, int T, int d, float divisor, float* sd_ft, int accumulate, cudaStream_t stream);
+
 struct DtpScoreArgs {
   int B, n, T;                // n prunable tokens (sequence position 1..n), T codebook entries
   const float* col_part;      // [B, n_parts, n+1] partial column sums from attn_stats (index 0 = CLS, unused)

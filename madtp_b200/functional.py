@@ -153,7 +153,10 @@ def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int,
     accumulate = sd_ft is not None
     if sd_ft is None:
         sd_ft = torch.empty(B, T, d, dtype=torch.float32, device=x3d.device)
-    L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate)
+    if n >= 64 and x3d.is_contiguous() and d % 32 == 0:     # tensor-core path over the dense rows of x3d
+        L.query_sdft_tc(ta3, cm, cs, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate)
+    else:
+        L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate)
     return ta3[:, :, :T], sd_ft
 
 

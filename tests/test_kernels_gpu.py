@@ -344,3 +344,22 @@ def test_attention_tensor_core_path(lib, dev, B, H, N, masked):
     assert (cls_attn[:, 1:].double() - cls_ref).abs().max().item() < 1e-6
     a = col_part.double().sum(dim=1)[:, 1:]
     assert ((a - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 3e-6
+
+
+@pytest.mark.parametrize("B,n,T,d", [(3, 196, 100, 768), (2, 576, 100, 768), (4, 19, 100, 768), (2, 76, 100, 512)])
+def test_query_sdft_tensor_core(lib, dev, B, n, T, d):
+    """sd_ft = softmax_tokens(token_att / sqrt(d))^T . x on tcgen05 (operands re-laid out K-major in shared memory)."""
+    g = torch.Generator(device="cpu").manual_seed(n + d)
+    N = n + 1
+    x = torch.randn(B, N, d, generator=g).to(dev)
+    ta = (torch.randn(B, N, 128, generator=g) * 20).to(dev)
+    ta_p = ta[:, 1:, :]
+    div = math.sqrt(d)
+    cm, cs = lib.token_colstats(ta_p, n, T, div)
+    sd = torch.full((B, T, d), float("nan"), device=dev)
+    lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, False)
+    w = torch.softmax(ta_p[..., :T].double() / div, dim=1)
+    ref = w.transpose(1, 2) @ x[:, 1:, :].double()
+    assert _rel(sd, ref) < 5e-6
+    lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, True)
+    assert _rel(sd, 2 * ref) < 5e-6

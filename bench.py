@@ -214,11 +214,23 @@ def main():
         pred = model(images_d, text_d, PAIRS, temp, train=False)
         return mdist.all_gather_rows(pred)
 
+    from madtp_b200.pipeline import InputPrefetcher
+    feeder = InputPrefetcher(dev, (images_h, ids_h, mask_h))
+    e2e_state = {"i": 0, "end": 0}
+
     def step_e2e():
-        im = images_h.to(dev, non_blocking=True)
-        tx = TokenizedText(ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True))
-        pred = mdist.all_gather_rows(model(im, tx, PAIRS, temp, train=False))
+        """Public API with HOST inputs: every step's pinned-host -> HBM copy (issued one step ahead on a side stream,
+        inside the timed region) and the device -> host read of the logits."""
+        i = e2e_state["i"]
+        if i == e2e_state["start"]:
+            feeder.submit(i, (images_h, ids_h, mask_h))
+        if i + 1 < e2e_state["end"]:
+            feeder.submit(i + 1, (images_h, ids_h, mask_h))
+        im, ids_g, mask_g = feeder.acquire(i)
+        pred = mdist.all_gather_rows(model(im, TokenizedText(ids_g, mask_g), PAIRS, temp, train=False))
+        feeder.release(i)
         logits_h.copy_(pred, non_blocking=True)
+        e2e_state["i"] = i + 1
         return pred
 
     # ---- warm-up; the first warm-up step is fully instrumented to find the dominant kernel ----
@@ -260,8 +272,10 @@ def main():
     # that produces `value`: ~250 extra event records per step are not free on the host side of a 27 ms step)
     ms_instr, _, t_top = timed(step_resident, args.steps, only=[top])
     clocks = sampler.stop() if sampler else None
+    e2e_state.update(i=0, start=0, end=1)
     step_e2e()
     torch.cuda.synchronize()
+    e2e_state.update(start=e2e_state["i"], end=e2e_state["i"] + args.steps)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
     images_per_step = 2 * PAIRS * world

@@ -94,6 +94,17 @@ int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int
                    int causal, void* stream);
 
 /*
+ * Self-attention of a SHORT sequence (L <= 64, the text encoders) with every pruning statistic in one launch:
+ * context as madtp_attn_fwd, col_sum[b, j] = sum_{i >= 1} max_h P[b,h,i,j] and cls_attn[b, j] as madtp_attn_stats
+ * (col_sum / cls_attn both NULL: context only; otherwise `scratch` provides B*H*L*(L+1) floats).
+ * nlvr_encoder.py:174-235,404-406 / med.py:175-235,348-350.
+ */
+int madtp_attn_small_self(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk,
+                          const float* v, int64_t ldv, int64_t bsv, int B, int H, int L, float scale,
+                          const float* key_mask, void* out_f16, int64_t ldo, int64_t bso, float* col_sum,
+                          float* cls_attn, float* scratch, int causal, void* stream);
+
+/*
  * Pruning statistics of a self-attention (Nq == Nk == N), from the row statistics of madtp_attn_fwd:
  *   col_part[b, it, j] = sum_{i in query tile it, i >= 1} max_h P[b,h,i,j]      (vit.py:126-127; sum `it` in order)
  *   cls_attn[b, j]     = sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)   (vit.py:96-100)

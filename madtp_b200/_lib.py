@@ -39,6 +39,8 @@ SIGNATURES = {
                        _i64, _i64, _vp, _vp, _vp, _i32, _vp],
     "madtp_attn_stats": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
                          _vp],
+    "madtp_attn_small_self": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
+                              _i64, _vp, _vp, _vp, _i32, _vp],
     "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
@@ -423,3 +425,20 @@ def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T,
                int(row_stride), int(first_row), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
                1 if accumulate else 0, _stream())
     _check(st, "madtp_query_sdft_tc")
+
+
+def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, cls_attn=None, causal=False):
+    """Self-attention of a short sequence (L <= 64) with optional fused pruning statistics (col_sum, cls_attn [B, L])."""
+    B, Ltok, _ = q.shape
+    ldq, bsq = _qkv_strides(q, "q")
+    ldk, bsk = _qkv_strides(k, "k")
+    ldv, bsv = _qkv_strides(v, "v")
+    ldo, bso = _qkv_strides(out_f16, "out_f16")
+    if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Ltok):
+        raise RuntimeError("madtp_b200.attn_small_self: key_mask must be contiguous [B, L]")
+    st = _call("madtp_attn_small_self", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
+               _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Ltok, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
+               _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(col_sum), _ptr(cls_attn),
+               _ptr(None if col_sum is None else torch.empty(B * H * Ltok * (Ltok + 1), dtype=torch.float32,
+                                                             device=q.device)), 1 if causal else 0, _stream())
+    _check(st, "madtp_attn_small_self")

@@ -44,6 +44,9 @@ int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);
 
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream);
+// Short-sequence self-attention (small_attn.cu): Nq == Nk <= 64, context + (optionally) col_sum[B,L] =
+// sum_{i>=1} max_h P and cls_attn[B,L]; scratch holds B*H*L*(L+1) floats when statistics are requested.
+int launch_small_self_attn(const AttnArgs& a, float* col_sum, float* cls_attn, float* scratch, cudaStream_t stream);
 int launch_attn_stats(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace madtp

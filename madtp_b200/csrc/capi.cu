@@ -143,6 +143,23 @@ int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, i
   return counted(launch_attn_stats(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
+int madtp_attn_small_self(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk,
+                          const float* v, int64_t ldv, int64_t bsv, int B, int H, int L, float scale,
+                          const float* key_mask, void* out_f16, int64_t ldo, int64_t bso, float* col_sum,
+                          float* cls_attn, float* scratch, int causal, void* stream) {
+  AttnArgs a = {};
+  a.q = q; a.ldq = ldq; a.bsq = bsq;
+  a.k = k; a.ldk = ldk; a.bsk = bsk;
+  a.v = v; a.ldv = ldv; a.bsv = bsv;
+  a.B = B; a.H = H; a.Nq = L; a.Nk = L;
+  a.scale = scale;
+  a.key_mask = key_mask;
+  a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
+  a.causal = causal;
+  return counted(launch_small_self_attn(a, col_sum, cls_attn, scratch, as_stream(stream)),
+                 B > 0 ? (col_sum ? 2 : 1) : 0);
+}
+
 int madtp_token_colstats(const float* token_att, int64_t ld_ta, int64_t bs_ta, int B, int n, int T, float divisor,
                          float* col_max, float* col_sum, void* stream) {
   return counted(launch_token_colstats(token_att, ld_ta, bs_ta, B, n, T, divisor, col_max, col_sum, as_stream(stream)),

@@ -178,6 +178,15 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
     dev = q.device
     if ctx16 is None:
         ctx16 = torch.empty(B, N, C, dtype=torch.float16, device=dev)
+    if N <= 64:     # short text sequences: per-(head, sequence) CTAs + one statistics pass
+        if not want_stats:
+            L.attn_small_self(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal)
+            return ctx16, None
+        col_part = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
+        cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
+        L.attn_small_self(q, k, v, H, scale, ctx16, key_mask=key_mask, col_sum=col_part, cls_attn=cls_attn,
+                          causal=causal)
+        return ctx16, AttnStats(col_part, cls_attn)
     if not want_stats:
         L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal)
         return ctx16, None

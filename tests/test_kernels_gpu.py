@@ -363,3 +363,43 @@ def test_query_sdft_tensor_core(lib, dev, B, n, T, d):
     assert _rel(sd, ref) < 5e-6
     lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, True)
     assert _rel(sd, 2 * ref) < 5e-6
+
+
+@pytest.mark.parametrize("B,H,L,masked,causal", [(3, 12, 20, True, False), (2, 12, 35, True, False), (2, 8, 64, False, True),
+                                                 (4, 12, 7, False, False), (1, 12, 1, False, False)])
+def test_small_self_attention_fused_stats(lib, dev, B, H, L, masked, causal):
+    g = torch.Generator(device="cpu").manual_seed(L * 5 + B)
+    qkv = torch.randn(B, L, 3 * H * 64, generator=g).to(dev)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, L // 2), L + 1, (B,), generator=g)
+        mask = torch.zeros(B, L)
+        for b in range(B):
+            mask[b, lens[b]:] = -10000.0
+        mask = mask.to(dev)
+    out = torch.empty(B, L, H * 64, device=dev, dtype=torch.float16)
+    col = torch.full((B, L), float("nan"), device=dev)
+    cls_attn = torch.full((B, L), float("nan"), device=dev)
+    lib.attn_small_self(q, k, v, H, 0.125, out, key_mask=mask, col_sum=col, cls_attn=cls_attn, causal=causal)
+
+    def heads(t):
+        return t.reshape(B, L, H, 64).permute(0, 2, 1, 3).double()
+    s = heads(q) @ heads(k).transpose(-1, -2) * 0.125
+    if mask is not None:
+        s = s + mask.double()[:, None, None, :]
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=dev, dtype=torch.float64).triu_(1)
+    p = torch.softmax(s, dim=-1)
+    o = p @ heads(v)
+    assert _rel(out, o.permute(0, 2, 1, 3).reshape(B, L, H * 64)) < 6e-4
+    if L > 1:
+        hi = o[..., 1:, :].norm(dim=-1)
+        hi = hi / (hi.sum(dim=1, keepdim=True) + 1e-8)
+        cls_ref = (p[:, :, 0, 1:] * hi).sum(dim=1)
+        a_ref = p[:, :, 1:, 1:].max(dim=1)[0].sum(dim=1)
+        assert (cls_attn[:, 1:].double() - cls_ref).abs().max().item() < 1e-6
+        assert ((col[:, 1:].double() - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 2e-6
+    out2 = torch.empty_like(out)
+    lib.attn_small_self(q, k, v, H, 0.125, out2, key_mask=mask, causal=causal)
+    assert torch.equal(out, out2)

@@ -146,7 +146,15 @@ def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int,
     hi, lo, T = book
     ta = torch.empty(B * N, TA_LD, dtype=torch.float32, device=x3d.device)
     L.gemm(L.GEMM_TF32X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo)
-    ta3 = ta.view(B, N, TA_LD)[:, first_token:, :]
+    return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token)
+
+
+def query_model_from_token_att(ta_full: Tensor, x3d: Tensor, T: int, sd_dim: int, sd_ft: Optional[Tensor],
+                               first_token: int = 1):
+    """Second half of Query_model given token_att for every row (ta_full [B, N, >=T] view, unit inner stride):
+    over-token softmax statistics and the aggregated feature. Returns (token_att view [B, n, T], sd_ft)."""
+    B, N, d = x3d.shape
+    ta3 = ta_full[:, first_token:, :]
     n = N - first_token
     div = math.sqrt(sd_dim)
     cm, cs = L.token_colstats(ta3, n, T, div)

@@ -146,10 +146,32 @@ class BertSelfAttention(nn.Module):
             f16=True))
 
     # -- kernels ----------------------------------------------------------------------------------------------
-    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True):
+    def _qkv_book_tf32(self, space_dict):
+        """[Wq; Wk; Wv; codebook (zero-padded to 128 rows)]: BERT's q/k/v and the Query_model dots share the operand
+        h, so one GEMM produces both (the ViT cannot do this: its q/k/v read LayerNorm(x), its codebook dots read x)."""
+        ps = [self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight, self.value.bias,
+              space_dict]
+
+        def build():
+            pad = torch.zeros(Fn.TA_LD, space_dict.shape[1], dtype=torch.float32, device=space_dict.device)
+            pad[:space_dict.shape[0]] = space_dict.detach()
+            w = torch.cat([self.query.weight, self.key.weight, self.value.weight, pad], 0)
+            b = torch.cat([self.query.bias, self.key.bias, self.value.bias,
+                           torch.zeros(Fn.TA_LD, dtype=torch.float32, device=space_dict.device)], 0)
+            return Fn.PreparedLinear(w, b, tf32=True)
+        return self._cache.get("qkv_book", ps, build)
+
+    def project_qkv_and_token_att(self, h_hi, h_lo, B, Ltok, space_dict):
+        """One TF32x3 GEMM -> (qkv view [B, L, 3C], token_att view [B, L, 128]) over the same rows."""
+        C = self.all_head_size
+        out = Fn.linear_tf32(h_hi, h_lo, self._qkv_book_tf32(space_dict)).view(B, Ltok, 3 * C + Fn.TA_LD)
+        return out[..., :3 * C], out[..., 3 * C:]
+
+    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None):
         """Self-attention on the scoring lane. Returns ctx16 [B,L,C]; stores AttnStats + cls_attn (:213-235)."""
         C = self.all_head_size
-        qkv = Fn.linear_tf32(h_hi, h_lo, self._qkv_tf32()).view(B, Ltok, 3 * C)
+        if qkv is None:
+            qkv = Fn.linear_tf32(h_hi, h_lo, self._qkv_tf32()).view(B, Ltok, 3 * C)
         ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_attention_heads,
                                          1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats)
         self.save_attention_map(stats)
@@ -268,6 +290,7 @@ class BertAttention(nn.Module):
         self.output = BertSelfOutput(config, twin=is_cross_attention, merge=(is_cross_attention and layer_num >= 6))
         self.is_cross_attention = bool(is_cross_attention)
         self.pruned_heads = set()
+        self._qcache = Fn.WeightCache()
 
     def prune_heads(self, heads):
         if len(heads):
@@ -374,7 +397,7 @@ class BertLayer(nn.Module):
                                   temperature, _kv)
 
     def _forward_impl(self, hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
-                      past_key_value, output_attentions, mode, token_attn, temperature, _kv):
+                      past_key_value, output_attentions, mode, token_attn, temperature, _kv, _qkv=None):
         Fn.require_cuda(hidden_states, "hidden_states")
         _eval_only(self)
         _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
@@ -386,9 +409,12 @@ class BertLayer(nn.Module):
             raise RuntimeError("madtp_b200: temperature > 0 needs token_attn")
 
         # self-attention + output LayerNorm (:501-509)
-        h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
         sa = self.attention.self
-        ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune)
+        if _qkv is not None:      # BertEncoder already projected q|k|v together with the codebook dots
+            ctx16 = sa.self_rows(None, None, B, Ltok, key_mask, want_stats=prune, qkv=_qkv)
+        else:
+            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+            ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune)
         att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=not prune)
         att_f32, att16 = att["y"].view(B, Ltok, d), att.get("y16")
 
@@ -428,8 +454,13 @@ class BertLayer(nn.Module):
         C = selfs[0].all_head_size
         nb = len(selfs)
         ctx = torch.empty(B, Ltok, nb * C, dtype=torch.float16, device=att_rows.device)
+        if nb == 2:   # both query projections read the same rows: one GEMM over [Wq0; Wq1]
+            ps = [p for s in selfs for p in (s.query.weight, s.query.bias)]
+            wq = ca._qcache.get("q01", ps, lambda: Fn.PreparedLinear(
+                torch.cat([s.query.weight for s in selfs], 0), torch.cat([s.query.bias for s in selfs], 0), f16=True))
+            q_all = Fn.linear_f16(att16, wq).view(B, Ltok, nb * C)
         for i, s in enumerate(selfs):
-            q = Fn.linear_f16(att16, s._q_f16()).view(B, Ltok, C)
+            q = q_all[..., i * C:(i + 1) * C] if nb == 2 else Fn.linear_f16(att16, s._q_f16()).view(B, Ltok, C)
             Nk = enc[i].shape[1]
             if kv is not None:
                 k, v = kv[i]
@@ -503,14 +534,20 @@ class BertEncoder(nn.Module):
         for i, layer_module in enumerate(self.layer):
             h = hidden_states.contiguous()
             Ltok, d = h.shape[1], h.shape[2]
-            token_attn = None
-            if space_dict is not None:
+            token_attn = qkv = None
+            if space_dict is not None and not self.txt_query_model.map_func:
+                # q|k|v and the codebook dots share the operand h: one TF32x3 GEMM (see _qkv_book_tf32)
+                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+                qkv, ta_full = layer_module.attention.self.project_qkv_and_token_att(h_hi, h_lo, B, Ltok, space_dict)
+                token_attn, sd_txt_ft_all = Fn.query_model_from_token_att(ta_full, h, space_dict.shape[0],
+                                                                          self.txt_query_model.att_dim, sd_txt_ft_all)
+            elif space_dict is not None:
                 h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
                 token_attn, sd_txt_ft_all = self.txt_query_model.forward_rows(h, h_hi, h_lo, space_dict,
                                                                               sd_txt_ft_all)
             layer_outputs = layer_module._forward_impl(h, attention_mask, None, encoder_hidden_states,
                                                        encoder_attention_mask, None, False, mode, token_attn,
-                                                       temperature, None if kv is None else kv[i])
+                                                       temperature, None if kv is None else kv[i], _qkv=qkv)
             hidden_states = layer_outputs[0]
             attention_mask = layer_outputs[-1]
         if not return_dict:

@@ -27,10 +27,11 @@ constexpr int LDS = 68;   // shared-memory row pitch in floats
 constexpr int NTHREADS = 128;
 
 // Copy a [64 x 64] fp32 tile (rows row0.. of a [n_rows, ld] matrix) into shared memory, zero-filling past n_rows.
+template <int ROWS = T>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, long long ld, int row0,
                                           int n_rows, int tid) {
 #pragma unroll
-  for (int it = 0; it < (T * T / 4) / NTHREADS; ++it) {
+  for (int it = 0; it < (ROWS * T / 4) / NTHREADS; ++it) {
     const int idx = tid + it * NTHREADS;
     const int r = idx >> 4, c4 = idx & 15;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -40,20 +41,21 @@ __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ 
 }
 
 // s[r][c] = sum_k Qs[ty+16r][k] * Ks[tx+8c][k], k ascending (the order is part of the contract between passes).
-__device__ __forceinline__ void qk_tile(const float* Qs, const float* Ks, int ty, int tx, float (&s)[4][8]) {
+template <int RT>
+__device__ __forceinline__ void qk_tile(const float* Qs, const float* Ks, int ty, int tx, float (&s)[RT][8]) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < RT; ++r)
 #pragma unroll
     for (int c = 0; c < 8; ++c) s[r][c] = 0.f;
 #pragma unroll 2
   for (int k4 = 0; k4 < T / 4; ++k4) {
-    float4 qa[4], kb[8];
+    float4 qa[RT], kb[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) qa[r] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * r) * LDS + k4 * 4);
+    for (int r = 0; r < RT; ++r) qa[r] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * r) * LDS + k4 * 4);
 #pragma unroll
     for (int c = 0; c < 8; ++c) kb[c] = *reinterpret_cast<const float4*>(Ks + (tx + 8 * c) * LDS + k4 * 4);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < RT; ++r)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         s[r][c] = fmaf(qa[r].x, kb[c].x, s[r][c]);
@@ -65,7 +67,8 @@ __device__ __forceinline__ void qk_tile(const float* Qs, const float* Ks, int ty
 }
 
 // logits = s * scale + mask[j];  keys past Nk get -inf
-__device__ __forceinline__ void finish_logits(float (&s)[4][8], float scale, const float* Ms, int j0, int Nk, int tx,
+template <int RT>
+__device__ __forceinline__ void finish_logits(float (&s)[RT][8], float scale, const float* Ms, int j0, int Nk, int tx,
                                               int causal, int i_first) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -73,7 +76,7 @@ __device__ __forceinline__ void finish_logits(float (&s)[4][8], float scale, con
     const bool valid = (j0 + jl) < Nk;
     const float mk = Ms[jl];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RT; ++r) {
       const bool vis = valid && (!causal || (j0 + jl) <= (i_first + 16 * r));
       s[r][c] = vis ? fmaf(s[r][c], scale, mk) : -INFINITY;
     }
@@ -99,26 +102,30 @@ __device__ __forceinline__ float group8_sum(float v) {
 // Pass 1: context = softmax(QK^T * scale + mask) V, row statistics, context row norms.
 // grid = (ceil(Nq/64), H, B)
 // ------------------------------------------------------------------------------------------------
+// RT = query-row groups per thread: the query tile has 16*RT rows (RT = 4: 64 rows; RT = 2: 32 rows for the
+// cross-attention of a few text queries over many image keys, where a 64-row tile would be mostly padding).
+template <int RT>
 __global__ void __launch_bounds__(NTHREADS)
 attn_fwd_kernel(AttnArgs a) {
+  constexpr int BQ = 16 * RT;
   extern __shared__ float sm[];
   float* Qs = sm;
-  float* Ks = Qs + T * LDS;
+  float* Ks = Qs + BQ * LDS;
   float* Vs = Ks + T * LDS;
   float* Ps = Vs + T * LDS;
-  float* Ms = Ps + T * LDS;  // [64] additive key mask of the current key tile
+  float* Ms = Ps + BQ * LDS;  // [64] additive key mask of the current key tile
 
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
-  const int i0 = blockIdx.x * T, h = blockIdx.y, b = blockIdx.z;
+  const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const float* q = a.q + b * a.bsq + h * T;
   const float* k = a.k + b * a.bsk + h * T;
   const float* v = a.v + b * a.bsv + h * T;
 
-  load_tile(Qs, q, a.ldq, i0, a.Nq, tid);
+  load_tile<BQ>(Qs, q, a.ldq, i0, a.Nq, tid);
 
-  float m[4], l[4], o[4][8];
+  float m[RT], l[RT], o[RT][8];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < RT; ++r) {
     m[r] = -INFINITY;
     l[r] = 0.f;
 #pragma unroll
@@ -132,12 +139,12 @@ attn_fwd_kernel(AttnArgs a) {
     if (tid < T) Ms[tid] = (a.key_mask != nullptr && j0 + tid < a.Nk) ? a.key_mask[b * a.Nk + j0 + tid] : 0.f;
     __syncthreads();
 
-    float s[4][8];
-    qk_tile(Qs, Ks, ty, tx, s);
-    finish_logits(s, a.scale, Ms, j0, a.Nk, tx, a.causal, i0 + ty);
+    float s[RT][8];
+    qk_tile<RT>(Qs, Ks, ty, tx, s);
+    finish_logits<RT>(s, a.scale, Ms, j0, a.Nk, tx, a.causal, i0 + ty);
 
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RT; ++r) {
       float mx = s[r][0];
 #pragma unroll
       for (int c = 1; c < 8; ++c) mx = fmaxf(mx, s[r][c]);
@@ -162,15 +169,15 @@ attn_fwd_kernel(AttnArgs a) {
     // o[r][0..3] -> d = tx*4 + {0..3};  o[r][4..7] -> d = 32 + tx*4 + {0..3}
 #pragma unroll 2
     for (int j4 = 0; j4 < T / 4; ++j4) {
-      float4 pa[4];
+      float4 pa[RT];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) pa[r] = *reinterpret_cast<const float4*>(Ps + (ty + 16 * r) * LDS + j4 * 4);
+      for (int r = 0; r < RT; ++r) pa[r] = *reinterpret_cast<const float4*>(Ps + (ty + 16 * r) * LDS + j4 * 4);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const float4 v0 = *reinterpret_cast<const float4*>(Vs + (j4 * 4 + jj) * LDS + tx * 4);
         const float4 v1 = *reinterpret_cast<const float4*>(Vs + (j4 * 4 + jj) * LDS + 32 + tx * 4);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < RT; ++r) {
           const float p = jj == 0 ? pa[r].x : jj == 1 ? pa[r].y : jj == 2 ? pa[r].z : pa[r].w;
           o[r][0] = fmaf(p, v0.x, o[r][0]);
           o[r][1] = fmaf(p, v0.y, o[r][1]);
@@ -186,7 +193,7 @@ attn_fwd_kernel(AttnArgs a) {
   }
 
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < RT; ++r) {
     const int i = i0 + ty + 16 * r;
     const float inv = 1.0f / l[r];
     float nsq = 0.f;
@@ -261,8 +268,8 @@ attn_stats_kernel(AttnArgs a) {
     load_tile(Ks, a.k + b * a.bsk + h * T, a.ldk, j0, N, tid);
     __syncthreads();
     float s[4][8];
-    qk_tile(Qs, Ks, ty, tx, s);
-    finish_logits(s, a.scale, Ms, j0, N, tx, a.causal, i0 + ty);
+    qk_tile<4>(Qs, Ks, ty, tx, s);
+    finish_logits<4>(s, a.scale, Ms, j0, N, tx, a.causal, i0 + ty);
     const long long sbase = (static_cast<long long>(b) * a.H + h) * N;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -341,14 +348,24 @@ int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   MADTP_CHECK_ARG((a.row_max == nullptr) == (a.row_sum == nullptr) && (a.row_max == nullptr) == (a.out_norm == nullptr),
                   "attn_fwd: row_max/row_sum/out_norm come together");
   if (a.B == 0) return kOk;
-  const int smem = (4 * T * LDS + T) * sizeof(float);
+  const bool small_q = a.Nq <= 32 && a.row_max == nullptr;   // few queries: 32-row tiles waste far less
   static bool attr_done = false;
   if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (4 * T * LDS + T) * (int)sizeof(float)));
+    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ((2 * 32 + 2 * T) * LDS + T) * (int)sizeof(float)));
     attr_done = true;
   }
-  dim3 grid((a.Nq + T - 1) / T, a.H, a.B);
-  attn_fwd_kernel<<<grid, NTHREADS, smem, stream>>>(a);
+  if (small_q) {
+    const int smem = ((2 * 32 + 2 * T) * LDS + T) * sizeof(float);
+    dim3 grid((a.Nq + 31) / 32, a.H, a.B);
+    attn_fwd_kernel<2><<<grid, NTHREADS, smem, stream>>>(a);
+  } else {
+    const int smem = (4 * T * LDS + T) * sizeof(float);
+    dim3 grid((a.Nq + T - 1) / T, a.H, a.B);
+    attn_fwd_kernel<4><<<grid, NTHREADS, smem, stream>>>(a);
+  }
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

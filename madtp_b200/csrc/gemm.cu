@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace madtp {
 
@@ -449,7 +450,10 @@ struct Tf32Cfg {
   static constexpr int COLS_PER_WARP = BLOCK_N / 2;
 };
 
-template <int BLOCK_N>
+// CL = 1: independent CTAs. CL = 2: clusters of two CTAs that work on vertically adjacent output tiles (same n-tile)
+// and share the B operand: each CTA fetches half of the B tile and TMA-multicasts it to both, which halves the L2 ->
+// shared-memory traffic of the (weight) operand -- the K = 768 projections are L2-bandwidth bound otherwise.
+template <int BLOCK_N, int CL>
 __global__ void __launch_bounds__(320, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -471,8 +475,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;   // work items per cluster: CL vertically adjacent tiles
   const int num_kb = (K + Cfg::K_ELEMS - 1) / Cfg::K_ELEMS;
+  const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -483,7 +489,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -497,6 +503,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -504,18 +511,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+        const int m0 = ((tile / n_tiles) * CL + rank) * Cfg::BLOCK_M;
         const int n0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);   // CL > 1: BOTH CTAs have retired their MMAs on this stage
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * Cfg::K_ELEMS;
           tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
-          tma_load_2d(&tm_b, &full_bar[stage], s + Cfg::A_BYTES, k0, n0);
           tma_load_2d(&tm_a_lo, &full_bar[stage], s + Cfg::A_BYTES + Cfg::B_BYTES, k0, m0);
-          tma_load_2d(&tm_b_lo, &full_bar[stage], s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+          if (CL == 1) {
+            tma_load_2d(&tm_b, &full_bar[stage], s + Cfg::A_BYTES, k0, n0);
+            tma_load_2d(&tm_b_lo, &full_bar[stage], s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, n0);
+          } else {   // this CTA's half of the B tile, delivered to both CTAs of the cluster
+            constexpr int HB = Cfg::B_BYTES / CL;
+            const int nr = n0 + rank * (BLOCK_N / CL);
+            tma_load_2d_multicast(&tm_b, &full_bar[stage], s + Cfg::A_BYTES + rank * HB, k0, nr, (1u << CL) - 1);
+            tma_load_2d_multicast(&tm_b_lo, &full_bar[stage], s + 2 * Cfg::A_BYTES + Cfg::B_BYTES + rank * HB, k0, nr,
+                                  (1u << CL) - 1);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -530,7 +545,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       uint32_t phase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tmem_empty[buf], buf_phase ^ 1u);
           mbar_wait(&full_bar[stage], phase);
@@ -549,7 +564,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
-          umma_commit(&empty_bar[stage]);
+          if (CL == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_multicast(&empty_bar[stage], (1u << CL) - 1);   // frees the stage in both CTAs
           umma_commit(&tmem_full[buf]);
           if (++stage == STAGES) {
             stage = 0;
@@ -566,8 +582,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int buf = 0;
     uint32_t buf_phase = 0;
     const bool vec_ok = epilogue_vec_ok(ep, N);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+    for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      const int m0 = ((tile / n_tiles) * CL + rank) * Cfg::BLOCK_M;
       const int n0 = (tile % n_tiles) * BLOCK_N;
       float sum[CW];
 #pragma unroll
@@ -638,6 +654,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -768,27 +785,54 @@ static int launch_tc(const void* a, const void* a_lo, long long lda, const void*
 }
 
 
-template <int BLOCK_N>
-static int launch_tf32(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
-                       const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+template <int BLOCK_N, int CL>
+static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
+                          long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
   using Cfg = Tf32Cfg<BLOCK_N>;
   CUtensorMap ta, tal, tb, tbl;
   int st;
   if ((st = make_tmap(&ta, a, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
-  if ((st = make_tmap(&tb, b, true, N, K, ldb, BLOCK_N)) != kOk) return st;
+  if ((st = make_tmap(&tb, b, true, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   if ((st = make_tmap(&tal, a_lo, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
-  if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N)) != kOk) return st;
+  if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   static bool attr_done = false;
   if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int tiles = ((M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tf32x3_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, ep, M, N, K);
-  MADTP_LAUNCH_CHECK();
+  const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int items = ((m_tiles + CL - 1) / CL) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int max_clusters = num_sms() / CL;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL>, ta, tal, tb, tbl, ep, M, N, K));
   return kOk;
+}
+
+// Clusters of two with a TMA-multicast B operand are implemented and verified but OFF by default: measured on B200
+// (M=36928, N=2304, K=768) 585 us with clusters vs 560 us without -- this kernel is bound by its two-deep operand
+// pipeline (TMA latency), not by L2 bandwidth, and pairing CTAs adds lock-step stalls. MADTP_CLUSTER=1 enables it.
+template <int BLOCK_N>
+static int launch_tf32(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
+                       const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+  const int m_tiles = (M + 127) / 128;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  static const bool use_cluster = getenv("MADTP_CLUSTER") != nullptr;
+  if (use_cluster && m_tiles >= 2 && static_cast<long long>(m_tiles) * n_tiles >= 2LL * num_sms())
+    return launch_tf32_cl<BLOCK_N, 2>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+  return launch_tf32_cl<BLOCK_N, 1>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
 }
 
 int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,

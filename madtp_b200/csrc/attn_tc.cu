@@ -92,10 +92,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
   uint64_t* k_empty = bars + 4;    // [3]
   uint64_t* v_full = bars + 7;     // [2]
   uint64_t* v_empty = bars + 9;    // [2]
-  uint64_t* s_full = bars + 11;    // [2]
-  uint64_t* s_empty = bars + 13;   // [2]
-  uint64_t* p_full = bars + 15;
-  uint64_t* o_full = bars + 16;
+  uint64_t* s_full = bars + 11;    // S(t) complete in TMEM
+  uint64_t* s_empty = bars + 12;   // S(t) copied to registers by all eight softmax warps
+  uint64_t* p_full = bars + 13;    // [2] P(t) stored (parity t & 1)
+  uint64_t* o_full = bars + 15;    // [2] P(t) V(t) complete (parity t & 1): O partial ready, P buffer free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   float* xch = reinterpret_cast<float*>(smem + FwdSmem::XCH_OFF);   // [parity][half][row]
 
@@ -121,11 +121,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 8);
+      mbar_init(&p_full[s], 8);
+      mbar_init(&o_full[s], 1);
     }
-    mbar_init(p_full, 8);
-    mbar_init(o_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -136,38 +136,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S buffers (slice A | slice B) at 0 and 128, P hi at 256, P lo at 320, O partial at 384
-  constexpr uint32_t kP_HI = 256, kP_LO = 320, kO = 384;
+  // TMEM columns: S (slice A | slice B) at 0; P hi, P lo and the O partial are double-buffered by tile parity so that
+  // softmax(t+1) never waits for P(t) V(t): P hi at 128 / 192, P lo at 256 / 320, O partial at 384 / 448
+  constexpr uint32_t kP_HI = 128, kP_LO = 256, kO = 384;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp == 0) {   // warp-uniform control flow, one elected lane issues the TMA
+    {
       const int qrow = b * N + i0;
-      mbar_arrive_expect_tx(q_full, FwdSmem::Q_BYTES);
-      for (int c = 0; c < 2; ++c) {
-        tma_load_2d(&tm_q_hi, q_full, q_s + (c * 2 + 0) * BM * 128, h * 64 + c * BOX, qrow);
-        tma_load_2d(&tm_q_lo, q_full, q_s + (c * 2 + 1) * BM * 128, h * 64 + c * BOX, qrow);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, FwdSmem::Q_BYTES);
+        for (int c = 0; c < 2; ++c) {
+          tma_load_2d(&tm_q_hi, q_full, q_s + (c * 2 + 0) * BM * 128, h * 64 + c * BOX, qrow);
+          tma_load_2d(&tm_q_lo, q_full, q_s + (c * 2 + 1) * BM * 128, h * 64 + c * BOX, qrow);
+        }
       }
+      __syncwarp();
       auto load_k = [&](int t) {
         const int st = t % FwdSmem::K_STAGES;
         mbar_wait(&k_empty[st], ((t / FwdSmem::K_STAGES) & 1) ^ 1);
         uint8_t* s = k_s + st * FwdSmem::TILE_BYTES;
-        mbar_arrive_expect_tx(&k_full[st], FwdSmem::TILE_BYTES);
         const int krow = b * N + t * 64;
-        for (int c = 0; c < 2; ++c) {
-          tma_load_2d(&tm_k_hi, &k_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
-          tma_load_2d(&tm_k_lo, &k_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], FwdSmem::TILE_BYTES);
+          for (int c = 0; c < 2; ++c) {
+            tma_load_2d(&tm_k_hi, &k_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+            tma_load_2d(&tm_k_lo, &k_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
+          }
         }
+        __syncwarp();
       };
       auto load_v = [&](int t) {
         const int st = t & 1;
         mbar_wait(&v_empty[st], ((t >> 1) & 1) ^ 1);
         uint8_t* s = v_s + st * FwdSmem::TILE_BYTES;
-        mbar_arrive_expect_tx(&v_full[st], FwdSmem::TILE_BYTES);
         const int vrow = (b * a.H + h) * 64;
-        for (int c = 0; c < 2; ++c) {
-          tma_load_2d(&tm_v_hi, &v_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
-          tma_load_2d(&tm_v_lo, &v_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], FwdSmem::TILE_BYTES);
+          for (int c = 0; c < 2; ++c) {
+            tma_load_2d(&tm_v_hi, &v_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+            tma_load_2d(&tm_v_lo, &v_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
+          }
         }
+        __syncwarp();
       };
       load_k(0);
       for (int t = 0; t < T; ++t) {
@@ -176,44 +186,52 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2u, BM, 64);
-      const uint32_t q_u = smem_u32(q_s);
-      auto issue_qk = [&](int t) {
-        const int st = t % FwdSmem::K_STAGES, sb = t & 1;
-        mbar_wait(&k_full[st], (t / FwdSmem::K_STAGES) & 1);
-        mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint32_t k_u = smem_u32(k_s + st * FwdSmem::TILE_BYTES);
+    // The whole warp runs this loop and ONE elected lane issues: with warp-uniform control flow the descriptors stay
+    // in uniform registers. (Guarding the loop with `lane == 0` instead makes every tcgen05.mma a ~100-cycle
+    // R2UR + waterfall sequence -- measured: that, not the tensor pipe or the softmax, bounded this kernel.)
+    constexpr uint32_t idesc = make_idesc(2u, BM, 64);
+    const uint32_t q_u = smem_u32(q_s);
+    auto issue_qk = [&](int t) {
+      const int st = t % FwdSmem::K_STAGES;
+      mbar_wait(&k_full[st], (t / FwdSmem::K_STAGES) & 1);
+      mbar_wait(s_empty, (t & 1) ^ 1);       // softmax(t-1) has S(t-1) in registers
+      tcgen05_fence_after();
+      const uint32_t k_u = smem_u32(k_s + st * FwdSmem::TILE_BYTES);
+      if (elect_one()) {
         for (int c = 0; c < 2; ++c)
-          issue_slice_ss(tmem_base + sb * 128 + c * 64, q_u + (c * 2 + 0) * BM * 128, q_u + (c * 2 + 1) * BM * 128,
+          issue_slice_ss(tmem_base + c * 64, q_u + (c * 2 + 0) * BM * 128, q_u + (c * 2 + 1) * BM * 128,
                          k_u + (c * 2 + 0) * FwdSmem::KBOX, k_u + (c * 2 + 1) * FwdSmem::KBOX, idesc);
-        umma_commit(&s_full[sb]);
+        umma_commit(s_full);
         umma_commit(&k_empty[st]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_qk(t + 1);
-        mbar_wait(&v_full[t & 1], (t >> 1) & 1);
-        mbar_wait(p_full, t & 1);
-        tcgen05_fence_after();
-        const uint32_t v_u = smem_u32(v_s + (t & 1) * FwdSmem::TILE_BYTES);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) issue_qk(t + 1);
+      const int pb = t & 1;
+      mbar_wait(&v_full[pb], (t >> 1) & 1);
+      mbar_wait(&p_full[pb], (t >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t v_u = smem_u32(v_s + pb * FwdSmem::TILE_BYTES);
+      if (elect_one()) {
         // O_t = P_lo V_hi + P_hi V_lo + P_hi V_hi over 8 k-steps of 8 keys
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t pa = tmem_base + (pass == 0 ? kP_LO : kP_HI);
+          const uint32_t pa = tmem_base + (pass == 0 ? kP_LO : kP_HI) + pb * 64;
           const int vplane = (pass == 1) ? 1 : 0;  // pass 1 multiplies by V_lo
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t bd =
                 make_sw128_kmajor_desc(v_u + ((ks >> 2) * 2 + vplane) * FwdSmem::KBOX) + 2 * (ks & 3);
-            umma_tf32_ts(tmem_base + kO, pa + ks * 8, bd, idesc, (pass | ks) != 0 ? 1u : 0u);
+            umma_tf32_ts(tmem_base + kO + pb * 64, pa + ks * 8, bd, idesc, (pass | ks) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(o_full);
-        umma_commit(&v_empty[t & 1]);
+        umma_commit(&o_full[pb]);
+        umma_commit(&v_empty[pb]);
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -223,19 +241,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
     float m = -INFINITY, l = 0.f;
+    float m_hist[2] = {-INFINITY, -INFINITY};   // running max at tiles t-2 / t-1 (indexed by tile parity)
     float o[32];
 #pragma unroll
     for (int d = 0; d < 32; ++d) o[d] = 0.f;
 
+    // drain the partial product of tile u (buffer u & 1, relative to the running max m_u) into o (relative to m_now)
+    auto drain = [&](int u, float m_u, float m_now) {
+      mbar_wait_spin(&o_full[u & 1], (u >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + (u & 1) * 64 + hf * 32, v);
+      tmem_ld_wait();
+      const float f = expf(m_u - m_now);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) o[k] = fmaf(__uint_as_float(v[k]), f, o[k]);
+    };
+
     for (int t = 0; t < T; ++t) {
-      const int sb = t & 1;
-      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      mbar_wait_spin(s_full, t & 1);
       tcgen05_fence_after();
       float s[32];
-      ld2_add(tmem_base + lane_off + sb * 128 + hf * 32, tmem_base + lane_off + sb * 128 + 64 + hf * 32, s);
+      ld2_add(tmem_base + lane_off + hf * 32, tmem_base + lane_off + 64 + hf * 32, s);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      if (lane == 0) mbar_arrive(s_empty);
 
       const int j0 = t * 64 + hf * 32;
       float mx = -INFINITY;
@@ -270,16 +300,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
       }
       l = l * corr + ps;
       m = m_new;
-
-      if (t > 0) {  // drain the previous tile's P V partial (it is relative to the previous running max)
-        mbar_wait(o_full, (t - 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_off + kO + hf * 32, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) o[k] = (o[k] + __uint_as_float(v[k])) * corr;
-      }
+      for (int k = 0; k < 32; ++k) o[k] *= corr;     // o is now relative to m_new
+      // the P buffer of this parity was last read by P(t-2) V(t-2): drain that partial, which also frees the buffer
+      if (t >= 2) drain(t - 2, m_hist[t & 1], m_new);
+      m_hist[t & 1] = m_new;
 
       // P -> TMEM as tf32 hi / lo (A operand of the P V MMAs)
       {
@@ -291,23 +316,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
           hi[k] = __float_as_uint(ph);
           lo[k] = __float_as_uint(p - ph);
         }
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + hf * 32, hi);
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + hf * 32, lo);
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + (t & 1) * 64 + hf * 32, hi);
+        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + (t & 1) * 64 + hf * 32, lo);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[t & 1]);
     }
-    mbar_wait(o_full, (T - 1) & 1);
-    tcgen05_fence_after();
-    {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + hf * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(v[k]);
-    }
+    if (T >= 2) drain(T - 2, m_hist[(T - 2) & 1], m);
+    drain(T - 1, m_hist[(T - 1) & 1], m);
     // row sum and squared norm: combine the two column halves (buffers of parity T&1 are free: their last readers
     // passed the barrier of tile T-2 ... T-1 uses the other parity)
     float* x = xch + (T & 1) * 2 * BM;
@@ -412,35 +430,37 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int u = 0; u < 2 * H; ++u) {
-        const int st = u % StatsSmem::STAGES, hh = u >> 1, c = u & 1;
-        mbar_wait(&empty[st], ((u / StatsSmem::STAGES) & 1) ^ 1);
-        uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
+  if (warp == 0) {   // warp-uniform control flow, one elected lane issues
+    for (int u = 0; u < 2 * H; ++u) {
+      const int st = u % StatsSmem::STAGES, hh = u >> 1, c = u & 1;
+      mbar_wait(&empty[st], ((u / StatsSmem::STAGES) & 1) ^ 1);
+      uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[st], StatsSmem::STAGE_BYTES);
         tma_load_2d(&tm_hi, &full[st], s, hh * 64 + c * BOX, b * N + i0);
         tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64 + c * BOX, b * N + i0);
         tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
         tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2u, BM, BM);
-      for (int hh = 0; hh < H; ++hh) {
-        const int hb = hh & 1;
-        mbar_wait(&s_empty[hb], ((hh >> 1) & 1) ^ 1);
-        for (int c = 0; c < 2; ++c) {
-          const int u = hh * 2 + c, st = u % StatsSmem::STAGES;
-          mbar_wait(&full[st], (u / StatsSmem::STAGES) & 1);
-          tcgen05_fence_after();
-          const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
+    constexpr uint32_t idesc = make_idesc(2u, BM, BM);
+    for (int hh = 0; hh < H; ++hh) {
+      const int hb = hh & 1;
+      mbar_wait(&s_empty[hb], ((hh >> 1) & 1) ^ 1);
+      for (int c = 0; c < 2; ++c) {
+        const int u = hh * 2 + c, st = u % StatsSmem::STAGES;
+        mbar_wait(&full[st], (u / StatsSmem::STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
+        if (elect_one()) {
           issue_slice_ss(tmem_base + hb * 256 + c * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
                          s + 3 * StatsSmem::BOX_BYTES, idesc);
           umma_commit(&empty[st]);
+          if (c == 1) umma_commit(&s_full[hb]);
         }
-        umma_commit(&s_full[hb]);
+        __syncwarp();
       }
     }
   } else {

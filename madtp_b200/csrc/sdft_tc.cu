@@ -74,28 +74,29 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int c = 0; c < chunks; ++c) {
-        const int st = c & 1;
-        mbar_wait(&empty[st], ((c >> 1) & 1) ^ 1);   // chunk c-2 fully consumed (its builders finished long before)
-        uint8_t* xs = smem + st * STAGE;
+  if (warp == 0) {   // warp-uniform control flow, one elected lane issues
+    for (int c = 0; c < chunks; ++c) {
+      const int st = c & 1;
+      mbar_wait(&empty[st], ((c >> 1) & 1) ^ 1);   // chunk c-2 fully consumed (its builders finished long before)
+      uint8_t* xs = smem + st * STAGE;
+      const int row = b * a.row_stride + a.first_row + c * TCH;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&raw_full[st], RAW_BYTES);
-        const int row = b * a.row_stride + a.first_row + c * TCH;
         for (int g = 0; g < DN / 32; ++g) tma_load_2d(&tm_x, &raw_full[st], xs + g * TCH * 128, d0 + g * 32, row);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2u, TM, DN);
-      for (int c = 0; c < chunks; ++c) {
-        const int st = c & 1;
-        mbar_wait(&op_full[st], (c >> 1) & 1);
-        tcgen05_fence_after();
-        const uint32_t base = smem_u32(smem + st * STAGE + RAW_BYTES);
-        const uint64_t w_hi = make_sw128_kmajor_desc(base), w_lo = make_sw128_kmajor_desc(base + OP_BYTES);
-        const uint64_t x_hi = make_sw128_kmajor_desc(base + 2 * OP_BYTES);
-        const uint64_t x_lo = make_sw128_kmajor_desc(base + 3 * OP_BYTES);
+    constexpr uint32_t idesc = make_idesc(2u, TM, DN);
+    for (int c = 0; c < chunks; ++c) {
+      const int st = c & 1;
+      mbar_wait(&op_full[st], (c >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t base = smem_u32(smem + st * STAGE + RAW_BYTES);
+      const uint64_t w_hi = make_sw128_kmajor_desc(base), w_lo = make_sw128_kmajor_desc(base + OP_BYTES);
+      const uint64_t x_hi = make_sw128_kmajor_desc(base + 2 * OP_BYTES);
+      const uint64_t x_lo = make_sw128_kmajor_desc(base + 3 * OP_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, w_lo + 2 * k, x_hi + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
 #pragma unroll
@@ -103,8 +104,9 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, w_hi + 2 * k, x_hi + 2 * k, idesc, 1u);
         umma_commit(&empty[st]);
+        if (c == chunks - 1) umma_commit(acc_full);
       }
-      umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // eight builder warps: thread (t, half) owns row t of both K-major operand tiles and 16 of the chunk's 32 tokens

@@ -78,6 +78,17 @@ class BLIP_Retrieval(nn.Module):
         return Fn.linear_f32(out.last_hidden_state[:, 0, :].contiguous(), self._lin("itm_head"))
 
     @torch.no_grad()
+    def itm_rerank(self, image_feat, input_ids, attention_mask, temperature=0):
+        """ITM rerank of ONE image against k_test candidate captions (compress_retrieval_dtp.py:166-177).
+        image_feat [N', d] or [1, N', d]; input_ids / attention_mask [k_test, L]. The image's cross-attention K/V
+        projections are computed once and broadcast over the candidates (the reference repeats the image k_test times
+        and re-projects it for every caption). Returns the ITM logits [k_test, 2]."""
+        if image_feat.dim() == 2:
+            image_feat = image_feat.unsqueeze(0)
+        feats = image_feat.expand(input_ids.shape[0], -1, -1)        # zero batch stride, nothing is copied
+        return self.itm_score(input_ids, attention_mask, feats, temperature)
+
+    @torch.no_grad()
     def forward(self, image, caption, alpha=0.0, idx=None, temperature=0, train=True):
         """Evaluation-path forward (BASELINE config 3): image encoder + text-only encoder + one multimodal ITM pass
         over the matched pairs. `caption` is pre-tokenised (input_ids, attention_mask) or text for `tokenizer`."""

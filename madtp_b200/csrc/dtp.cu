@@ -277,6 +277,7 @@ dtp_score_kernel(DtpScoreArgs a) {
 }
 
 int launch_dtp_score(const DtpScoreArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return kOk;   // empty batch: nothing to do (and torch hands out null pointers for empty tensors)
   MADTP_CHECK_ARG(a.col_part && a.cls_attn && a.token_att && a.score && a.threshold && a.count && a.topk,
                   "dtp_score: null pointer");
   MADTP_CHECK_ARG(a.B >= 0 && a.n > 0 && a.n <= kDtpMaxTokens, "dtp_score: n=%d out of range (1..%d)", a.n,
@@ -390,6 +391,7 @@ dtp_select_kernel(DtpSelectArgs a) {
 }
 
 int launch_dtp_select(const DtpSelectArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return kOk;   // empty batch: nothing to do (and torch hands out null pointers for empty tensors)
   MADTP_CHECK_ARG(a.score && a.topk && a.keep && a.dst && a.tail_w && a.tail_idx, "dtp_select: null pointer");
   MADTP_CHECK_ARG(a.B >= 0 && a.n > 0 && a.n <= kDtpMaxTokens, "dtp_select: n=%d out of range (1..%d)", a.n,
                   kDtpMaxTokens);
@@ -481,6 +483,7 @@ dtp_gather_kernel(DtpGatherArgs a) {
 }
 
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return kOk;   // empty batch: nothing to do (and torch hands out null pointers for empty tensors)
   MADTP_CHECK_ARG(a.x && a.topk && a.dst && a.tail_w && a.tail_idx && a.out, "dtp_gather: null pointer");
   MADTP_CHECK_ARG(a.B >= 0 && a.n > 0 && a.d > 0 && a.d % 4 == 0 && a.d <= 1024 && a.bsx % 4 == 0 && a.bso % 4 == 0 && a.B <= 65535,
                   "dtp_gather: bad shape");

@@ -509,8 +509,15 @@ class BertEncoder(nn.Module):
         for name, e in zip(names, encs):
             Fn.require_cuda(e, "encoder_hidden_states")
             B, Nk, w = e.shape
-            e16 = L.cast_f16(e.contiguous().view(B * Nk, w))
-            allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(B, Nk, -1)
+            if B > 1 and e.stride(0) == 0:
+                # the same encoder states for every text of the batch (ITM rerank: one image against k_test captions,
+                # compress_retrieval_dtp.py:166-176): project the image ONCE and let the attention kernels broadcast it
+                # through a zero batch stride -- the reference recomputes the K/V projections k_test times
+                e16 = L.cast_f16(e[0].contiguous().view(Nk, w))
+                allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(1, Nk, -1).expand(B, Nk, -1)
+            else:
+                e16 = L.cast_f16(e.contiguous().view(B * Nk, w))
+                allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(B, Nk, -1)
             for i in range(len(self.layer)):
                 o = i * 2 * C
                 per_layer[i].append((allkv[..., o:o + C], allkv[..., o + C:o + 2 * C]))

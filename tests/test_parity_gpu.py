@@ -450,3 +450,62 @@ def test_clip_encode_text_unpruned_and_full_depth_shapes(dev):
     assert emb.shape == (4, 512) and len(ks) > 0 and ks[-1] < 441
     assert rel(emb, emb_o) < 2e-2        # free-running over 12 pruned layers
     assert rel(sd_ft, sd_ft_o) < 2e-2
+
+
+def test_itm_rerank_broadcasts_image_kv(dev):
+    """one image against k candidate captions -- the image K/V projections are computed once and
+    broadcast (zero batch stride); results must equal the repeated-image computation the reference performs."""
+    from madtp_b200.blip_retrieval import BLIP_Retrieval
+    sd = weights.retrieval_state_dict(4321, img_size=224)
+    model = BLIP_Retrieval(image_size=224, evaluate=True)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    images, ids, mask = weights.retrieval_inputs(6, 224, 35, seed=3)
+    temp = 8.0
+    with torch.no_grad():
+        feat, _ = model.encode_image(images[:1].to(dev), temp)
+        idg, mg = ids.to(dev), mask.to(dev)
+        n0 = model.text_encoder.encoder._cache  # noqa: F841  (weights prepared once)
+        a = model.itm_rerank(feat[0], idg, mg, temp)
+        b = model.itm_score(idg, mg, feat.repeat(6, 1, 1), temp)     # what the reference does (:168)
+        feat_o = feat.cpu()
+        ids2 = ids.clone()
+        ids2[:, 0] = 30523
+        mm, _ = O.med_text_encoder(ids2, mask, sd, "text_encoder.", feat_o.repeat(6, 1, 1), sd["space_dict"], temp,
+                                   "multimodal")
+        itm_o = O.linear(mm[:, 0, :], sd, "itm_head")
+    assert torch.equal(a, b), "broadcast K/V must be bit-identical to the repeated-image path"
+    assert (a.cpu() - itm_o).abs().max().item() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# edge cases of the DTP kernels through the C ABI
+# ---------------------------------------------------------------------------------------------------------------
+def test_dtp_edge_cases(lib, dev):
+    # exact ties (pad rows with identical scores): lower token index wins, as a stable descending sort does
+    B, n, d = 2, 12, 128
+    score = torch.tensor([[3., 1., 1., 1., 2., 1., 1., 0., 1., 1., 5., 1.]] * B, device=dev)
+    topk = torch.tensor([5], dtype=torch.int32, device=dev)
+    keep, dst, tail_w, tail_idx, _ = lib.dtp_select(score, topk)
+    order = torch.sort(score, dim=1, descending=True, stable=True)[1]
+    ref = torch.zeros(B, n, dtype=torch.bool, device=dev).scatter_(1, order[:, :5], True)
+    assert torch.equal(keep.bool(), ref)
+    assert keep[0].nonzero().flatten().tolist() == [0, 1, 2, 4, 10]
+    # nothing pruned: k < 1, n - k <= 1, and the CLIP guard k <= max_keep
+    x = torch.randn(B, n + 1, d, device=dev)
+    for k, mk in ((0, 0), (n - 1, 0), (n, 0), (5, 5), (5, 7)):
+        topk = torch.tensor([k], dtype=torch.int32, device=dev)
+        keep, dst, tail_w, tail_idx, _ = lib.dtp_select(score, topk, max_keep=mk)
+        assert bool(keep.all()), (k, mk)
+        assert torch.equal(dst, torch.arange(n, dtype=torch.int32, device=dev).expand(B, n))
+    # largest supported sequence (n = 1024) and an empty batch
+    g = torch.Generator().manual_seed(0)
+    big = torch.rand(1, 1024, generator=g).to(dev)
+    topk = torch.tensor([700], dtype=torch.int32, device=dev)
+    keep, *_ = lib.dtp_select(big, topk)
+    assert int(keep.sum()) == 700 and bool((big[0][keep[0].bool()].min() >= big[0][~keep[0].bool()].max()))
+    with pytest.raises(RuntimeError, match="out of range"):
+        lib.dtp_select(torch.rand(1, 1025, device=dev), topk)
+    empty = torch.empty(0, 16, device=dev)
+    keep, dst, tail_w, tail_idx, _ = lib.dtp_select(empty, topk)
+    assert keep.shape == (0, 16)

@@ -105,20 +105,27 @@ small_self_attn_kernel(SmallSelfArgs a) {
   }
 }
 
-// grid B, block 64: max over heads, column sums over the non-CLS queries, head-importance-weighted CLS row
-__global__ void __launch_bounds__(64)
+// grid B, block 256: max over heads, column sums over the non-CLS queries, head-importance-weighted CLS row.
+// Thread (i-slice s = tid / 64, column j = tid % 64): partial column sums over rows i = 1 + s, 5 + s, ... combined in
+// slice order (fixed order, deterministic).
+__global__ void __launch_bounds__(256)
 small_self_stats_kernel(SmallSelfArgs a) {
-  const int j = threadIdx.x, b = blockIdx.x, L = a.L, H = a.H;
-  if (j >= L) return;
+  __shared__ float part[4][SL];
+  const int j = threadIdx.x & 63, sl = threadIdx.x >> 6, b = blockIdx.x, L = a.L, H = a.H;
   const float* P = a.p_scratch + static_cast<long long>(b) * H * L * L;
   const float* Nr = a.n_scratch + static_cast<long long>(b) * H * L;
   float col = 0.f;
-  for (int i = 1; i < L; ++i) {          // fixed order
-    float mx = 0.f;
-    for (int h = 0; h < H; ++h) mx = fmaxf(mx, P[(h * L + i) * L + j]);
-    col += mx;
+  if (j < L) {
+    for (int i = 1 + sl; i < L; i += 4) {
+      float mx = 0.f;
+      for (int h = 0; h < H; ++h) mx = fmaxf(mx, __ldg(P + (h * L + i) * L + j));
+      col += mx;
+    }
   }
-  a.col_sum[static_cast<long long>(b) * L + j] = col;
+  part[sl][j] = col;
+  __syncthreads();
+  if (sl != 0 || j >= L) return;
+  a.col_sum[static_cast<long long>(b) * L + j] = (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
   float hs = 0.f;
   for (int h = 0; h < H; ++h) hs += Nr[h * L + j];
   hs += 1e-8f;
@@ -155,7 +162,7 @@ int launch_small_self_attn(const AttnArgs& g, float* col_sum, float* cls_attn, f
   small_self_attn_kernel<<<dim3(g.H, g.B), 128, smem, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   if (col_sum != nullptr) {
-    small_self_stats_kernel<<<g.B, 64, 0, stream>>>(a);
+    small_self_stats_kernel<<<g.B, 256, 0, stream>>>(a);
     MADTP_LAUNCH_CHECK();
   }
   return kOk;

@@ -193,7 +193,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -222,6 +222,25 @@ def algorithmic_flops(name, meta):
     return 0.0
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print there (NCCL's version banner, torchrun notices) are sent
+    to stderr for the rest of the process."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,6 +249,7 @@ def main():
     ap.add_argument("--impl", default="madtp_b200", choices=["madtp_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "madtp_b200" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference_arm(args)
@@ -380,7 +400,7 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roofline, "kernel_ms_one_step": breakdown,
                 "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -28,6 +28,7 @@ extern "C" {
 #define MADTP_GEMM_F16 0     /* fp16 operands, fp32 accumulate, tcgen05 kind::f16 */
 #define MADTP_GEMM_TF32X3 1  /* fp32 operands pre-split into tf32 hi/lo, 3 tcgen05 kind::tf32 MMAs per k-step */
 #define MADTP_GEMM_SIMT 2    /* fp32 FFMA on CUDA cores (device-side checker, tiny shapes) */
+#define MADTP_GEMM_F16X3 3   /* fp32 operands pre-split into fp16 hi/lo planes, 3 tcgen05 kind::f16 MMAs per k-step */
 
 /* GEMM epilogue activation */
 #define MADTP_ACT_NONE 0
@@ -45,8 +46,9 @@ long long madtp_launch_count(void);
  * Replaces every nn.Linear on the path: vit.py:48-49,77,92 (qkv, proj), vit.py:24-26 (fc1, fc2),
  * nlvr_encoder.py:103-109 (query/key/value), :247-263 (dense0/dense1/merge_layer), :371,385 (intermediate, output),
  * models/utils.py:170 (token . codebook^T), blip_nlvr.py:56-60 (cls_head), timm PatchEmbed conv (vit.py:241).
- * a_lo / b_lo: tf32 residual halves, only for MADTP_GEMM_TF32X3 (see madtp_split_tf32 / madtp_layernorm).
- * c_f16 != 0 writes fp16 output. bias, residual may be NULL. MADTP_GEMM_F16 reads fp16 a, b; the others fp32.
+ * a_lo / b_lo: residual planes, only for MADTP_GEMM_TF32X3 (fp32 planes, madtp_split_tf32) and MADTP_GEMM_F16X3 (fp16
+ * planes, madtp_split_f16 / madtp_layernorm; fold the weight's power-of-two scale into alpha).
+ * c_f16 != 0 writes fp16 output. bias, residual may be NULL. MADTP_GEMM_F16 / _F16X3 read fp16 a, b; the others fp32.
  */
 int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, const void* b, const void* b_lo,
                int64_t ldb, void* c, int64_t ldc, int c_f16, const float* bias, const float* residual, int64_t ldr,
@@ -55,23 +57,27 @@ int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, cons
 /*
  * Row LayerNorm with fused GEMM-operand preparation. Replaces nn.LayerNorm at vit.py:111,115,239 (eps 1e-6) and
  * nlvr_encoder.py:54,243,381 / med.py:54,242,324 (eps 1e-12).
- * Outputs are optional (NULL to skip), each [rows, d] contiguous: y_f32; y_hi/y_lo (tf32 split of y); y_f16;
- * x_hi/x_lo (tf32 split of the un-normalised input row, operand of the Query_model product).
+ * Outputs are optional (NULL to skip), each [rows, d] contiguous: y_f32; y_hi/y_lo (fp16 hi/lo split of y: hi = fp16(y),
+ * lo = fp16(y - hi), the operand planes of MADTP_GEMM_F16X3); y_f16; x_hi/x_lo (the same split of the un-normalised
+ * input row, operand of the Query_model product).
  * gamma == beta == NULL: only x_hi/x_lo are produced. d must be a multiple of 128, <= 1024.
  */
 int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
-                    float* y_f32, float* y_hi, float* y_lo, void* y_f16, float* x_hi, float* x_lo, void* stream);
+                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, void* stream);
 
 /* hi = round_to_tf32(x), lo = x - hi (exact). Used once per weight at load time. */
 int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* fp16 split for MADTP_GEMM_F16X3: hi = fp16(scale*x), lo = fp16(scale*x - hi); scale is a power of two (weights are
+ * scaled up at load time so that lo stays a normal fp16 number; the GEMM's alpha takes the scale out again). */
+int madtp_split_f16(const float* x, void* hi_f16, void* lo_f16, int64_t n, float scale, void* stream);
 /* y = (fp16) x */
 int madtp_cast_f16(const float* x, void* y_f16, int64_t n, void* stream);
 
 /*
  * ViT stem (timm PatchEmbed = Conv2d(C, D, P, stride P), vit.py:241-242,284): non-overlapping patches of
- * img[B,C,H,W] as GEMM rows [B*(H/P)*(W/P), C*P*P] in Conv2d weight order, written as tf32 hi/lo.
+ * img[B,C,H,W] as GEMM rows [B*(H/P)*(W/P), C*P*P] in Conv2d weight order, written as fp16 hi/lo planes.
  */
-int madtp_patchify(const float* img, float* rows_hi, float* rows_lo, int B, int C, int H, int W, int P, void* stream);
+int madtp_patchify(const float* img, void* rows_hi, void* rows_lo, int B, int C, int H, int W, int P, void* stream);
 /* x[b,0,:] = cls + pos[0]; x[b,1+p,:] = patches[b,p,:] + pos[1+p]   (vit.py:286-289) */
 int madtp_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
                           void* stream);
@@ -171,9 +177,9 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
  * madtp_attn_tc_stats: col_part[b, it, j] = sum_{i in 128-query tile it, i >= 1} max_h P[b,h,i,j]  (n_parts =
  * ceil(N/128)) and cls_attn[b, j] as in madtp_attn_stats. Head dim 64.
  */
-int madtp_gemm_qkv(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo, int64_t ldb,
-                   const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo, int64_t ld_qk,
-                   float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream);
+int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
+                   const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+                   int64_t ld_qk, float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream);
 int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, const float* vt_hi, const float* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream);

@@ -17,7 +17,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
 _lib = None
 
-GEMM_F16, GEMM_TF32X3, GEMM_SIMT = 0, 1, 2
+GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
@@ -31,6 +31,7 @@ SIGNATURES = {
                    _i32, _vp],
     "madtp_layernorm": [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
+    "madtp_split_f16": [_vp, _vp, _vp, _i64, C.c_float, _vp],
     "madtp_cast_f16": [_vp, _vp, _i64, _vp],
     "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "madtp_assemble_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
@@ -48,7 +49,8 @@ SIGNATURES = {
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
-    "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
+    "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
+                       _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
     "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
 }
@@ -102,7 +104,7 @@ class LaunchTimer:
 
 _timer = None
 # positions of the shape arguments recorded with each timed launch
-_META_ARGS = {"madtp_gemm": (0, 15, 16, 17), "madtp_gemm_qkv": (7, 8, 10), "madtp_attn_tc_fwd": (6, 7, 8),
+_META_ARGS = {"madtp_gemm": (0, 15, 16, 17), "madtp_gemm_qkv": (8, 9, 11), "madtp_attn_tc_fwd": (6, 7, 8),
               "madtp_attn_tc_stats": (3, 4, 5), "madtp_attn_fwd": (9, 10, 11, 12), "madtp_attn_stats": (6, 7, 8),
               "madtp_layernorm": (2, 3), "madtp_dtp_gather": (0, 1, 2), "madtp_dtp_score": (0, 1, 2),
               "madtp_dtp_select": (0, 1)}
@@ -119,7 +121,7 @@ def _call(name, *args):
     t = _timer
     if t is None:
         return fn(*args)
-    key = name if name != "madtp_gemm" else "madtp_gemm:" + ("f16", "tf32x3", "simt")[args[0]]
+    key = name if name != "madtp_gemm" else "madtp_gemm:" + ("f16", "tf32x3", "simt", "f16x3")[args[0]]
     if t.only is not None and key not in t.only:
         return fn(*args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -173,7 +175,8 @@ def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None
     N = b.shape[0]
     if b.shape[1] != K or out.shape[0] != M or out.shape[1] != N:
         raise RuntimeError(f"madtp_b200.gemm: shape mismatch a{tuple(a.shape)} b{tuple(b.shape)} out{tuple(out.shape)}")
-    op_dtype = torch.float16 if precision == GEMM_F16 else torch.float32
+    op_dtype = torch.float16 if precision in (GEMM_F16, GEMM_F16X3) else torch.float32
+    lo_dtype = torch.float16 if precision == GEMM_F16X3 else torch.float32
     if out.dtype not in (torch.float32, torch.float16):
         raise RuntimeError("madtp_b200.gemm: out must be fp32 or fp16")
     ldr = 0
@@ -185,8 +188,8 @@ def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None
         raise RuntimeError("madtp_b200.gemm: a_lo layout must match a")
     if b_lo is not None and (b_lo.shape != b.shape or b_lo.stride(0) != ldb):
         raise RuntimeError("madtp_b200.gemm: b_lo layout must match b")
-    st = _call("madtp_gemm", precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, torch.float32, "a_lo"), lda,
-                           _ptr(b, op_dtype, "b"), _ptr(b_lo, torch.float32, "b_lo"), ldb, _ptr(out, None, "out"),
+    st = _call("madtp_gemm", precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, lo_dtype, "a_lo"), lda,
+                           _ptr(b, op_dtype, "b"), _ptr(b_lo, lo_dtype, "b_lo"), ldb, _ptr(out, None, "out"),
                            ldc, 1 if out.dtype == torch.float16 else 0, _ptr(bias, torch.float32, "bias"),
                            _ptr(residual, torch.float32, "residual"), ldr, act, float(alpha), M, N, K, _stream())
     _check(st, "madtp_gemm")
@@ -197,8 +200,8 @@ def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=No
     """x: [rows, d] fp32 (row stride free). Every output is optional and contiguous [rows, d]."""
     ldx = _rowmajor(x, "x")
     rows, d = x.shape
-    for nm, t, dt in (("y_f32", y_f32, torch.float32), ("y_hi", y_hi, torch.float32), ("y_lo", y_lo, torch.float32),
-                      ("y_f16", y_f16, torch.float16), ("x_hi", x_hi, torch.float32), ("x_lo", x_lo, torch.float32)):
+    for nm, t, dt in (("y_f32", y_f32, torch.float32), ("y_hi", y_hi, torch.float16), ("y_lo", y_lo, torch.float16),
+                      ("y_f16", y_f16, torch.float16), ("x_hi", x_hi, torch.float16), ("x_lo", x_lo, torch.float16)):
         if t is not None and (t.dtype != dt or not t.is_contiguous() or t.numel() != rows * d):
             raise RuntimeError(f"madtp_b200.layernorm: bad output {nm}")
     st = _call("madtp_layernorm", _ptr(x, torch.float32, "x"), ldx, rows, d, _ptr(gamma, torch.float32, "gamma"),
@@ -215,6 +218,16 @@ def split_tf32(x):
     return hi, lo
 
 
+def split_f16(x, scale=1.0):
+    """fp16 hi/lo planes of scale * x (scale: a power of two)."""
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    _check(_call("madtp_split_f16", _ptr(x, torch.float32, "x"), _ptr(hi), _ptr(lo), x.numel(), float(scale), _stream()),
+           "madtp_split_f16")
+    return hi, lo
+
+
 def cast_f16(x):
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=torch.float16, device=x.device)
@@ -226,7 +239,7 @@ def patchify(img, P):
     B, Cc, H, W = img.shape
     img = img.contiguous()
     rows = B * (H // P) * (W // P)
-    hi = torch.empty(rows, Cc * P * P, dtype=torch.float32, device=img.device)
+    hi = torch.empty(rows, Cc * P * P, dtype=torch.float16, device=img.device)
     lo = torch.empty_like(hi)
     _check(_call("madtp_patchify", _ptr(img, torch.float32, "img"), _ptr(hi), _ptr(lo), B, Cc, H, W, P, _stream()),
            "madtp_patchify")
@@ -375,7 +388,7 @@ def gather_rows(x, idx):
 
 
 
-def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads):
+def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
     """Fused q|k|v projection for the tensor-core attention: returns (qk_hi, qk_lo [M, 2*heads*64], vt_hi, vt_lo
     [B*heads*64, n_pad]) -- see madtp_gemm_qkv in include/madtp_b200.h."""
     M, K = a_hi.shape
@@ -386,9 +399,9 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads):
     qk_lo = torch.empty_like(qk_hi)
     vt_hi = torch.empty(B * heads * 64, n_pad, dtype=torch.float32, device=dev)
     vt_lo = torch.empty_like(vt_hi)
-    st = _call("madtp_gemm_qkv", _ptr(a_hi, torch.float32, "a_hi"), _ptr(a_lo, torch.float32, "a_lo"),
-               _rowmajor(a_hi, "a_hi"), _ptr(w_hi, torch.float32, "w_hi"), _ptr(w_lo, torch.float32, "w_lo"),
-               _rowmajor(w_hi, "w_hi"), _ptr(bias, torch.float32, "bias"), M, K, n_tok, heads, _ptr(qk_hi),
+    st = _call("madtp_gemm_qkv", _ptr(a_hi, torch.float16, "a_hi"), _ptr(a_lo, torch.float16, "a_lo"),
+               _rowmajor(a_hi, "a_hi"), _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"),
+               _rowmajor(w_hi, "w_hi"), _ptr(bias, torch.float32, "bias"), float(alpha), M, K, n_tok, heads, _ptr(qk_hi),
                _ptr(qk_lo), qk_hi.stride(0), _ptr(vt_hi), _ptr(vt_lo), n_pad, _stream())
     _check(st, "madtp_gemm_qkv")
     return qk_hi, qk_lo, vt_hi, vt_lo

@@ -68,7 +68,7 @@ int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, cons
 }
 
 int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
-                    float* y_f32, float* y_hi, float* y_lo, void* y_f16, float* x_hi, float* x_lo, void* stream) {
+                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, void* stream) {
   LayerNormArgs a;
   a.x = x;
   a.ldx = ldx;
@@ -78,22 +78,25 @@ int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* g
   a.beta = beta;
   a.eps = eps;
   a.y_f32 = y_f32;
-  a.y_hi = y_hi;
-  a.y_lo = y_lo;
+  a.y_hi = static_cast<__half*>(y_hi);
+  a.y_lo = static_cast<__half*>(y_lo);
   a.y_f16 = static_cast<__half*>(y_f16);
-  a.x_hi = x_hi;
-  a.x_lo = x_lo;
+  a.x_hi = static_cast<__half*>(x_hi);
+  a.x_lo = static_cast<__half*>(x_lo);
   return counted(launch_layernorm(a, as_stream(stream)), rows > 0 ? 1 : 0);
 }
 
 int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   return counted(launch_split_tf32(x, hi, lo, n, as_stream(stream)), n > 0 ? 1 : 0);
 }
+int madtp_split_f16(const float* x, void* hi_f16, void* lo_f16, int64_t n, float scale, void* stream) {
+  return counted(launch_split_f16(x, hi_f16, lo_f16, n, scale, as_stream(stream)), n > 0 ? 1 : 0);
+}
 int madtp_cast_f16(const float* x, void* y_f16, int64_t n, void* stream) {
   return counted(launch_cast_f16(x, y_f16, n, as_stream(stream)), n > 0 ? 1 : 0);
 }
 
-int madtp_patchify(const float* img, float* rows_hi, float* rows_lo, int B, int C, int H, int W, int P, void* stream) {
+int madtp_patchify(const float* img, void* rows_hi, void* rows_lo, int B, int C, int H, int W, int P, void* stream) {
   return counted(launch_patchify(img, rows_hi, rows_lo, B, C, H, W, P, as_stream(stream)), B > 0 ? 1 : 0);
 }
 int madtp_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
@@ -218,10 +221,10 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
   return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
-int madtp_gemm_qkv(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo, int64_t ldb,
-                   const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo, int64_t ld_qk,
-                   float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream) {
-  return counted(launch_gemm_qkv(a_hi, a_lo, lda, w_hi, w_lo, ldb, bias, M, K, n_tok, heads, qk_hi, qk_lo, ld_qk, vt_hi,
+int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
+                   const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+                   int64_t ld_qk, float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream) {
+  return counted(launch_gemm_qkv(a_hi, a_lo, lda, w_hi, w_lo, ldb, bias, alpha, M, K, n_tok, heads, qk_hi, qk_lo, ld_qk, vt_hi,
                                  vt_lo, ld_vt, as_stream(stream)),
                  M > 0 ? 1 : 0);
 }

@@ -444,6 +444,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 //   warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: drain + epilogue (warp%4 = TMEM lane quadrant,
 //   (warp-2)/4 = column half of the tile).
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
+__device__ __forceinline__ void umma_x(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  if (F16) umma_f16(d_tmem, a, b, idesc, accumulate);
+  else umma_tf32(d_tmem, a, b, idesc, accumulate);
+}
+
 template <int BLOCK_N>
 struct Tf32Cfg {
   static constexpr int BLOCK_M = 128;
@@ -462,7 +468,9 @@ struct Tf32Cfg {
 // CL = 1: independent CTAs. CL = 2: clusters of two CTAs that work on vertically adjacent output tiles (same n-tile)
 // and share the B operand: each CTA fetches half of the B tile and TMA-multicasts it to both, which halves the L2 ->
 // shared-memory traffic of the (weight) operand -- the K = 768 projections are L2-bandwidth bound otherwise.
-template <int BLOCK_N, int CL>
+// F16 = true: the same pipeline with fp16 hi/lo planes (kind::f16): a 128-byte operand row then holds 64 k-elements
+// instead of 32 and every MMA covers 16 of them, so a k-block costs the same bytes and MMA slots but twice the K.
+template <int BLOCK_N, int CL, bool F16 = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -485,7 +493,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;   // work items per cluster: CL vertically adjacent tiles
-  const int num_kb = (K + Cfg::K_ELEMS - 1) / Cfg::K_ELEMS;
+  constexpr int K_ELEMS = F16 ? 64 : Cfg::K_ELEMS;
+  const int num_kb = (K + K_ELEMS - 1) / K_ELEMS;
   const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
@@ -526,7 +535,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);   // CL > 1: BOTH CTAs have retired their MMAs on this stage
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
-          const int k0 = kb * Cfg::K_ELEMS;
+          const int k0 = kb * K_ELEMS;
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
@@ -552,7 +561,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else if (warp == 1) {
     {
-      constexpr uint32_t idesc = make_idesc(2u, Cfg::BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, Cfg::BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
@@ -572,11 +581,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           // accumulates truncate at the full partial-sum magnitude
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
             if (CL == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_multicast(&empty_bar[stage], (1u << CL) - 1);   // frees the stage in both CTAs
             umma_commit(&tmem_full[buf]);
@@ -641,7 +650,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                   (static_cast<long long>(b * ep.heads + (vc >> 6)) * 64 + (vc & 63)) * ep.ld_vt + i;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float o = sum[c * 32 + j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
+                const float o = fmaf(ep.alpha, sum[c * 32 + j], ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
                 const float h = tf32_hi(o);
                 ep.vt_hi[off + j * ep.ld_vt] = h;
                 ep.vt_lo[off + j * ep.ld_vt] = o - h;
@@ -800,19 +809,19 @@ static int launch_tc(const void* a, const void* a_lo, long long lda, const void*
 }
 
 
-template <int BLOCK_N, int CL>
+template <int BLOCK_N, int CL, bool F16 = false>
 static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
                           long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
   using Cfg = Tf32Cfg<BLOCK_N>;
   CUtensorMap ta, tal, tb, tbl;
   int st;
-  if ((st = make_tmap(&ta, a, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
-  if ((st = make_tmap(&tb, b, true, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
-  if ((st = make_tmap(&tal, a_lo, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
-  if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
+  if ((st = make_tmap(&ta, a, !F16, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+  if ((st = make_tmap(&tb, b, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
+  if ((st = make_tmap(&tal, a_lo, !F16, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
+  if ((st = make_tmap(&tbl, b_lo, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   static bool attr_done = false;
   if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_done = true;
   }
@@ -832,16 +841,17 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL>, ta, tal, tb, tbl, ep, M, N, K));
+  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL, F16>, ta, tal, tb, tbl, ep, M, N, K));
   return kOk;
 }
 
 // Clusters of two with a TMA-multicast B operand are implemented and verified but OFF by default: measured on B200
 // (M=36928, N=2304, K=768) 585 us with clusters vs 560 us without -- this kernel is bound by its two-deep operand
 // pipeline (TMA latency), not by L2 bandwidth, and pairing CTAs adds lock-step stalls. MADTP_CLUSTER=1 enables it.
-template <int BLOCK_N>
+template <int BLOCK_N, bool F16 = false>
 static int launch_tf32(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
                        const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
+  if (F16) return launch_tf32_cl<BLOCK_N, 1, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
   const int m_tiles = (M + 127) / 128;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   static const bool use_cluster = getenv("MADTP_CLUSTER") != nullptr;
@@ -850,8 +860,9 @@ static int launch_tf32(const void* a, const void* a_lo, long long lda, const voi
   return launch_tf32_cl<BLOCK_N, 1>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
 }
 
-int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
-                    long long ldb, const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi,
+                    float* qk_lo,
                     long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream) {
   MADTP_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && qk_hi && qk_lo && vt_hi && vt_lo, "gemm_qkv: null pointer");
   MADTP_CHECK_ARG(M >= 0 && K > 0 && n_tok > 0 && heads > 0 && M % n_tok == 0, "gemm_qkv: bad shape M=%d n_tok=%d", M,
@@ -866,7 +877,7 @@ int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const f
   ep.c_lo = qk_lo;
   ep.ldc = ld_qk;
   ep.bias = bias;
-  ep.alpha = 1.0f;
+  ep.alpha = alpha;
   ep.mode = 1;
   ep.vt_hi = vt_hi;
   ep.vt_lo = vt_lo;
@@ -874,7 +885,7 @@ int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const f
   ep.n_tok = n_tok;
   ep.heads = heads;
   ep.qk_cols = 2 * heads * 64;
-  return launch_tf32<256>(a_hi, a_lo, lda, w_hi, w_lo, ldb, ep, M, 3 * heads * 64, K, stream);
+  return launch_tf32<256, true>(a_hi, a_lo, lda, w_hi, w_lo, ldb, ep, M, 3 * heads * 64, K, stream);
 }
 
 // Pick the N tile that wastes the fewest SM-waves (persistent grid of num_sms CTAs).
@@ -906,6 +917,11 @@ int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, c
     MADTP_CHECK_ARG(a_lo && b_lo, "TF32x3 GEMM needs the lo halves of both operands");
     return bn == 256 ? launch_tf32<256>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream)
                      : launch_tf32<128>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+  }
+  if (precision == kGemmF16x3) {
+    MADTP_CHECK_ARG(a_lo && b_lo, "F16x3 GEMM needs the lo halves of both operands");
+    return bn == 256 ? launch_tf32<256, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream)
+                     : launch_tf32<128, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
   }
   if (precision == kGemmF16) {
     return bn == 256 ? launch_tc<256, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream)

@@ -32,6 +32,7 @@ enum GemmPrecision : int {
   kGemmF16 = 0,      // fp16 operands, fp32 accumulate (kind::f16), one MMA per k-step
   kGemmTF32x3 = 1,   // fp32 operands pre-split into tf32 hi/lo; hi*hi + hi*lo + lo*hi (kind::tf32)
   kGemmSimtF32 = 2,  // CUDA-core fp32 FFMA (device-side checker and tiny shapes)
+  kGemmF16x3 = 3,    // fp32 operands pre-split into fp16 hi/lo planes (madtp_split_f16); same three products, kind::f16
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -55,8 +56,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld, int box_rows);
 
 // Fused q|k|v projection (TF32x3) with the split / transposed epilogue described at GemmEpilogue::mode.
-int launch_gemm_qkv(const float* a_hi, const float* a_lo, long long lda, const float* w_hi, const float* w_lo,
-                    long long ldb, const float* bias, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
+int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi,
+                    float* qk_lo,
                     long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream);
 
 int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,

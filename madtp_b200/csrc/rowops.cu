@@ -1,5 +1,5 @@
-// Row-wise HBM-bound kernels around the GEMMs: LayerNorm with fused operand preparation (tf32 hi/lo split, fp16
-// copy), the tf32 split itself, patch extraction for the ViT stem, token assembly and the BERT embedding lookup.
+// Row-wise HBM-bound kernels around the GEMMs: LayerNorm with fused operand preparation (fp16 hi/lo split, fp16
+// copy), the splits themselves, patch extraction for the ViT stem, token assembly and the BERT embedding lookup.
 // One warp owns one row; rows are d <= 1024 floats held in registers, accessed with 128-bit loads/stores.
 #include "rowops.cuh"
 
@@ -8,6 +8,20 @@ namespace madtp {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (two-pass in registers: mean, then centred variance) + optional operand preparation.
 // ------------------------------------------------------------------------------------------------
+// fp16 hi/lo split of four consecutive values: hi = fp16(v), lo = fp16(v - hi); 8-byte stores.
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, long long idx4, const float4& v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<const uint32_t*>(&h0);
+  ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+  pl.x = *reinterpret_cast<const uint32_t*>(&l0);
+  pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+  reinterpret_cast<uint2*>(hi)[idx4] = ph;
+  reinterpret_cast<uint2*>(lo)[idx4] = pl;
+}
+
 template <int V>  // V float4 per lane: d == 128 * V
 __global__ void __launch_bounds__(256)
 layernorm_kernel(LayerNormArgs a) {
@@ -20,15 +34,9 @@ layernorm_kernel(LayerNormArgs a) {
 #pragma unroll
   for (int i = 0; i < V; ++i) v[i] = xin[lane + 32 * i];
 
-  if (a.x_hi) {  // tf32 split of the *input* row (operand of the token/codebook product)
-    float4* hi = reinterpret_cast<float4*>(a.x_hi + row * a.d);
-    float4* lo = reinterpret_cast<float4*>(a.x_lo + row * a.d);
+  if (a.x_hi) {  // hi/lo split of the *input* row (operand of the token/codebook product)
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-      hi[lane + 32 * i] = h;
-      lo[lane + 32 * i] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-    }
+    for (int i = 0; i < V; ++i) store_split4(a.x_hi + row * a.d, a.x_lo + row * a.d, lane + 32 * i, v[i]);
   }
   if (a.gamma == nullptr) return;  // split-only call
 
@@ -57,11 +65,7 @@ layernorm_kernel(LayerNormArgs a) {
     y.w = (v[i].w - mean) * rstd * g.w + b.w;
     const int c = lane + 32 * i;
     if (a.y_f32) reinterpret_cast<float4*>(a.y_f32 + row * a.d)[c] = y;
-    if (a.y_hi) {
-      float4 h = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
-      reinterpret_cast<float4*>(a.y_hi + row * a.d)[c] = h;
-      reinterpret_cast<float4*>(a.y_lo + row * a.d)[c] = make_float4(y.x - h.x, y.y - h.y, y.z - h.z, y.w - h.w);
-    }
+    if (a.y_hi) store_split4(a.y_hi + row * a.d, a.y_lo + row * a.d, c, y);
     if (a.y_f16) {
       __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
       uint2 pk;
@@ -108,6 +112,19 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     lo[i] = v - h;
   }
 }
+// fp16 hi/lo split of scale * x: hi = fp16(scale*x), lo = fp16(scale*x - hi). scale is a power of two chosen by the
+// caller so that hi stays finite and lo stays a normal fp16 number for all but negligible elements.
+__global__ void split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 long long n, float scale) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = x[i] * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
 __global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
   long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -123,6 +140,16 @@ int launch_split_tf32(const float* x, float* hi, float* lo, long long n, cudaStr
   MADTP_LAUNCH_CHECK();
   return kOk;
 }
+int launch_split_f16(const float* x, void* hi, void* lo, long long n, float scale, cudaStream_t stream) {
+  MADTP_CHECK_ARG(x && hi && lo && n >= 0 && scale > 0.f, "split_f16: bad arguments");
+  if (n == 0) return kOk;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  split_f16_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(x, static_cast<__half*>(hi), static_cast<__half*>(lo),
+                                                                 n, scale);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
 int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t stream) {
   MADTP_CHECK_ARG(x && y && n >= 0, "cast_f16: bad arguments");
   if (n == 0) return kOk;
@@ -135,10 +162,10 @@ int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------
 // ViT stem: non-overlapping PxP patches of [B,C,H,W] -> rows [B*gh*gw, C*P*P] (Conv2d weight order c,py,px),
-// written as tf32 hi/lo so the projection runs on the error-compensated tensor-core path.
+// written as fp16 hi/lo planes so the projection runs on the error-compensated tensor-core path.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ img, float* __restrict__ hi, float* __restrict__ lo, int B, int C, int H,
+patchify_kernel(const float* __restrict__ img, __half* __restrict__ hi, __half* __restrict__ lo, int B, int C, int H,
                 int W, int P) {
   const int gh = H / P, gw = W / P;
   const int kdim = C * P * P;
@@ -153,20 +180,19 @@ patchify_kernel(const float* __restrict__ img, float* __restrict__ hi, float* __
     const int b = static_cast<int>(prow / (static_cast<long long>(gw) * gh));
     const float4 v = *reinterpret_cast<const float4*>(
         img + ((static_cast<long long>(b) * C + c) * H + (gy * P + py)) * W + gx * P + px);
-    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    reinterpret_cast<float4*>(hi)[i] = h;
-    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    store_split4(hi, lo, i, v);
   }
 }
 
-int launch_patchify(const float* img, float* hi, float* lo, int B, int C, int H, int W, int P, cudaStream_t stream) {
+int launch_patchify(const float* img, void* hi, void* lo, int B, int C, int H, int W, int P, cudaStream_t stream) {
   MADTP_CHECK_ARG(img && hi && lo, "patchify: null pointer");
   MADTP_CHECK_ARG(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "patchify: H,W must be multiples of P, P of 4");
   const long long total4 = static_cast<long long>(B) * (H / P) * (W / P) * C * P * P / 4;
   if (total4 == 0) return kOk;
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  patchify_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(img, hi, lo, B, C, H, W, P);
+  patchify_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(img, static_cast<__half*>(hi), static_cast<__half*>(lo), B, C,
+                                                                H, W, P);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

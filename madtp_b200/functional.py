@@ -30,17 +30,29 @@ def require_cuda(t: Tensor, name: str):
 # ------------------------------------------------------------------------------------------------------------------
 # prepared weights
 # ------------------------------------------------------------------------------------------------------------------
+def pow2_scale(w: Tensor, target: float = 16384.0) -> float:
+    """Power of two s with max|s * w| <= target: puts a weight's magnitude where both fp16 planes of its hi/lo split
+    are normal numbers. One host sync, at weight-preparation time only."""
+    m = float(w.detach().abs().max()) if w.numel() else 0.0
+    if not (m > 0.0) or not math.isfinite(m):
+        return 1.0
+    return 2.0 ** max(-24, min(24, math.floor(math.log2(target / m))))
+
+
 class PreparedLinear:
-    """GEMM-ready copies of an nn.Linear: tf32 hi/lo split (scoring lane) and/or fp16 (value lane)."""
-    __slots__ = ("hi", "lo", "w16", "w32", "bias", "out_features", "in_features")
+    """GEMM-ready copies of an nn.Linear: fp16 hi/lo split of scale * W (scoring lane; `tf32=True` for historical
+    reasons selects this error-compensated lane) and/or plain fp16 (value lane)."""
+    __slots__ = ("hi", "lo", "scale", "w16", "w32", "bias", "out_features", "in_features")
 
     def __init__(self, weight: Tensor, bias: Optional[Tensor], tf32: bool = False, f16: bool = False,
                  f32: bool = False, bias_scale: float = 1.0):
         w = weight.detach().to(torch.float32).contiguous()
         self.out_features, self.in_features = w.shape
         self.hi = self.lo = self.w16 = self.w32 = None
+        self.scale = 1.0
         if tf32:
-            self.hi, self.lo = L.split_tf32(w)
+            self.scale = pow2_scale(w)
+            self.hi, self.lo = L.split_f16(w, self.scale)
         if f16:
             self.w16 = L.cast_f16(w)
         if f32:
@@ -87,18 +99,18 @@ def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor],
     if f32:
         out["y"] = new()
     if tf32:
-        out["y_hi"], out["y_lo"] = new(), new()
+        out["y_hi"], out["y_lo"] = new(torch.float16), new(torch.float16)
     if f16:
         out["y16"] = new(torch.float16)
     if split_x:
-        out["x_hi"], out["x_lo"] = new(), new()
+        out["x_hi"], out["x_lo"] = new(torch.float16), new(torch.float16)
     L.layernorm(x2d, gamma, beta, eps, y_f32=out.get("y"), y_hi=out.get("y_hi"), y_lo=out.get("y_lo"),
                 y_f16=out.get("y16"), x_hi=out.get("x_hi"), x_lo=out.get("x_lo"))
     return out
 
 
 def split_rows(x2d: Tensor) -> Tuple[Tensor, Tensor]:
-    """tf32 hi/lo split of fp32 rows (the operand format of the TF32x3 GEMM)."""
+    """fp16 hi/lo split of fp32 rows (the operand format of the F16x3 GEMM)."""
     o = layernorm_rows(x2d, None, None, 0.0, split_x=True)
     return o["x_hi"], o["x_lo"]
 
@@ -107,8 +119,8 @@ def linear_tf32(a_hi: Tensor, a_lo: Tensor, lin: PreparedLinear, out: Optional[T
                 act=L.ACT_NONE, alpha=1.0) -> Tensor:
     if out is None:
         out = torch.empty(a_hi.shape[0], lin.out_features, dtype=torch.float32, device=a_hi.device)
-    return L.gemm(L.GEMM_TF32X3, a_hi, lin.hi, out, a_lo=a_lo, b_lo=lin.lo, bias=lin.bias, residual=residual, act=act,
-                  alpha=alpha)
+    return L.gemm(L.GEMM_F16X3, a_hi, lin.hi, out, a_lo=a_lo, b_lo=lin.lo, bias=lin.bias, residual=residual, act=act,
+                  alpha=alpha / lin.scale)
 
 
 def linear_f16(a16: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, out_dtype=torch.float32,
@@ -128,14 +140,16 @@ def linear_f32(a: Tensor, lin: PreparedLinear, *, act=L.ACT_NONE) -> Tensor:
 # Query_model  (reference models/utils.py:147-183)
 # ------------------------------------------------------------------------------------------------------------------
 def prepare_codebook(space_dict: Tensor):
-    """space_dict [T, sd_dim] -> tf32 hi/lo, rows padded to TA_LD so token_att rows are 16-byte aligned."""
+    """space_dict [T, sd_dim] -> (fp16 hi, lo planes of scale * book, T, scale), rows padded to TA_LD so token_att rows
+    are 16-byte aligned."""
     T, d = space_dict.shape
     if T > TA_LD:
         raise RuntimeError(f"madtp_b200: codebook size {T} exceeds the supported {TA_LD}")
     pad = torch.zeros(TA_LD, d, dtype=torch.float32, device=space_dict.device)
     pad[:T] = space_dict.detach()
-    hi, lo = L.split_tf32(pad)
-    return hi, lo, T
+    scale = pow2_scale(pad)
+    hi, lo = L.split_f16(pad, scale)
+    return hi, lo, T, scale
 
 
 def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int, sd_ft: Optional[Tensor],
@@ -143,9 +157,9 @@ def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int,
     """token_att for EVERY row of x3d [B,N,d] (one GEMM over the flat rows), then the over-token softmax
     aggregation over tokens first_token..N-1.  Returns (token_att view [B, N-first_token, T], sd_ft [B,T,d])."""
     B, N, d = x3d.shape
-    hi, lo, T = book
+    hi, lo, T, scale = book
     ta = torch.empty(B * N, TA_LD, dtype=torch.float32, device=x3d.device)
-    L.gemm(L.GEMM_TF32X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo)
+    L.gemm(L.GEMM_F16X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo, alpha=1.0 / scale)
     return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token)
 
 
@@ -214,7 +228,7 @@ def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N
     fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
     Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
     dev = y_hi.device
-    qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H)
+    qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H, alpha=1.0 / qkv.scale)
     ctx16 = torch.empty(B, N, H * 64, dtype=torch.float16, device=dev)
     rows = torch.empty(2, B, H, N, dtype=torch.float32, device=dev)
     L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1])

@@ -65,6 +65,30 @@ def test_gemm_tf32x3(lib, dev, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("w_std", [1.0, 0.02])
+def test_gemm_f16x3(lib, dev, M, N, K, w_std):
+    """The product path's scoring-lane GEMM: fp16 hi/lo planes, weights scaled by a power of two, alpha removes it."""
+    if K % 8:
+        pytest.skip("row pitch must be a multiple of 16 bytes")
+    from madtp_b200.functional import pow2_scale
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + 2)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = (torch.randn(N, K, generator=g) * w_std).to(dev)
+    bias = (torch.randn(N, generator=g) * w_std).to(dev)
+    s = pow2_scale(b)
+    a_hi, a_lo = lib.split_f16(a)
+    b_hi, b_lo = lib.split_f16(b, s)
+    assert torch.equal(a_hi, a.half())
+    assert bool(((b_hi.double() + b_lo.double()) / s - b.double()).abs().max() <= b.abs().max().double() * 2.0 ** -22)
+    out = torch.full((M, N), float("nan"), device=dev)
+    lib.gemm(lib.GEMM_F16X3, a_hi, b_hi, out, a_lo=a_lo, b_lo=b_lo, bias=bias, alpha=1.0 / s)
+    ref = a.double() @ b.double().T + bias.double()
+    err = _rel(out, ref)
+    print(f"f16x3 M={M} N={N} K={K} w_std={w_std}: rel err {err:.3e}")
+    assert err < 6e-7, f"F16x3 relative error {err:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_f16(lib, dev, M, N, K):
     if K % 8:
         pytest.skip("row pitch must be a multiple of 16 bytes")
@@ -115,13 +139,18 @@ def test_layernorm(lib, dev, rows, d, eps):
     x = (torch.randn(rows, d, generator=g) * 3 + 0.5).to(dev)
     gamma = torch.randn(d, generator=g).to(dev)
     beta = torch.randn(d, generator=g).to(dev)
-    outs = {k: torch.empty(rows, d, device=dev) for k in ("y_f32", "y_hi", "y_lo", "x_hi", "x_lo")}
+    outs = {k: torch.empty(rows, d, device=dev, dtype=torch.float32 if k == "y_f32" else torch.float16)
+            for k in ("y_f32", "y_hi", "y_lo", "x_hi", "x_lo")}
     y16 = torch.empty(rows, d, device=dev, dtype=torch.float16)
     lib.layernorm(x, gamma, beta, eps, y_f16=y16, **outs)
     ref = torch.nn.functional.layer_norm(x.double(), (d,), gamma.double(), beta.double(), eps)
     assert (outs["y_f32"].double() - ref).abs().max().item() < 5e-6
-    assert torch.equal(outs["y_hi"] + outs["y_lo"], outs["y_f32"])
-    assert torch.equal(outs["x_hi"] + outs["x_lo"], x)
+    # fp16 hi/lo planes: hi = fp16(v), lo = fp16(v - hi) => |hi + lo - v| <= 2^-23 |v| (+ half a subnormal step)
+    for planes, v in ((("y_hi", "y_lo"), outs["y_f32"]), (("x_hi", "x_lo"), x)):
+        hi, lo = outs[planes[0]], outs[planes[1]]
+        assert torch.equal(hi, v.half())
+        err = (hi.double() + lo.double() - v.double()).abs()
+        assert bool((err <= v.double().abs() * 2.0 ** -22 + 2.0 ** -25).all())
     assert torch.equal(y16, outs["y_f32"].half())
 
 
@@ -132,11 +161,12 @@ def test_patchify_matches_conv(lib, dev):
     w = (torch.randn(D, C, P, P, generator=g) * 0.02).to(dev)
     bias = torch.randn(D, generator=g).to(dev)
     hi, lo = lib.patchify(img, P)
-    assert torch.equal((hi + lo).view(B, H // P, W // P, C, P, P),
-                       img.view(B, C, H // P, P, W // P, P).permute(0, 2, 4, 1, 3, 5))
-    w_hi, w_lo = lib.split_tf32(w.view(D, -1))
+    want = img.view(B, C, H // P, P, W // P, P).permute(0, 2, 4, 1, 3, 5).double()
+    got = (hi.double() + lo.double()).view(B, H // P, W // P, C, P, P)
+    assert bool(((got - want).abs() <= want.abs() * 2.0 ** -22 + 2.0 ** -25).all())
+    w_hi, w_lo = lib.split_f16(w.view(D, -1), 2.0 ** 16)
     out = torch.empty(hi.shape[0], D, device=dev)
-    lib.gemm(lib.GEMM_TF32X3, hi, w_hi, out, a_lo=lo, b_lo=w_lo, bias=bias)
+    lib.gemm(lib.GEMM_F16X3, hi, w_hi, out, a_lo=lo, b_lo=w_lo, bias=bias, alpha=2.0 ** -16)
     ref = torch.nn.functional.conv2d(img.double(), w.double(), bias.double(), stride=P).flatten(2).transpose(1, 2)
     assert _rel(out.view(B, -1, D), ref) < 6e-7
 
@@ -297,9 +327,9 @@ def test_attention_tensor_core_path(lib, dev, B, H, N, masked):
     x = torch.randn(B * N, K, generator=g).to(dev)
     w = (torch.randn(3 * HD, K, generator=g) * 0.08).to(dev)
     bias = (torch.randn(3 * HD, generator=g) * 0.1).to(dev)
-    x_hi, x_lo = lib.split_tf32(x)
-    w_hi, w_lo = lib.split_tf32(w)
-    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(x_hi, x_lo, w_hi, w_lo, bias, N, H)
+    x_hi, x_lo = lib.split_f16(x)
+    w_hi, w_lo = lib.split_f16(w, 2.0 ** 14)
+    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(x_hi, x_lo, w_hi, w_lo, bias, N, H, alpha=2.0 ** -14)
     ref = x.double() @ w.double().T + bias.double()
     qk = qk_hi + qk_lo
     assert int((qk_hi.view(torch.int32) & 0x1FFF).abs().max()) == 0

@@ -170,20 +170,24 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
 
 /*
  * Tensor-core self-attention for the scoring lane (vit.py:75-103 without materialising P). madtp_gemm_qkv is the
- * fused q|k|v projection (vit.py:77) with an epilogue that writes q and k as tf32 hi/lo planes [M, ld_qk] (q of head
- * h at column h*64, k at heads*64 + h*64) and v transposed per (sequence, head) as hi/lo planes
- * vt[((b*heads + h)*64 + d) * ld_vt + token] (keys contiguous). M = B * n_tok rows, K = model width.
+ * fused q|k|v projection (vit.py:77; a_hi/a_lo and w_hi/w_lo are fp16 hi/lo planes as for MADTP_GEMM_F16X3, alpha
+ * removes the weight's scale) with an epilogue that writes q and k as fp16 hi/lo planes of MADTP_QK_PLANE_SCALE * value,
+ * [M, ld_qk] (q of head h at column h*64, k at heads*64 + h*64), and v transposed per (sequence, head) as fp16 hi/lo
+ * planes of MADTP_V_PLANE_SCALE * value, vt[((b*heads + h)*64 + d) * ld_vt + token] (keys contiguous; ld_vt a multiple
+ * of 8). M = B * n_tok rows, K = model width. hi = fp16(s*x), lo = fp16(s*x - hi): hi + lo carries 22 mantissa bits.
  * madtp_attn_tc_fwd: context (fp16, heads merged), row_lse[b,h,i] = log sum_j exp(logit) and out_norm[b,h,i].
  * madtp_attn_tc_stats: col_part[b, it, j] = sum_{i in 128-query tile it, i >= 1} max_h P[b,h,i,j]  (n_parts =
  * ceil(N/128)) and cls_attn[b, j] as in madtp_attn_stats. Head dim 64.
  */
+#define MADTP_QK_PLANE_SCALE 8.0f
+#define MADTP_V_PLANE_SCALE 16.0f
 int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
-                   const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
-                   int64_t ld_qk, float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream);
-int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, const float* vt_hi, const float* vt_lo,
+                   const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi, void* qk_lo,
+                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, void* stream);
+int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream);
-int madtp_attn_tc_stats(const float* qk_hi, const float* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
+int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
                         int n_parts, float* cls_attn, float* cls_scratch /* [B,H,N] workspace */, void* stream);
 

@@ -18,6 +18,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
 _lib = None
 
 GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
+QK_PLANE_SCALE, V_PLANE_SCALE = 8.0, 16.0     # include/madtp_b200.h MADTP_QK_PLANE_SCALE / MADTP_V_PLANE_SCALE
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
 
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
@@ -389,15 +390,16 @@ def gather_rows(x, idx):
 
 
 def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
-    """Fused q|k|v projection for the tensor-core attention: returns (qk_hi, qk_lo [M, 2*heads*64], vt_hi, vt_lo
-    [B*heads*64, n_pad]) -- see madtp_gemm_qkv in include/madtp_b200.h."""
+    """Fused q|k|v projection for the tensor-core attention: returns fp16 planes (qk_hi, qk_lo [M, 2*heads*64] of
+    QK_PLANE_SCALE * value, vt_hi, vt_lo [B*heads*64, n_pad] of V_PLANE_SCALE * value) -- see madtp_gemm_qkv in
+    include/madtp_b200.h."""
     M, K = a_hi.shape
     B = M // n_tok
-    n_pad = (n_tok + 3) // 4 * 4
+    n_pad = (n_tok + 7) // 8 * 8
     dev = a_hi.device
-    qk_hi = torch.empty(M, 2 * heads * 64, dtype=torch.float32, device=dev)
+    qk_hi = torch.empty(M, 2 * heads * 64, dtype=torch.float16, device=dev)
     qk_lo = torch.empty_like(qk_hi)
-    vt_hi = torch.empty(B * heads * 64, n_pad, dtype=torch.float32, device=dev)
+    vt_hi = torch.empty(B * heads * 64, n_pad, dtype=torch.float16, device=dev)
     vt_lo = torch.empty_like(vt_hi)
     st = _call("madtp_gemm_qkv", _ptr(a_hi, torch.float16, "a_hi"), _ptr(a_lo, torch.float16, "a_lo"),
                _rowmajor(a_hi, "a_hi"), _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"),
@@ -409,8 +411,8 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
 
 def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None):
     ldo, bso = _qkv_strides(out_f16, "out_f16")
-    st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float32, "qk_hi"), _ptr(qk_lo, torch.float32, "qk_lo"),
-               qk_hi.stride(0), _ptr(vt_hi, torch.float32, "vt_hi"), _ptr(vt_lo, torch.float32, "vt_lo"),
+    st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
+               qk_hi.stride(0), _ptr(vt_hi, torch.float16, "vt_hi"), _ptr(vt_lo, torch.float16, "vt_lo"),
                vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
                _ptr(out_norm, torch.float32, "out_norm"), _stream())
@@ -418,7 +420,7 @@ def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, ou
 
 
 def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, *, key_mask=None):
-    st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float32, "qk_hi"), _ptr(qk_lo, torch.float32, "qk_lo"),
+    st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
                _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
                _ptr(cls_attn, torch.float32, "cls_attn"),

@@ -24,12 +24,12 @@ struct AttnArgs {
   float* cls_attn;          // [B, Nk]  sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8); entry 0 unused
 };
 
-// Tensor-core path (attn_tc.cu). q and k are tf32 hi/lo planes [B*N, ld_qk] (q of head h at column h*64, k at
-// H*64 + h*64); v is stored transposed per (sequence, head): vt[((b*H + h)*64 + d) * ld_vt + token]. Both are written
-// by launch_gemm_qkv.
+// Tensor-core path (attn_tc.cu). q and k are fp16 hi/lo planes of kQkPlaneScale * value, [B*N, ld_qk] (q of head h at
+// column h*64, k at H*64 + h*64); v is stored transposed per (sequence, head) as fp16 hi/lo planes of kVPlaneScale *
+// value: vt[((b*H + h)*64 + d) * ld_vt + token]. Both are written by launch_gemm_qkv (gemm.cuh).
 struct AttnTcArgs {
-  const float* qk_hi; const float* qk_lo; long long ld_qk;
-  const float* vt_hi; const float* vt_lo; long long ld_vt;
+  const __half* qk_hi; const __half* qk_lo; long long ld_qk;
+  const __half* vt_hi; const __half* vt_lo; long long ld_vt;
   int B, H, N;
   float scale;
   const float* key_mask;                 // additive [B, N] or nullptr

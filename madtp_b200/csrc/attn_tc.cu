@@ -1,108 +1,144 @@
 // Tensor-core self-attention with fused token-pruning statistics (head dim 64) for the scoring lane.
 //
 // Same three outputs as attention.cu (context, ||context|| per head and token, column sums of max_h P, the
-// head-importance-weighted CLS row) but the two big contractions run on tcgen05 with error-compensated tf32
-// operands (hi/lo planes written by the fused q|k|v projection, gemm.cu launch_gemm_qkv):
+// head-importance-weighted CLS row) but the two big contractions run on tcgen05 with error-compensated fp16
+// operands: q, k and v arrive as fp16 hi/lo planes (hi = fp16(s x), lo = fp16(s x - hi), 22 mantissa bits together)
+// written by the fused q|k|v projection (gemm.cu launch_gemm_qkv) and every product is lo*hi + hi*lo + hi*hi.
 //
 //   attn_fwd_tc_kernel    one CTA per (128-query tile, head, sequence); 64-key tiles.
-//       S   = Q K^T           2 x 12 MMAs per key tile: each 32-wide slice of the head dim accumulates in its own
-//                             TMEM buffer and the two partials are added in fp32 registers (the tensor core's
-//                             accumulator truncates, so long in-TMEM accumulations lose accuracy -- DESIGN.md section 3)
-//       P   = online softmax   4 warps, one query row per thread, fp32, expf
-//       O_t = P V              P goes back to TMEM as tf32 hi/lo (tcgen05.st) and is the A operand of 24 MMAs against
-//                             V^T tiles (keys contiguous, written transposed by the projection epilogue); every key
-//                             tile's partial product is drained and accumulated in fp32 registers with the usual
-//                             running-max correction.
+//       S   = Q K^T           12 MMAs per key tile (the head dim is one 128-byte operand row) into one of two S buffers
+//       P   = online softmax   8 or 16 warps, thread = (query row, 32 or 16 of the tile's keys), fp32, expf
+//       O_t = P V              256 P goes back to TMEM as packed fp16 hi/lo (tcgen05.st) and is the A operand of 12
+//                             MMAs against V^T tiles (keys contiguous, written transposed by the projection epilogue);
+//                             every key tile's partial product is drained and accumulated in fp32 registers with the
+//                             usual running-max correction (the tensor core's accumulator truncates, so long in-TMEM
+//                             accumulations lose accuracy -- DESIGN.md section 3).
 //   attn_stats_tc_kernel  one CTA per (128-query tile, 128-key tile, sequence), looping over the heads.
 //       log P_h(i,j) = S_h(i,j) * scale + mask_j - lse_h(i) is formed for every head, the running max over heads is
 //       kept in registers (exp is monotone, so ONE expf per (i,j) after the head loop replaces one per head), then
 //       the tile is column-summed over its query rows in a fixed order.
-//   attn_cls_kernel       the CLS query row of every head (tiny, fp32 FFMA) weighted by the per-head context norms.
+//   attn_cls_*_kernel     the CLS query row of every head (tiny, fp32 FFMA) weighted by the per-head context norms.
 //
-// Warp roles in both tensor-core kernels: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane),
-// warps 2..5 = consumers (TMEM lane quadrant = warp % 4, thread = query row).
+// Warp roles in both tensor-core kernels: warp 0 = TMA producer, warp 1 = MMA issuer (warp-uniform loops, one elected
+// lane issues), warps 2.. = consumers (TMEM lane quadrant = warp % 4, thread = query row).
 #include "attention.cuh"
 #include "gemm.cuh"
 
 namespace madtp {
 
+#ifdef MADTP_ATTN_TRACE
+// Development aid: clock64() timeline of one CTA of attn_fwd_tc_kernel (roles x tiles x slots), read back through
+// madtp_debug_read_attn_trace. Never compiled into the shipped library.
+__device__ unsigned long long g_attn_trace[4 * 64 * 8];
+#define ATT_TRACE(role, tile, slot)                                                                      \
+  do {                                                                                                   \
+    if (trace_cta && (tile) < 64) g_attn_trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64();         \
+  } while (0)
+extern "C" int madtp_debug_read_attn_trace(void* dst) {
+  return static_cast<int>(cudaMemcpyFromSymbol(dst, g_attn_trace, sizeof(g_attn_trace)));
+}
+#else
+#define ATT_TRACE(role, tile, slot) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int BM = 128;        // query rows per CTA
-constexpr int BOX = 32;        // floats per 128-byte swizzled row
-constexpr int TC_THREADS = 192;
+constexpr int BM = 128;             // query rows per CTA
+constexpr float kPScale = 256.0f;   // P is stored as fp16 planes of 256 * exp(s - m): lo stays normal down to P ~ 5e-4
 
-__device__ __forceinline__ void ld2_add(uint32_t ta, uint32_t tb, float (&out)[32]) {
-  uint32_t a[32], b[32];
-  tmem_ld_32x32b_x32(ta, a);
-  tmem_ld_32x32b_x32(tb, b);
-  tmem_ld_wait();
-#pragma unroll
-  for (int k = 0; k < 32; ++k) out[k] = __uint_as_float(a[k]) + __uint_as_float(b[k]);
-}
-
-// 12 tf32 MMAs = one 32-wide K slice of an error-compensated product (lo*hi, hi*lo, hi*hi per 8-element k-step)
+// 12 fp16 MMAs = one 64-wide K slice of an error-compensated product (lo*hi, hi*lo, hi*hi per 16-element k-step)
 __device__ __forceinline__ void issue_slice_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                                uint32_t b_lo, uint32_t idesc) {
   const uint64_t dah = make_sw128_kmajor_desc(a_hi), dal = make_sw128_kmajor_desc(a_lo);
   const uint64_t dbh = make_sw128_kmajor_desc(b_hi), dbl = make_sw128_kmajor_desc(b_lo);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, k != 0 ? 1u : 0u);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, k != 0 ? 1u : 0u);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1u);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1u);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1u);
 }
+
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
+template <int W>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_st_cols<16>(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st_32x32b_x16(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_st_cols<8>(uint32_t taddr, const uint32_t (&v)[8]) { tmem_st_32x32b_x8(taddr, v); }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Pass 1
-//   warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 softmax: TMEM lane quadrant = warp % 4 (query rows), column
-//   half = (warp - 2) / 4 (32 of the tile's 64 keys, and 32 of the 64 output dims), so every query row is shared by
-//   two threads that exchange their tile maxima through shared memory.
-//   K tiles ride a 3-deep ring and V^T tiles a 2-deep ring: K(t+1) is requested two tiles ahead of its QK^T, V(t) is
-//   only needed after softmax(t), so neither TMA latency sits on the critical path.
+// Pass 1 (persistent: every CTA walks a strided list of (sequence, head, 128-query tile) work items)
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2.. softmax: TMEM lane quadrant = warp % 4 (query rows), column
+//   group = (warp - 2) / 4 (KW of the tile's 64 keys, and KW of the 64 output dims), so every query row is shared by
+//   64 / KW threads that exchange their tile maxima through shared memory.
+//   All rings and TMEM buffers are indexed by a tile counter g that runs ACROSS work items, so the producer and the
+//   MMA warp run ahead into the next item (its Q, K(0), K(1) are in shared memory and S(0) is in TMEM) while the
+//   softmax warps finish the current one: the TMA / MMA start-up latency of an item (~3.5k cycles, measured, against
+//   ~1.5k per key tile) is paid once per CTA instead of once per item.
+//   K tiles ride a 3-deep ring and V^T tiles a 2-deep ring; Q, S, P and the O partial are double-buffered.
 // ------------------------------------------------------------------------------------------------
-struct FwdSmem {
-  static constexpr int Q_BYTES = 4 * BM * 128;              // (slice 0/1) x (hi/lo) boxes of [128 x 32]
-  static constexpr int KBOX = 64 * 128;                     // [64 keys x 32] or [64 dims x 32 keys]
-  static constexpr int TILE_BYTES = 4 * KBOX;               // one K tile or one V^T tile: (slice 0/1) x (hi/lo)
-  static constexpr int K_STAGES = 3, V_STAGES = 2;
-  static constexpr int K_OFF = Q_BYTES;
+template <int KW, int NB>   // NB = P / O-partial buffers in TMEM: 2 (one CTA per SM) or 1 (two co-resident CTAs per SM)
+struct FwdCfg {
+  static constexpr int NG = 64 / KW;                       // column groups per tile
+  static constexpr int THREADS = 64 + 128 * NG;            // 320 (KW = 32) or 576 (KW = 16)
+  static constexpr int Q_BYTES = 2 * BM * 128;             // hi, lo boxes of [128 rows x 64 halves]
+  static constexpr int Q_STAGES = NB;                      // 2 query buffers when the CTA owns the SM
+  static constexpr int KBOX = 64 * 128;                    // [64 keys x 64 dims] or [64 dims x 64 keys] halves
+  static constexpr int TILE_BYTES = 2 * KBOX;              // hi, lo
+  static constexpr int K_STAGES = NB == 2 ? 3 : 2, V_STAGES = 2;
+  static constexpr int TMEM_COLS = NB == 2 ? 512 : 256;
+  static constexpr int CTAS_PER_SM = NB == 2 ? 1 : 2;
+  static constexpr int K_OFF = Q_STAGES * Q_BYTES;
   static constexpr int V_OFF = K_OFF + K_STAGES * TILE_BYTES;
   static constexpr int BAR_OFF = V_OFF + V_STAGES * TILE_BYTES;
-  static constexpr int XCH_OFF = BAR_OFF + 256;             // [2][2][128] floats: per-row exchange between column halves
-  static constexpr int TOTAL = XCH_OFF + 2 * 2 * BM * 4;
+  static constexpr int XCH_OFF = BAR_OFF + 256;            // [3][NG][128] floats: per-row exchange between groups
+  static constexpr int TOTAL = XCH_OFF + 3 * NG * BM * 4;
 };
-constexpr int FWD_THREADS = 320;
 
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+template <int KW, int NB>
+__global__ void __launch_bounds__(FwdCfg<KW, NB>::THREADS, FwdCfg<KW, NB>::CTAS_PER_SM)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                    const __grid_constant__ CUtensorMap tm_k_hi, const __grid_constant__ CUtensorMap tm_k_lo,
                    const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
                    AttnTcArgs a) {
+  using Cfg = FwdCfg<KW, NB>;
+  constexpr int NG = Cfg::NG;
+  constexpr int QS = Cfg::Q_STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* q_s = smem;
-  uint8_t* k_s = smem + FwdSmem::K_OFF;
-  uint8_t* v_s = smem + FwdSmem::V_OFF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR_OFF);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;     // [3]
-  uint64_t* k_empty = bars + 4;    // [3]
-  uint64_t* v_full = bars + 7;     // [2]
-  uint64_t* v_empty = bars + 9;    // [2]
-  uint64_t* s_full = bars + 11;    // S(t) complete in TMEM
-  uint64_t* s_empty = bars + 12;   // S(t) copied to registers by all eight softmax warps
-  uint64_t* p_full = bars + 13;    // [2] P(t) stored (parity t & 1)
-  uint64_t* o_full = bars + 15;    // [2] P(t) V(t) complete (parity t & 1): O partial ready, P buffer free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-  float* xch = reinterpret_cast<float*>(smem + FwdSmem::XCH_OFF);   // [parity][half][row]
+  uint8_t* k_s = smem + Cfg::K_OFF;
+  uint8_t* v_s = smem + Cfg::V_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2] every QK^T of the item that used this query buffer has retired
+  uint64_t* k_full = bars + 4;     // [3]
+  uint64_t* k_empty = bars + 7;    // [3]
+  uint64_t* v_full = bars + 10;    // [2]
+  uint64_t* v_empty = bars + 12;   // [2]
+  uint64_t* s_full = bars + 14;    // [2] S(g) complete in TMEM (parity g & 1)
+  uint64_t* s_empty = bars + 16;   // [2] S(g) copied to registers by all softmax warps
+  uint64_t* p_full = bars + 18;    // [2] P(g) stored
+  uint64_t* o_full = bars + 20;    // [2] P(g) V(g) complete: O partial ready, P buffer free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::XCH_OFF);   // [parity | item end][group][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int N = a.N, HD = a.H * 64;
-  const int T = (N + 63) / 64;   // key tiles
+  const int T = (N + 63) / 64;           // key tiles per item
+  const int QT = (N + BM - 1) / BM;      // query tiles per (sequence, head)
+  const int items = QT * a.H * a.B;
+#ifdef MADTP_ATTN_TRACE
+  const bool trace_cta = blockIdx.x == gridDim.x / 2 && lane == 0;
+  if (warp == 0) ATT_TRACE(0, 63, 0);
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q_hi);
@@ -113,69 +149,69 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
     tma_prefetch_desc(&tm_v_lo);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < FwdSmem::K_STAGES; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-      mbar_init(&p_full[s], 8);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4 * NG);
+      mbar_init(&p_full[s], 4 * NG);
       mbar_init(&o_full[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S (slice A | slice B) at 0; P hi, P lo and the O partial are double-buffered by tile parity so that
-  // softmax(t+1) never waits for P(t) V(t): P hi at 128 / 192, P lo at 256 / 320, O partial at 384 / 448
-  constexpr uint32_t kP_HI = 128, kP_LO = 256, kO = 384;
+  // TMEM columns: S double-buffered by tile parity at (g&1)*64; NB buffers (pb = g % NB) of P hi (packed fp16 pairs,
+  // 32 columns each) at 128, of P lo behind them and of the O partial (64 columns each) behind those
+  constexpr uint32_t kP_HI = 128, kP_LO = 128 + NB * 32, kO = 128 + NB * 64;
 
   if (warp == 0) {   // warp-uniform control flow, one elected lane issues the TMA
-    {
-      const int qrow = b * N + i0;
+    int g = 0, it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int qt = item % QT, bh = item / QT, h = bh % a.H, b = bh / a.H;
+      const int qb = it % QS;
+      mbar_wait(&q_empty[qb], ((it / QS) & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, FwdSmem::Q_BYTES);
-        for (int c = 0; c < 2; ++c) {
-          tma_load_2d(&tm_q_hi, q_full, q_s + (c * 2 + 0) * BM * 128, h * 64 + c * BOX, qrow);
-          tma_load_2d(&tm_q_lo, q_full, q_s + (c * 2 + 1) * BM * 128, h * 64 + c * BOX, qrow);
-        }
+        mbar_arrive_expect_tx(&q_full[qb], Cfg::Q_BYTES);
+        tma_load_2d(&tm_q_hi, &q_full[qb], q_s + qb * Cfg::Q_BYTES, h * 64, b * N + qt * BM);
+        tma_load_2d(&tm_q_lo, &q_full[qb], q_s + qb * Cfg::Q_BYTES + BM * 128, h * 64, b * N + qt * BM);
       }
       __syncwarp();
       auto load_k = [&](int t) {
-        const int st = t % FwdSmem::K_STAGES;
-        mbar_wait(&k_empty[st], ((t / FwdSmem::K_STAGES) & 1) ^ 1);
-        uint8_t* s = k_s + st * FwdSmem::TILE_BYTES;
+        const int gk = g + t, st = gk % Cfg::K_STAGES;
+        mbar_wait(&k_empty[st], ((gk / Cfg::K_STAGES) & 1) ^ 1);
+        ATT_TRACE(0, gk, 0);
+        uint8_t* s = k_s + st * Cfg::TILE_BYTES;
         const int krow = b * N + t * 64;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&k_full[st], FwdSmem::TILE_BYTES);
-          for (int c = 0; c < 2; ++c) {
-            tma_load_2d(&tm_k_hi, &k_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
-            tma_load_2d(&tm_k_lo, &k_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, HD + h * 64 + c * BOX, krow);
-          }
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+          tma_load_2d(&tm_k_hi, &k_full[st], s, HD + h * 64, krow);
+          tma_load_2d(&tm_k_lo, &k_full[st], s + Cfg::KBOX, HD + h * 64, krow);
         }
         __syncwarp();
       };
       auto load_v = [&](int t) {
-        const int st = t & 1;
-        mbar_wait(&v_empty[st], ((t >> 1) & 1) ^ 1);
-        uint8_t* s = v_s + st * FwdSmem::TILE_BYTES;
+        const int gv = g + t, st = gv & 1;
+        mbar_wait(&v_empty[st], ((gv >> 1) & 1) ^ 1);
+        ATT_TRACE(0, gv, 1);
+        uint8_t* s = v_s + st * Cfg::TILE_BYTES;
         const int vrow = (b * a.H + h) * 64;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&v_full[st], FwdSmem::TILE_BYTES);
-          for (int c = 0; c < 2; ++c) {
-            tma_load_2d(&tm_v_hi, &v_full[st], s + (c * 2 + 0) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
-            tma_load_2d(&tm_v_lo, &v_full[st], s + (c * 2 + 1) * FwdSmem::KBOX, t * 64 + c * BOX, vrow);
-          }
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+          tma_load_2d(&tm_v_hi, &v_full[st], s, t * 64, vrow);
+          tma_load_2d(&tm_v_lo, &v_full[st], s + Cfg::KBOX, t * 64, vrow);
         }
         __syncwarp();
       };
@@ -184,207 +220,278 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         if (t + 1 < T) load_k(t + 1);
         load_v(t);
       }
+      g += T;
     }
   } else if (warp == 1) {
     // The whole warp runs this loop and ONE elected lane issues: with warp-uniform control flow the descriptors stay
     // in uniform registers. (Guarding the loop with `lane == 0` instead makes every tcgen05.mma a ~100-cycle
     // R2UR + waterfall sequence -- measured: that, not the tensor pipe or the softmax, bounded this kernel.)
-    constexpr uint32_t idesc = make_idesc(2u, BM, 64);
-    const uint32_t q_u = smem_u32(q_s);
-    auto issue_qk = [&](int t) {
-      const int st = t % FwdSmem::K_STAGES;
-      mbar_wait(&k_full[st], (t / FwdSmem::K_STAGES) & 1);
-      mbar_wait(s_empty, (t & 1) ^ 1);       // softmax(t-1) has S(t-1) in registers
+    constexpr uint32_t idesc = make_idesc(0u, BM, 64);
+    // S(g) = Q K(g)^T for tile g of the item whose query sits in buffer qb; `last` releases that buffer
+    auto issue_qk = [&](int g, int qb, bool last) {
+      const int st = g % Cfg::K_STAGES;
+      ATT_TRACE(1, g, 0);
+      mbar_wait(&k_full[st], (g / Cfg::K_STAGES) & 1);
+      mbar_wait(&s_empty[g & 1], ((g >> 1) & 1) ^ 1);   // softmax(g-2) has S(g-2) in registers
       tcgen05_fence_after();
-      const uint32_t k_u = smem_u32(k_s + st * FwdSmem::TILE_BYTES);
+      ATT_TRACE(1, g, 1);
+      const uint32_t q_u = smem_u32(q_s + qb * Cfg::Q_BYTES);
+      const uint32_t k_u = smem_u32(k_s + st * Cfg::TILE_BYTES);
       if (elect_one()) {
-        for (int c = 0; c < 2; ++c)
-          issue_slice_ss(tmem_base + c * 64, q_u + (c * 2 + 0) * BM * 128, q_u + (c * 2 + 1) * BM * 128,
-                         k_u + (c * 2 + 0) * FwdSmem::KBOX, k_u + (c * 2 + 1) * FwdSmem::KBOX, idesc);
-        umma_commit(s_full);
+        issue_slice_ss(tmem_base + (g & 1) * 64, q_u, q_u + BM * 128, k_u, k_u + Cfg::KBOX, idesc);
+        umma_commit(&s_full[g & 1]);
         umma_commit(&k_empty[st]);
+        if (last) umma_commit(&q_empty[qb]);
       }
       __syncwarp();
+      ATT_TRACE(1, g, 2);
     };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int t = 0; t < T; ++t) {
-      if (t + 1 < T) issue_qk(t + 1);
-      const int pb = t & 1;
-      mbar_wait(&v_full[pb], (t >> 1) & 1);
-      mbar_wait(&p_full[pb], (t >> 1) & 1);
-      tcgen05_fence_after();
-      const uint32_t v_u = smem_u32(v_s + pb * FwdSmem::TILE_BYTES);
-      if (elect_one()) {
-        // O_t = P_lo V_hi + P_hi V_lo + P_hi V_hi over 8 k-steps of 8 keys
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t pa = tmem_base + (pass == 0 ? kP_LO : kP_HI) + pb * 64;
-          const int vplane = (pass == 1) ? 1 : 0;  // pass 1 multiplies by V_lo
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd =
-                make_sw128_kmajor_desc(v_u + ((ks >> 2) * 2 + vplane) * FwdSmem::KBOX) + 2 * (ks & 3);
-            umma_tf32_ts(tmem_base + kO + pb * 64, pa + ks * 8, bd, idesc, (pass | ks) != 0 ? 1u : 0u);
-          }
+    int g = 0, it = 0;
+    if (blockIdx.x < items) {
+      mbar_wait(&q_full[0], 0);
+      issue_qk(0, 0, T == 1);
+    }
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int qb = it % QS;
+      const bool has_next = item + static_cast<int>(gridDim.x) < items;
+      for (int t = 0; t < T; ++t, ++g) {
+        // look one tile ahead, across the item boundary
+        if (t + 1 < T) {
+          issue_qk(g + 1, qb, t + 2 == T);
+        } else if (has_next) {
+          const int nqb = (it + 1) % QS;
+          mbar_wait(&q_full[nqb], ((it + 1) / QS) & 1);
+          issue_qk(g + 1, nqb, T == 1);
         }
-        umma_commit(&o_full[pb]);
-        umma_commit(&v_empty[pb]);
+        const int pb = g % NB, vb = g & 1;
+        mbar_wait(&v_full[vb], (g >> 1) & 1);
+        ATT_TRACE(1, g, 3);
+        mbar_wait(&p_full[pb], (g / NB) & 1);
+        tcgen05_fence_after();
+        ATT_TRACE(1, g, 4);
+        const uint32_t v_u = smem_u32(v_s + vb * Cfg::TILE_BYTES);
+        if (elect_one()) {
+          // O_g = P_lo V_hi + P_hi V_lo + P_hi V_hi over 4 k-steps of 16 keys (8 packed TMEM columns each)
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t pa = tmem_base + (pass == 0 ? kP_LO : kP_HI) + pb * 32;
+            const uint64_t bd = make_sw128_kmajor_desc(v_u + (pass == 1 ? Cfg::KBOX : 0));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16_ts(tmem_base + kO + pb * 64, pa + ks * 8, bd + 2 * ks, idesc, (pass | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[pb]);
+          umma_commit(&v_empty[vb]);
+        }
+        __syncwarp();
+        ATT_TRACE(1, g, 5);
       }
-      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
-    const int hf = (warp - 2) >> 2;                 // column half
+    const int grp = (warp - 2) >> 2;                // column group
     const int r = quad * 32 + lane;                 // row within the tile
-    const int i = i0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
-    float m = -INFINITY, l = 0.f;
-    float m_hist[2] = {-INFINITY, -INFINITY};   // running max at tiles t-2 / t-1 (indexed by tile parity)
-    float o[32];
+    // Everything below works in the log2 domain on the raw accumulator: y = S * c1 (+ mask * log2e), p = 2^(y - m)
+    // with the running maximum m of y; one FFMA + one MUFU.EX2 per element. The FFMA rounds y once (|error| <=
+    // 2^-24 |y|), i.e. an ABSOLUTE error of at most ~3e-8 on p relative to the row maximum -- the size of one fp32
+    // rounding of the row sum.
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float c1 = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale)) * kLog2e;
+    const float mask_to_raw = kLog2e / c1;      // additive key mask expressed in raw-accumulator units
+    constexpr float kLogP = 8.0f;               // log2(kPScale): p is produced as 256 * 2^(y - m) directly
+    int g = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int qt = item % QT, bh = item / QT, h = bh % a.H, b = bh / a.H;
+      const int i = qt * BM + r;
+      const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
+      float m = -INFINITY, l = 0.f;               // m in raw units * c1 (log2 domain); l = 256 * sum of p
+      float m_hist[2] = {-INFINITY, -INFINITY};   // running max at the NB previous tiles (indexed by g % NB)
+      float o[KW];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+      for (int d = 0; d < KW; ++d) o[d] = 0.f;
 
-    // drain the partial product of tile u (buffer u & 1, relative to the running max m_u) into o (relative to m_now)
-    auto drain = [&](int u, float m_u, float m_now) {
-      mbar_wait_spin(&o_full[u & 1], (u >> 1) & 1);
-      tcgen05_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + kO + (u & 1) * 64 + hf * 32, v);
-      tmem_ld_wait();
-      const float f = expf(m_u - m_now);
+      // drain the partial product of tile u (buffer u % NB, relative to the running max m_u) into o (relative to m_now)
+      auto drain = [&](int u, float m_u, float m_now) {
+        mbar_wait_spin(&o_full[u % NB], (u / NB) & 1);
+        tcgen05_fence_after();
+        uint32_t v[KW];
+        tmem_ld_cols<KW>(tmem_base + lane_off + kO + (u % NB) * 64 + grp * KW, v);
+        tmem_ld_wait();
+        const float f = ex2_approx(m_u - m_now);
 #pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] = fmaf(__uint_as_float(v[k]), f, o[k]);
-    };
+        for (int k = 0; k < KW; ++k) o[k] = fmaf(__uint_as_float(v[k]), f, o[k]);
+      };
 
-    for (int t = 0; t < T; ++t) {
-      mbar_wait_spin(s_full, t & 1);
-      tcgen05_fence_after();
-      float s[32];
-      ld2_add(tmem_base + lane_off + hf * 32, tmem_base + lane_off + 64 + hf * 32, s);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-
-      const int j0 = t * 64 + hf * 32;
-      float mx = -INFINITY;
-      if (mask == nullptr && j0 + 32 <= N) {        // interior tile: no bounds or mask handling
+      for (int t = 0; t < T; ++t, ++g) {
+        if (warp == 2) ATT_TRACE(2, g, 0);
+        mbar_wait_spin(&s_full[g & 1], (g >> 1) & 1);
+        tcgen05_fence_after();
+        if (warp == 2) ATT_TRACE(2, g, 1);
+        float s[KW];
+        {
+          uint32_t v[KW];
+          tmem_ld_cols<KW>(tmem_base + lane_off + (g & 1) * 64 + grp * KW, v);
+          tmem_ld_wait();
+          ATT_TRACE(3, g, (warp - 2) & 7);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          s[k] *= a.scale;
-          mx = fmaxf(mx, s[k]);
+          for (int k = 0; k < KW; ++k) s[k] = __uint_as_float(v[k]);
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int j = j0 + k;
-          const float mk = (mask != nullptr && j < N) ? __ldg(mask + j) : 0.f;
-          s[k] = (j < N) ? fmaf(s[k], a.scale, mk) : -INFINITY;
-          mx = fmaxf(mx, s[k]);
-        }
-      }
-      // joint maximum of the row over both column halves
-      float* x = xch + (t & 1) * 2 * BM;
-      x[hf * BM + r] = mx;
-      named_bar_sync(1 + quad, 64);
-      mx = fmaxf(mx, x[(hf ^ 1) * BM + r]);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[g & 1]);
+        if (warp == 2) ATT_TRACE(2, g, 2);
 
-      const float m_new = fmaxf(m, mx);
-      const float corr = (m == -INFINITY) ? 0.f : expf(m - m_new);
-      float ps = 0.f;
+        const int j0 = t * 64 + grp * KW;
+        if (mask != nullptr) {                       // additive key mask, in raw units (warp-uniform branch)
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        s[k] = expf(s[k] - m_new);
-        ps += s[k];
-      }
-      l = l * corr + ps;
-      m = m_new;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] *= corr;     // o is now relative to m_new
-      // the P buffer of this parity was last read by P(t-2) V(t-2): drain that partial, which also frees the buffer
-      if (t >= 2) drain(t - 2, m_hist[t & 1], m_new);
-      m_hist[t & 1] = m_new;
-
-      // P -> TMEM as tf32 hi / lo (A operand of the P V MMAs)
-      {
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float p = s[k];
-          const float ph = tf32_hi(p);
-          hi[k] = __float_as_uint(ph);
-          lo[k] = __float_as_uint(p - ph);
+          for (int k = 0; k < KW; ++k)
+            if (j0 + k < N) s[k] = fmaf(__ldg(mask + j0 + k), mask_to_raw, s[k]);
         }
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_HI + (t & 1) * 64 + hf * 32, hi);
-        tmem_st_32x32b_x32(tmem_base + lane_off + kP_LO + (t & 1) * 64 + hf * 32, lo);
-      }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t & 1]);
-    }
-    if (T >= 2) drain(T - 2, m_hist[(T - 2) & 1], m);
-    drain(T - 1, m_hist[(T - 1) & 1], m);
-    // row sum and squared norm: combine the two column halves (buffers of parity T&1 are free: their last readers
-    // passed the barrier of tile T-2 ... T-1 uses the other parity)
-    float* x = xch + (T & 1) * 2 * BM;
-    x[hf * BM + r] = l;
-    named_bar_sync(1 + quad, 64);
-    const float l_tot = l + x[(hf ^ 1) * BM + r];
-    const float inv = 1.0f / l_tot;
-    float nsq = 0.f;
+        if (j0 + KW > N) {                           // last tile: keys past the sequence end
 #pragma unroll
-    for (int d = 0; d < 32; ++d) {
-      o[d] *= inv;
-      nsq = fmaf(o[d], o[d], nsq);
-    }
-    named_bar_sync(1 + quad, 64);                    // both halves have read l before the buffer is reused
-    x[hf * BM + r] = nsq;
-    named_bar_sync(1 + quad, 64);
-    const float nsq_tot = (hf == 0) ? (nsq + x[BM + r]) : (x[r] + nsq);   // dims 0..31 first, then 32..63
-    if (i < N) {
-      __half* dst = a.out_f16 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64 + hf * 32;
+          for (int k = 0; k < KW; ++k) s[k] = (j0 + k < N) ? s[k] : -INFINITY;
+        }
+        float mx = s[0];
 #pragma unroll
-      for (int d = 0; d < 32; d += 8) {
-        __half2 h0 = __floats2half2_rn(o[d], o[d + 1]), h1 = __floats2half2_rn(o[d + 2], o[d + 3]);
-        __half2 h2 = __floats2half2_rn(o[d + 4], o[d + 5]), h3 = __floats2half2_rn(o[d + 6], o[d + 7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(dst + d) = pk;
+        for (int k = 1; k < KW; ++k) mx = fmaxf(mx, s[k]);
+        mx *= c1;                                    // c1 > 0: the maximum commutes with the scaling
+        // joint maximum of the row over all column groups
+        float* x = xch + (g & 1) * NG * BM;
+        x[grp * BM + r] = mx;
+        named_bar_sync(1 + quad, 32 * NG);
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) mx = fmaxf(mx, x[gg * BM + r]);
+        if (warp == 2) ATT_TRACE(2, g, 3);
+
+        const float m_new = fmaxf(m, mx);
+        const float corr = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new);
+        const float off = kLogP - m_new;
+        // The two halves of the work -- the MUFU-bound exponentials and the FMA / TMEM-bound rescale-and-drain of the
+        // older partial product -- are done in opposite order by even and odd column groups: the warps of one
+        // scheduler run in lockstep behind the barrier above, and this keeps them off the same pipe.
+        auto do_exp = [&]() {
+          float ps = 0.f;
+#pragma unroll
+          for (int k = 0; k < KW; ++k) {
+            s[k] = ex2_approx(fmaf(s[k], c1, off));
+            ps += s[k];
+          }
+          l = fmaf(l, corr, ps);
+        };
+        auto do_drain = [&]() {
+          if (__any_sync(0xffffffffu, corr != 1.0f)) {   // the running maximum rarely moves after the first tiles
+#pragma unroll
+            for (int k = 0; k < KW; ++k) o[k] *= corr;   // o is now relative to m_new
+          }
+          // this tile's P buffer was last read by P(g-NB) V(g-NB): drain that partial, which also frees the buffer
+          if (t >= NB) drain(g - NB, m_hist[g % NB], m_new);
+        };
+        if (grp & 1) {
+          do_drain();
+          do_exp();
+        } else {
+          do_exp();
+          do_drain();
+        }
+        m = m_new;
+        m_hist[g % NB] = m_new;
+        if (warp == 2) ATT_TRACE(2, g, 5);
+
+        // 256 p -> TMEM as packed fp16 hi / lo (A operand of the P V MMAs; low half = even key)
+        {
+          uint32_t hi[KW / 2], lo[KW / 2];
+#pragma unroll
+          for (int k = 0; k < KW / 2; ++k) {
+            const float p0 = s[2 * k], p1 = s[2 * k + 1];
+            const __half2 ph = __floats2half2_rn(p0, p1);
+            const float2 pf = __half22float2(ph);
+            const __half2 pl = __floats2half2_rn(p0 - pf.x, p1 - pf.y);
+            hi[k] = *reinterpret_cast<const uint32_t*>(&ph);
+            lo[k] = *reinterpret_cast<const uint32_t*>(&pl);
+          }
+          tmem_st_cols<KW / 2>(tmem_base + lane_off + kP_HI + (g % NB) * 32 + grp * (KW / 2), hi);
+          tmem_st_cols<KW / 2>(tmem_base + lane_off + kP_LO + (g % NB) * 32 + grp * (KW / 2), lo);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g % NB]);
+        if (warp == 2) ATT_TRACE(2, g, 6);
       }
-      if (hf == 0) {
-        const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
-        a.row_lse[sidx] = m + logf(l_tot);
-        a.out_norm[sidx] = sqrtf(nsq_tot);
+      // g is now one past the item's last tile
+      if (NB == 2 && T >= 2) drain(g - 2, m_hist[(g - 2) % NB], m);
+      drain(g - 1, m_hist[(g - 1) % NB], m);
+      // row sum and squared norm: combine the column groups in group order through the item-end exchange buffer (its
+      // previous use, at the end of the last item, is separated from this one by at least one tile barrier)
+      float* x = xch + 2 * NG * BM;
+      x[grp * BM + r] = l;
+      named_bar_sync(1 + quad, 32 * NG);
+      float l_tot = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) l_tot += x[gg * BM + r];
+      const float inv = 1.0f / (l_tot * kVPlaneScale);   // l carries the factor kPScale that o carries too
+      float nsq = 0.f;
+#pragma unroll
+      for (int d = 0; d < KW; ++d) {
+        o[d] *= inv;
+        nsq = fmaf(o[d], o[d], nsq);
+      }
+      named_bar_sync(1 + quad, 32 * NG);               // every group has read l before the buffer is reused
+      x[grp * BM + r] = nsq;
+      named_bar_sync(1 + quad, 32 * NG);
+      float nsq_tot = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) nsq_tot += x[gg * BM + r];   // dims in ascending order
+      if (i < N) {
+        __half* dst = a.out_f16 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64 + grp * KW;
+#pragma unroll
+        for (int d = 0; d < KW; d += 8) {
+          __half2 h0 = __floats2half2_rn(o[d], o[d + 1]), h1 = __floats2half2_rn(o[d + 2], o[d + 3]);
+          __half2 h2 = __floats2half2_rn(o[d + 4], o[d + 5]), h3 = __floats2half2_rn(o[d + 6], o[d + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2);
+          pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dst + d) = pk;
+        }
+        if (grp == 0) {
+          const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
+          a.row_lse[sidx] = fmaf(m, 0.6931471805599453f, logf(l_tot * (1.0f / kPScale)));
+          a.out_norm[sidx] = sqrtf(nsq_tot);
+        }
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+#ifdef MADTP_ATTN_TRACE
+  if (warp == 0) ATT_TRACE(0, 63, 1);
+#endif
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Pass 2
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 consumers: TMEM lane quadrant = warp % 4 (query rows), column
+//   half = (warp - 2) / 4 (64 of the tile's 128 keys).
 // ------------------------------------------------------------------------------------------------
 struct StatsSmem {
-  static constexpr int BOX_BYTES = BM * 128;                // [128 rows x 32 floats]
-  static constexpr int STAGE_BYTES = 4 * BOX_BYTES;         // Q hi, Q lo, K hi, K lo of one (head, 32-wide slice)
+  static constexpr int BOX_BYTES = BM * 128;                // [128 rows x 64 halves]
+  static constexpr int STAGE_BYTES = 4 * BOX_BYTES;         // Q hi, Q lo, K hi, K lo of one head
   static constexpr int STAGES = 3;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 1024 + 1024;
   static constexpr int RED_LD = 129;                        // column-sum staging pitch (floats), reuses the stages
+  static constexpr int THREADS = 320;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(StatsSmem::THREADS, 1)
 attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                      AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -412,15 +519,15 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
+      mbar_init(&s_empty[s], 8);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<256>(tmem_slot);
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int c = threadIdx.x - 64;
     const int j = j0 + c;
     colmask[c] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f) : -INFINITY;
@@ -431,83 +538,90 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {   // warp-uniform control flow, one elected lane issues
-    for (int u = 0; u < 2 * H; ++u) {
-      const int st = u % StatsSmem::STAGES, hh = u >> 1, c = u & 1;
-      mbar_wait(&empty[st], ((u / StatsSmem::STAGES) & 1) ^ 1);
+    for (int hh = 0; hh < H; ++hh) {
+      const int st = hh % StatsSmem::STAGES;
+      mbar_wait(&empty[st], ((hh / StatsSmem::STAGES) & 1) ^ 1);
       uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(&full[st], StatsSmem::STAGE_BYTES);
-        tma_load_2d(&tm_hi, &full[st], s, hh * 64 + c * BOX, b * N + i0);
-        tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64 + c * BOX, b * N + i0);
-        tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
-        tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64 + c * BOX, b * N + j0);
+        tma_load_2d(&tm_hi, &full[st], s, hh * 64, b * N + i0);
+        tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64, b * N + i0);
+        tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + j0);
+        tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + j0);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(2u, BM, BM);
+    constexpr uint32_t idesc = make_idesc(0u, BM, BM);
     for (int hh = 0; hh < H; ++hh) {
-      const int hb = hh & 1;
+      const int hb = hh & 1, st = hh % StatsSmem::STAGES;
       mbar_wait(&s_empty[hb], ((hh >> 1) & 1) ^ 1);
-      for (int c = 0; c < 2; ++c) {
-        const int u = hh * 2 + c, st = u % StatsSmem::STAGES;
-        mbar_wait(&full[st], (u / StatsSmem::STAGES) & 1);
-        tcgen05_fence_after();
-        const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
-        if (elect_one()) {
-          issue_slice_ss(tmem_base + hb * 256 + c * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
-                         s + 3 * StatsSmem::BOX_BYTES, idesc);
-          umma_commit(&empty[st]);
-          if (c == 1) umma_commit(&s_full[hb]);
-        }
-        __syncwarp();
+      mbar_wait(&full[st], (hh / StatsSmem::STAGES) & 1);
+      tcgen05_fence_after();
+      const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
+      if (elect_one()) {
+        issue_slice_ss(tmem_base + hb * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
+                       s + 3 * StatsSmem::BOX_BYTES, idesc);
+        umma_commit(&empty[st]);
+        umma_commit(&s_full[hb]);
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;          // row within the tile
     const int i = i0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const bool row_ok = (i >= 1) && (i < N);  // the CLS query row is excluded (reference vit.py:126)
-    float mx[BM];
+    const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
+    float mx[64];
 #pragma unroll
-    for (int c = 0; c < BM; ++c) mx[c] = -INFINITY;
+    for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
+    const float* lse_p = a.row_lse + static_cast<long long>(b) * H * N + (i < N ? i : 0);
+    float lse_next = (i < N) ? __ldg(lse_p) : 0.f;
     for (int hh = 0; hh < H; ++hh) {
       const int hb = hh & 1;
-      const float lse = (i < N) ? a.row_lse[(static_cast<long long>(b) * H + hh) * N + i] : 0.f;
+      const float lse = lse_next;
+      if (hh + 1 < H && i < N) lse_next = __ldg(lse_p + static_cast<long long>(hh + 1) * N);   // hidden by this head
       mbar_wait(&s_full[hb], (hh >> 1) & 1);
       tcgen05_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float s[32];
-        ld2_add(tmem_base + lane_off + hb * 256 + cc * 32, tmem_base + lane_off + hb * 256 + 128 + cc * 32, s);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float t = fmaf(s[k], a.scale, colmask[cc * 32 + k]) - lse;
-          mx[cc * 32 + k] = fmaxf(mx[cc * 32 + k], t);
-        }
-      }
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64, v0);
+      tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64 + 32, v1);
+      tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[hb]);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float t0 = fmaf(__uint_as_float(v0[k]), sc, colmask[half * 64 + k]) - lse;
+        const float t1 = fmaf(__uint_as_float(v1[k]), sc, colmask[half * 64 + 32 + k]) - lse;
+        mx[k] = fmaxf(mx[k], t0);
+        mx[32 + k] = fmaxf(mx[32 + k], t1);
+      }
     }
     // every MMA has retired (the last s_full fired), so the operand stages can be reused as the reduction tile
     float* red = reinterpret_cast<float*>(smem);
+    float* part = red + BM * StatsSmem::RED_LD;   // [2][128] partial column sums (rows 0..63 / 64..127)
 #pragma unroll
-    for (int c = 0; c < BM; ++c) red[r * StatsSmem::RED_LD + c] = row_ok ? expf(mx[c]) : 0.f;
-    named_bar_sync(1, 128);
-    const int c = threadIdx.x - 64;
-    const int j = j0 + c;
+    for (int c = 0; c < 64; ++c) red[r * StatsSmem::RED_LD + half * 64 + c] = row_ok ? expf(mx[c]) : 0.f;
+    named_bar_sync(1, 256);
+    const int tid = threadIdx.x - 64;
+    const int c = tid & 127, ph = tid >> 7;
     float sum = 0.f;
-    for (int rr = 0; rr < BM; ++rr) sum += red[rr * StatsSmem::RED_LD + c];   // fixed order: deterministic
-    if (j < N) a.col_part[(static_cast<long long>(b) * a.n_parts + it) * N + j] = sum;
+    for (int rr = ph * 64; rr < ph * 64 + 64; ++rr) sum += red[rr * StatsSmem::RED_LD + c];   // fixed order
+    part[ph * BM + c] = sum;
+    named_bar_sync(1, 256);
+    const int j = j0 + c;
+    if (ph == 0 && j < N) a.col_part[(static_cast<long long>(b) * a.n_parts + it) * N + j] = part[c] + part[BM + c];
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -516,35 +630,42 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 //   attn_cls_head_kernel     grid (H, B), block 256: the CLS query row of one head (fp32 FFMA, own softmax) -> scratch
 //   attn_cls_combine_kernel  grid (ceil(N/256), B): head-importance weighting and the sum over heads (h ascending)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot8_planes(const uint4& x, const uint4& y, const float* q) {
+  const __half2* xh = reinterpret_cast<const __half2*>(&x);
+  const __half2* yh = reinterpret_cast<const __half2*>(&y);
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 xf = __half22float2(xh[e]), yf = __half22float2(yh[e]);
+    s = fmaf(q[2 * e], xf.x + yf.x, s);
+    s = fmaf(q[2 * e + 1], xf.y + yf.y, s);
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(256)
 attn_cls_head_kernel(AttnTcArgs a) {
   extern __shared__ float sm[];
   const int N = a.N, H = a.H, HD = H * 64;
-  float* q0 = sm;        // [64]
+  float* q0 = sm;        // [64]   (kQkPlaneScale * q)
   float* red = sm + 64;  // [16]
   float* P = sm + 80;    // [N]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hh = blockIdx.x, b = blockIdx.y;
-  const float* row0_hi = a.qk_hi + static_cast<long long>(b) * N * a.ld_qk;
-  const float* row0_lo = a.qk_lo + static_cast<long long>(b) * N * a.ld_qk;
-  if (tid < 64) q0[tid] = row0_hi[hh * 64 + tid] + row0_lo[hh * 64 + tid];
+  const __half* row0_hi = a.qk_hi + static_cast<long long>(b) * N * a.ld_qk;
+  const __half* row0_lo = a.qk_lo + static_cast<long long>(b) * N * a.ld_qk;
+  const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
+  if (tid < 64) q0[tid] = __half2float(row0_hi[hh * 64 + tid]) + __half2float(row0_lo[hh * 64 + tid]);
   __syncthreads();
   float mx = -INFINITY;
   for (int j = tid; j < N; j += 256) {
-    const float4* kh = reinterpret_cast<const float4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
-    const float4* kl = reinterpret_cast<const float4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+    const uint4* kh = reinterpret_cast<const uint4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
+    const uint4* kl = reinterpret_cast<const uint4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
     float s = 0.f;
 #pragma unroll
-    for (int d4 = 0; d4 < 16; ++d4) {
-      const float4 x = kh[d4], y = kl[d4];
-      const float4 q = *reinterpret_cast<const float4*>(q0 + d4 * 4);
-      s = fmaf(q.x, x.x + y.x, s);
-      s = fmaf(q.y, x.y + y.y, s);
-      s = fmaf(q.z, x.z + y.z, s);
-      s = fmaf(q.w, x.w + y.w, s);
-    }
+    for (int d8 = 0; d8 < 8; ++d8) s += dot8_planes(kh[d8], kl[d8], q0 + d8 * 8);
     const float mk = a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f;
-    const float lg = fmaf(s, a.scale, mk);
+    const float lg = fmaf(s, sc, mk);
     P[j] = lg;
     mx = fmaxf(mx, lg);
   }
@@ -590,35 +711,52 @@ attn_cls_combine_kernel(AttnTcArgs a) {
 static int check_tc(const AttnTcArgs& a) {
   MADTP_CHECK_ARG(a.qk_hi && a.qk_lo, "attn_tc: null q/k planes");
   MADTP_CHECK_ARG(a.B >= 0 && a.H > 0 && a.N > 0, "attn_tc: bad shape B=%d H=%d N=%d", a.B, a.H, a.N);
-  MADTP_CHECK_ARG(a.ld_qk >= 2LL * a.H * 64 && a.ld_qk % 4 == 0, "attn_tc: bad q/k leading dimension");
+  MADTP_CHECK_ARG(a.ld_qk >= 2LL * a.H * 64 && a.ld_qk % 8 == 0, "attn_tc: bad q/k leading dimension");
   MADTP_CHECK_ARG(a.B <= 65535 && a.H <= 65535, "attn_tc: B and H must fit the grid limits");
+  return kOk;
+}
+
+template <int KW, int NB>
+static int launch_fwd_kw(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tk_hi,
+                         const CUtensorMap& tk_lo, const CUtensorMap& tv_hi, const CUtensorMap& tv_lo,
+                         const AttnTcArgs& a, cudaStream_t stream) {
+  using Cfg = FwdCfg<KW, NB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<KW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::TOTAL));
+    attr_done = true;
+  }
+  const long long items = static_cast<long long>((a.N + BM - 1) / BM) * a.H * a.B;
+  const long long slots = static_cast<long long>(num_sms()) * Cfg::CTAS_PER_SM;
+  const int grid = static_cast<int>(items < slots ? items : slots);
+  attn_fwd_tc_kernel<KW, NB><<<grid, Cfg::THREADS, Cfg::TOTAL, stream>>>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a);
+  MADTP_LAUNCH_CHECK();
   return kOk;
 }
 
 int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
   int st = check_tc(a);
   if (st != kOk) return st;
-  MADTP_CHECK_ARG(a.vt_hi && a.vt_lo && a.ld_vt >= a.N && a.ld_vt % 4 == 0, "attn_fwd_tc: bad V^T planes");
+  MADTP_CHECK_ARG(a.vt_hi && a.vt_lo && a.ld_vt >= a.N && a.ld_vt % 8 == 0, "attn_fwd_tc: bad V^T planes");
   MADTP_CHECK_ARG(a.out_f16 && a.ldo % 8 == 0 && a.bso % 8 == 0 && a.row_lse && a.out_norm, "attn_fwd_tc: bad outputs");
   if (a.B == 0) return kOk;
   const long long rows = static_cast<long long>(a.B) * a.N;
   CUtensorMap tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo;
-  if ((st = make_tmap(&tq_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
-  if ((st = make_tmap(&tq_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
-  if ((st = make_tmap(&tk_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
-  if ((st = make_tmap(&tk_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
+  if ((st = make_tmap(&tq_hi, a.qk_hi, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&tq_lo, a.qk_lo, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&tk_hi, a.qk_hi, false, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
+  if ((st = make_tmap(&tk_lo, a.qk_lo, false, rows, 2LL * a.H * 64, a.ld_qk, 64)) != kOk) return st;
   const long long vrows = static_cast<long long>(a.B) * a.H * 64;
-  if ((st = make_tmap(&tv_hi, a.vt_hi, true, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
-  if ((st = make_tmap(&tv_lo, a.vt_lo, true, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
-    attr_done = true;
-  }
-  dim3 grid((a.N + BM - 1) / BM, a.H, a.B);
-  attn_fwd_tc_kernel<<<grid, FWD_THREADS, FwdSmem::TOTAL, stream>>>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a);
-  MADTP_LAUNCH_CHECK();
-  return kOk;
+  if ((st = make_tmap(&tv_hi, a.vt_hi, false, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
+  if ((st = make_tmap(&tv_lo, a.vt_lo, false, vrows, a.N, a.ld_vt, 64)) != kOk) return st;
+  // variants (development switch): 0 = 16 softmax warps x 16 keys, one CTA per SM; 1 = 8 warps x 32 keys, one CTA per
+  // SM; 2 = 8 warps x 32 keys, two co-resident CTAs per SM (single-buffered P / O partial, 256 TMEM columns each)
+  const char* var = getenv("MADTP_ATTN_VARIANT");
+  const int v = var ? atoi(var) : 1;
+  if (v == 2) return launch_fwd_kw<32, 1>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a, stream);
+  if (v == 1) return launch_fwd_kw<32, 2>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a, stream);
+  return launch_fwd_kw<16, 2>(tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, a, stream);
 }
 
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
@@ -631,8 +769,8 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   if (a.B == 0) return kOk;
   const long long rows = static_cast<long long>(a.B) * a.N;
   CUtensorMap t_hi, t_lo;
-  if ((st = make_tmap(&t_hi, a.qk_hi, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
-  if ((st = make_tmap(&t_lo, a.qk_lo, true, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&t_hi, a.qk_hi, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
+  if ((st = make_tmap(&t_lo, a.qk_lo, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
   static bool attr_done = false;
   if (!attr_done) {
     MADTP_CUDA(cudaFuncSetAttribute(attn_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -640,7 +778,7 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid(a.n_parts, a.n_parts, a.B);
-  attn_stats_tc_kernel<<<grid, TC_THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
+  attn_stats_tc_kernel<<<grid, StatsSmem::THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
   MADTP_LAUNCH_CHECK();
   const size_t cls_smem = (80 + static_cast<size_t>(a.N)) * sizeof(float);
   attn_cls_head_kernel<<<dim3(a.H, a.B), 256, cls_smem, stream>>>(a);

@@ -28,7 +28,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MADTP_NVCC_EXTRA", "").split()
 
 
 def _digest() -> str:

@@ -222,30 +222,30 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
 }
 
 int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
-                   const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi, float* qk_lo,
-                   int64_t ld_qk, float* vt_hi, float* vt_lo, int64_t ld_vt, void* stream) {
+                   const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi, void* qk_lo,
+                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, void* stream) {
   return counted(launch_gemm_qkv(a_hi, a_lo, lda, w_hi, w_lo, ldb, bias, alpha, M, K, n_tok, heads, qk_hi, qk_lo, ld_qk, vt_hi,
                                  vt_lo, ld_vt, as_stream(stream)),
                  M > 0 ? 1 : 0);
 }
 
-int madtp_attn_tc_fwd(const float* qk_hi, const float* qk_lo, int64_t ld_qk, const float* vt_hi, const float* vt_lo,
+int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream) {
   AttnTcArgs a = {};
-  a.qk_hi = qk_hi; a.qk_lo = qk_lo; a.ld_qk = ld_qk;
-  a.vt_hi = vt_hi; a.vt_lo = vt_lo; a.ld_vt = ld_vt;
+  a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
+  a.vt_hi = static_cast<const __half*>(vt_hi); a.vt_lo = static_cast<const __half*>(vt_lo); a.ld_vt = ld_vt;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
   a.row_lse = row_lse; a.out_norm = out_norm;
   return counted(launch_attn_fwd_tc(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
-int madtp_attn_tc_stats(const float* qk_hi, const float* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
+int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
                         int n_parts, float* cls_attn, float* cls_scratch, void* stream) {
   AttnTcArgs a = {};
-  a.qk_hi = qk_hi; a.qk_lo = qk_lo; a.ld_qk = ld_qk;
+  a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.row_lse = const_cast<float*>(row_lse); a.out_norm = const_cast<float*>(out_norm);
   a.col_part = col_part; a.n_parts = n_parts; a.cls_attn = cls_attn; a.cls_scratch = cls_scratch;

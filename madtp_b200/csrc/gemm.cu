@@ -181,12 +181,19 @@ __device__ __forceinline__ void store_chunk_coalesced(const GemmEpilogue& ep, co
       if (RES) {
         o.x += rv[it].x; o.y += rv[it].y; o.z += rv[it].z; o.w += rv[it].w;
       }
-      if (SPLIT) {
+      if (SPLIT) {   // fp16 hi/lo planes of kQkPlaneScale * o
         if (col_ok && row < M) {
-          const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.c) + row * ep.ldc + col) = h;
-          *reinterpret_cast<float4*>(ep.c_lo + row * ep.ldc + col) =
-              make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+          o.x *= kQkPlaneScale; o.y *= kQkPlaneScale; o.z *= kQkPlaneScale; o.w *= kQkPlaneScale;
+          const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2half2_rn(o.z - f1.x, o.w - f1.y);
+          uint2 ph, pl;
+          ph.x = *reinterpret_cast<const uint32_t*>(&h0);
+          ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+          pl.x = *reinterpret_cast<const uint32_t*>(&l0);
+          pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ep.c) + row * ep.ldc + col) = ph;
+          *reinterpret_cast<uint2*>(ep.c_lo + row * ep.ldc + col) = pl;
         }
       } else if (col_ok && row < M) {
         if (ep.c_f16) {
@@ -650,10 +657,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                   (static_cast<long long>(b * ep.heads + (vc >> 6)) * 64 + (vc & 63)) * ep.ld_vt + i;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float o = fmaf(ep.alpha, sum[c * 32 + j], ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
-                const float h = tf32_hi(o);
+                const float o =
+                    kVPlaneScale * fmaf(ep.alpha, sum[c * 32 + j], ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
+                const __half h = __float2half_rn(o);
                 ep.vt_hi[off + j * ep.ld_vt] = h;
-                ep.vt_lo[off + j * ep.ld_vt] = o - h;
+                ep.vt_lo[off + j * ep.ld_vt] = __float2half_rn(o - __half2float(h));
               }
             }
           } else if (vec_ok && ep.act == 0) {
@@ -861,26 +869,26 @@ static int launch_tf32(const void* a, const void* a_lo, long long lda, const voi
 }
 
 int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
-                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi,
-                    float* qk_lo,
-                    long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream) {
+                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi,
+                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, cudaStream_t stream) {
   MADTP_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && qk_hi && qk_lo && vt_hi && vt_lo, "gemm_qkv: null pointer");
   MADTP_CHECK_ARG(M >= 0 && K > 0 && n_tok > 0 && heads > 0 && M % n_tok == 0, "gemm_qkv: bad shape M=%d n_tok=%d", M,
                   n_tok);
-  MADTP_CHECK_ARG(ld_qk % 4 == 0 && ld_qk >= 2LL * heads * 64 && ld_vt >= n_tok, "gemm_qkv: bad leading dimensions");
+  MADTP_CHECK_ARG(ld_qk % 8 == 0 && ld_qk >= 2LL * heads * 64 && ld_vt >= n_tok && ld_vt % 8 == 0,
+                  "gemm_qkv: bad leading dimensions");
   MADTP_CHECK_ARG((reinterpret_cast<uintptr_t>(qk_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(qk_lo) & 15) == 0 &&
                       (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                   "gemm_qkv: outputs and bias must be 16-byte aligned");
   if (M == 0) return kOk;
   GemmEpilogue ep = {};
   ep.c = qk_hi;
-  ep.c_lo = qk_lo;
+  ep.c_lo = static_cast<__half*>(qk_lo);
   ep.ldc = ld_qk;
   ep.bias = bias;
   ep.alpha = alpha;
   ep.mode = 1;
-  ep.vt_hi = vt_hi;
-  ep.vt_lo = vt_lo;
+  ep.vt_hi = static_cast<__half*>(vt_hi);
+  ep.vt_lo = static_cast<__half*>(vt_lo);
   ep.ld_vt = ld_vt;
   ep.n_tok = n_tok;
   ep.heads = heads;

@@ -14,19 +14,25 @@ struct GemmEpilogue {
   long long ldr;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU, 3 QuickGELU (x * sigmoid(1.702 x))
   float alpha;
-  // ---- mode 1 (TF32x3 kernel only): fused q|k|v projection feeding the tensor-core attention kernels ----
-  // columns [0, qk_cols) are written as tf32 hi/lo planes into c / c_lo ([M, ldc] each); columns [qk_cols, N) (the
-  // value projection, head h = (col - qk_cols) / 64) are written TRANSPOSED per sequence as hi/lo planes
-  // vt[((b * heads + h) * 64 + d) * ld_vt + i] for token i of sequence b = row / n_tok, so that keys are contiguous.
+  // ---- mode 1 (split-operand kernel only): fused q|k|v projection feeding the tensor-core attention kernels ----
+  // columns [0, qk_cols) are written as fp16 hi/lo planes of kQkPlaneScale * value into c / c_lo ([M, ldc] halves
+  // each); columns [qk_cols, N) (the value projection, head h = (col - qk_cols) / 64) are written TRANSPOSED per
+  // sequence as fp16 hi/lo planes of kVPlaneScale * value, vt[((b * heads + h) * 64 + d) * ld_vt + i] for token i of
+  // sequence b = row / n_tok, so that keys are contiguous.
   int mode;
-  float* c_lo;
-  float* vt_hi;
-  float* vt_lo;
+  __half* c_lo;
+  __half* vt_hi;
+  __half* vt_lo;
   long long ld_vt;
   int n_tok;
   int heads;
   int qk_cols;
 };
+
+// Power-of-two scales of the q/k and v operand planes (keep the lo plane of typical activations a normal fp16 number;
+// the attention kernels fold them back into the softmax scale and the output normalisation).
+constexpr float kQkPlaneScale = 8.0f;
+constexpr float kVPlaneScale = 16.0f;
 
 enum GemmPrecision : int {
   kGemmF16 = 0,      // fp16 operands, fp32 accumulate (kind::f16), one MMA per k-step
@@ -55,11 +61,10 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // box of box_rows x 128 bytes and the 128-byte swizzle; out-of-bounds elements read as zero.
 int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld, int box_rows);
 
-// Fused q|k|v projection (TF32x3) with the split / transposed epilogue described at GemmEpilogue::mode.
+// Fused q|k|v projection (F16x3) with the split / transposed epilogue described at GemmEpilogue::mode.
 int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
-                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, float* qk_hi,
-                    float* qk_lo,
-                    long long ld_qk, float* vt_hi, float* vt_lo, long long ld_vt, cudaStream_t stream);
+                    long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi,
+                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, cudaStream_t stream);
 
 int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
                 long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream);

@@ -224,7 +224,7 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
 
 def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N: int, H: int, scale: float,
                       want_stats: bool):
-    """Tensor-core scoring-lane self-attention from the tf32 split of the normalised rows [B*N, C]:
+    """Tensor-core scoring-lane self-attention from the fp16 hi/lo planes of the normalised rows [B*N, C]:
     fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
     Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
     dev = y_hi.device

@@ -2,6 +2,7 @@
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import os
 import torch
 from madtp_b200 import _lib as lib
 dev = torch.device("cuda:0")
@@ -11,8 +12,8 @@ for N in (577, 346, 256):
     x = torch.randn(B * N, 768, generator=g).to(dev)
     w = (torch.randn(3 * H * 64, 768, generator=g) * 0.03).to(dev)
     bias = torch.zeros(3 * H * 64, device=dev)
-    xh, xl = lib.split_tf32(x); wh, wl = lib.split_tf32(w)
-    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(xh, xl, wh, wl, bias, N, H)
+    xh, xl = lib.split_f16(x); wh, wl = lib.split_f16(w, 2.0 ** 14)
+    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(xh, xl, wh, wl, bias, N, H, alpha=2.0 ** -14)
     out = torch.empty(B, N, H * 64, device=dev, dtype=torch.float16)
     lse = torch.empty(B, H, N, device=dev); norm = torch.empty(B, H, N, device=dev)
     n_parts = (N + 127) // 128
@@ -25,7 +26,12 @@ for N in (577, 346, 256):
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e3
-    f = t(lambda: lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm))
+    fv = []
+    for var in ("0", "1", "2"):
+        os.environ["MADTP_ATTN_VARIANT"] = var
+        fv.append(t(lambda: lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm)))
+    os.environ.pop("MADTP_ATTN_VARIANT", None)
+    f = min(fv)
     s = t(lambda: lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, 0.125, lse, norm, col, cls))
-    q = t(lambda: lib.gemm_qkv(xh, xl, wh, wl, bias, N, H))
-    print(f"N={N}: attn_tc_fwd {f:.1f} us ({4.0*B*H*N*N*64/f/1e6:.0f} TFLOP/s alg), attn_tc_stats {s:.1f} us, gemm_qkv {q:.1f} us")
+    q = t(lambda: lib.gemm_qkv(xh, xl, wh, wl, bias, N, H, alpha=2.0 ** -14))
+    print(f"N={N}: attn_tc_fwd variants {fv[0]:.1f} / {fv[1]:.1f} / {fv[2]:.1f} us ({4.0*B*H*N*N*64/f/1e6:.0f} TFLOP/s alg), attn_tc_stats {s:.1f} us, gemm_qkv {q:.1f} us")

@@ -177,16 +177,17 @@ int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Importance score, threshold and survivor count. grid = B, block = 512 (16 warps).
+// Importance score, threshold and survivor count. grid = B, block = 1024 (32 warps): one CTA per sequence is all the
+// parallelism there is across CTAs (B = 64 on 148 SMs), so the block is as wide as the hardware allows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 dtp_score_kernel(DtpScoreArgs a) {
   __shared__ float S[kDtpMaxTokens];      // a_j, then the score
   __shared__ float Bm[kDtpMaxTokens];     // max_t token_att[j,t]
   __shared__ double red[32];
   __shared__ int redi[32];
-  __shared__ float pmax[4][128];
-  __shared__ double pnum[4][128], pden[4][128];
+  __shared__ float pmax[8][128];
+  __shared__ double pnum[8][128], pden[8][128];
   __shared__ float thr_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -205,7 +206,7 @@ dtp_score_kernel(DtpScoreArgs a) {
 
   // (B) alignment statistic: b_j = max_t token_att[j,t]
   part = 0.0;
-  for (int j = warp; j < n; j += 16) {
+  for (int j = warp; j < n; j += 32) {
     float mx = -INFINITY;
     for (int t = lane; t < a.T; t += 32) mx = fmaxf(mx, ta[j * a.ld_ta + t]);
     mx = warp_max(mx);
@@ -228,21 +229,22 @@ dtp_score_kernel(DtpScoreArgs a) {
   __syncthreads();
 
   // (D) threshold = min_t  sum_j softmax_j(token_att[j,t] / temperature) * score_j
-  //     warp w: column group g = w % 4 (t = 32 g + lane), row split q = w / 4
+  //     warp w: column group g = w % 4 (t = 32 g + lane), row split q = w / 4 (eight splits)
   const int g = warp & 3, qd = warp >> 2;
   const int ngroups = (a.T + 31) / 32;  // <= 4
   const int t = g * 32 + lane;
   const bool tok = (g < ngroups) && (t < a.T);
   float mx = -INFINITY;
   if (tok)
-    for (int j = qd; j < n; j += 4) mx = fmaxf(mx, __fdiv_rn(ta[j * a.ld_ta + t], a.temperature));
+    for (int j = qd; j < n; j += 8) mx = fmaxf(mx, __fdiv_rn(ta[j * a.ld_ta + t], a.temperature));
   pmax[qd][g * 32 + lane] = mx;
   __syncthreads();
-  const float gmx = fmaxf(fmaxf(pmax[0][g * 32 + lane], pmax[1][g * 32 + lane]),
-                          fmaxf(pmax[2][g * 32 + lane], pmax[3][g * 32 + lane]));
+  float gmx = pmax[0][g * 32 + lane];
+#pragma unroll
+  for (int q = 1; q < 8; ++q) gmx = fmaxf(gmx, pmax[q][g * 32 + lane]);
   double num = 0.0, den = 0.0;
   if (tok)
-    for (int j = qd; j < n; j += 4) {
+    for (int j = qd; j < n; j += 8) {
       const float e = expf(__fdiv_rn(ta[j * a.ld_ta + t], a.temperature) - gmx);
       den += static_cast<double>(e);
       num += static_cast<double>(e) * static_cast<double>(S[j]);
@@ -253,8 +255,12 @@ dtp_score_kernel(DtpScoreArgs a) {
   if (warp < 4) {
     float v = INFINITY;
     if (tok) {
-      const double nn = (pnum[0][t] + pnum[1][t]) + (pnum[2][t] + pnum[3][t]);
-      const double dd = (pden[0][t] + pden[1][t]) + (pden[2][t] + pden[3][t]);
+      double nn = 0.0, dd = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {   // fixed order
+        nn += pnum[q][t];
+        dd += pden[q][t];
+      }
       v = static_cast<float>(nn / dd);
     }
     v = warp_min(v);
@@ -286,7 +292,7 @@ int launch_dtp_score(const DtpScoreArgs& a, cudaStream_t stream) {
   MADTP_CHECK_ARG(a.temperature > 0.f, "dtp_score: temperature must be > 0");
   MADTP_CHECK_ARG(a.n_parts > 0, "dtp_score: n_parts must be > 0");
   if (a.B == 0) return kOk;
-  dtp_score_kernel<<<a.B, 512, 0, stream>>>(a);
+  dtp_score_kernel<<<a.B, 1024, 0, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

@@ -191,6 +191,20 @@ int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
                         int n_parts, float* cls_attn, float* cls_scratch /* [B,H,N] workspace */, void* stream);
 
+/*
+ * Tensor-core cross-attention of text queries over image tokens (nlvr_encoder.py:174-219, med.py:175-217 with
+ * is_cross_attention; value lane, fp16 operands). Lq <= 128, Nk <= 256, head dim 64; larger problems use madtp_attn_fwd.
+ * q [B*Lq, ldq] and k [B*Nk, ldk] fp16 row-major (head h at column h*64); V^T [H*64, ld_vt] fp16 with the keys of
+ * sequence b at columns b*vt_cols_per_batch + j (the value projection run as W_v . X^T); v_bias [H*64] is added to the
+ * normalised output (rows of P sum to one). k_rows_per_batch / vt_cols_per_batch: per-sequence pitch (>= Nk; for V^T
+ * a multiple of 8 so that every TMA box origin is 16-byte aligned), or 0 when every sequence attends to the same keys
+ * (ITM rerank of one image against many captions). out[b, i, h*64 + d] fp16.
+ */
+int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
+                        const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
+                        int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
+                        void* stream);
+
 /* vector_gather (models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :], x [B,L,d] with batch stride bsx, idx [B,K]
  * (indices are clamped to [0, L)), out [B,K,d] contiguous. */
 int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,

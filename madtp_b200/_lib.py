@@ -32,6 +32,8 @@ SIGNATURES = {
                    _i32, _vp],
     "madtp_layernorm": [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
+    "madtp_attn_cross_tc": [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
+                            _i64, _vp],
     "madtp_split_f16": [_vp, _vp, _vp, _i64, C.c_float, _vp],
     "madtp_cast_f16": [_vp, _vp, _i64, _vp],
     "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -291,6 +293,39 @@ def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None, causal=Fa
                                _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
                                bso, _ptr(rm), _ptr(rs), _ptr(on), 1 if causal else 0, _stream())
     _check(st, "madtp_attn_fwd")
+
+
+def cross_tc_supported(Lq, Nk):
+    return Lq <= 128 and Nk <= 256
+
+
+def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_bias=None, key_mask=None):
+    """Tensor-core cross-attention (value lane). q16 [B,Lq,H*64] fp16 view of a row-major matrix (batch stride =
+    Lq * row stride). keys_per_batch = P > 0 (a multiple of 8, default: Nk rounded up): k16 [B,Nk,H*64] fp16 view with
+    batch stride P rows, vt16 [H*64, >= B*P] fp16 (V^T, keys of sequence b at columns b*P ..). keys_per_batch = 0:
+    every sequence attends to the same keys, k16 [Nk,H*64], vt16 [H*64, >= Nk]. out_f16 [B,Lq,H*64] fp16 view."""
+    B, Lq, C = q16.shape
+    if q16.stride(2) != 1 or (B > 1 and q16.stride(0) != Lq * q16.stride(1)):
+        raise RuntimeError("madtp_b200.attn_cross_tc: q must be a [B*Lq, ld] row-major view")
+    if keys_per_batch == 0:
+        Nk, ldk, per = k16.shape[0], k16.stride(0), 0
+        need = Nk
+    else:
+        Nk, ldk = k16.shape[1], k16.stride(1)
+        per = (Nk + 7) // 8 * 8 if keys_per_batch is None else int(keys_per_batch)
+        if k16.stride(2) != 1 or (B > 1 and k16.stride(0) != per * ldk):
+            raise RuntimeError("madtp_b200.attn_cross_tc: k must be a [B*keys_per_batch, ld] row-major view")
+        need = (B - 1) * per + Nk
+    if vt16.dim() != 2 or vt16.stride(1) != 1 or vt16.shape[0] != C or vt16.shape[1] < need:
+        raise RuntimeError("madtp_b200.attn_cross_tc: vt must be [H*64, >= B*keys_per_batch] with unit inner stride")
+    if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Nk):
+        raise RuntimeError("madtp_b200.attn_cross_tc: key_mask must be contiguous [B, Nk]")
+    ldo, bso = _qkv_strides(out_f16, "out_f16")
+    st = _call("madtp_attn_cross_tc", _ptr(q16, torch.float16, "q"), q16.stride(1), _ptr(k16, torch.float16, "k"), ldk,
+               per, _ptr(vt16, torch.float16, "vt"), vt16.stride(0), per, _ptr(v_bias, torch.float32, "v_bias"), B, H, Lq,
+               Nk, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
+               bso, _stream())
+    _check(st, "madtp_attn_cross_tc")
 
 
 def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None, causal=False):

@@ -43,6 +43,22 @@ struct AttnTcArgs {
 int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);
 
+// Tensor-core cross-attention (cross_attn_tc.cu), value lane: q [B*Lq, ldq] and k [B*Nk or Nk, ldk] fp16 row-major
+// (head h at column h*64), V^T [H*64, ld_vt] fp16 with the keys of sequence b at columns b*vt_cols_per_batch + j.
+// k_rows_per_batch / vt_cols_per_batch (>= Nk, the latter a multiple of 8: TMA box origins are 16-byte aligned) are
+// the per-sequence pitches, or 0 when every sequence attends to the same keys (broadcast).
+struct CrossTcArgs {
+  const __half* q; long long ldq;
+  const __half* k; long long ldk; int k_rows_per_batch;
+  const __half* vt; long long ld_vt; int vt_cols_per_batch;
+  const float* v_bias;                   // [H*64] added to the normalised output, or nullptr
+  int B, H, Lq, Nk;
+  float scale;
+  const float* key_mask;                 // additive [B, Nk] or nullptr
+  __half* out_f16; long long ldo, bso;
+};
+int launch_cross_attn_tc(const CrossTcArgs& a, cudaStream_t stream);
+
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream);
 // Short-sequence self-attention (small_attn.cu): Nq == Nk <= 64, context + (optionally) col_sum[B,L] =
 // sum_{i>=1} max_h P and cls_attn[B,L]; scratch holds B*H*L*(L+1) floats when statistics are requested.

@@ -252,6 +252,20 @@ int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int
   return counted(launch_attn_stats_tc(a, as_stream(stream)), B > 0 ? 3 : 0);
 }
 
+int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
+                        const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
+                        int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
+                        void* stream) {
+  CrossTcArgs a = {};
+  a.q = static_cast<const __half*>(q_f16); a.ldq = ldq;
+  a.k = static_cast<const __half*>(k_f16); a.ldk = ldk; a.k_rows_per_batch = k_rows_per_batch;
+  a.vt = static_cast<const __half*>(vt_f16); a.ld_vt = ld_vt; a.vt_cols_per_batch = vt_cols_per_batch;
+  a.v_bias = v_bias;
+  a.B = B; a.H = H; a.Lq = Lq; a.Nk = Nk; a.scale = scale; a.key_mask = key_mask;
+  a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
+  return counted(launch_cross_attn_tc(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
 int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,
                       void* stream) {
   return counted(launch_gather_rows(x, bsx, idx, out, B, L, K, d, as_stream(stream)), (B > 0 && K > 0) ? 1 : 0);

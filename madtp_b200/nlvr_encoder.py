@@ -54,6 +54,16 @@ def _key_mask(ext_mask: Optional[torch.Tensor], B: int, N: int) -> Optional[torc
     return m.to(torch.float32).contiguous()
 
 
+class CrossKV:
+    """Operands of the tensor-core cross-attention for one layer and branch: k16 [B,Nk,C] (or [Nk,C] when broadcast)
+    fp16 view, vt16 [C, >= B*P] fp16 (V^T, keys contiguous, P = keys_per_batch columns per sequence, 0 = broadcast),
+    v_bias [C] fp32."""
+    __slots__ = ("k16", "vt16", "v_bias", "keys_per_batch")
+
+    def __init__(self, k16, vt16, v_bias, keys_per_batch):
+        self.k16, self.vt16, self.v_bias, self.keys_per_batch = k16, vt16, v_bias, keys_per_batch
+
+
 class BertEmbeddings(nn.Module):
     """word + position embeddings -> LayerNorm (models/nlvr_encoder.py:43-85)."""
 
@@ -454,13 +464,24 @@ class BertLayer(nn.Module):
         C = selfs[0].all_head_size
         nb = len(selfs)
         ctx = torch.empty(B, Ltok, nb * C, dtype=torch.float16, device=att_rows.device)
+        use_tc = kv is not None and all(isinstance(kv[i], CrossKV) for i in range(nb))   # tensor-core kernel operands
+        qdt = torch.float16 if use_tc else torch.float32
         if nb == 2:   # both query projections read the same rows: one GEMM over [Wq0; Wq1]
             ps = [p for s in selfs for p in (s.query.weight, s.query.bias)]
             wq = ca._qcache.get("q01", ps, lambda: Fn.PreparedLinear(
                 torch.cat([s.query.weight for s in selfs], 0), torch.cat([s.query.bias for s in selfs], 0), f16=True))
-            q_all = Fn.linear_f16(att16, wq).view(B, Ltok, nb * C)
+            q_all = Fn.linear_f16(att16, wq, out_dtype=qdt).view(B, Ltok, nb * C)
         for i, s in enumerate(selfs):
-            q = q_all[..., i * C:(i + 1) * C] if nb == 2 else Fn.linear_f16(att16, s._q_f16()).view(B, Ltok, C)
+            q = q_all[..., i * C:(i + 1) * C] if nb == 2 else Fn.linear_f16(att16, s._q_f16(),
+                                                                             out_dtype=qdt).view(B, Ltok, C)
+            em = masks[i] if s.CROSS_ATTENTION_MASK else None
+            out = ctx[..., i * C:(i + 1) * C]
+            if use_tc:
+                ckv = kv[i]
+                Nk = ckv.k16.shape[-2]
+                L.attn_cross_tc(q, ckv.k16, ckv.vt16, s.num_attention_heads, 1.0 / math.sqrt(s.attention_head_size), out,
+                                keys_per_batch=ckv.keys_per_batch, v_bias=ckv.v_bias, key_mask=_key_mask(em, B, Nk))
+                continue
             Nk = enc[i].shape[1]
             if kv is not None:
                 k, v = kv[i]
@@ -468,8 +489,7 @@ class BertLayer(nn.Module):
                 e16 = L.cast_f16(enc[i].contiguous().view(B * Nk, -1))
                 kvp = s.project_kv(e16).view(B, Nk, 2 * C)
                 k, v = kvp[..., :C], kvp[..., C:]
-            em = masks[i] if s.CROSS_ATTENTION_MASK else None
-            s.cross_rows(q, k, v, _key_mask(em, B, Nk), ctx[..., i * C:(i + 1) * C])
+            s.cross_rows(q, k, v, _key_mask(em, B, Nk), out)
         o = ca.output.rows(ctx.view(B * Ltok, nb * C), att_rows, f16=True)
         return o["y"], o["y16"]
 
@@ -500,24 +520,60 @@ class BertEncoder(nn.Module):
             torch.cat([torch.cat([s.key.weight, s.value.weight], 0) for s in selfs], 0),
             torch.cat([torch.cat([s.key.bias, s.value.bias], 0) for s in selfs], 0), f16=True))
 
-    def _project_encoder_states(self, enc):
-        """Returns per-layer [(k0, v0), (k1, v1)] (or [(k, v)]) fp32 views [B, Nk, C] for every layer."""
+    def _all_k_vt_weights(self, which: str):
+        """Tensor-core cross-attention operands: key weights of every layer stacked along N (K = X . Wk^T, fp16 out),
+        value weights stacked along M (V^T = Wv . X^T, keys contiguous) and the value biases [layers, C], which the
+        attention kernel adds to its normalised output (rows of P sum to one)."""
+        selfs = [getattr(l.crossattention, which) for l in self.layer]
+        ps = [p for s in selfs for p in (s.key.weight, s.key.bias, s.value.weight, s.value.bias)]
+
+        def build():
+            wk = Fn.PreparedLinear(torch.cat([s.key.weight for s in selfs], 0),
+                                   torch.cat([s.key.bias for s in selfs], 0), f16=True)
+            wv16 = L.cast_f16(torch.cat([s.value.weight for s in selfs], 0).detach().float())
+            vb = torch.stack([s.value.bias.detach().float() for s in selfs], 0).contiguous()
+            return wk, wv16, vb
+        return self._cache.get("kvt_" + which, ps, build)
+
+    def _project_encoder_states(self, enc, Lq: int = 1 << 30):
+        """Returns for every layer a list with one entry per cross-attention branch: CrossKV (fp16 K, V^T and value
+        bias for the tensor-core kernel) when the problem fits it, else (k, v) fp32 views [B, Nk, C]."""
         names = ["self0", "self1"] if type(enc) == list else ["self"]
         encs = enc if type(enc) == list else [enc]
         C = self.config.hidden_size
         per_layer = [[] for _ in self.layer]
+        use_tc = C % 64 == 0 and all(L.cross_tc_supported(Lq, e.shape[1]) for e in encs)
         for name, e in zip(names, encs):
             Fn.require_cuda(e, "encoder_hidden_states")
             B, Nk, w = e.shape
-            if B > 1 and e.stride(0) == 0:
-                # the same encoder states for every text of the batch (ITM rerank: one image against k_test captions,
-                # compress_retrieval_dtp.py:166-176): project the image ONCE and let the attention kernels broadcast it
-                # through a zero batch stride -- the reference recomputes the K/V projections k_test times
-                e16 = L.cast_f16(e[0].contiguous().view(Nk, w))
-                allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(1, Nk, -1).expand(B, Nk, -1)
-            else:
-                e16 = L.cast_f16(e.contiguous().view(B * Nk, w))
-                allkv = Fn.linear_f16(e16, self._all_kv_weights(name)).view(B, Nk, -1)
+            # the same encoder states for every text of the batch (ITM rerank: one image against k_test captions,
+            # compress_retrieval_dtp.py:166-176): project the image ONCE and let the attention kernels broadcast it
+            # -- the reference recomputes the K/V projections k_test times
+            broadcast = B > 1 and e.stride(0) == 0
+            if use_tc:
+                # every sequence owns P = Nk rounded up to 8 key rows / V^T columns: TMA box origins must be 16-byte
+                # aligned; the padding rows are zero and masked out by the kernel (keys >= Nk)
+                wk, wv16, vb = self._all_k_vt_weights(name)
+                Bk = 1 if broadcast else B
+                P = (Nk + 7) // 8 * 8
+                src = (e[:1] if broadcast else e)
+                if P == Nk:
+                    e16 = L.cast_f16(src.contiguous().view(Bk * Nk, w))
+                else:
+                    e16 = torch.zeros(Bk, P, w, dtype=torch.float16, device=e.device)
+                    e16[:, :Nk] = L.cast_f16(src.contiguous().view(Bk * Nk, w)).view(Bk, Nk, w)
+                    e16 = e16.view(Bk * P, w)
+                allk = Fn.linear_f16(e16, wk, out_dtype=torch.float16).view(Bk, P, -1)        # [Bk, P, layers*C]
+                allvt = torch.empty(wv16.shape[0], Bk * P, dtype=torch.float16, device=e.device)  # [layers*C, Bk*P]
+                L.gemm(L.GEMM_F16, wv16, e16, allvt)
+                for i in range(len(self.layer)):
+                    k16 = allk[:, :Nk, i * C:(i + 1) * C]
+                    per_layer[i].append(CrossKV(k16[0] if broadcast else k16, allvt[i * C:(i + 1) * C], vb[i],
+                                                0 if broadcast else P))
+                continue
+            e16 = L.cast_f16((e[0] if broadcast else e).contiguous().view(-1, w))
+            allkv = Fn.linear_f16(e16, self._all_kv_weights(name))
+            allkv = allkv.view(1, Nk, -1).expand(B, Nk, -1) if broadcast else allkv.view(B, Nk, -1)
             for i in range(len(self.layer)):
                 o = i * 2 * C
                 per_layer[i].append((allkv[..., o:o + C], allkv[..., o + C:o + 2 * C]))
@@ -536,7 +592,7 @@ class BertEncoder(nn.Module):
         reduce_num = int((token_num - 1) // self.config.num_hidden_layers)
         kv = None
         if mode == 'multimodal' and encoder_hidden_states is not None:
-            kv = self._project_encoder_states(encoder_hidden_states)
+            kv = self._project_encoder_states(encoder_hidden_states, hidden_states.shape[1])
         sd_txt_ft_all = None
         for i, layer_module in enumerate(self.layer):
             h = hidden_states.contiguous()

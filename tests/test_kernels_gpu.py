@@ -435,3 +435,47 @@ def test_small_self_attention_fused_stats(lib, dev, B, H, L, masked, causal):
     out2 = torch.empty_like(out)
     lib.attn_small_self(q, k, v, H, 0.125, out2, key_mask=mask, causal=causal)
     assert torch.equal(out, out2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tensor-core cross-attention (value lane): text queries over image tokens
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,Lq,Nk,masked,broadcast", [(4, 12, 20, 255, False, False), (3, 12, 35, 197, True, False),
+                                                        (2, 4, 128, 256, False, False), (5, 12, 20, 130, False, True),
+                                                        (2, 12, 7, 64, True, False), (1, 2, 1, 3, False, False)])
+def test_cross_attention_tensor_core(lib, dev, B, H, Lq, Nk, masked, broadcast):
+    g = torch.Generator(device="cpu").manual_seed(Lq * 31 + Nk)
+    C = H * 64
+    # q and k are column slices of wider row-major buffers, as in the encoders (merged q01 / all-layer K projections);
+    # every sequence owns P = Nk rounded up to 8 key rows / V^T columns (TMA box origins are 16-byte aligned)
+    q_buf = torch.randn(B * Lq, 2 * C, generator=g).to(dev).half()
+    q16 = q_buf.view(B, Lq, 2 * C)[..., C:]
+    Bk = 1 if broadcast else B
+    P = (Nk + 7) // 8 * 8
+    k_buf = torch.randn(Bk, P, 3 * C, generator=g).to(dev).half()
+    k16 = k_buf[:, :Nk, C:2 * C]
+    v_pad = torch.randn(Bk, P, C, generator=g).to(dev).half()
+    v = v_pad[:, :Nk]
+    vt = torch.zeros(2 * C, Bk * P, device=dev, dtype=torch.float16)
+    vt[C:] = v_pad.reshape(Bk * P, C).t()
+    v_bias = torch.randn(C, generator=g).to(dev)
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, Nk // 2), Nk + 1, (B,), generator=g)
+        mask = torch.zeros(B, Nk)
+        for b in range(B):
+            mask[b, lens[b]:] = -10000.0
+        mask = mask.to(dev)
+    out = torch.full((B, Lq, C), float("nan"), device=dev, dtype=torch.float16)
+    scale = 0.125
+    lib.attn_cross_tc(q16, k16[0] if broadcast else k16, vt[C:], H, scale, out, keys_per_batch=0 if broadcast else P,
+                      v_bias=v_bias, key_mask=mask)
+    qd = q16.double().view(B, Lq, H, 64).permute(0, 2, 1, 3)
+    kd = k16.double().expand(B, Nk, C).reshape(B, Nk, H, 64).permute(0, 2, 1, 3)
+    vd = v.double().expand(B, Nk, C).reshape(B, Nk, H, 64).permute(0, 2, 1, 3)
+    s = qd @ kd.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + mask.double()[:, None, None, :]
+    ref = (torch.softmax(s, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(B, Lq, C) + v_bias.double()
+    assert not torch.isnan(out).any()
+    assert _rel(out, ref) < 1.5e-3

@@ -128,7 +128,7 @@ __device__ __forceinline__ void load_residual(const GemmEpilogue& ep, long long 
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
-  if (ACT == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  if (ACT == 1) return gelu_erf(x);
   if (ACT == 2) return fmaxf(x, 0.0f);
   if (ACT == 3) return x / (1.0f + __expf(-1.702f * x));
   return x;

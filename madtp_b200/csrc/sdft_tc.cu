@@ -1,15 +1,15 @@
 // Query_model's aggregated feature on the tensor cores (reference models/utils.py:174-178):
 //   sd_ft[b, t, :] (+)= sum_j softmax_j(token_att[b, j, t] / divisor) * x[b, j, :]
 // i.e. out[T, d] = W^T . X with the contraction over TOKENS, the slow index of both operands (token_att is
-// [tokens, T], x is [tokens, d], both row-major). Measured on B200: tcgen05 kind::tf32 with the MN-major ("transpose")
-// descriptor bits returns zeros, so both operands are re-laid out K-major in shared memory instead -- nothing
+// [tokens, T], x is [tokens, d], both row-major). Both operands are re-laid out K-major in shared memory -- nothing
 // transposed ever goes through HBM:
-//   * X chunks [32 tokens x 128 dims] arrive by TMA (fp32, 128-byte swizzle); four warps read them column-wise
-//     (conflict-free under the swizzle), split into tf32 hi/lo and write [128 dims x 32 tokens] K-major tiles;
-//   * W chunks are computed on the fly by the same warps (exp of the scaled dot products against the column
-//     statistics) and written as [128 entries x 32 tokens] K-major hi/lo tiles.
-// Error-compensated tf32 (3 MMAs per product), accumulated in TMEM over the whole token range -- sd_ft is a model
-// output, not part of the scoring lane, so the ~1e-6 accumulation error is irrelevant.
+//   * X chunks [64 tokens x 128 dims] arrive by TMA (fp32, 128-byte swizzle); eight warps read them column-wise
+//     (conflict-free under the swizzle), split into fp16 hi/lo and write [128 dims x 64 tokens] K-major tiles;
+//   * W chunks are computed on the fly by the same warps (2^(y - max) / sum in the log2 domain, scaled by 2^10 so
+//     that the lo plane of a typical weight ~1/n stays a normal fp16 number) and written as [128 entries x 64 tokens]
+//     K-major hi/lo tiles.
+// Error-compensated fp16 (3 MMAs per product), accumulated in TMEM over the whole token range -- sd_ft is a model
+// output, not part of the scoring lane, so the ~1e-6 accumulation / ex2.approx error is irrelevant.
 //
 //   grid = (d / 128, B); warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = operand builders, 2..5 epilogue.
 #include "dtp.cuh"
@@ -18,17 +18,19 @@
 namespace madtp {
 
 namespace {
-constexpr int TCH = 32;                     // tokens per pipeline stage (one 128-byte K row, 4 k-steps of 8)
+constexpr int TCH = 64;                     // tokens per pipeline stage (one 128-byte K row of halves, 4 k-steps of 16)
 constexpr int TM = 128;                     // codebook entries per CTA (T <= 128, zero padded)
 constexpr int DN = 128;                     // feature columns per CTA
-constexpr int RAW_BYTES = (DN / 32) * TCH * 128;   // X as loaded: 4 boxes of [32 tokens x 32 floats]
-constexpr int OP_BYTES = 128 * 128;                // one K-major operand plane: [128 rows x 32 tokens]
-constexpr int STAGE = RAW_BYTES + 4 * OP_BYTES;    // raw X | W hi | W lo | X^T hi | X^T lo  = 80 KB
+constexpr int RAW_BYTES = (DN / 32) * TCH * 128;   // X as loaded: 4 boxes of [64 tokens x 32 floats]
+constexpr int OP_BYTES = 128 * 128;                // one K-major operand plane: [128 rows x 64 tokens] halves
+constexpr int STAGE = RAW_BYTES + 4 * OP_BYTES;    // raw X | W hi | W lo | X^T hi | X^T lo  = 96 KB
+constexpr float kWScale = 1024.0f;
 constexpr int STAGES = 2;
 constexpr int SMEM_TOTAL = STAGES * STAGE + 256;
 
-// byte offset of element (row, k) in a K-major [rows x 32 floats] tile with the 128-byte swizzle
-__device__ __forceinline__ int kmajor_off(int row, int k4) {   // k4 = index of the 16-byte granule (0..7)
+// byte offset of 16-byte granule k4 (0..7: eight tokens) of a row in a K-major [rows x 128 bytes] tile with the
+// 128-byte swizzle
+__device__ __forceinline__ int kmajor_off(int row, int k4) {
   return (row >> 3) * 1024 + (row & 7) * 128 + ((k4 ^ (row & 7)) << 4);
 }
 }  // namespace
@@ -87,7 +89,7 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
       __syncwarp();
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(2u, TM, DN);
+    constexpr uint32_t idesc = make_idesc(0u, TM, DN);
     for (int c = 0; c < chunks; ++c) {
       const int st = c & 1;
       mbar_wait(&op_full[st], (c >> 1) & 1);
@@ -98,25 +100,40 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
       const uint64_t x_lo = make_sw128_kmajor_desc(base + 3 * OP_BYTES);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, w_lo + 2 * k, x_hi + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, w_lo + 2 * k, x_hi + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, w_hi + 2 * k, x_lo + 2 * k, idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, w_hi + 2 * k, x_lo + 2 * k, idesc, 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, w_hi + 2 * k, x_hi + 2 * k, idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, w_hi + 2 * k, x_hi + 2 * k, idesc, 1u);
         umma_commit(&empty[st]);
         if (c == chunks - 1) umma_commit(acc_full);
       }
       __syncwarp();
     }
   } else {
-    // eight builder warps: thread (t, half) owns row t of both K-major operand tiles and 16 of the chunk's 32 tokens
+    // eight builder warps: thread (t, half) owns row t of both K-major operand tiles and 32 of the chunk's 64 tokens
     const int t = (threadIdx.x - 64) & 127;    // codebook entry (row of W^T) and feature column (row of X^T)
     const int half = (threadIdx.x - 64) >> 7;
     const bool t_ok = t < a.T;
-    const float cmx = t_ok ? a.col_max[b * a.T + t] : 0.f;
-    const float cinv = t_ok ? 1.0f / a.col_sum[b * a.T + t] : 0.f;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float c1 = kLog2e / a.divisor;
+    const float off = t_ok ? -a.col_max[b * a.T + t] * kLog2e : 0.f;
+    const float cinv = t_ok ? kWScale / a.col_sum[b * a.T + t] : 0.f;
     const float* tab = a.ta + b * a.bs_ta + t;
     const int grp = t >> 5, tl = t & 31;
+    auto store_split8 = [](uint8_t* hi, uint8_t* lo, int offb, const float (&v)[8]) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&h);
+        pl[e] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      *reinterpret_cast<uint4*>(hi + offb) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(lo + offb) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    };
     for (int c = 0; c < chunks; ++c) {
       const int st = c & 1;
       uint8_t* stage = smem + st * STAGE;
@@ -124,43 +141,34 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
       uint8_t* w_lo = w_hi + OP_BYTES;
       uint8_t* x_hi = w_lo + OP_BYTES;
       uint8_t* x_lo = x_hi + OP_BYTES;
-      // token_att values of this thread's 16 tokens: all loads in flight before anything depends on them
-      float tv[16];
+      // token_att values of this thread's 32 tokens: all loads in flight before anything depends on them
+      float tv[32];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int j = c * TCH + half * 16 + u;
-        tv[u] = (t_ok && j < a.n) ? __ldg(tab + j * a.ld_ta) : 0.f;
+      for (int u = 0; u < 32; ++u) {
+        const int j = c * TCH + half * 32 + u;
+        tv[u] = (t_ok && j < a.n) ? __ldg(tab + j * a.ld_ta) : -INFINITY;
       }
       mbar_wait(&empty[st], ((c >> 1) & 1) ^ 1);  // operand tiles of chunk c-2 no longer read by the tensor core
-      // ---- W^T row t ----
+      // ---- W^T row t: 1024 * softmax weight of each token (2^-inf = 0 past the sequence end / codebook size) ----
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float w[4];
+        float w[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = c * TCH + half * 16 + q * 4 + u;
-          w[u] = (t_ok && j < a.n) ? expf(__fdiv_rn(tv[q * 4 + u], a.divisor) - cmx) * cinv : 0.f;
-        }
-        const float4 h = make_float4(tf32_hi(w[0]), tf32_hi(w[1]), tf32_hi(w[2]), tf32_hi(w[3]));
-        const int off = kmajor_off(t, half * 4 + q);
-        *reinterpret_cast<float4*>(w_hi + off) = h;
-        *reinterpret_cast<float4*>(w_lo + off) = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
+        for (int u = 0; u < 8; ++u) w[u] = ex2_approx(fmaf(tv[q * 8 + u], c1, off)) * cinv;
+        store_split8(w_hi, w_lo, kmajor_off(t, half * 4 + q), w);
       }
-      // ---- X^T row (feature d0 + t): gather the column of the raw [32 tokens x 128 dims] chunk ----
+      // ---- X^T row (feature d0 + t): gather the column of the raw [64 tokens x 128 dims] chunk ----
       mbar_wait(&raw_full[st], (c >> 1) & 1);
       const uint8_t* raw = stage + grp * TCH * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float x[4];
+        float x[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = half * 16 + q * 4 + u;   // token row within the chunk
+        for (int u = 0; u < 8; ++u) {
+          const int r = half * 32 + q * 8 + u;   // token row within the chunk
           x[u] = *reinterpret_cast<const float*>(raw + r * 128 + (((tl >> 2) ^ (r & 7)) << 4) + ((tl & 3) << 2));
         }
-        const float4 h = make_float4(tf32_hi(x[0]), tf32_hi(x[1]), tf32_hi(x[2]), tf32_hi(x[3]));
-        const int off = kmajor_off(t, half * 4 + q);
-        *reinterpret_cast<float4*>(x_hi + off) = h;
-        *reinterpret_cast<float4*>(x_lo + off) = make_float4(x[0] - h.x, x[1] - h.y, x[2] - h.z, x[3] - h.w);
+        store_split8(x_hi, x_lo, kmajor_off(t, half * 4 + q), x);
       }
       fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -181,8 +189,9 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
       if (row < a.T && d0 + cc * 32 < a.d) {
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          float4 o = make_float4(__uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
-                                 __uint_as_float(v[k + 3]));
+          constexpr float kUn = 1.0f / kWScale;
+          float4 o = make_float4(__uint_as_float(v[k]) * kUn, __uint_as_float(v[k + 1]) * kUn,
+                                 __uint_as_float(v[k + 2]) * kUn, __uint_as_float(v[k + 3]) * kUn);
           float4* p = reinterpret_cast<float4*>(orow + cc * 32 + k);
           if (a.accumulate) {
             const float4 q = *p;

@@ -31,6 +31,23 @@ FLAGS = [
 ] + os.environ.get("MADTP_NVCC_EXTRA", "").split()
 
 
+FASTCALL = CSRC.parent / "_fastcall.so"
+
+
+def build_fastcall(force: bool = False) -> Path:
+    """The CPython trampoline extension (fastcall.c): gcc only, x86-64 only. Optional -- _lib.py falls back to ctypes."""
+    import sysconfig
+    src = CSRC / "fastcall.c"
+    if not force and FASTCALL.exists() and FASTCALL.stat().st_mtime >= src.stat().st_mtime:
+        return FASTCALL
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"], str(src),
+           "-o", str(FASTCALL)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"fastcall build failed:\n{r.stdout}\n{r.stderr}")
+    return FASTCALL
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for name in SOURCES + HEADERS:
@@ -43,6 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
     stamp = BUILD / "digest.txt"
     digest = _digest()
+    build_fastcall(force)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
 

@@ -192,6 +192,16 @@ int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int
                         int n_parts, float* cls_attn, float* cls_scratch /* [B,H,N] workspace */, void* stream);
 
 /*
+ * Asynchronous read-back of a few bytes (the per-layer topk_num, vit.py:145 `.item()`): begin records an event on
+ * `stream` (after the score kernel), a library-owned side stream waits for it and copies src_dev -> dst_pinned (pinned
+ * host memory); wait blocks the host until that copy is done. Work queued on `stream` after begin (the attention output
+ * projection, independent of the pruning decision) runs while the host waits. slot in [0, 8): one outstanding read-back
+ * per slot. The side stream and its events are the only resources the library keeps (one set per device).
+ */
+int madtp_readback_begin(const void* src_dev, void* dst_pinned, int64_t bytes, int slot, void* stream);
+int madtp_readback_wait(int slot);
+
+/*
  * Tensor-core cross-attention of text queries over image tokens (nlvr_encoder.py:174-219, med.py:175-217 with
  * is_cross_attention; value lane, fp16 operands). Lq <= 128, Nk <= 256, head dim 64; larger problems use madtp_attn_fwd.
  * q [B*Lq, ldq] and k [B*Nk, ldk] fp16 row-major (head h at column h*64); V^T [H*64, ld_vt] fp16 with the keys of

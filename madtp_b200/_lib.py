@@ -34,6 +34,8 @@ SIGNATURES = {
     "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
     "madtp_attn_cross_tc": [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
                             _i64, _vp],
+    "madtp_readback_begin": [_vp, _vp, _i64, _i32, _vp],
+    "madtp_readback_wait": [_i32],
     "madtp_split_f16": [_vp, _vp, _vp, _i64, C.c_float, _vp],
     "madtp_cast_f16": [_vp, _vp, _i64, _vp],
     "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -322,6 +324,30 @@ def attn_fwd(q, k, v, H, scale, out_f16, *, key_mask=None, stats=None, causal=Fa
                                _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
                                bso, _ptr(rm), _ptr(rs), _ptr(on), 1 if causal else 0, _stream())
     _check(st, "madtp_attn_fwd")
+
+
+_rb_host = {}     # device index -> pinned int32 [8]: one slot per outstanding read-back
+_rb_next = [0]
+
+
+def readback_begin(src):
+    """Start the asynchronous device->host copy of the int32 scalar `src` behind everything queued so far on the
+    current stream; returns a slot for readback_wait. Kernels launched afterwards overlap the host's wait."""
+    dev = src.device.index
+    host = _rb_host.get(dev)
+    if host is None:
+        host = _rb_host[dev] = torch.zeros(8, dtype=torch.int32).pin_memory()
+    slot = _rb_next[0]
+    _rb_next[0] = (slot + 1) & 7
+    _check(_call("madtp_readback_begin", _ptr(src, torch.int32, "src"), host.data_ptr() + 4 * slot, 4, slot, _stream()),
+           "madtp_readback_begin")
+    return dev, slot
+
+
+def readback_wait(handle) -> int:
+    dev, slot = handle
+    _check(_call("madtp_readback_wait", slot), "madtp_readback_wait")
+    return int(_rb_host[dev][slot])
 
 
 def cross_tc_supported(Lq, Nk):

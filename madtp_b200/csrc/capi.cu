@@ -266,6 +266,56 @@ int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64
   return counted(launch_cross_attn_tc(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
+// ---- asynchronous scalar read-back (the per-layer `topk_num`) --------------------------------------------------
+// The reference reads topk_num with .item() (models/vit.py:145), a device->host copy ordered behind everything already
+// queued on the compute stream. Here the copy runs on a library-owned side stream behind an event recorded right after
+// the score kernel, so kernels queued later on the compute stream (the attention output projection, which does not
+// depend on the pruning decision) execute while the host waits for the four bytes.
+namespace {
+constexpr int kRbSlots = 8, kRbDevices = 16;
+struct ReadbackState {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready[kRbSlots] = {}, done[kRbSlots] = {};
+};
+ReadbackState g_rb[kRbDevices];
+int readback_state(ReadbackState** out) {
+  int dev = 0;
+  MADTP_CUDA(cudaGetDevice(&dev));
+  MADTP_CHECK_ARG(dev >= 0 && dev < kRbDevices, "readback: device index %d out of range", dev);
+  ReadbackState& st = g_rb[dev];
+  if (st.side == nullptr) {
+    MADTP_CUDA(cudaStreamCreateWithFlags(&st.side, cudaStreamNonBlocking));
+    for (int i = 0; i < kRbSlots; ++i) {
+      MADTP_CUDA(cudaEventCreateWithFlags(&st.ready[i], cudaEventDisableTiming));
+      MADTP_CUDA(cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &st;
+  return kOk;
+}
+}  // namespace
+
+int madtp_readback_begin(const void* src_dev, void* dst_pinned, int64_t bytes, int slot, void* stream) {
+  MADTP_CHECK_ARG(src_dev && dst_pinned && bytes > 0 && slot >= 0 && slot < kRbSlots, "readback_begin: bad arguments");
+  ReadbackState* st = nullptr;
+  int rc = readback_state(&st);
+  if (rc != kOk) return rc;
+  MADTP_CUDA(cudaEventRecord(st->ready[slot], as_stream(stream)));
+  MADTP_CUDA(cudaStreamWaitEvent(st->side, st->ready[slot], 0));
+  MADTP_CUDA(cudaMemcpyAsync(dst_pinned, src_dev, static_cast<size_t>(bytes), cudaMemcpyDeviceToHost, st->side));
+  MADTP_CUDA(cudaEventRecord(st->done[slot], st->side));
+  return kOk;
+}
+
+int madtp_readback_wait(int slot) {
+  MADTP_CHECK_ARG(slot >= 0 && slot < kRbSlots, "readback_wait: bad slot");
+  ReadbackState* st = nullptr;
+  int rc = readback_state(&st);
+  if (rc != kOk) return rc;
+  MADTP_CUDA(cudaEventSynchronize(st->done[slot]));
+  return kOk;
+}
+
 int madtp_gather_rows(const float* x, int64_t bsx, const int32_t* idx, float* out, int B, int L, int K, int d,
                       void* stream) {
   return counted(launch_gather_rows(x, bsx, idx, out, B, L, K, d, as_stream(stream)), (B > 0 && K > 0) ? 1 : 0);

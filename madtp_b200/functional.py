@@ -253,18 +253,41 @@ class PruneResult:
     mask: Optional[Tensor] = None   # [B, k+2] additive mask (text)
 
 
-def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,
-              mask_in: Optional[Tensor] = None, max_keep: int = 0) -> PruneResult:
-    """Reduce_token on x [B, n+1, d] (position 0 always survives). reference models/vit.py:123-163,
-    models/nlvr_encoder.py:400-454 (mask_mode 1), models/med.py:345-391 (mask_mode 2)."""
-    B, N, d = x.shape
-    n = N - 1
+class PendingPrune:
+    """Score kernel launched, topk_num on its way to the host (dtp_score_async); dtp_finish completes the pruning."""
+    __slots__ = ("score", "thr", "cnt", "topk", "handle")
+
+    def __init__(self, score, thr, cnt, topk, handle):
+        self.score, self.thr, self.cnt, self.topk, self.handle = score, thr, cnt, topk, handle
+
+
+def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: int) -> PendingPrune:
+    """First half of Reduce_token: importance score, threshold, survivor counts and their batch maximum (reference
+    models/vit.py:126-145), plus an asynchronous read-back of that maximum. Launch work that does not depend on the
+    pruning decision between this and dtp_finish: it runs while the host waits for topk_num."""
     T = token_att.shape[2]
     score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature)
-    k = int(topk.item())            # the reference's one host sync per pruned layer (models/vit.py:145)
+    return PendingPrune(score, thr, cnt, topk, L.readback_begin(topk))
+
+
+def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Optional[Tensor] = None,
+               max_keep: int = 0) -> PruneResult:
+    """Second half of Reduce_token on x [B, n+1, d] (position 0 always survives): select, gather, merge."""
+    B, N, d = x.shape
+    n = N - 1
+    score, thr, cnt, topk = pend.score, pend.thr, pend.cnt, pend.topk
+    k = L.readback_wait(pend.handle)        # the reference's one host sync per pruned layer (models/vit.py:145)
     if k <= max_keep or n - k <= 1:         # models/vit.py:148-149 (max_keep = 0); clip/model.py:220
         return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
     keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
                                                          max_keep=max_keep)
     out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep)
     return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2])
+
+
+def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,
+              mask_in: Optional[Tensor] = None, max_keep: int = 0) -> PruneResult:
+    """Reduce_token on x [B, n+1, d] (position 0 always survives). reference models/vit.py:123-163,
+    models/nlvr_encoder.py:400-454 (mask_mode 1), models/med.py:345-391 (mask_mode 2)."""
+    pend = dtp_score_async(stats, token_att, temperature, x.shape[1] - 1)
+    return dtp_finish(x, pend, mask_mode=mask_mode, mask_in=mask_in, max_keep=max_keep)

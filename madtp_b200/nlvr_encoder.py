@@ -425,6 +425,8 @@ class BertLayer(nn.Module):
         else:
             h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
             ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune)
+        # score kernel + read-back of topk_num first: the output dense + LayerNorm below do not depend on them
+        pend = Fn.dtp_score_async(sa.get_attention_map(), token_attn, float(temperature), Ltok - 1) if prune else None
         att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=not prune)
         att_f32, att16 = att["y"].view(B, Ltok, d), att.get("y16")
 
@@ -433,8 +435,7 @@ class BertLayer(nn.Module):
         if prune:
             if key_mask is None:
                 key_mask = torch.zeros(B, Ltok, dtype=torch.float32, device=h.device)
-            res = Fn.dtp_prune(att_f32, sa.get_attention_map(), token_attn, float(temperature),
-                               mask_mode=self.MASK_MODE, mask_in=key_mask)
+            res = Fn.dtp_finish(att_f32, pend, mask_mode=self.MASK_MODE, mask_in=key_mask)
             self.last_prune = res
             att_f32 = res.x
             if res.pruned:

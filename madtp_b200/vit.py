@@ -120,12 +120,20 @@ class Attention(nn.Module):
     def forward_rows(self, y_hi, y_lo, B, N, residual=None, want_stats=True):
         """y_hi/y_lo: tf32 split of the normalised input rows [B*N, C]. Returns fp32 [B*N, C] = proj(ctx) (+residual)
         and stores the pruning statistics (models/vit.py:83,96-101)."""
-        qkv_w, proj_w = self._prepared()
-        C = self.dim
+        ctx16 = self.attend_rows(y_hi, y_lo, B, N, want_stats)
+        return self.project_rows(ctx16, B, N, residual)
+
+    def attend_rows(self, y_hi, y_lo, B, N, want_stats=True):
+        """q|k|v projection, attention and (optionally) the pruning statistics; returns the fp16 context [B,N,C]."""
+        qkv_w, _ = self._prepared()
         ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, self.scale, want_stats)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
-        return Fn.linear_f16(ctx16.view(B * N, C), proj_w, residual=residual)
+        return ctx16
+
+    def project_rows(self, ctx16, B, N, residual=None):
+        _, proj_w = self._prepared()
+        return Fn.linear_f16(ctx16.view(B * N, self.dim), proj_w, residual=residual)
 
     def forward(self, x, register_hook=False):
         Fn.require_cuda(x, "x")
@@ -174,11 +182,14 @@ class Block(nn.Module):
         """x [B,N,C] fp32 contiguous; ln1 = functional.layernorm_rows(..., tf32=True) of norm1(x)."""
         B, N, C = x.shape
         prune = temperature > 0
-        x1 = self.attn.forward_rows(ln1["y_hi"], ln1["y_lo"], B, N, residual=x.view(B * N, C), want_stats=prune)
-        x1 = x1.view(B, N, C)
+        ctx16 = self.attn.attend_rows(ln1["y_hi"], ln1["y_lo"], B, N, want_stats=prune)
+        # the score kernel and the read-back of topk_num go first; the output projection does not depend on them and
+        # runs while the host waits for the four bytes
+        pend = Fn.dtp_score_async(self.attn.get_attention_map(), token_attn, float(temperature), N - 1) if prune else None
+        x1 = self.attn.project_rows(ctx16, B, N, residual=x.view(B * N, C)).view(B, N, C)
         self.last_prune = None
         if prune:
-            res = Fn.dtp_prune(x1, self.attn.get_attention_map(), token_attn, float(temperature))
+            res = Fn.dtp_finish(x1, pend)
             self.last_prune = res
             x1 = res.x
         N2 = x1.shape[1]

@@ -457,12 +457,12 @@ __device__ __forceinline__ void umma_x(uint32_t d_tmem, uint64_t a, uint64_t b, 
   else umma_tf32(d_tmem, a, b, idesc, accumulate);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 struct Tf32Cfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int K_ELEMS = 32;
   static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;   // a CTA of a pair stages half of B's rows
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -477,14 +477,18 @@ struct Tf32Cfg {
 // shared-memory traffic of the (weight) operand -- the K = 768 projections are L2-bandwidth bound otherwise.
 // F16 = true: the same pipeline with fp16 hi/lo planes (kind::f16): a 128-byte operand row then holds 64 k-elements
 // instead of 32 and every MMA covers 16 of them, so a k-block costs the same bytes and MMA slots but twice the K.
-template <int BLOCK_N, int CL, bool F16 = false>
+// PAIR = true (with CL = 2, F16): the two CTAs form a cta_group::2 pair -- ONE MMA of M = 256 spans both SMs, every
+// CTA stages its own 128 rows of A and only HALF of B's rows (64 KB per k-block instead of 96 KB: this kernel is bound
+// by the L2 -> shared-memory operand traffic), the leader issues all MMAs and owns the operand-full barriers.
+template <int BLOCK_N, int CL, bool F16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
                    GemmEpilogue ep, int M, int N, int K) {
-  using Cfg = Tf32Cfg<BLOCK_N>;
+  using Cfg = Tf32Cfg<BLOCK_N, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = Cfg::COLS_PER_WARP;
+  static_assert(!PAIR || (CL == 2 && F16), "the CTA-pair variant is the fp16-plane kernel on clusters of two");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -502,6 +506,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;   // work items per cluster: CL vertically adjacent tiles
   constexpr int K_ELEMS = F16 ? 64 : Cfg::K_ELEMS;
   const int num_kb = (K + K_ELEMS - 1) / K_ELEMS;
+  const int chunk = ep.chunk_kb > 0 ? ep.chunk_kb : 1;   // k-blocks accumulated in TMEM between two drains
   const int rank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
@@ -514,17 +519,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
+      mbar_init(&empty_bar[s], PAIR ? 1 : CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], PAIR ? 16 : 8);   // pair: the epilogue warps of BOTH CTAs release the leader's buffer
     }
     fence_mbar_init();
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -543,7 +549,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1u);   // CL > 1: BOTH CTAs have retired their MMAs on this stage
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           const int k0 = kb * K_ELEMS;
-          if (elect_one()) {
+          if (PAIR) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (elect_one()) {
+              const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const int nr = n0 + rank * (BLOCK_N / 2);
+              tma_load_2d_pair(&tm_a, bar, s, k0, m0);
+              tma_load_2d_pair(&tm_b, bar, s + Cfg::A_BYTES, k0, nr);
+              tma_load_2d_pair(&tm_a_lo, bar, s + Cfg::A_BYTES + Cfg::B_BYTES, k0, m0);
+              tma_load_2d_pair(&tm_b_lo, bar, s + 2 * Cfg::A_BYTES + Cfg::B_BYTES, k0, nr);
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
             tma_load_2d(&tm_a_lo, &full_bar[stage], s + Cfg::A_BYTES + Cfg::B_BYTES, k0, m0);
@@ -567,15 +584,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    {
-      constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, Cfg::BLOCK_M, BLOCK_N);
+    if (!PAIR || rank == 0) {   // pair: only the leader issues MMAs
+      constexpr uint32_t idesc = make_idesc(F16 ? 0u : 2u, PAIR ? 2 * Cfg::BLOCK_M : Cfg::BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
       for (int tile = first_item; tile < num_tiles; tile += item_stride) {
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&tmem_empty[buf], buf_phase ^ 1u);
+          const bool chunk_first = (kb % chunk) == 0;                       // first k-block of a drained chunk
+          const bool chunk_last = ((kb + 1) % chunk) == 0 || kb + 1 == num_kb;
+          if (chunk_first) mbar_wait(&tmem_empty[buf], buf_phase ^ 1u);   // (polling here measured 6 % slower)
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BLOCK_N);
@@ -586,24 +605,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint64_t b_lo = make_sw128_kmajor_desc(s + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
           // cross terms first (tiny partial sums), then the dominant hi*hi products: only the last four
           // accumulates truncate at the full partial-sum magnitude
-          if (elect_one()) {
+          if (PAIR) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, k != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (k != 0 || !chunk_first) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+              umma_commit_pair(&empty_bar[stage], 3);   // frees the stage and publishes the chunk in both CTAs
+              if (chunk_last) umma_commit_pair(&tmem_full[buf], 3);
+            }
+          } else if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_x<F16>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (k != 0 || !chunk_first) ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_x<F16>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
             if (CL == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_multicast(&empty_bar[stage], (1u << CL) - 1);   // frees the stage in both CTAs
-            umma_commit(&tmem_full[buf]);
+            if (chunk_last) umma_commit(&tmem_full[buf]);
           }
           __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
-          buf ^= 1;
-          if (buf == 0) buf_phase ^= 1u;
+          if (chunk_last) {
+            buf ^= 1;
+            if (buf == 0) buf_phase ^= 1u;
+          }
         }
       }
     }
@@ -613,13 +647,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int buf = 0;
     uint32_t buf_phase = 0;
     const bool vec_ok = epilogue_vec_ok(ep, N);
+    const int num_chunks = (num_kb + chunk - 1) / chunk;
     for (int tile = first_item; tile < num_tiles; tile += item_stride) {
       const int m0 = ((tile / n_tiles) * CL + rank) * Cfg::BLOCK_M;
       const int n0 = (tile % n_tiles) * BLOCK_N;
       float sum[CW];
 #pragma unroll
       for (int j = 0; j < CW; ++j) sum[j] = 0.f;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int ch = 0; ch < num_chunks; ++ch) {
         mbar_wait(&tmem_full[buf], buf_phase);
         tcgen05_fence_after();
         const uint32_t tbase =
@@ -634,7 +669,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0));
+          else mbar_arrive(&tmem_empty[buf]);
+        }
         buf ^= 1;
         if (buf == 0) buf_phase ^= 1u;
       }
@@ -689,7 +727,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   if (CL > 1) cluster_sync();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -817,10 +856,10 @@ static int launch_tc(const void* a, const void* a_lo, long long lda, const void*
 }
 
 
-template <int BLOCK_N, int CL, bool F16 = false>
+template <int BLOCK_N, int CL, bool F16 = false, bool PAIR = false>
 static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
                           long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = Tf32Cfg<BLOCK_N>;
+  using Cfg = Tf32Cfg<BLOCK_N, PAIR>;
   CUtensorMap ta, tal, tb, tbl;
   int st;
   if ((st = make_tmap(&ta, a, !F16, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
@@ -829,9 +868,14 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   if ((st = make_tmap(&tbl, b_lo, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   static bool attr_done = false;
   if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES));
     attr_done = true;
+  }
+  GemmEpilogue epc = ep;
+  if (epc.chunk_kb <= 0) {
+    static const int env_chunk = getenv("MADTP_CHUNK_KB") ? atoi(getenv("MADTP_CHUNK_KB")) : 0;
+    epc.chunk_kb = env_chunk > 0 ? env_chunk : (F16 ? kF16ChunkKb : 1);
   }
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int items = ((m_tiles + CL - 1) / CL) * ((N + BLOCK_N - 1) / BLOCK_N);
@@ -849,7 +893,7 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL, F16>, ta, tal, tb, tbl, ep, M, N, K));
+  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>, ta, tal, tb, tbl, epc, M, N, K));
   return kOk;
 }
 
@@ -859,7 +903,16 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
 template <int BLOCK_N, bool F16 = false>
 static int launch_tf32(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
                        const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
-  if (F16) return launch_tf32_cl<BLOCK_N, 1, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+  if (F16) {
+    // CTA pairs (cta_group::2) are implemented and verified but OFF by default (MADTP_PAIR=1 enables them). Measured on
+    // B200, M=36928 N=2304 K=768: 360 us against 350 us with one drained chunk per k-block (the leader's accumulator
+    // hand-off then crosses the cluster 12 times per tile), 323 against 332 us with two k-blocks per chunk, 272 against
+    // 309 us with a single drain per tile -- the pair pays off only where the chunked accumulation is not needed.
+    const bool pair = BLOCK_N == 256 && getenv("MADTP_PAIR") != nullptr &&
+                      static_cast<long long>((M + 127) / 128) * ((N + BLOCK_N - 1) / BLOCK_N) >= 2LL * num_sms();
+    if (pair) return launch_tf32_cl<256, 2, true, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+    return launch_tf32_cl<BLOCK_N, 1, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
+  }
   const int m_tiles = (M + 127) / 128;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   static const bool use_cluster = getenv("MADTP_CLUSTER") != nullptr;

@@ -19,6 +19,7 @@ struct GemmEpilogue {
   // each); columns [qk_cols, N) (the value projection, head h = (col - qk_cols) / 64) are written TRANSPOSED per
   // sequence as fp16 hi/lo planes of kVPlaneScale * value, vt[((b * heads + h) * 64 + d) * ld_vt + i] for token i of
   // sequence b = row / n_tok, so that keys are contiguous.
+  int chunk_kb;           // split-operand kernels: k-blocks accumulated in TMEM per drained chunk (0 = default)
   int mode;
   __half* c_lo;
   __half* vt_hi;
@@ -31,6 +32,10 @@ struct GemmEpilogue {
 
 // Power-of-two scales of the q/k and v operand planes (keep the lo plane of typical activations a normal fp16 number;
 // the attention kernels fold them back into the softmax scale and the output normalisation).
+// k-blocks (64 k-elements each) the fp16-plane kernel lets the tensor core accumulate before a chunk is drained into
+// fp32 registers. The accumulator truncates on every add, so the error grows with the chunk; the TMEM read-back of a
+// 128 x 256 chunk (128 KB at ~64 B/clk) costs more than its MMAs, so the speed grows with it too (measured: DESIGN.md).
+constexpr int kF16ChunkKb = 1;
 constexpr float kQkPlaneScale = 8.0f;
 constexpr float kVPlaneScale = 16.0f;
 

@@ -477,19 +477,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 2
+// Pass 2 (persistent: every CTA walks a strided list of (sequence, 128-query tile, 128-key tile) work items)
 //   warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 consumers: TMEM lane quadrant = warp % 4 (query rows), column
 //   half = (warp - 2) / 4 (64 of the tile's 128 keys).
+//   The operand ring and the two S buffers are indexed by a head counter that runs ACROSS work items, so the producer
+//   and the MMA warp are already several heads into the next item while the consumers reduce the current one (measured
+//   on the one-item-per-CTA version: 4.4k cycles of start-up and 6.1k cycles of reduction around 15.6k cycles of MMAs).
+//   The column sums over the 128 query rows are formed without shared-memory staging: a transposing butterfly over the
+//   32 lanes of every warp (fixed order, deterministic) and a four-way sum over the lane quadrants.
 // ------------------------------------------------------------------------------------------------
 struct StatsSmem {
   static constexpr int BOX_BYTES = BM * 128;                // [128 rows x 64 halves]
   static constexpr int STAGE_BYTES = 4 * BOX_BYTES;         // Q hi, Q lo, K hi, K lo of one head
   static constexpr int STAGES = 3;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 1024 + 1024;
-  static constexpr int RED_LD = 129;                        // column-sum staging pitch (floats), reuses the stages
+  static constexpr int MASK_OFF = BAR_OFF + 128;            // [2][128] additive key mask of the tile (log2 domain)
+  static constexpr int PART_OFF = MASK_OFF + 2 * 128 * 4;   // [2][4][128] per-quadrant column sums
+  static constexpr int TOTAL = PART_OFF + 2 * 4 * 128 * 4 + 1024;
   static constexpr int THREADS = 320;
 };
+
+// x[0..31] of the 32 lanes -> lane l returns sum over lanes of x[l] (31 shuffles; fixed summation tree)
+__device__ __forceinline__ float warp_transpose_sum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? x[i] : x[i + s];
+      const float keep = up ? x[i + s] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
 
 __global__ void __launch_bounds__(StatsSmem::THREADS, 1)
 attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -502,11 +523,14 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   uint64_t* s_full = bars + 6;     // [2]
   uint64_t* s_empty = bars + 8;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* colmask = reinterpret_cast<float*>(bars + 12);  // [128] additive mask of this key tile (-inf past N)
+  float* colmask = reinterpret_cast<float*>(smem + StatsSmem::MASK_OFF);   // [item parity][128]
+  float* part = reinterpret_cast<float*>(smem + StatsSmem::PART_OFF);      // [item parity][quadrant][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * BM, it = blockIdx.y, i0 = it * BM, b = blockIdx.z;
   const int N = a.N, H = a.H, HD = a.H * 64;
+  const int NT = a.n_parts;                      // tiles per side
+  const int items = NT * NT * a.B;
+  constexpr float kLog2e = 1.4426950408889634f;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_hi);
@@ -527,94 +551,111 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     __syncwarp();
     tmem_alloc<256>(tmem_slot);
   }
-  if (warp >= 2 && warp < 6) {
-    const int c = threadIdx.x - 64;
-    const int j = j0 + c;
-    colmask[c] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f) : -INFINITY;
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {   // warp-uniform control flow, one elected lane issues
-    for (int hh = 0; hh < H; ++hh) {
-      const int st = hh % StatsSmem::STAGES;
-      mbar_wait(&empty[st], ((hh / StatsSmem::STAGES) & 1) ^ 1);
-      uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], StatsSmem::STAGE_BYTES);
-        tma_load_2d(&tm_hi, &full[st], s, hh * 64, b * N + i0);
-        tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64, b * N + i0);
-        tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + j0);
-        tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + j0);
+    int gh = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int jt = item % NT, it = (item / NT) % NT, b = item / (NT * NT);
+      for (int hh = 0; hh < H; ++hh, ++gh) {
+        const int st = gh % StatsSmem::STAGES;
+        mbar_wait(&empty[st], ((gh / StatsSmem::STAGES) & 1) ^ 1);
+        uint8_t* s = smem + st * StatsSmem::STAGE_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[st], StatsSmem::STAGE_BYTES);
+          tma_load_2d(&tm_hi, &full[st], s, hh * 64, b * N + it * BM);
+          tma_load_2d(&tm_lo, &full[st], s + StatsSmem::BOX_BYTES, hh * 64, b * N + it * BM);
+          tma_load_2d(&tm_hi, &full[st], s + 2 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + jt * BM);
+          tma_load_2d(&tm_lo, &full[st], s + 3 * StatsSmem::BOX_BYTES, HD + hh * 64, b * N + jt * BM);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(0u, BM, BM);
-    for (int hh = 0; hh < H; ++hh) {
-      const int hb = hh & 1, st = hh % StatsSmem::STAGES;
-      mbar_wait(&s_empty[hb], ((hh >> 1) & 1) ^ 1);
-      mbar_wait(&full[st], (hh / StatsSmem::STAGES) & 1);
-      tcgen05_fence_after();
-      const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
-      if (elect_one()) {
-        issue_slice_ss(tmem_base + hb * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
-                       s + 3 * StatsSmem::BOX_BYTES, idesc);
-        umma_commit(&empty[st]);
-        umma_commit(&s_full[hb]);
+    int gh = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      for (int hh = 0; hh < H; ++hh, ++gh) {
+        const int hb = gh & 1, st = gh % StatsSmem::STAGES;
+        mbar_wait(&s_empty[hb], ((gh >> 1) & 1) ^ 1);
+        mbar_wait(&full[st], (gh / StatsSmem::STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t s = smem_u32(smem + st * StatsSmem::STAGE_BYTES);
+        if (elect_one()) {
+          issue_slice_ss(tmem_base + hb * 128, s, s + StatsSmem::BOX_BYTES, s + 2 * StatsSmem::BOX_BYTES,
+                         s + 3 * StatsSmem::BOX_BYTES, idesc);
+          umma_commit(&empty[st]);
+          umma_commit(&s_full[hb]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;          // row within the tile
-    const int i = i0 + r;
+    const int tid = threadIdx.x - 64;        // 0..255 among the consumers
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const bool row_ok = (i >= 1) && (i < N);  // the CLS query row is excluded (reference vit.py:126)
-    const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
-    float mx[64];
+    // log2 domain: t = S * c1 + mask * log2e - lse * log2e,  P = 2^t
+    const float c1 = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale)) * kLog2e;
+    int gh = 0, ip = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ip ^= 1) {
+      const int jt = item % NT, it = (item / NT) % NT, b = item / (NT * NT);
+      const int i = it * BM + r, j0 = jt * BM;
+      const bool row_ok = (i >= 1) && (i < N);  // the CLS query row is excluded (reference vit.py:126)
+      float* cm = colmask + ip * 128;
+      if (tid < 128) {
+        const int j = j0 + tid;
+        cm[tid] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] * kLog2e : 0.f) : -INFINITY;
+      }
+      named_bar_sync(2, 256);   // mask of this item visible (its buffer was last read two items ago)
+      float mx[64];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
-    const float* lse_p = a.row_lse + static_cast<long long>(b) * H * N + (i < N ? i : 0);
-    float lse_next = (i < N) ? __ldg(lse_p) : 0.f;
-    for (int hh = 0; hh < H; ++hh) {
-      const int hb = hh & 1;
-      const float lse = lse_next;
-      if (hh + 1 < H && i < N) lse_next = __ldg(lse_p + static_cast<long long>(hh + 1) * N);   // hidden by this head
-      mbar_wait(&s_full[hb], (hh >> 1) & 1);
-      tcgen05_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64, v0);
-      tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64 + 32, v1);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[hb]);
+      for (int c = 0; c < 64; ++c) mx[c] = -INFINITY;
+      const float* lse_p = a.row_lse + static_cast<long long>(b) * H * N + (i < N ? i : 0);
+      float lse_next = (i < N) ? __ldg(lse_p) : 0.f;
+      for (int hh = 0; hh < H; ++hh, ++gh) {
+        const int hb = gh & 1;
+        const float lse2 = lse_next * kLog2e;
+        if (hh + 1 < H && i < N) lse_next = __ldg(lse_p + static_cast<long long>(hh + 1) * N);   // hidden by this head
+        mbar_wait(&s_full[hb], (gh >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64, v0);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + hb * 128 + half * 64 + 32, v1);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[hb]);
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float t0 = fmaf(__uint_as_float(v0[k]), sc, colmask[half * 64 + k]) - lse;
-        const float t1 = fmaf(__uint_as_float(v1[k]), sc, colmask[half * 64 + 32 + k]) - lse;
-        mx[k] = fmaxf(mx[k], t0);
-        mx[32 + k] = fmaxf(mx[32 + k], t1);
+        for (int k = 0; k < 32; ++k) {
+          const float t0 = fmaf(__uint_as_float(v0[k]), c1, cm[half * 64 + k]) - lse2;
+          const float t1 = fmaf(__uint_as_float(v1[k]), c1, cm[half * 64 + 32 + k]) - lse2;
+          mx[k] = fmaxf(mx[k], t0);
+          mx[32 + k] = fmaxf(mx[32 + k], t1);
+        }
+      }
+      // column sums over this warp's 32 query rows (lane l ends up with columns l and 32 + l of its half), then over
+      // the four lane quadrants in quadrant order
+      float* pt = part + ip * 4 * 128;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float p[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) p[c] = row_ok ? ex2_approx(mx[g * 32 + c]) : 0.f;
+        const float tot = warp_transpose_sum32(p, lane);
+        pt[quad * 128 + half * 64 + g * 32 + lane] = tot;
+      }
+      named_bar_sync(3, 256);
+      if (tid < 128) {
+        const int j = j0 + tid;
+        const float sum = ((pt[tid] + pt[128 + tid]) + pt[256 + tid]) + pt[384 + tid];
+        if (j < N) a.col_part[(static_cast<long long>(b) * a.n_parts + it) * N + j] = sum;
       }
     }
-    // every MMA has retired (the last s_full fired), so the operand stages can be reused as the reduction tile
-    float* red = reinterpret_cast<float*>(smem);
-    float* part = red + BM * StatsSmem::RED_LD;   // [2][128] partial column sums (rows 0..63 / 64..127)
-#pragma unroll
-    for (int c = 0; c < 64; ++c) red[r * StatsSmem::RED_LD + half * 64 + c] = row_ok ? expf(mx[c]) : 0.f;
-    named_bar_sync(1, 256);
-    const int tid = threadIdx.x - 64;
-    const int c = tid & 127, ph = tid >> 7;
-    float sum = 0.f;
-    for (int rr = ph * 64; rr < ph * 64 + 64; ++rr) sum += red[rr * StatsSmem::RED_LD + c];   // fixed order
-    part[ph * BM + c] = sum;
-    named_bar_sync(1, 256);
-    const int j = j0 + c;
-    if (ph == 0 && j < N) a.col_part[(static_cast<long long>(b) * a.n_parts + it) * N + j] = part[c] + part[BM + c];
   }
 
   tcgen05_fence_before();
@@ -777,7 +818,8 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
                                     StatsSmem::TOTAL));
     attr_done = true;
   }
-  dim3 grid(a.n_parts, a.n_parts, a.B);
+  const long long items = static_cast<long long>(a.n_parts) * a.n_parts * a.B;
+  const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   attn_stats_tc_kernel<<<grid, StatsSmem::THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
   MADTP_LAUNCH_CHECK();
   const size_t cls_smem = (80 + static_cast<size_t>(a.N)) * sizeof(float);

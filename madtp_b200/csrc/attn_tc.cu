@@ -292,20 +292,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
     const int grp = (warp - 2) >> 2;                // column group
     const int r = quad * 32 + lane;                 // row within the tile
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    // Everything below works in the log2 domain on the raw accumulator: y = S * c1 (+ mask * log2e), p = 2^(y - m)
-    // with the running maximum m of y; one FFMA + one MUFU.EX2 per element. The FFMA rounds y once (|error| <=
-    // 2^-24 |y|), i.e. an ABSOLUTE error of at most ~3e-8 on p relative to the row maximum -- the size of one fp32
-    // rounding of the row sum.
+    // p = 256 exp(S sc - m) with the running maximum m of the logits, as d = fma(S, sc, -m) (ONE rounding of a quantity
+    // that is small wherever p matters; sc = scale / 64 is a power of two for the usual head dim) followed by
+    // 2^(d log2e + 8) on the SFU: two FFMAs and one MUFU.EX2 per element, relative error ~2^-22 -- the accuracy of
+    // expf without its range reduction.
     constexpr float kLog2e = 1.4426950408889634f;
-    const float c1 = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale)) * kLog2e;
-    const float mask_to_raw = kLog2e / c1;      // additive key mask expressed in raw-accumulator units
-    constexpr float kLogP = 8.0f;               // log2(kPScale): p is produced as 256 * 2^(y - m) directly
+    const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
+    const float mask_to_raw = 1.0f / sc;        // additive key mask expressed in raw-accumulator units
+    constexpr float kLogP = 8.0f;               // log2(kPScale): p is produced as 256 * exp(.) directly
     int g = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int qt = item % QT, bh = item / QT, h = bh % a.H, b = bh / a.H;
       const int i = qt * BM + r;
       const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
-      float m = -INFINITY, l = 0.f;               // m in raw units * c1 (log2 domain); l = 256 * sum of p
+      float m = -INFINITY, l = 0.f;               // m: running maximum of the logits; l = 256 * sum of p
       float m_hist[2] = {-INFINITY, -INFINITY};   // running max at the NB previous tiles (indexed by g % NB)
       float o[KW];
 #pragma unroll
@@ -318,7 +318,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         uint32_t v[KW];
         tmem_ld_cols<KW>(tmem_base + lane_off + kO + (u % NB) * 64 + grp * KW, v);
         tmem_ld_wait();
-        const float f = ex2_approx(m_u - m_now);
+        const float f = ex2_approx((m_u - m_now) * kLog2e);
 #pragma unroll
         for (int k = 0; k < KW; ++k) o[k] = fmaf(__uint_as_float(v[k]), f, o[k]);
       };
@@ -355,7 +355,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         float mx = s[0];
 #pragma unroll
         for (int k = 1; k < KW; ++k) mx = fmaxf(mx, s[k]);
-        mx *= c1;                                    // c1 > 0: the maximum commutes with the scaling
+        mx *= sc;                                    // sc > 0: the maximum commutes with the scaling
         // joint maximum of the row over all column groups
         float* x = xch + (g & 1) * NG * BM;
         x[grp * BM + r] = mx;
@@ -365,8 +365,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         if (warp == 2) ATT_TRACE(2, g, 3);
 
         const float m_new = fmaxf(m, mx);
-        const float corr = (m == -INFINITY) ? 0.f : ex2_approx(m - m_new);
-        const float off = kLogP - m_new;
+        const float corr = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * kLog2e);
+        const float neg_m = -m_new;
         // The two halves of the work -- the MUFU-bound exponentials and the FMA / TMEM-bound rescale-and-drain of the
         // older partial product -- are done in opposite order by even and odd column groups: the warps of one
         // scheduler run in lockstep behind the barrier above, and this keeps them off the same pipe.
@@ -374,7 +374,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
           float ps = 0.f;
 #pragma unroll
           for (int k = 0; k < KW; ++k) {
-            s[k] = ex2_approx(fmaf(s[k], c1, off));
+            s[k] = ex2_approx(fmaf(fmaf(s[k], sc, neg_m), kLog2e, kLogP));
             ps += s[k];
           }
           l = fmaf(l, corr, ps);
@@ -458,7 +458,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
         }
         if (grp == 0) {
           const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
-          a.row_lse[sidx] = fmaf(m, 0.6931471805599453f, logf(l_tot * (1.0f / kPScale)));
+          a.row_lse[sidx] = m + logf(l_tot * (1.0f / kPScale));
           a.out_norm[sidx] = sqrtf(nsq_tot);
         }
       }
@@ -599,8 +599,9 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     const int r = quad * 32 + lane;          // row within the tile
     const int tid = threadIdx.x - 64;        // 0..255 among the consumers
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    // log2 domain: t = S * c1 + mask * log2e - lse * log2e,  P = 2^t
-    const float c1 = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale)) * kLog2e;
+    // log P = S sc + mask - lse in the natural domain (sc = scale / 64: a power of two for the usual head dim, so the
+    // product is exact and the only rounding is the final subtraction); one 2^(t log2e) per (i, j) after the head loop
+    const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
     int gh = 0, ip = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ip ^= 1) {
       const int jt = item % NT, it = (item / NT) % NT, b = item / (NT * NT);
@@ -609,7 +610,7 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       float* cm = colmask + ip * 128;
       if (tid < 128) {
         const int j = j0 + tid;
-        cm[tid] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] * kLog2e : 0.f) : -INFINITY;
+        cm[tid] = (j < N) ? (a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f) : -INFINITY;
       }
       named_bar_sync(2, 256);   // mask of this item visible (its buffer was last read two items ago)
       float mx[64];
@@ -619,7 +620,7 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       float lse_next = (i < N) ? __ldg(lse_p) : 0.f;
       for (int hh = 0; hh < H; ++hh, ++gh) {
         const int hb = gh & 1;
-        const float lse2 = lse_next * kLog2e;
+        const float lse = lse_next;
         if (hh + 1 < H && i < N) lse_next = __ldg(lse_p + static_cast<long long>(hh + 1) * N);   // hidden by this head
         mbar_wait(&s_full[hb], (gh >> 1) & 1);
         tcgen05_fence_after();
@@ -632,8 +633,8 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         if (lane == 0) mbar_arrive(&s_empty[hb]);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          const float t0 = fmaf(__uint_as_float(v0[k]), c1, cm[half * 64 + k]) - lse2;
-          const float t1 = fmaf(__uint_as_float(v1[k]), c1, cm[half * 64 + 32 + k]) - lse2;
+          const float t0 = fmaf(__uint_as_float(v0[k]), sc, cm[half * 64 + k]) - lse;
+          const float t1 = fmaf(__uint_as_float(v1[k]), sc, cm[half * 64 + 32 + k]) - lse;
           mx[k] = fmaxf(mx[k], t0);
           mx[32 + k] = fmaxf(mx[32 + k], t1);
         }
@@ -645,7 +646,7 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       for (int g = 0; g < 2; ++g) {
         float p[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) p[c] = row_ok ? ex2_approx(mx[g * 32 + c]) : 0.f;
+        for (int c = 0; c < 32; ++c) p[c] = row_ok ? ex2_approx(mx[g * 32 + c] * kLog2e) : 0.f;
         const float tot = warp_transpose_sum32(p, lane);
         pt[quad * 128 + half * 64 + g * 32 + lane] = tot;
       }

@@ -175,9 +175,11 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
  * [M, ld_qk] (q of head h at column h*64, k at heads*64 + h*64), and v transposed per (sequence, head) as fp16 hi/lo
  * planes of MADTP_V_PLANE_SCALE * value, vt[((b*heads + h)*64 + d) * ld_vt + token] (keys contiguous; ld_vt a multiple
  * of 8). M = B * n_tok rows, K = model width. hi = fp16(s*x), lo = fp16(s*x - hi): hi + lo carries 22 mantissa bits.
- * madtp_attn_tc_fwd: context (fp16, heads merged), row_lse[b,h,i] = log sum_j exp(logit) and out_norm[b,h,i].
+ * madtp_attn_tc_fwd: context (fp16, heads merged), row_lse[b,h,i] = log sum_j exp(logit) and out_norm[b,h,i];
+ * optionally (both or neither) the CLS query row of every head as cls_p[b,h,j] = 256 exp(logit_j - cls_tile_max[b,h,
+ * j/64]) with cls_tile_max [B,H,ceil(N/64)] the running row maximum at each 64-key tile.
  * madtp_attn_tc_stats: col_part[b, it, j] = sum_{i in 128-query tile it, i >= 1} max_h P[b,h,i,j]  (n_parts =
- * ceil(N/128)) and cls_attn[b, j] as in madtp_attn_stats. Head dim 64.
+ * ceil(N/128)) and cls_attn[b, j] as in madtp_attn_stats, from cls_p / cls_tile_max of the forward pass. Head dim 64.
  */
 #define MADTP_QK_PLANE_SCALE 8.0f
 #define MADTP_V_PLANE_SCALE 16.0f
@@ -186,10 +188,11 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
                    int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, void* stream);
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
-                      int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream);
+                      int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
+                      void* stream);
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, float* cls_scratch /* [B,H,N] workspace */, void* stream);
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, void* stream);
 
 /*
  * Asynchronous read-back of a few bytes (the per-layer topk_num, vit.py:145 `.item()`): begin records an event on

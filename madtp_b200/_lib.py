@@ -56,8 +56,9 @@ SIGNATURES = {
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
                        _vp],
-    "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp],
-    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
+                          _vp],
+    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
 }
 
 
@@ -499,22 +500,26 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
     return qk_hi, qk_lo, vt_hi, vt_lo
 
 
-def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None):
+def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None, cls_p=None,
+                cls_tile_max=None):
+    """cls_p [B,H,N] / cls_tile_max [B,H,ceil(N/64)] fp32 (both or neither): the CLS query row for attn_tc_stats."""
     ldo, bso = _qkv_strides(out_f16, "out_f16")
     st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), _ptr(vt_hi, torch.float16, "vt_hi"), _ptr(vt_lo, torch.float16, "vt_lo"),
                vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
-               _ptr(out_norm, torch.float32, "out_norm"), _stream())
+               _ptr(out_norm, torch.float32, "out_norm"), _ptr(cls_p, torch.float32, "cls_p"),
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _stream())
     _check(st, "madtp_attn_tc_fwd")
 
 
-def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, *, key_mask=None):
+def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, cls_p, cls_tile_max, *,
+                  key_mask=None):
     st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
                _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
-               _ptr(cls_attn, torch.float32, "cls_attn"),
-               _ptr(torch.empty(B, H, N, dtype=torch.float32, device=qk_hi.device)), _stream())
+               _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(cls_p, torch.float32, "cls_p"),
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _stream())
     _check(st, "madtp_attn_tc_stats")
 
 

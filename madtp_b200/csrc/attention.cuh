@@ -38,7 +38,8 @@ struct AttnTcArgs {
   float* out_norm;                       // [B, H, N]  || context[b, h, i, :] ||_2
   float* col_part; int n_parts;          // [B, ceil(N/128), N]
   float* cls_attn;                       // [B, N]
-  float* cls_scratch;                    // [B, H, N] workspace: the CLS query row of every head
+  float* cls_p;                          // [B, H, N] CLS query row: 256 * exp(logit - max of its 64-key tile)
+  float* cls_tile_max;                   // [B, H, ceil(N/64)] those maxima (running row maximum at each key tile)
 };
 int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);

@@ -17,7 +17,7 @@
 //       log P_h(i,j) = S_h(i,j) * scale + mask_j - lse_h(i) is formed for every head, the running max over heads is
 //       kept in registers (exp is monotone, so ONE expf per (i,j) after the head loop replaces one per head), then
 //       the tile is column-summed over its query rows in a fixed order.
-//   attn_cls_*_kernel     the CLS query row of every head (tiny, fp32 FFMA) weighted by the per-head context norms.
+//   attn_cls_combine      the CLS query row of every head (kept by the forward pass) weighted by the context norms.
 //
 // Warp roles in both tensor-core kernels: warp 0 = TMA producer, warp 1 = MMA issuer (warp-uniform loops, one elected
 // lane issues), warps 2.. = consumers (TMEM lane quadrant = warp % 4, thread = query row).
@@ -305,6 +305,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
       const int qt = item % QT, bh = item / QT, h = bh % a.H, b = bh / a.H;
       const int i = qt * BM + r;
       const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * N : nullptr;
+      const bool cls_warp = a.cls_p != nullptr && qt == 0 && quad == 0;
       float m = -INFINITY, l = 0.f;               // m: running maximum of the logits; l = 256 * sum of p
       float m_hist[2] = {-INFINITY, -INFINITY};   // running max at the NB previous tiles (indexed by g % NB)
       float o[KW];
@@ -378,6 +379,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
             ps += s[k];
           }
           l = fmaf(l, corr, ps);
+          // the CLS query row (row 0 of query tile 0) feeds cls_attn: keep its 256 p and the maximum they are relative
+          // to; the statistics pass turns them into probabilities with the final log-sum-exp (vit.py:96-100)
+          if (cls_warp) {               // warp-uniform: only the warps that own row 0 of query tile 0 get here
+            if (lane == 0) {
+              float* cp = a.cls_p + static_cast<long long>(bh) * N + j0;
+#pragma unroll
+              for (int k = 0; k < KW; ++k)
+                if (j0 + k < N) cp[k] = s[k];
+              if (grp == 0) a.cls_tile_max[static_cast<long long>(bh) * T + t] = m_new;
+            }
+          }
         };
         auto do_drain = [&]() {
           if (__any_sync(0xffffffffu, corr != 1.0f)) {   // the running maximum rarely moves after the first tiles
@@ -669,72 +681,13 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 
 // ------------------------------------------------------------------------------------------------
 // CLS row: cls_attn[b,j] = sum_h softmax_j(q_0 . k_j)_h * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)
-//   attn_cls_head_kernel     grid (H, B), block 256: the CLS query row of one head (fp32 FFMA, own softmax) -> scratch
-//   attn_cls_combine_kernel  grid (ceil(N/256), B): head-importance weighting and the sum over heads (h ascending)
+//   The forward pass leaves the CLS query row of every head as 256 p relative to per-key-tile maxima (cls_p,
+//   cls_tile_max); attn_cls_combine_kernel (grid (ceil(N/256), B)) normalises it with the row's log-sum-exp, applies
+//   the head-importance weighting and sums over heads (h ascending).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dot8_planes(const uint4& x, const uint4& y, const float* q) {
-  const __half2* xh = reinterpret_cast<const __half2*>(&x);
-  const __half2* yh = reinterpret_cast<const __half2*>(&y);
-  float s = 0.f;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 xf = __half22float2(xh[e]), yf = __half22float2(yh[e]);
-    s = fmaf(q[2 * e], xf.x + yf.x, s);
-    s = fmaf(q[2 * e + 1], xf.y + yf.y, s);
-  }
-  return s;
-}
-
-__global__ void __launch_bounds__(256)
-attn_cls_head_kernel(AttnTcArgs a) {
-  extern __shared__ float sm[];
-  const int N = a.N, H = a.H, HD = H * 64;
-  float* q0 = sm;        // [64]   (kQkPlaneScale * q)
-  float* red = sm + 64;  // [16]
-  float* P = sm + 80;    // [N]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hh = blockIdx.x, b = blockIdx.y;
-  const __half* row0_hi = a.qk_hi + static_cast<long long>(b) * N * a.ld_qk;
-  const __half* row0_lo = a.qk_lo + static_cast<long long>(b) * N * a.ld_qk;
-  const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
-  if (tid < 64) q0[tid] = __half2float(row0_hi[hh * 64 + tid]) + __half2float(row0_lo[hh * 64 + tid]);
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = tid; j < N; j += 256) {
-    const uint4* kh = reinterpret_cast<const uint4*>(row0_hi + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
-    const uint4* kl = reinterpret_cast<const uint4*>(row0_lo + static_cast<long long>(j) * a.ld_qk + HD + hh * 64);
-    float s = 0.f;
-#pragma unroll
-    for (int d8 = 0; d8 < 8; ++d8) s += dot8_planes(kh[d8], kl[d8], q0 + d8 * 8);
-    const float mk = a.key_mask ? a.key_mask[static_cast<long long>(b) * N + j] : 0.f;
-    const float lg = fmaf(s, sc, mk);
-    P[j] = lg;
-    mx = fmaxf(mx, lg);
-  }
-  mx = warp_max(mx);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
-  float sum = 0.f;
-  for (int j = tid; j < N; j += 256) {
-    const float e = expf(P[j] - mx);
-    P[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) red[8 + warp] = sum;
-  __syncthreads();
-  float tot = 0.f;
-  for (int w = 0; w < 8; ++w) tot += red[8 + w];
-  const float inv = 1.0f / tot;
-  float* out = a.cls_scratch + (static_cast<long long>(b) * H + hh) * N;
-  for (int j = tid; j < N; j += 256) out[j] = P[j] * inv;
-}
-
 __global__ void __launch_bounds__(256)
 attn_cls_combine_kernel(AttnTcArgs a) {
-  const int N = a.N, H = a.H;
+  const int N = a.N, H = a.H, T = (N + 63) / 64;
   const int j = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
   if (j >= N) return;
   const long long base = static_cast<long long>(b) * H * N + j;
@@ -742,8 +695,12 @@ attn_cls_combine_kernel(AttnTcArgs a) {
   for (int hh = 0; hh < H; ++hh) hs += a.out_norm[base + static_cast<long long>(hh) * N];
   hs += 1e-8f;
   float acc = 0.f;
-  for (int hh = 0; hh < H; ++hh)
-    acc += a.cls_scratch[base + static_cast<long long>(hh) * N] * (a.out_norm[base + static_cast<long long>(hh) * N] / hs);
+  for (int hh = 0; hh < H; ++hh) {
+    const long long bh = static_cast<long long>(b) * H + hh;
+    // P[b,h,0,j] = exp(logit_j - lse) = (256 p_j / 256) * exp(max of its key tile - lse of the CLS row)
+    const float p = a.cls_p[bh * N + j] * (1.0f / kPScale) * expf(a.cls_tile_max[bh * T + (j >> 6)] - a.row_lse[bh * N]);
+    acc += p * (a.out_norm[base + static_cast<long long>(hh) * N] / hs);
+  }
   a.cls_attn[static_cast<long long>(b) * N + j] = acc;
 }
 
@@ -782,6 +739,7 @@ int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
   if (st != kOk) return st;
   MADTP_CHECK_ARG(a.vt_hi && a.vt_lo && a.ld_vt >= a.N && a.ld_vt % 8 == 0, "attn_fwd_tc: bad V^T planes");
   MADTP_CHECK_ARG(a.out_f16 && a.ldo % 8 == 0 && a.bso % 8 == 0 && a.row_lse && a.out_norm, "attn_fwd_tc: bad outputs");
+  MADTP_CHECK_ARG((a.cls_p == nullptr) == (a.cls_tile_max == nullptr), "attn_fwd_tc: cls_p / cls_tile_max come in pairs");
   if (a.B == 0) return kOk;
   const long long rows = static_cast<long long>(a.B) * a.N;
   CUtensorMap tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo;
@@ -804,7 +762,7 @@ int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream) {
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   int st = check_tc(a);
   if (st != kOk) return st;
-  MADTP_CHECK_ARG(a.row_lse && a.out_norm && a.col_part && a.cls_attn && a.cls_scratch,
+  MADTP_CHECK_ARG(a.row_lse && a.out_norm && a.col_part && a.cls_attn && a.cls_p && a.cls_tile_max,
                   "attn_stats_tc: null statistics buffer");
   MADTP_CHECK_ARG(a.n_parts == (a.N + BM - 1) / BM, "attn_stats_tc: n_parts must be ceil(N/128)");
   MADTP_CHECK_ARG(a.N <= 8192, "attn_stats_tc: sequence too long for the CLS-row kernel");
@@ -822,9 +780,6 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   const long long items = static_cast<long long>(a.n_parts) * a.n_parts * a.B;
   const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   attn_stats_tc_kernel<<<grid, StatsSmem::THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
-  MADTP_LAUNCH_CHECK();
-  const size_t cls_smem = (80 + static_cast<size_t>(a.N)) * sizeof(float);
-  attn_cls_head_kernel<<<dim3(a.H, a.B), 256, cls_smem, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   attn_cls_combine_kernel<<<dim3((a.N + 255) / 256, a.B), 256, 0, stream>>>(a);
   MADTP_LAUNCH_CHECK();

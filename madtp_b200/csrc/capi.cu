@@ -231,25 +231,28 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
-                      int64_t ldo, int64_t bso, float* row_lse, float* out_norm, void* stream) {
+                      int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
+                      void* stream) {
   AttnTcArgs a = {};
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.vt_hi = static_cast<const __half*>(vt_hi); a.vt_lo = static_cast<const __half*>(vt_lo); a.ld_vt = ld_vt;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
   a.row_lse = row_lse; a.out_norm = out_norm;
+  a.cls_p = cls_p; a.cls_tile_max = cls_tile_max;
   return counted(launch_attn_fwd_tc(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, float* cls_scratch, void* stream) {
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, void* stream) {
   AttnTcArgs a = {};
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.row_lse = const_cast<float*>(row_lse); a.out_norm = const_cast<float*>(out_norm);
-  a.col_part = col_part; a.n_parts = n_parts; a.cls_attn = cls_attn; a.cls_scratch = cls_scratch;
-  return counted(launch_attn_stats_tc(a, as_stream(stream)), B > 0 ? 3 : 0);
+  a.col_part = col_part; a.n_parts = n_parts; a.cls_attn = cls_attn;
+  a.cls_p = const_cast<float*>(cls_p); a.cls_tile_max = const_cast<float*>(cls_tile_max);
+  return counted(launch_attn_stats_tc(a, as_stream(stream)), B > 0 ? 2 : 0);
 }
 
 int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,

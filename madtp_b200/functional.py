@@ -230,14 +230,17 @@ def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N
     dev = y_hi.device
     qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H, alpha=1.0 / qkv.scale)
     ctx16 = torch.empty(B, N, H * 64, dtype=torch.float16, device=dev)
-    rows = torch.empty(2, B, H, N, dtype=torch.float32, device=dev)
-    L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1])
+    rows = torch.empty(3 if want_stats else 2, B, H, N, dtype=torch.float32, device=dev)
     if not want_stats:
+        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1])
         return ctx16, None
+    cls_tile_max = torch.empty(B, H, (N + 63) // 64, dtype=torch.float32, device=dev)
+    L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], cls_p=rows[2],
+                  cls_tile_max=cls_tile_max)
     n_parts = (N + 127) // 128
     col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
     cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
-    L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn)
+    L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn, rows[2], cls_tile_max)
     return ctx16, AttnStats(col_part, cls_attn)
 
 

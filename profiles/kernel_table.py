@@ -1,4 +1,5 @@
-"""Builds profiles/r1e_kernels.md from the raw ncu pages exported on the GPU box (gpurun_out/r1e_{vit,text}_raw.csv)."""
+"""Builds profiles/<tag>_kernels.md from the raw ncu page exported on the GPU box (gpurun_out/<tag>_layers_raw.csv):
+    python profiles/kernel_table.py r1f"""
 import csv
 import json
 import re
@@ -24,15 +25,16 @@ def val(d, unit, key):
         return float("nan")
 
 
-out = ["# Per-kernel ncu evidence -- round 1, final kernels", "",
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1f"
+out = [f"# Per-kernel ncu evidence -- {TAG}", "",
        "One BLIP-NLVR forward at the bench configuration (32 pairs = 64 images 384x384, temperature 3.5894): every launch",
-       "of two consecutive pruned ViT layers (about 347 and 321 tokens x 64 images) and of one text layer (20 tokens x 32",
-       "sentences, 255 image tokens each), captured with `ncu --set full --clock-control none` on `scripts/layer_once.py`",
-       "and exported on the GPU box (`--page raw --csv`); each window is a contiguous slice of the launch stream.",
+       "of ViT blocks 2 and 3 (about 347 and 321 tokens x 64 images) and of text layer 1 (about 20 tokens x 32 sentences,",
+       "255 image tokens each), captured with `ncu --set full --clock-control none --nvtx --nvtx-include cap/` on",
+       "`scripts/layer_once.py` and exported on the GPU box (`--page raw --csv`).",
        "Durations are ncu-serialised and cold-cache (compare shares, not absolutes).",
        f"Denominators (MEASURED_PEAKS.json): HBM {HBM} GB/s; tensor % = sm__pipe_tensor_cycles_active, pct of peak sustained active.",
        "", "| kernel | grid | time us | tensor % | DRAM MB (r + w) | DRAM GB/s | % of HBM peak | regs |", "|---|---|---|---|---|---|---|---|"]
-for title, name in (("two consecutive ViT layers", "r1e_vit_raw.csv"), ("one NLVR text layer", "r1e_text_raw.csv")):
+for title, name in (("ViT blocks 2, 3 and text layer 1, in launch order", f"{TAG}_layers_raw.csv"),):
     rows, unit = load(ROOT / "gpurun_out" / name)
     out.append(f"| **{title}** | | | | | | | |")
     for d in rows:
@@ -45,5 +47,5 @@ for title, name in (("two consecutive ViT layers", "r1e_vit_raw.csv"), ("one NLV
         tens = val(d, {}, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
         out.append(f"| {k} | {d.get('launch__grid_size', '')} | {t:.1f} | {tens:.1f} | {rd / 1e6:.1f} + {wr / 1e6:.1f} | "
                    f"{gbs:.0f} | {100 * gbs / HBM:.1f} | {d.get('launch__registers_per_thread', '')} |")
-(ROOT / "profiles" / "r1e_kernels.md").write_text("\n".join(out) + "\n")
+(ROOT / "profiles" / f"{TAG}_kernels.md").write_text("\n".join(out) + "\n")
 print("\n".join(out[:60]))

@@ -18,6 +18,7 @@ for N in (577, 346, 256):
     lse = torch.empty(B, H, N, device=dev); norm = torch.empty(B, H, N, device=dev)
     n_parts = (N + 127) // 128
     col = torch.empty(B, n_parts, N, device=dev); cls = torch.empty(B, N, device=dev)
+    cls_p = torch.zeros(B, H, N, device=dev); cls_m = torch.zeros(B, H, (N + 63) // 64, device=dev)
     def t(fn, n=10):
         for _ in range(2): fn()
         torch.cuda.synchronize()
@@ -29,9 +30,9 @@ for N in (577, 346, 256):
     fv = []
     for var in ("0", "1", "2"):
         os.environ["MADTP_ATTN_VARIANT"] = var
-        fv.append(t(lambda: lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm)))
+        fv.append(t(lambda: lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm, cls_p=cls_p, cls_tile_max=cls_m)))
     os.environ.pop("MADTP_ATTN_VARIANT", None)
     f = min(fv)
-    s = t(lambda: lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, 0.125, lse, norm, col, cls))
+    s = t(lambda: lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, 0.125, lse, norm, col, cls, cls_p, cls_m))
     q = t(lambda: lib.gemm_qkv(xh, xl, wh, wl, bias, N, H, alpha=2.0 ** -14))
     print(f"N={N}: attn_tc_fwd variants {fv[0]:.1f} / {fv[1]:.1f} / {fv[2]:.1f} us ({4.0*B*H*N*N*64/f/1e6:.0f} TFLOP/s alg), attn_tc_stats {s:.1f} us, gemm_qkv {q:.1f} us")

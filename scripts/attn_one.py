@@ -19,8 +19,10 @@ norm = torch.empty(B, H, N, device=dev)
 n_parts = (N + 127) // 128
 col = torch.empty(B, n_parts, N, device=dev)
 cls = torch.empty(B, N, device=dev)
+cls_p = torch.zeros(B, H, N, device=dev)
+cls_m = torch.zeros(B, H, (N + 63) // 64, device=dev)
 for _ in range(2):
     qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(xh, xl, wh, wl, bias, N, H, alpha=2.0 ** -14)
-    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm)
-    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, 0.125, lse, norm, col, cls)
+    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, 0.125, out, lse, norm, cls_p=cls_p, cls_tile_max=cls_m)
+    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, 0.125, lse, norm, col, cls, cls_p, cls_m)
 torch.cuda.synchronize()

@@ -351,11 +351,13 @@ def test_attention_tensor_core_path(lib, dev, monkeypatch, B, H, N, masked, vari
     out = torch.empty(B, N, HD, device=dev, dtype=torch.float16)
     lse = torch.empty(B, H, N, device=dev)
     norm = torch.empty(B, H, N, device=dev)
-    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out, lse, norm, key_mask=mask)
+    cls_p = torch.zeros(B, H, N, device=dev)
+    cls_m = torch.zeros(B, H, (N + 63) // 64, device=dev)
+    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out, lse, norm, key_mask=mask, cls_p=cls_p, cls_tile_max=cls_m)
     n_parts = (N + 127) // 128
     col_part = torch.zeros(B, n_parts, N, device=dev)
     cls_attn = torch.zeros(B, N, device=dev)
-    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, lse, norm, col_part, cls_attn, key_mask=mask)
+    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, lse, norm, col_part, cls_attn, cls_p, cls_m, key_mask=mask)
 
     # fp64 reference from the very operands the kernels consumed (so projection rounding does not enter)
     q = qk[:, :HD].reshape(B, N, H, 64).permute(0, 2, 1, 3).double()

@@ -24,14 +24,14 @@ namespace madtp {
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool TF32X3>
+template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 struct GemmCfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int ROW_BYTES = 128;                       // one 128B swizzle atom of K per stage
   static constexpr int K_ELEMS = TF32X3 ? 32 : 64;            // K elements per stage
   static constexpr int UMMA_K_BYTES = 32;                     // K bytes per tcgen05.mma
   static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
-  static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * ROW_BYTES;   // a CTA of a pair stages half of B
   static constexpr int STAGE_BYTES = (TF32X3 ? 2 : 1) * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;               // double-buffered fp32 accumulator
@@ -247,13 +247,17 @@ __device__ __forceinline__ void epilogue_chunks_tmem(const GemmEpilogue& ep, uin
   }
 }
 
-template <int BLOCK_N, bool TF32X3>
+// PAIR = true: clusters of two CTAs form a cta_group::2 pair working on two vertically adjacent output tiles (same
+// n-tile): ONE MMA of M = 256 spans both SMs, every CTA stages its own 128 rows of A and only half of B's rows, the
+// leader (cluster rank 0) issues all MMAs and owns the operand-full barriers (see gemm_tf32x3_kernel).
+template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
                     GemmEpilogue ep, int M, int N, int K) {
-  using Cfg = GemmCfg<BLOCK_N, TF32X3>;
+  using Cfg = GemmCfg<BLOCK_N, TF32X3, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!PAIR || !TF32X3, "the CTA-pair variant is fp16 only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -268,8 +272,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = m_tiles * n_tiles;
+  constexpr int CL = PAIR ? 2 : 1;
+  const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;   // work items (a pair owns CL vertically adjacent tiles)
   const int num_kb = (K + Cfg::K_ELEMS - 1) / Cfg::K_ELEMS;
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -286,16 +293,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], PAIR ? 16 : 8);   // pair: the epilogue warps of both CTAs release the leader's buffer
     }
     fence_mbar_init();
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -307,14 +316,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+        const int m0 = ((tile / n_tiles) * CL + rank) * Cfg::BLOCK_M;
         const int n0 = (tile % n_tiles) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* s = smem + stage * Cfg::STAGE_BYTES;
           const int k0 = kb * Cfg::K_ELEMS;
-          if (elect_one()) {
+          if (PAIR) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            if (elect_one()) {
+              const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_2d_pair(&tm_a, bar, s, k0, m0);
+              tma_load_2d_pair(&tm_b, bar, s + Cfg::A_BYTES, k0, n0 + rank * (BLOCK_N / 2));
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             tma_load_2d(&tm_a, &full_bar[stage], s, k0, m0);
             tma_load_2d(&tm_b, &full_bar[stage], s + Cfg::A_BYTES, k0, n0);
@@ -333,13 +350,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    {
-      constexpr uint32_t idesc = make_idesc(TF32X3 ? 2u : 0u, Cfg::BLOCK_M, BLOCK_N);
+    if (!PAIR || rank == 0) {   // pair: only the leader issues MMAs
+      constexpr uint32_t idesc = make_idesc(TF32X3 ? 2u : 0u, PAIR ? 2 * Cfg::BLOCK_M : Cfg::BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -361,12 +378,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 umma_tf32(d_tmem, a_lo + koff, b_hi + koff, idesc, first);
                 umma_tf32(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
                 umma_tf32(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+              } else if (PAIR) {
+                umma_f16_pair(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
               } else {
                 umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
               }
             }
-            umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
-            if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage], 3);                          // frees the stage in both CTAs
+              if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc], 3);      // accumulators complete in both CTAs
+            } else {
+              umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+              if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -388,8 +412,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const bool vec_ok = epilogue_vec_ok(ep, N);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * Cfg::BLOCK_M;
+    for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      const int m0 = ((tile / n_tiles) * CL + rank) * Cfg::BLOCK_M;
       const int n0 = (tile % n_tiles) * BLOCK_N;
       const long long row_base = m0 + quad * 32;
       const int col_begin = n0 + half * (BLOCK_N / 2);
@@ -424,7 +448,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -432,9 +459,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync();   // no CTA leaves while its peer may still arrive on its barriers or read its operands
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -825,14 +854,14 @@ int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long 
   return kOk;
 }
 
-template <int BLOCK_N, bool TF32X3>
+template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 static int launch_tc(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
                      const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, TF32X3>;
+  using Cfg = GemmCfg<BLOCK_N, TF32X3, PAIR>;
   CUtensorMap ta, tal, tb, tbl;
   int st;
   if ((st = make_tmap(&ta, a, TF32X3, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
-  if ((st = make_tmap(&tb, b, TF32X3, N, K, ldb, BLOCK_N)) != kOk) return st;
+  if ((st = make_tmap(&tb, b, TF32X3, N, K, ldb, PAIR ? BLOCK_N / 2 : BLOCK_N)) != kOk) return st;
   if (TF32X3) {
     if ((st = make_tmap(&tal, a_lo, true, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
     if ((st = make_tmap(&tbl, b_lo, true, N, K, ldb, BLOCK_N)) != kOk) return st;
@@ -842,16 +871,29 @@ static int launch_tc(const void* a, const void* a_lo, long long lda, const void*
   }
   static bool attr_done = false;
   if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES));
+    MADTP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, TF32X3, PAIR>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
+  constexpr int CL = PAIR ? 2 : 1;
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<BLOCK_N, TF32X3><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tal, tb, tbl, ep, M, N, K);
-  MADTP_LAUNCH_CHECK();
+  const int items = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const int max_clusters = num_sms() / CL;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, TF32X3, PAIR>, ta, tal, tb, tbl, ep, M, N, K));
   return kOk;
 }
 
@@ -958,7 +1000,10 @@ static int pick_block_n(int M, int N) {
     const long long waves = (tiles + sms - 1) / sms;
     return waves * bn;  // time ~ waves x tile width
   };
-  return cost(256) <= cost(128) ? 256 : 128;
+  // a 128-wide tile re-reads A twice as often and pays the per-tile epilogue twice per output column: measured on
+  // B200 (M = 22208, fc1 + fc2) 245 us against 184 us for the 256-wide tile at equal wave counts, so the narrow tile
+  // must save more than a quarter of the waves to win
+  return 4 * cost(256) <= 5 * cost(128) ? 256 : 128;
 }
 
 int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
@@ -985,6 +1030,13 @@ int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, c
                      : launch_tf32<128, true>(a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, stream);
   }
   if (precision == kGemmF16) {
+    // CTA pairs (cta_group::2, 256 x 256 per pair) are implemented and verified but OFF by default (MADTP_PAIR=1):
+    // measured on B200 they gain 3-7 % on warm, isolated GEMMs (fc2 at M = 36928: 154 us against 165 us) and nothing
+    // inside the forward, where these GEMMs start on cold operands.
+    static const bool use_pair = getenv("MADTP_PAIR") != nullptr;
+    const long long tiles256 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256);
+    if (use_pair && bn == 256 && tiles256 >= 2LL * num_sms())
+      return launch_tc<256, false, true>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
     return bn == 256 ? launch_tc<256, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream)
                      : launch_tc<128, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
   }

@@ -356,6 +356,48 @@ def test_blip_vqa_question_encoder_480(dev):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# BASELINE configuration 2 at FULL size (32 pairs, 384 x 384, tau calibrated for p = 0.5): the oracle's trajectory is
+# stored in tests/golden/calib_nlvr_p50_b32.npz, so nothing CPU-heavy runs here; plus size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_against_calibration_fixture_and_properties(dev):
+    from madtp_b200.blip_nlvr import TokenizedText
+    cal = np.load(GOLDEN / "calib_nlvr_p50_b32.npz")
+    pairs, size, text_len, temp = int(cal["pairs"]), int(cal["image_size"]), int(cal["text_len"]), float(cal["temperature"])
+    model, _sd, _inp, _tr, _pred = nlvr_setup(dev, size, 2, text_len, 3.5894)      # shares the cached 384 model
+    images, ids, mask = weights.nlvr_inputs(pairs, size, text_len, seed=0)
+    assert weights.tensor_digest(images, ids, mask) == str(cal["input_digest"]), "fixture was generated from other inputs"
+    images_d, text = images.to(dev), TokenizedText(ids.to(dev), mask.to(dev))
+    with torch.no_grad():
+        pred = model(images_d, text, pairs, temp, train=False)
+    blocks = model.visual_encoder.blocks
+    # layer 0 sees bit-identical inputs on both sides: keep-mask, counts and topk_num must match the oracle exactly
+    res0 = blocks[0].last_prune
+    assert res0.k == int(cal["vit_k"][0])
+    assert torch.equal(res0.count.cpu().to(torch.int64), torch.from_numpy(cal["vit0_count"]).to(torch.int64))
+    keep0 = np.unpackbits(cal["vit0_keep"], axis=1)[:, :res0.keep.shape[1]].astype(bool)
+    assert np.array_equal(res0.keep.cpu().numpy().astype(bool), keep0)
+    # later layers run free (fp16 value lane): the survivor counts follow the oracle's trajectory within a few tokens
+    for i, blk in enumerate(blocks):
+        k_ref = int(cal["vit_k"][i])
+        r = blk.last_prune
+        if k_ref < 0:
+            assert r is None or not r.pruned
+        else:
+            assert r is not None and abs(r.k - k_ref) <= 3, (i, r.k, k_ref)
+    assert rel(pred, torch.from_numpy(cal["pred"])) < 1e-2
+    # determinism: a second forward is bit-identical
+    with torch.no_grad():
+        pred2 = model(images_d, text, pairs, temp, train=False)
+    assert torch.equal(pred, pred2)
+    # batch-permutation equivariance: topk_num is a batch maximum, everything else is per pair
+    perm = torch.randperm(pairs, generator=torch.Generator().manual_seed(5))
+    img_p = torch.cat([images[:pairs][perm], images[pairs:][perm]], 0).to(dev)
+    with torch.no_grad():
+        pred_p = model(img_p, TokenizedText(ids[perm].to(dev), mask[perm].to(dev)), pairs, temp, train=False)
+    assert torch.equal(pred_p, pred[perm.to(dev)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # CLIP (clip/model.py ResidualAttentionBlock + patched MHA): vision tower and causal text blocks with the EOT guard
 # ---------------------------------------------------------------------------------------------------------------
 def clip_setup(dev, layers):

@@ -86,6 +86,15 @@ int madtp_bert_embed(const int64_t* ids, const float* word, const float* positio
                      int vocab, void* stream);
 
 /*
+ * Language-model head statistics per logits row (VQA answer ranking: models/med.py:1040-1047 CrossEntropyLoss with
+ * label_smoothing 0.1 and reduction 'none'; models/blip_vqa.py:168-171 softmax of the first-token logits):
+ *   lse[r] = log sum_v exp(logits[r, v]);   loss[r] = (1 - eps)(lse - logits[r, label]) + eps (lse - mean_v logits[r, v]),
+ * 0 where label < 0 (ignore_index). labels/loss come in pairs and may be NULL; lse may be NULL.
+ */
+int madtp_lm_nll(const float* logits, int64_t ld, int R, int V, const int64_t* labels, float label_smoothing,
+                 float* loss, float* lse, void* stream);
+
+/*
  * Multi-head attention, head dim 64: context = softmax(q.k^T * scale + key_mask) v, heads merged into
  * out_f16[b, i, h*64 + :]. Replaces vit.py:79-91, nlvr_encoder.py:174-219 / med.py:175-217 (self and cross
  * attention) without materialising the [B,H,N,N] probabilities.

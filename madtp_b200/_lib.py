@@ -36,6 +36,7 @@ SIGNATURES = {
                             _i64, _vp],
     "madtp_readback_begin": [_vp, _vp, _i64, _i32, _vp],
     "madtp_readback_wait": [_i32],
+    "madtp_lm_nll": [_vp, _i64, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
     "madtp_split_f16": [_vp, _vp, _vp, _i64, C.c_float, _vp],
     "madtp_cast_f16": [_vp, _vp, _i64, _vp],
     "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -349,6 +350,21 @@ def readback_wait(handle) -> int:
     dev, slot = handle
     _check(_call("madtp_readback_wait", slot), "madtp_readback_wait")
     return int(_rb_host[dev][slot])
+
+
+def lm_nll(logits, labels=None, label_smoothing=0.0):
+    """logits [R, V] fp32 (row stride free). Returns (loss [R] or None, lse [R]) -- see madtp_lm_nll."""
+    ld = _rowmajor(logits, "logits")
+    R, V = logits.shape
+    lse = torch.empty(R, dtype=torch.float32, device=logits.device)
+    loss = None
+    if labels is not None:
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != R:
+            raise RuntimeError("madtp_b200.lm_nll: labels must be contiguous int64 [R]")
+        loss = torch.empty(R, dtype=torch.float32, device=logits.device)
+    _check(_call("madtp_lm_nll", _ptr(logits, torch.float32, "logits"), ld, R, V, _ptr(labels, torch.int64, "labels"),
+                 float(label_smoothing), _ptr(loss), _ptr(lse), _stream()), "madtp_lm_nll")
+    return loss, lse
 
 
 def cross_tc_supported(Lq, Nk):

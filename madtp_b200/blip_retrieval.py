@@ -16,7 +16,7 @@ from . import _lib as L
 from . import functional as Fn
 from .blip_nlvr import ENC_TOKEN_ID, create_vit
 from .configuration import BertConfig
-from .med import BertModel
+from .med import BertLMHeadModel, BertModel
 
 
 def _med_config(med_config, vision_width, evaluate):
@@ -119,6 +119,7 @@ class BLIP_VQA(nn.Module):
         self.tokenizer = tokenizer
         cfg = _med_config(med_config, vision_width, evaluate)
         self.text_encoder = BertModel(config=cfg, add_pooling_layer=False, sd_dim=self.sd_dim)
+        self.text_decoder = BertLMHeadModel(config=_med_config(med_config, vision_width, evaluate), sd_dim=self.sd_dim)
 
     @torch.no_grad()
     def encode_question(self, image, input_ids, attention_mask, temperature=0):
@@ -132,7 +133,43 @@ class BLIP_VQA(nn.Module):
                                    temperature=temperature)
         return out.last_hidden_state, image_embeds
 
-    def forward(self, image, question, answer=None, n=None, weights=None, temperature=0, train=True,
+    @torch.no_grad()
+    def rank_answer(self, question_states, question_atts, answer_ids, answer_atts, k):
+        """models/blip_vqa.py:156-203: the first-token probabilities pick k candidate answers per question, the decoder
+        scores each of them by its label-smoothed log-likelihood, the best one wins. Returns max_ids [num_ques]
+        (indices into the answer list); the intermediate results are kept in `self.last_rank`."""
+        num_ques = question_states.size(0)
+        pad_id = getattr(self.tokenizer, "pad_token_id", 0)
+        start_ids = answer_ids[0, 0].repeat(num_ques, 1)                                      # bos token
+        start = self.text_decoder(start_ids, encoder_hidden_states=question_states,
+                                  encoder_attention_mask=question_atts, return_dict=True, reduction='none')
+        logits = start.logits[:, 0, :]                                                        # first token's logits
+        _, lse = L.lm_nll(logits)
+        answer_first_token = answer_ids[:, 1]
+        prob_first_token = torch.exp(logits.index_select(1, answer_first_token) - lse[:, None])
+        topk_probs, topk_ids = prob_first_token.topk(k, dim=1)
+        input_ids = torch.cat([answer_ids.index_select(0, t) for t in topk_ids], dim=0)
+        input_atts = torch.cat([answer_atts.index_select(0, t) for t in topk_ids], dim=0)
+        targets_ids = input_ids.masked_fill(input_ids == pad_id, -100)
+        # repeat the encoder's output for the k candidates of every question (tile(), :214-220)
+        q_states = question_states.repeat_interleave(k, dim=0)
+        q_atts = None if question_atts is None else question_atts.repeat_interleave(k, dim=0)
+        out = self.text_decoder(input_ids, attention_mask=input_atts, encoder_hidden_states=q_states,
+                                encoder_attention_mask=q_atts, labels=targets_ids, return_dict=True, reduction='none')
+        log_probs_sum = (-out.loss).view(num_ques, k)
+        max_topk_ids = log_probs_sum.argmax(dim=1)
+        max_ids = topk_ids[max_topk_ids >= 0, max_topk_ids]
+        self.last_rank = {"prob_first_token": prob_first_token, "topk_ids": topk_ids, "log_probs_sum": log_probs_sum}
+        return max_ids
+
+    @torch.no_grad()
+    def forward(self, image, question, answer=None, temperature=0, train=True, n=None, weights=None,
                 inference='rank', k_test=128):
-        raise NotImplementedError("madtp_b200: the VQA answer decoder (blip_vqa.py:156-203) is out of scope; "
-                                  "use encode_question for the pruned encoder path")
+        """Evaluation path of models/blip_vqa.py:58-154 with inference='rank'. `question` and `answer` are tokenised:
+        objects with .input_ids / .attention_mask (the HuggingFace tokenizer stays on the host, outside the hot path)."""
+        if train:
+            raise NotImplementedError("madtp_b200: evaluation only (train=False)")
+        if inference != 'rank':
+            raise NotImplementedError("madtp_b200: inference='generate' (beam search) is out of scope")
+        q_states, _ = self.encode_question(image, question.input_ids, question.attention_mask, temperature)
+        return self.rank_answer(q_states, question.attention_mask, answer.input_ids, answer.attention_mask, k_test)

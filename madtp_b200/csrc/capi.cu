@@ -110,6 +110,13 @@ int madtp_bert_embed(const int64_t* ids, const float* word, const float* positio
                  B > 0 ? 1 : 0);
 }
 
+int madtp_lm_nll(const float* logits, int64_t ld, int R, int V, const int64_t* labels, float label_smoothing,
+                 float* loss, float* lse, void* stream) {
+  return counted(launch_lm_nll(logits, ld, R, V, reinterpret_cast<const long long*>(labels), label_smoothing, loss, lse,
+                               as_stream(stream)),
+                 R > 0 ? 1 : 0);
+}
+
 int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk, const float* v,
                    int64_t ldv, int64_t bsv, int B, int H, int Nq, int Nk, float scale, const float* key_mask,
                    void* out_f16, int64_t ldo, int64_t bso, float* row_max, float* row_sum, float* out_norm,

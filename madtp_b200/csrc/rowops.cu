@@ -263,4 +263,69 @@ int launch_bert_embed(const long long* ids, const float* word, const float* pose
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Language-model head statistics of one logits row (VQA answer ranking, models/med.py:1040-1047 and
+// models/blip_vqa.py:168-171): lse = log sum_v exp(z_v) and, when labels are given, the label-smoothed cross entropy
+//   loss = (1 - eps) (lse - z_label) + eps (lse - mean_v z_v),   0 for ignored positions (label < 0).
+// One 256-thread CTA per row, two passes over the (L2-resident) row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lm_nll_kernel(const float* __restrict__ logits, long long ld, int V, const long long* __restrict__ labels, float eps,
+              float* __restrict__ loss, float* __restrict__ lse_out) {
+  __shared__ float red[8];
+  __shared__ float red2[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* z = logits + static_cast<long long>(blockIdx.x) * ld;
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += 256) mx = fmaxf(mx, z[v]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float se = 0.f, sz = 0.f;
+  for (int v = tid; v < V; v += 256) {
+    const float x = z[v];
+    se += expf(x - mx);
+    sz += x;
+  }
+  se = warp_sum(se);
+  sz = warp_sum(sz);
+  if (lane == 0) {
+    red[warp] = se;
+    red2[warp] = sz;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float tse = 0.f, tsz = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      tse += red[w];
+      tsz += red2[w];
+    }
+    const float lse = mx + logf(tse);
+    if (lse_out) lse_out[blockIdx.x] = lse;
+    if (loss) {
+      const long long lab = labels[blockIdx.x];
+      float l = 0.f;
+      if (lab >= 0 && lab < V) l = (1.0f - eps) * (lse - z[lab]) + eps * (lse - tsz / static_cast<float>(V));
+      loss[blockIdx.x] = l;
+    }
+  }
+}
+
+int launch_lm_nll(const float* logits, long long ld, int R, int V, const long long* labels, float eps, float* loss,
+                  float* lse, cudaStream_t stream) {
+  MADTP_CHECK_ARG(logits && R >= 0 && V > 0 && ld >= V, "lm_nll: bad arguments");
+  MADTP_CHECK_ARG((labels == nullptr) == (loss == nullptr), "lm_nll: labels and loss come in pairs");
+  MADTP_CHECK_ARG(loss || lse, "lm_nll: nothing to compute");
+  MADTP_CHECK_ARG(eps >= 0.f && eps < 1.f, "lm_nll: label smoothing must be in [0, 1)");
+  if (R == 0) return kOk;
+  lm_nll_kernel<<<R, 256, 0, stream>>>(logits, ld, V, labels, eps, loss, lse);
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
 }  // namespace madtp

@@ -27,6 +27,8 @@ int launch_cast_f16(const float* x, void* y, long long n, cudaStream_t stream);
 int launch_patchify(const float* img, void* hi, void* lo, int B, int C, int H, int W, int P, cudaStream_t stream);
 int launch_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
                            cudaStream_t stream);
+int launch_lm_nll(const float* logits, long long ld, int R, int V, const long long* labels, float eps, float* loss,
+                  float* lse, cudaStream_t stream);
 int launch_bert_embed(const long long* ids, const float* word, const float* posemb, float* out, int B, int L, int d,
                       int vocab, cudaStream_t stream);
 

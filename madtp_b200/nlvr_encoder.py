@@ -5,7 +5,7 @@ by BLIP-NLVR: BertEmbeddings (:43-85), BertSelfAttention (:88-237), BertSelfOutp
 from med.py), return arity and state-dict keys; executed by the sm_100a kernels of libmadtp_b200.so.
 
 Contract differences: evaluation forward only; `past_key_value`, `head_mask`, `output_attentions`,
-relative position embeddings and the decoder (`is_decoder=True`) are not on the pruned encoder path and raise;
+relative position embeddings are not on the pruned encoder path and raise; the (unpruned) decoder mode is `is_decoder=True`;
 attention maps are AttnStats handles; survivors keep ascending token order; the key/value cache slot of the returned
 tuples is None.
 """
@@ -177,13 +177,14 @@ class BertSelfAttention(nn.Module):
         out = Fn.linear_tf32(h_hi, h_lo, self._qkv_book_tf32(space_dict)).view(B, Ltok, 3 * C + Fn.TA_LD)
         return out[..., :3 * C], out[..., 3 * C:]
 
-    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None):
-        """Self-attention on the scoring lane. Returns ctx16 [B,L,C]; stores AttnStats + cls_attn (:213-235)."""
+    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None, causal=False):
+        """Self-attention on the scoring lane. Returns ctx16 [B,L,C]; stores AttnStats + cls_attn (:213-235).
+        causal=True: decoder self-attention (key j visible to query i only if j <= i, models/med.py:749-771)."""
         C = self.all_head_size
         if qkv is None:
             qkv = Fn.linear_tf32(h_hi, h_lo, self._qkv_tf32()).view(B, Ltok, 3 * C)
         ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_attention_heads,
-                                         1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats)
+                                         1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats, causal=causal)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return ctx16
@@ -407,7 +408,8 @@ class BertLayer(nn.Module):
                                   temperature, _kv)
 
     def _forward_impl(self, hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
-                      past_key_value, output_attentions, mode, token_attn, temperature, _kv, _qkv=None):
+                      past_key_value, output_attentions, mode, token_attn, temperature, _kv, _qkv=None,
+                      _causal=False):
         Fn.require_cuda(hidden_states, "hidden_states")
         _eval_only(self)
         _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
@@ -421,10 +423,10 @@ class BertLayer(nn.Module):
         # self-attention + output LayerNorm (:501-509)
         sa = self.attention.self
         if _qkv is not None:      # BertEncoder already projected q|k|v together with the codebook dots
-            ctx16 = sa.self_rows(None, None, B, Ltok, key_mask, want_stats=prune, qkv=_qkv)
+            ctx16 = sa.self_rows(None, None, B, Ltok, key_mask, want_stats=prune, qkv=_qkv, causal=_causal)
         else:
             h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
-            ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune)
+            ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune, causal=_causal)
         # score kernel + read-back of topk_num first: the output dense + LayerNorm below do not depend on them
         pend = Fn.dtp_score_async(sa.get_attention_map(), token_attn, float(temperature), Ltok - 1) if prune else None
         att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=not prune)
@@ -582,7 +584,8 @@ class BertEncoder(nn.Module):
 
     def forward(self, hidden_states, attention_mask=None, space_dict=None, temperature=0, head_mask=None,
                 encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None, use_cache=None,
-                output_attentions=False, output_hidden_states=False, return_dict=True, mode='multimodal'):
+                output_attentions=False, output_hidden_states=False, return_dict=True, mode='multimodal',
+                _causal=False):
         _unsupported(past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
                      output_hidden_states=output_hidden_states)
         Fn.require_cuda(hidden_states, "hidden_states")
@@ -611,7 +614,8 @@ class BertEncoder(nn.Module):
                                                                               sd_txt_ft_all)
             layer_outputs = layer_module._forward_impl(h, attention_mask, None, encoder_hidden_states,
                                                        encoder_attention_mask, None, False, mode, token_attn,
-                                                       temperature, None if kv is None else kv[i], _qkv=qkv)
+                                                       temperature, None if kv is None else kv[i], _qkv=qkv,
+                                                       _causal=_causal)
             hidden_states = layer_outputs[0]
             attention_mask = layer_outputs[-1]
         if not return_dict:
@@ -636,9 +640,9 @@ class BertModel(nn.Module):
 
     @staticmethod
     def get_extended_attention_mask(attention_mask, input_shape=None, device=None, is_decoder=False):
-        """(1 - mask) * -10000 broadcastable over heads and queries (:826-871)."""
-        if is_decoder:
-            raise NotImplementedError("madtp_b200: decoder (causal) masks are not on the pruned encoder path")
+        """(1 - mask) * -10000 broadcastable over heads and queries (:826-871). For a decoder (`is_decoder=True`) this
+        is only the key-padding factor of the reference's mask; the causal factor (models/med.py:749-771) is applied
+        inside the attention kernels (`causal` flag), never materialised."""
         if attention_mask.dim() != 2:
             raise NotImplementedError("madtp_b200: only [batch, seq] attention masks")
         return (1.0 - attention_mask[:, None, None, :].to(torch.float32)) * -10000.0
@@ -653,7 +657,9 @@ class BertModel(nn.Module):
         _eval_only(self)
         _unsupported(position_ids=position_ids, head_mask=head_mask, inputs_embeds=inputs_embeds,
                      past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
-                     output_hidden_states=output_hidden_states, is_decoder=is_decoder)
+                     output_hidden_states=output_hidden_states)
+        if is_decoder and temperature > 0:
+            raise NotImplementedError("madtp_b200: the decoder is unpruned in the reference (blip_vqa.py:161-190)")
         if input_ids is not None:
             B, Ltok = input_ids.shape
             device = input_ids.device
@@ -676,5 +682,5 @@ class BertModel(nn.Module):
         emb = self.embeddings(input_ids=input_ids) if encoder_embeds is None else encoder_embeds
         out, sd_txt_ft = self.encoder(emb, attention_mask=ext, space_dict=space_dict, temperature=temperature,
                                       encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=enc_ext,
-                                      mode=mode)
+                                      mode=mode, _causal=bool(is_decoder))
         return out, sd_txt_ft

@@ -129,6 +129,42 @@ def retrieval_state_dict(seed: int = 4321, img_size: int = 384, sd_num: int = 10
     return sd
 
 
+def vqa_state_dict(seed: int = 99, img_size: int = 480, sd_num: int = 100, sd_dim: int = 768,
+                   depth: int = 12) -> Dict[str, Tensor]:
+    """models/blip_vqa.py:BLIP_VQA: space_dict, visual_encoder.*, text_encoder.* and the answer decoder
+    text_decoder.{bert.*, cls.predictions.*} (models/med.py:BertLMHeadModel; the output embedding is tied to the input
+    embedding, models/med.py:947-950)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {"space_dict": torch.randn(sd_num, sd_dim, generator=g)}
+    sd.update(vit_state_dict(g, "visual_encoder.", img_size=img_size, depth=depth))
+    sd.update(med_text_state_dict(g, "text_encoder.", depth=depth))
+    sd.update(med_text_state_dict(g, "text_decoder.bert.", depth=depth))
+    # small-norm embeddings keep the tied LM head's logits in a softmax regime that still separates candidates
+    sd["text_decoder.bert.embeddings.word_embeddings.weight"] *= 0.05
+    p = "text_decoder.cls.predictions"
+    _linear(sd, g, p + ".transform.dense", 768, 768)
+    _ln(sd, p + ".transform.LayerNorm", 768)
+    sd[p + ".decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+    sd[p + ".bias"] = (torch.rand(sd[p + ".decoder.weight"].shape[0], generator=g) * 2 - 1) * 0.02
+    sd[p + ".decoder.bias"] = sd[p + ".bias"]
+    return sd
+
+
+def vqa_answer_candidates(n_answers: int = 6, max_len: int = 5, seed: int = 0, bos_id: int = 30522):
+    """Tokenised answer list as the VQA driver builds it (`padding='longest'`, first token = [DEC] bos): returns
+    (input_ids [n, L] long, attention_mask [n, L] long); every answer ends with [SEP] = 102, pads are 0."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.zeros(n_answers, max_len, dtype=torch.long)
+    mask = torch.zeros(n_answers, max_len, dtype=torch.long)
+    for a in range(n_answers):
+        n_tok = int(torch.randint(1, max_len - 1, (1,), generator=g))       # answer words
+        ids[a, 0] = bos_id
+        ids[a, 1:1 + n_tok] = torch.randint(1000, 30000, (n_tok,), generator=g)
+        ids[a, 1 + n_tok] = 102
+        mask[a, :2 + n_tok] = 1
+    return ids, mask
+
+
 def retrieval_inputs(batch: int, img_size: int = 384, max_len: int = 35, seed: int = 0):
     """BASELINE config 3 inputs: images ~ N(0,1); text padded to max_len (`padding='max_length'`,
     models/blip_retrieval.py:107) with true lengths ~ U[8, 20)."""

@@ -499,3 +499,57 @@ def med_text_encoder(ids: Tensor, attn_mask: Tensor, sd: SD, prefix: str, enc: O
         h, ext_mask = med_layer(h, ext_mask, sd, f"{prefix}encoder.layer.{i}", enc, temperature, token_attn, mode,
                                 trace=tr)
     return h, sd_ft_all
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VQA answer ranking  (models/blip_vqa.py:156-203 over models/med.py:BertLMHeadModel)
+# ---------------------------------------------------------------------------------------------------------------
+def med_decoder_forward(ids: Tensor, attn_mask: Tensor, sd: SD, prefix: str, enc: Tensor, depth: int = 12) -> Tensor:
+    """BertModel(is_decoder=True) without pruning: causal x padding mask (models/med.py:749-771), cross-attention to
+    `enc` with NO mask (:197). Returns the last hidden state [B, L, d]."""
+    B, L = ids.shape
+    seq = torch.arange(L)
+    causal = (seq[None, None, :].repeat(B, L, 1) <= seq[None, :, None]).to(torch.float32)     # :753-756
+    ext = causal[:, None, :, :] * attn_mask[:, None, None, :].to(torch.float32)               # :768
+    ext = (1.0 - ext) * -10000.0                                                              # :784-785
+    h = bert_embeddings(ids, sd, prefix + "embeddings.")
+    for i in range(depth):
+        h, _ = med_layer(h, ext, sd, f"{prefix}encoder.layer.{i}", enc, 0.0, None, "multimodal")
+    return h
+
+
+def lm_head(h: Tensor, sd: SD, prefix: str, eps: float = 1e-12) -> Tensor:
+    """BertOnlyMLMHead (models/med.py:615-657): dense -> GELU(erf) -> LayerNorm -> tied decoder + bias."""
+    t = layer_norm(F.gelu(linear(h, sd, prefix + ".transform.dense")), sd, prefix + ".transform.LayerNorm", eps)
+    return F.linear(t, sd[prefix + ".decoder.weight"], sd[prefix + ".bias"])
+
+
+def lm_sequence_loss(logits: Tensor, labels: Tensor) -> Tensor:
+    """models/med.py:1040-1047 with reduction='none': label-smoothed (0.1) next-token cross entropy, ignore_index -100,
+    summed over the positions of every sequence."""
+    B = logits.shape[0]
+    shifted = logits[:, :-1, :].contiguous()
+    lab = labels[:, 1:].contiguous()
+    loss = F.cross_entropy(shifted.view(-1, shifted.shape[-1]), lab.view(-1), reduction="none", label_smoothing=0.1)
+    return loss.view(B, -1).sum(1)
+
+
+def vqa_rank_answer(question_states: Tensor, answer_ids: Tensor, answer_atts: Tensor, k: int, sd: SD,
+                    prefix: str = "text_decoder.", pad_id: int = 0):
+    """models/blip_vqa.py:156-203. Returns (max_ids [Q], topk_ids [Q,k], log_probs_sum [Q,k], prob_first_token)."""
+    Q = question_states.shape[0]
+    start_ids = answer_ids[0, 0].repeat(Q, 1)
+    h0 = med_decoder_forward(start_ids, torch.ones_like(start_ids), sd, prefix + "bert.", question_states)
+    logits = lm_head(h0, sd, prefix + "cls.predictions")[:, 0, :]
+    prob_first = torch.softmax(logits, dim=1).index_select(1, answer_ids[:, 1])
+    topk_probs, topk_ids = prob_first.topk(k, dim=1)
+    input_ids = torch.cat([answer_ids.index_select(0, t) for t in topk_ids], 0)
+    input_atts = torch.cat([answer_atts.index_select(0, t) for t in topk_ids], 0)
+    targets = input_ids.masked_fill(input_ids == pad_id, -100)
+    qs = question_states.repeat_interleave(k, dim=0)                 # == tile(question_states, 0, k), :214-220
+    h = med_decoder_forward(input_ids, input_atts, sd, prefix + "bert.", qs)
+    loss = lm_sequence_loss(lm_head(h, sd, prefix + "cls.predictions"), targets)
+    log_probs_sum = (-loss).view(Q, k)
+    best = log_probs_sum.argmax(dim=1)
+    max_ids = topk_ids[best >= 0, best]
+    return max_ids, topk_ids, log_probs_sum, prob_first

@@ -37,6 +37,10 @@ GOLDEN = ROOT / "tests" / "golden"
 BLOCK_TEMPS = (1.0, 5.0, 50.0)
 
 
+def maxdiff(a, b) -> float:
+    return float((a.double() - b.double()).abs().max())
+
+
 def digest(*tensors) -> str:
     h = hashlib.sha256()
     for t in tensors:
@@ -545,6 +549,70 @@ def gen_calibration(pairs: int, image_size: int = 384, text_len: int = 20, p: fl
     np.savez_compressed(GOLDEN / f"calib_nlvr_p{int(p * 100)}_b{pairs}.npz", **out)
 
 
+def gen_vqa_rank():
+    """BLIP_VQA(inference='rank') of the unmodified reference (models/blip_vqa.py:117-203): pruned image + question
+    encoders, then the answer decoder ranks k_test candidates. The oracle must reproduce the chosen answers, the top-k
+    candidate sets and the summed log-probabilities."""
+    ref_shims.install()
+    import models.blip as blip
+    tok = ref_shims.FakeTokenizer()
+    blip.init_tokenizer = lambda: tok
+    import models.blip_vqa as bv
+    bv.init_tokenizer = lambda: tok
+    size, B, k_test, temp = 224, 3, 3, 6.0
+    model = bv.BLIP_VQA(med_config=os.path.join(ref_shims.REFERENCE_ROOT, "configs/med_config.json"), image_size=size,
+                        vit="base", evaluate=True)
+    sd = weights.vqa_state_dict(99, img_size=size)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys and all("position_ids" in k for k in msg.missing_keys), msg
+    model.eval()
+    images, ids, mask = weights.retrieval_inputs(B, size, 20, seed=3)
+    L = int(mask.sum(1).max())                       # padding='longest'
+    ids, mask = ids[:, :L].contiguous(), mask[:, :L].contiguous()
+    ans_ids, ans_mask = weights.vqa_answer_candidates(6, 5, seed=1, bos_id=tok.bos_token_id)
+    tok.next_ids = (ids, mask)
+
+    class Answer:
+        input_ids, attention_mask = ans_ids, ans_mask
+    cap = {}
+    orig_rank = model.rank_answer
+
+    def rank_spy(question_states, question_atts, answer_ids, answer_atts, k):
+        cap["question_states"] = question_states.detach().clone()
+        return orig_rank(question_states, question_atts, answer_ids, answer_atts, k)
+    model.rank_answer = rank_spy
+    dec_out = []
+    hook = model.text_decoder.register_forward_hook(lambda m, a, o: dec_out.append(o))
+    with torch.no_grad():
+        max_ids = model(images, ["q"] * B, Answer, temperature=temp, train=False, inference="rank", k_test=k_test)
+    hook.remove()
+    ref_first_logits = dec_out[0].logits[:, 0, :]
+    ref_prob_first = torch.softmax(ref_first_logits, dim=1).index_select(1, ans_ids[:, 1])
+    ref_logp = (-dec_out[1].loss).view(B, k_test)
+
+    # the oracle, end to end from the same inputs
+    with torch.no_grad():
+        feat, _ = O.vit_forward(images, sd, "visual_encoder.", sd["space_dict"], temp)
+        ids2 = ids.clone()
+        ids2[:, 0] = tok.enc_token_id
+        q_states, _ = O.med_text_encoder(ids2, mask, sd, "text_encoder.", feat, sd["space_dict"], temp, "multimodal")
+        o_max, o_topk, o_logp, o_prob = O.vqa_rank_answer(q_states, ans_ids, ans_mask, k_test, sd)
+    assert q_states.shape == cap["question_states"].shape, (q_states.shape, cap["question_states"].shape)
+    print("vqa: question states", maxdiff(q_states, cap["question_states"]), "prob_first", maxdiff(o_prob, ref_prob_first),
+          "log-probs", maxdiff(o_logp, ref_logp))
+    assert maxdiff(q_states, cap["question_states"]) < 2e-4
+    assert maxdiff(o_prob, ref_prob_first) < 1e-6 and maxdiff(o_logp, ref_logp) < 2e-3
+    assert torch.equal(o_max, max_ids), (o_max, max_ids)
+    assert torch.equal(o_topk.sort(1)[0], ref_prob_first.topk(k_test, dim=1)[1].sort(1)[0])
+    out = {"input_digest": np.array(digest(images, ids, mask, ans_ids, ans_mask)), "temperature": np.array(temp),
+           "k_test": np.array(k_test), "image_size": np.array(size), "ids": ids.numpy(), "mask": mask.numpy(),
+           "answer_ids": ans_ids.numpy(), "answer_mask": ans_mask.numpy(),
+           "question_states": cap["question_states"].numpy(), "prob_first": ref_prob_first.numpy(),
+           "topk_ids": ref_prob_first.topk(k_test, dim=1)[1].numpy(), "log_probs_sum": ref_logp.numpy(),
+           "max_ids": max_ids.numpy()}
+    np.savez_compressed(GOLDEN / "vqa_rank.npz", **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -560,6 +628,8 @@ if __name__ == "__main__":
         gen_clip()
     if a.only in ("all", "med"):
         gen_med()
+    if a.only in ("all", "vqa"):
+        gen_vqa_rank()
     if a.only in ("all", "nlvr384"):
         gen_nlvr(384, 2, 20, (1.5,), "nlvr_small384")
     if a.only in ("all", "calib"):

@@ -178,3 +178,21 @@ def test_oracle_clip_matches_reference_fixture():
         if k_ref > 0:
             assert tr.k == k_ref and torch.equal(tr.keep, unpack(gold[f"t{i}_keep"], x.shape[1] - 1))
         assert (y[:, :, ::4] - torch.from_numpy(gold[f"t{i}_out_s4"])).abs().max().item() < 2e-4
+
+
+def test_vqa_rank_oracle_against_reference_fixture():
+    """The answer decoder + ranking restatement (oracle.vqa_rank_answer) against what the unmodified reference produced
+    (tests/golden/vqa_rank.npz, oracle/gen_golden.py:gen_vqa_rank), teacher-forced with the reference's question states."""
+    from oracle import weights
+    fx = np.load(GOLDEN / "vqa_rank.npz")
+    sd = weights.vqa_state_dict(99, img_size=int(fx["image_size"]))
+    dec = {k: v for k, v in sd.items() if k.startswith("text_decoder.")}
+    q = torch.from_numpy(fx["question_states"])
+    with torch.no_grad():
+        max_ids, topk_ids, logp, prob = O.vqa_rank_answer(q, torch.from_numpy(fx["answer_ids"]),
+                                                          torch.from_numpy(fx["answer_mask"]), int(fx["k_test"]), dec)
+    assert torch.equal(max_ids, torch.from_numpy(fx["max_ids"]))
+    assert torch.equal(topk_ids.sort(1)[0], torch.from_numpy(fx["topk_ids"]).sort(1)[0])
+    assert (prob - torch.from_numpy(fx["prob_first"])).abs().max().item() < 1e-8
+    want = torch.from_numpy(fx["log_probs_sum"]).gather(1, torch.from_numpy(fx["topk_ids"]).argsort(1))
+    assert (logp.gather(1, topk_ids.argsort(1)) - want).abs().max().item() < 1e-3

@@ -331,10 +331,10 @@ def test_blip_vqa_question_encoder_480(dev):
     """Config 5 shapes: 480x480 images -> 901 tokens through the tensor-core attention path, question encoder with
     cross-attention over the pruned image tokens."""
     from madtp_b200.blip_retrieval import BLIP_VQA
-    sd = weights.retrieval_state_dict(99, img_size=480)
+    sd = weights.vqa_state_dict(99, img_size=480)
     model = BLIP_VQA(image_size=480, evaluate=True)
     msg = model.load_state_dict(sd, strict=False)
-    assert set(msg.unexpected_keys) <= {"itm_head.weight", "itm_head.bias"} and not msg.missing_keys
+    assert set(msg.unexpected_keys) <= {"text_decoder.cls.predictions.decoder.bias"} and not msg.missing_keys
     model = model.to(dev).eval()
     images, ids, mask = weights.retrieval_inputs(2, 480, 20, seed=2)
     temp = 6.0
@@ -395,6 +395,63 @@ def test_full_size_against_calibration_fixture_and_properties(dev):
     with torch.no_grad():
         pred_p = model(img_p, TokenizedText(ids[perm].to(dev), mask[perm].to(dev)), pairs, temp, train=False)
     assert torch.equal(pred_p, pred[perm.to(dev)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VQA answer ranking (models/blip_vqa.py:156-203) against the fixture generated from the reference
+# ---------------------------------------------------------------------------------------------------------------
+class _Tok:
+    def __init__(self, ids, mask):
+        self.input_ids, self.attention_mask = ids, mask
+
+
+def test_vqa_rank_answer_against_reference_fixture(dev):
+    from madtp_b200.blip_retrieval import BLIP_VQA
+    fx = np.load(GOLDEN / "vqa_rank.npz")
+    size, k, temp = int(fx["image_size"]), int(fx["k_test"]), float(fx["temperature"])
+    sd = weights.vqa_state_dict(99, img_size=size)
+    model = BLIP_VQA(image_size=size, evaluate=True)
+    msg = model.load_state_dict(sd, strict=False)
+    assert set(msg.unexpected_keys) <= {"text_decoder.cls.predictions.decoder.bias"} and not msg.missing_keys
+    model = model.to(dev).eval()
+    ans_ids, ans_mask = torch.from_numpy(fx["answer_ids"]).to(dev), torch.from_numpy(fx["answer_mask"]).to(dev)
+    ids, mask = torch.from_numpy(fx["ids"]), torch.from_numpy(fx["mask"])
+    images, ids_chk, mask_chk = weights.retrieval_inputs(ids.shape[0], size, 20, seed=3)
+    assert weights.tensor_digest(images, ids, mask, ans_ids.cpu(), ans_mask.cpu()) == str(fx["input_digest"])
+    # (1) the decoder alone, teacher-forced with the reference's question states
+    q_ref = torch.from_numpy(fx["question_states"]).to(dev)
+    max_ids = model.rank_answer(q_ref, mask.to(dev), ans_ids, ans_mask, k)
+    lr = model.last_rank
+    # the decoder's 12 layers run their projections / FFN / cross-attention on the fp16 value lane
+    assert rel(lr["prob_first_token"], torch.from_numpy(fx["prob_first"])) < 3e-3
+    assert torch.equal(lr["topk_ids"].cpu().sort(1)[0], torch.from_numpy(fx["topk_ids"]).sort(1)[0])
+    order = lr["topk_ids"].cpu().argsort(1)                    # compare per candidate, whatever order topk returned
+    ref_order = torch.from_numpy(fx["topk_ids"]).argsort(1)
+    got = lr["log_probs_sum"].cpu().gather(1, order)
+    want = torch.from_numpy(fx["log_probs_sum"]).gather(1, ref_order)
+    assert (got - want).abs().max().item() < 2e-2, (got, want)   # sums of ~5 token losses of magnitude ~10
+    assert torch.equal(max_ids.cpu(), torch.from_numpy(fx["max_ids"]))
+    # (2) the whole evaluation forward: pruned image + question encoders, then the ranking
+    out = model(images.to(dev), _Tok(ids.to(dev), mask.to(dev)), _Tok(ans_ids, ans_mask), temperature=temp,
+                train=False, inference='rank', k_test=k)
+    assert torch.equal(out.cpu(), torch.from_numpy(fx["max_ids"]))
+    got2 = model.last_rank["log_probs_sum"].cpu().gather(1, model.last_rank["topk_ids"].cpu().argsort(1))
+    assert (got2 - want).abs().max().item() < 0.3
+
+
+def test_lm_nll_kernel(lib, dev):
+    g = torch.Generator(device="cpu").manual_seed(11)
+    R, V = 37, 30524
+    buf = (torch.randn(R, V + 4, generator=g) * 4).to(dev)
+    logits = buf[:, :V]
+    labels = torch.randint(0, V, (R,), generator=g)
+    labels[::5] = -100
+    loss, lse = lib.lm_nll(logits, labels.to(dev), 0.1)
+    ref = torch.nn.functional.cross_entropy(logits.double().cpu(), labels, reduction="none", label_smoothing=0.1)
+    assert (loss.double().cpu() - ref).abs().max().item() < 2e-5
+    assert (lse.double().cpu() - torch.logsumexp(logits.double().cpu(), 1)).abs().max().item() < 1e-5
+    _, lse2 = lib.lm_nll(logits)
+    assert torch.equal(lse, lse2)
 
 
 # ---------------------------------------------------------------------------------------------------------------

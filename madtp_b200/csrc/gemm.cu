@@ -814,6 +814,38 @@ gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __rest
   }
 }
 
+// fp32 dot-product kernel for a handful of rows (M <= 64: cls_head / itm_head): one warp per output element, so even
+// a [32 x 2] output spreads over the machine instead of running as one 48-step dependent loop in a single CTA.
+__global__ void __launch_bounds__(256)
+gemm_rowdot_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
+                   GemmEpilogue ep, int M, int N, int K) {
+  const long long o = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= static_cast<long long>(M) * N) return;
+  const int row = static_cast<int>(o / N), col = static_cast<int>(o % N);
+  const float4* a4 = reinterpret_cast<const float4*>(A + row * lda);
+  const float4* b4 = reinterpret_cast<const float4*>(B + col * ldb);
+  float acc = 0.f;
+  for (int k4 = lane; k4 < K / 4; k4 += 32) {
+    const float4 x = __ldg(a4 + k4), y = __ldg(b4 + k4);
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc);
+    acc = fmaf(x.w, y.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float x = ep.alpha * acc;
+    if (ep.bias) x += ep.bias[col];
+    x = apply_act(x, ep.act);
+    if (ep.residual) x += ep.residual[row * ep.ldr + col];
+    if (ep.c_f16)
+      reinterpret_cast<__half*>(ep.c)[row * ep.ldc + col] = __float2half_rn(x);
+    else
+      reinterpret_cast<float*>(ep.c)[row * ep.ldc + col] = x;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor maps + dispatch
 // ------------------------------------------------------------------------------------------------
@@ -1011,6 +1043,15 @@ int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, c
   MADTP_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
   MADTP_CHECK_ARG(a && b && ep.c, "null GEMM operand");
   if (M == 0) return kOk;
+  if (precision == kGemmSimtF32 && M <= 64 && (K & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    // a handful of rows (classification heads): one warp per output element, 128-bit loads
+    const long long outs = static_cast<long long>(M) * N;
+    gemm_rowdot_kernel<<<static_cast<int>((outs + 7) / 8), 256, 0, stream>>>(
+        static_cast<const float*>(a), lda, static_cast<const float*>(b), ldb, ep, M, N, K);
+    MADTP_LAUNCH_CHECK();
+    return kOk;
+  }
   if (precision == kGemmSimtF32) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(a), lda, static_cast<const float*>(b), ldb,

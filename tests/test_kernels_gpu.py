@@ -40,6 +40,20 @@ def test_gemm_simt(lib, dev, M, N, K):
     assert _rel(out, ref) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K,act", [(32, 768, 768, 2), (32, 2, 768, 0), (64, 5, 132, 1), (1, 1, 4, 0)])
+def test_gemm_simt_few_rows(lib, dev, M, N, K, act):
+    """Classification heads (cls_head, itm_head): the one-warp-per-output kernel behind MADTP_GEMM_SIMT for M <= 64."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    out = torch.full((M, N), float("nan"), device=dev)
+    lib.gemm(lib.GEMM_SIMT, a, b, out, bias=bias, act=act)
+    ref = a.double() @ b.double().T + bias.double()
+    ref = {0: ref, 1: torch.nn.functional.gelu(ref), 2: torch.relu(ref)}[act]
+    assert _rel(out, ref) < 2e-6
+
+
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_tf32x3(lib, dev, M, N, K):
     if K % 4:

@@ -100,7 +100,8 @@ struct FwdCfg {
   static constexpr int V_OFF = K_OFF + K_STAGES * TILE_BYTES;
   static constexpr int BAR_OFF = V_OFF + V_STAGES * TILE_BYTES;
   static constexpr int XCH_OFF = BAR_OFF + 256;            // [3][NG][128] floats: per-row exchange between groups
-  static constexpr int TOTAL = XCH_OFF + 3 * NG * BM * 4;
+  static constexpr int CLS_OFF = XCH_OFF + 3 * NG * BM * 4;   // [64] floats: staging of the CLS query row
+  static constexpr int TOTAL = CLS_OFF + 64 * 4;
 };
 
 template <int KW, int NB>
@@ -129,6 +130,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
   uint64_t* o_full = bars + 20;    // [2] P(g) V(g) complete: O partial ready, P buffer free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   float* xch = reinterpret_cast<float*>(smem + Cfg::XCH_OFF);   // [parity | item end][group][row]
+  float* cls_stage = reinterpret_cast<float*>(smem + Cfg::CLS_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, HD = a.H * 64;
@@ -382,13 +384,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
           // the CLS query row (row 0 of query tile 0) feeds cls_attn: keep its 256 p and the maximum they are relative
           // to; the statistics pass turns them into probabilities with the final log-sum-exp (vit.py:96-100)
           if (cls_warp) {               // warp-uniform: only the warps that own row 0 of query tile 0 get here
+            // lane 0 holds the row: stage it in shared memory so that the warp writes it with one coalesced store
+            float* st = cls_stage + grp * KW;
             if (lane == 0) {
-              float* cp = a.cls_p + static_cast<long long>(bh) * N + j0;
 #pragma unroll
-              for (int k = 0; k < KW; ++k)
-                if (j0 + k < N) cp[k] = s[k];
+              for (int k = 0; k < KW; k += 4) *reinterpret_cast<float4*>(st + k) = make_float4(s[k], s[k + 1], s[k + 2], s[k + 3]);
               if (grp == 0) a.cls_tile_max[static_cast<long long>(bh) * T + t] = m_new;
             }
+            __syncwarp();
+            if (lane < KW && j0 + lane < N) a.cls_p[static_cast<long long>(bh) * N + j0 + lane] = st[lane];
+            __syncwarp();
           }
         };
         auto do_drain = [&]() {

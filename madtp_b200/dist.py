@@ -3,7 +3,7 @@
 The path shards over samples only: weights are replicated with ONE broadcast of a flat blob
 from rank 0, every rank runs the forward on its own pairs (topk_num is the max over the LOCAL batch, which is the
 reference's own multi-GPU evaluation semantics, compress_nlvr_dtp.py:131,210-211), and the logits are all-gathered.
-There is no collective on the data path between those two points.
+There is no collective on the data path between those two points unless the strict mode below is switched on.
 """
 from __future__ import annotations
 
@@ -70,6 +70,28 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- optional strict mode: the pruning of a sharded batch matches the single-process run on the whole batch ---------
+# topk_num is a maximum over the batch (models/vit.py:145), so sharding the batch changes how many tokens each sample
+# keeps. The reference's multi-GPU evaluation lives with that (every rank takes the max over its LOCAL batch); with
+# global_topk(True) one all-reduce(MAX) of the int32 scalar per pruned layer and modality (24 per forward, latency-bound)
+# runs before the read-back, and every rank prunes exactly as one process holding all samples would.
+_GLOBAL_TOPK = bool(int(os.environ.get("MADTP_GLOBAL_TOPK", "0")))
+
+
+def global_topk(enable: bool = None) -> bool:
+    global _GLOBAL_TOPK
+    if enable is not None:
+        _GLOBAL_TOPK = bool(enable)
+    return _GLOBAL_TOPK
+
+
+def allreduce_topk_(topk: torch.Tensor) -> torch.Tensor:
+    """In-place all-reduce(MAX) of the per-layer survivor count when the strict mode is on; otherwise a no-op."""
+    if _GLOBAL_TOPK and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(topk, op=dist.ReduceOp.MAX)
+    return topk
 
 
 def barrier():

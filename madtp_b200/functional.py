@@ -15,6 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib as L
+from . import dist as _dist
 
 Tensor = torch.Tensor
 TA_LD = 128  # row pitch of token_att buffers (T = 100 codebook entries padded to a 16-byte multiple of columns)
@@ -270,6 +271,7 @@ def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: 
     pruning decision between this and dtp_finish: it runs while the host waits for topk_num."""
     T = token_att.shape[2]
     score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature)
+    _dist.allreduce_topk_(topk)         # no-op unless madtp_b200.dist.global_topk(True) (strict multi-GPU mode)
     return PendingPrune(score, thr, cnt, topk, L.readback_begin(topk))
 
 

@@ -171,10 +171,11 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
 
 /*
  * DTP gather + merge (vit.py:154-161,202; models/utils.py:13-33 vector_gather): out[b] = [x[b,0], survivors in
- * ascending token order, sum_j tail_w[j] x[b,1+j]] -- shape [B, k+2, d] with batch stride bso.
+ * ascending token order, sum_j tail_w[j] x[b,1+j]] -- shape [B, k+2, d] with batch stride bso. out_f16 (may be NULL):
+ * an fp16 copy with the same layout, the operand of the GEMM that follows in the text encoders.
  */
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
-                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, int max_keep,
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* out_f16, int max_keep,
                      void* stream);
 
 /*

@@ -53,7 +53,7 @@ SIGNATURES = {
     "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
-    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp],
+    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
                        _vp],
@@ -469,18 +469,19 @@ def dtp_select(score, topk, *, mask_mode=0, mask_in=None, max_keep=0):
     return keep, dst, tail_w, tail_idx, mask_out
 
 
-def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0):
-    """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d]."""
+def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0, want_f16=False):
+    """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d] (and its fp16 copy if want_f16)."""
     B, N, d = x.shape
     if x.stride(2) != 1 or x.stride(1) != d:
         raise RuntimeError("madtp_b200.dtp_gather: x rows must be dense")
     out = torch.empty(B, k + 2, d, dtype=torch.float32, device=x.device)
+    out16 = torch.empty(B, k + 2, d, dtype=torch.float16, device=x.device) if want_f16 else None
     st = _call("madtp_dtp_gather", B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
                                  _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
-                                 _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), int(max_keep),
-                                 _stream())
+                                 _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _ptr(out16),
+                                 int(max_keep), _stream())
     _check(st, "madtp_dtp_gather")
-    return out
+    return (out, out16) if want_f16 else out
 
 
 def gather_rows(x, idx):

@@ -217,13 +217,14 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
 }
 
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
-                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, int max_keep,
+                     const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* out_f16, int max_keep,
                      void* stream) {
   DtpGatherArgs a;
   a.B = B; a.n = n; a.d = d;
   a.x = x; a.bsx = bsx;
   a.topk = topk; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
   a.out = out; a.bso = bso;
+  a.out_f16 = static_cast<__half*>(out_f16);
   a.max_keep = max_keep;
   return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
 }

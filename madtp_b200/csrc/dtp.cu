@@ -423,6 +423,14 @@ dtp_gather_kernel(DtpGatherArgs a) {
   const int k = identity ? n : k_in;
   const float4* xb = reinterpret_cast<const float4*>(a.x + b * a.bsx);
   float4* ob = reinterpret_cast<float4*>(a.out + b * a.bso);
+  uint2* ob16 = a.out_f16 ? reinterpret_cast<uint2*>(a.out_f16 + b * a.bso) : nullptr;
+  auto pack4 = [](const float4& v) {
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 p;
+    p.x = *reinterpret_cast<const uint32_t*>(&h0);
+    p.y = *reinterpret_cast<const uint32_t*>(&h1);
+    return p;
+  };
   const int* dst = a.dst + static_cast<long long>(b) * n;
   const float* tw = a.tail_w + static_cast<long long>(b) * n;
 
@@ -466,6 +474,7 @@ dtp_gather_kernel(DtpGatherArgs a) {
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
       }
       ob[static_cast<long long>(1 + k) * d4 + c] = t;
+      if (ob16) ob16[static_cast<long long>(1 + k) * d4 + c] = pack4(t);
     }
     return;
   }
@@ -484,7 +493,17 @@ dtp_gather_kernel(DtpGatherArgs a) {
     }
     const float4* src = xb + static_cast<long long>(r) * d4;
     float4* o = ob + static_cast<long long>(slot) * d4;
-    for (int c = lane; c < d4; c += 32) o[c] = src[c];
+    // all loads of the row in flight before the first store (d <= 1024: at most eight float4 per lane)
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (lane + 32 * c < d4) v[c] = src[lane + 32 * c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (lane + 32 * c < d4) {
+        o[lane + 32 * c] = v[c];
+        if (ob16) ob16[static_cast<long long>(slot) * d4 + lane + 32 * c] = pack4(v[c]);
+      }
   }
 }
 

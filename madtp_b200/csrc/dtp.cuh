@@ -65,6 +65,7 @@ struct DtpGatherArgs {
   const int* tail_idx;
   float* out;                 // [B, k+2, d] packed survivors: [cls, survivors ascending, merged]
   long long bso;              // batch stride of out (elements) -- the caller sizes it with the k it read back
+  __half* out_f16;            // optional fp16 copy of out with the same batch stride (operand of the next GEMM)
   int max_keep;
 };
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);

@@ -255,6 +255,7 @@ class PruneResult:
     count: Tensor                   # [B] int32
     keep: Optional[Tensor] = None   # [B, n] uint8
     mask: Optional[Tensor] = None   # [B, k+2] additive mask (text)
+    x16: Optional[Tensor] = None    # fp16 copy of x when the caller asked for it (dtp_finish(want_f16=True))
 
 
 class PendingPrune:
@@ -276,7 +277,7 @@ def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: 
 
 
 def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Optional[Tensor] = None,
-               max_keep: int = 0) -> PruneResult:
+               max_keep: int = 0, want_f16: bool = False) -> PruneResult:
     """Second half of Reduce_token on x [B, n+1, d] (position 0 always survives): select, gather, merge."""
     B, N, d = x.shape
     n = N - 1
@@ -286,8 +287,9 @@ def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Op
         return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
     keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
                                                          max_keep=max_keep)
-    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep)
-    return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2])
+    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep, want_f16=want_f16)
+    out, out16 = out if want_f16 else (out, None)
+    return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2], out16)
 
 
 def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,

@@ -429,7 +429,7 @@ class BertLayer(nn.Module):
             ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune, causal=_causal)
         # score kernel + read-back of topk_num first: the output dense + LayerNorm below do not depend on them
         pend = Fn.dtp_score_async(sa.get_attention_map(), token_attn, float(temperature), Ltok - 1) if prune else None
-        att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=not prune)
+        att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=True)
         att_f32, att16 = att["y"].view(B, Ltok, d), att.get("y16")
 
         # dynamic token pruning between self- and cross-attention (:519-533)
@@ -437,14 +437,14 @@ class BertLayer(nn.Module):
         if prune:
             if key_mask is None:
                 key_mask = torch.zeros(B, Ltok, dtype=torch.float32, device=h.device)
-            res = Fn.dtp_finish(att_f32, pend, mask_mode=self.MASK_MODE, mask_in=key_mask)
+            res = Fn.dtp_finish(att_f32, pend, mask_mode=self.MASK_MODE, mask_in=key_mask, want_f16=True)
             self.last_prune = res
             att_f32 = res.x
-            if res.pruned:
+            if res.pruned:          # the gather kernel also wrote the fp16 operand of the next GEMM
                 key_mask = res.mask.contiguous()
                 Ltok = att_f32.shape[1]
+                att16 = res.x16.view(B * Ltok, d)
             attention_mask = key_mask.view(B, 1, 1, Ltok)
-            att16 = L.cast_f16(att_f32.reshape(B * Ltok, d))
         att_rows = att_f32.reshape(B * Ltok, d)
 
         if mode == 'multimodal':

@@ -312,6 +312,8 @@ def test_dtp_score_select_gather(lib, dev, B, n, temp):
         keep_ref.scatter_(1, order[:, :k], True)
         assert torch.equal(keep.bool(), keep_ref)
         out = lib.dtp_gather(x, topk, dst, tail_w, tail_idx, k)
+        out_b, out16 = lib.dtp_gather(x, topk, dst, tail_w, tail_idx, k, want_f16=True)
+        assert torch.equal(out_b, out) and torch.equal(out16, out.half())
         for b in range(B):
             idx = keep_ref[b].nonzero().flatten()
             assert torch.equal(out[b, 0], x[b, 0])

@@ -142,8 +142,7 @@ int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const
                      float* sd_ft, int accumulate, void* stream);
 
 /* madtp_query_sdft on the tensor cores: ft is the dense fp32 matrix x [x_rows, d] (token j of batch b at row
- * b*row_stride + first_row + j); both operands are re-laid out K-major in shared memory, nothing transposed touches HBM.
- * col_max == col_sum == NULL: the kernel computes the column statistics itself (no madtp_token_colstats launch). */
+ * b*row_stride + first_row + j); both operands are re-laid out K-major in shared memory, nothing transposed touches HBM. */
 int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
                         const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
                         float divisor, float* sd_ft, int accumulate, void* stream);

@@ -26,8 +26,7 @@ constexpr int OP_BYTES = 128 * 128;                // one K-major operand plane:
 constexpr int STAGE = RAW_BYTES + 4 * OP_BYTES;    // raw X | W hi | W lo | X^T hi | X^T lo  = 96 KB
 constexpr float kWScale = 1024.0f;
 constexpr int STAGES = 2;
-constexpr int STAT_OFF = STAGES * STAGE + 256;       // [2 halves][max | sum][128] floats for the fused column statistics
-constexpr int SMEM_TOTAL = STAT_OFF + 2 * 2 * 128 * 4;
+constexpr int SMEM_TOTAL = STAGES * STAGE + 256;
 
 // byte offset of 16-byte granule k4 (0..7: eight tokens) of a row in a K-major [rows x 128 bytes] tile with the
 // 128-byte swizzle
@@ -53,7 +52,6 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
   uint64_t* empty = bars + 4;      // [2] MMAs of the stage retired
   uint64_t* acc_full = bars + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  float* stat = reinterpret_cast<float*>(smem + STAT_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d0 = blockIdx.x * DN, b = blockIdx.y;
@@ -119,43 +117,9 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
     const bool t_ok = t < a.T;
     constexpr float kLog2e = 1.4426950408889634f;
     const float c1 = kLog2e / a.divisor;
+    const float off = t_ok ? -a.col_max[b * a.T + t] * kLog2e : 0.f;
+    const float cinv = t_ok ? kWScale / a.col_sum[b * a.T + t] : 0.f;
     const float* tab = a.ta + b * a.bs_ta + t;
-    float off = 0.f, cinv = 0.f;
-    if (a.col_max != nullptr) {          // column statistics from madtp_token_colstats
-      off = t_ok ? -a.col_max[b * a.T + t] * kLog2e : 0.f;
-      cinv = t_ok ? kWScale / a.col_sum[b * a.T + t] : 0.f;
-    } else {
-      // fused statistics: online max / sum of 2^(y - max) over this thread's half of the tokens (eight loads in
-      // flight), combined with the other half through shared memory
-      float m = -INFINITY, ssum = 0.f;
-      const int jb = half ? (a.n + 1) / 2 : 0, je = half ? a.n : (a.n + 1) / 2;
-      if (t_ok) {
-        for (int j = jb; j < je; j += 8) {
-          float y[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) y[u] = (j + u < je) ? __ldg(tab + (j + u) * a.ld_ta) * c1 : -INFINITY;
-          float mx = y[0];
-#pragma unroll
-          for (int u = 1; u < 8; ++u) mx = fmaxf(mx, y[u]);
-          const float m_new = fmaxf(m, mx);
-          float add = 0.f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) add += ex2_approx(y[u] - m_new);
-          ssum = fmaf(ssum, ex2_approx(m - m_new), add);
-          m = m_new;
-        }
-      }
-      stat[half * 256 + t] = m;
-      stat[half * 256 + 128 + t] = ssum;
-      named_bar_sync(1, 256);
-      if (t_ok) {
-        const float m0 = stat[t], s0 = stat[128 + t], m1 = stat[256 + t], s1 = stat[256 + 128 + t];
-        const float mm = fmaxf(m0, m1);      // the first half is never empty, so mm is finite
-        const float tot = s0 * ex2_approx(m0 - mm) + (m1 == -INFINITY ? 0.f : s1 * ex2_approx(m1 - mm));
-        off = -mm;
-        cinv = kWScale / tot;
-      }
-    }
     const int grp = t >> 5, tl = t & 31;
     auto store_split8 = [](uint8_t* hi, uint8_t* lo, int offb, const float (&v)[8]) {
       uint32_t ph[4], pl[4];
@@ -252,8 +216,7 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
 int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
                          const float* col_sum, const float* x, long long x_rows, int row_stride, int first_row, int B,
                          int n, int T, int d, float divisor, float* sd_ft, int accumulate, cudaStream_t stream) {
-  MADTP_CHECK_ARG(token_att && x && sd_ft, "query_sdft_tc: null pointer");
-  MADTP_CHECK_ARG((col_max == nullptr) == (col_sum == nullptr), "query_sdft_tc: col_max / col_sum come in pairs");
+  MADTP_CHECK_ARG(token_att && col_max && col_sum && x && sd_ft, "query_sdft_tc: null pointer");
   MADTP_CHECK_ARG(B >= 0 && n > 0 && T > 0 && T <= TM && d > 0 && d % 32 == 0 && B <= 65535,
                   "query_sdft_tc: unsupported shape (T=%d must be <= 128, d=%d a multiple of 32)", T, d);
   if (B == 0) return kOk;

@@ -172,14 +172,13 @@ def query_model_from_token_att(ta_full: Tensor, x3d: Tensor, T: int, sd_dim: int
     ta3 = ta_full[:, first_token:, :]
     n = N - first_token
     div = math.sqrt(sd_dim)
+    cm, cs = L.token_colstats(ta3, n, T, div)
     accumulate = sd_ft is not None
     if sd_ft is None:
         sd_ft = torch.empty(B, T, d, dtype=torch.float32, device=x3d.device)
-    if n >= 64 and x3d.is_contiguous() and d % 32 == 0:
-        # tensor-core path over the dense rows of x3d; the kernel computes the over-token softmax statistics itself
-        L.query_sdft_tc(ta3, None, None, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate)
+    if n >= 64 and x3d.is_contiguous() and d % 32 == 0:     # tensor-core path over the dense rows of x3d
+        L.query_sdft_tc(ta3, cm, cs, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate)
     else:
-        cm, cs = L.token_colstats(ta3, n, T, div)
         L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate)
     return ta3[:, :, :T], sd_ft
 

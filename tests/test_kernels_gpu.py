@@ -413,9 +413,6 @@ def test_query_sdft_tensor_core(lib, dev, B, n, T, d):
     assert _rel(sd, ref) < 5e-6
     lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, True)
     assert _rel(sd, 2 * ref) < 5e-6
-    sd2 = torch.full((B, T, d), float("nan"), device=dev)      # column statistics computed inside the kernel
-    lib.query_sdft_tc(ta_p, None, None, x.view(B * N, d), N, 1, n, T, div, sd2, False)
-    assert _rel(sd2, ref) < 5e-6
 
 
 @pytest.mark.parametrize("B,H,L,masked,causal", [(3, 12, 20, True, False), (2, 12, 35, True, False), (2, 8, 64, False, True),

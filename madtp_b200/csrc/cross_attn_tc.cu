@@ -7,7 +7,8 @@
 //   warp 0   TMA: Q [128 x 64], K as up to four [64 keys x 64] boxes, V^T as up to four [64 dims x 64 keys] boxes
 //   warp 1   S = Q K^T (4 MMAs, N = 64 * key tiles) -> TMEM; after the softmax O = P V (4 MMAs per key tile, P from TMEM)
 //   warps 2..9  softmax in the log2 domain, thread = (query row, half of the keys); two passes over S in TMEM (maximum,
-//            then exponentials) so that S never has to live in registers; 256 p goes back to TMEM as packed fp16.
+//            then exponentials) so that S never has to live in registers; 256 p goes back to TMEM as packed fp16, in
+//            place over the consumed part of S (256 TMEM columns in all: two CTAs per SM).
 //   Only the TMEM lane quadrants that hold real queries do any softmax work (20 text tokens -> one quadrant).
 // V arrives transposed (keys contiguous), produced by running the value projection as W_v . X^T; its bias is added to
 // the normalised output instead (the probabilities of a row sum to one).
@@ -31,7 +32,7 @@ struct CrossSmem {
 
 }  // namespace
 
-__global__ void __launch_bounds__(CrossSmem::THREADS, 1)
+__global__ void __launch_bounds__(CrossSmem::THREADS, 2)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, CrossTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -52,7 +53,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int Lq = a.Lq, Nk = a.Nk;
   const int KT = (Nk + 63) / 64;   // key tiles (1..4)
   const int NKP = KT * 64;         // padded key count = N of the first MMA
-  constexpr uint32_t kP = 256, kO = 384;   // TMEM columns: S at 0 (256), packed P at 256 (128), O at 384 (64)
+  // 256 TMEM columns, so that two CTAs share an SM: S at 0 (N = NKP <= 256 columns). The packed P of each column half
+  // is written IN PLACE over the part of that half's S the writing thread has already consumed (half 0: columns
+  // [0, NH/2), half 1: [NH, NH + NH/2), NH = NKP/2); O at 192..255, which the MMA only writes after every softmax warp
+  // is done with S.
+  constexpr uint32_t kO = 192;
+  const int NH = NKP / 2;                  // keys per column half (a multiple of 32)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -68,7 +74,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<256>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -103,8 +109,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       for (int t = 0; t < KT; ++t) {
         const uint64_t vd = make_sw128_kmajor_desc(smem_u32(v_s + t * CrossSmem::KBOX));
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16_ts(tmem_base + kO, tmem_base + kP + t * 32 + ks * 8, vd + 2 * ks, idesc_o, (t | ks) != 0 ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const int key0 = t * 64 + ks * 16;   // 16 keys = 8 packed columns, in the half that owns them
+          const uint32_t pcol = key0 < NH ? key0 / 2 : NH + (key0 - NH) / 2;
+          umma_f16_ts(tmem_base + kO, tmem_base + pcol, vd + 2 * ks, idesc_o, (t | ks) != 0 ? 1u : 0u);
+        }
       }
       umma_commit(o_full);
     }
@@ -122,7 +131,6 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const float c1 = a.scale * kLog2e;
       const float mask_to_raw = kLog2e / c1;
       const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * Nk : nullptr;
-      const int NH = NKP / 2;                  // keys per half (a multiple of 32)
       const int col0 = half * NH;
       mbar_wait_spin(s_full, 0);
       tcgen05_fence_after();
@@ -169,7 +177,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const __half2 ph = __floats2half2_rn(p0, p1);
           pk[k] = *reinterpret_cast<const uint32_t*>(&ph);
         }
-        tmem_st_32x32b_x16(tmem_base + lane_off + kP + (col0 + c * 32) / 2, pk);
+        tmem_st_32x32b_x16(tmem_base + lane_off + col0 + c * 16, pk);   // over this thread's consumed S columns
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -208,7 +216,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 

@@ -1078,6 +1078,13 @@ int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, c
     const long long tiles256 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256);
     if (use_pair && bn == 256 && tiles256 >= 2LL * num_sms())
       return launch_tc<256, false, true>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
+    // few rows (the text encoders: M = 640 and shrinking): a launch is bound by how fast each SM can pull its own
+    // operands through the pipeline, so 64-wide tiles on twice as many SMs finish sooner
+    const long long m_tiles = (M + 127) / 128;
+    const long long tiles128 = m_tiles * ((N + 127) / 128), tiles64 = m_tiles * ((N + 63) / 64);
+    static const bool no_bn64 = getenv("MADTP_NO_BN64") != nullptr;
+    if (!no_bn64 && bn == 128 && 2 * tiles128 <= num_sms() && tiles64 <= num_sms())
+      return launch_tc<64, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
     return bn == 256 ? launch_tc<256, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream)
                      : launch_tc<128, false>(a, nullptr, lda, b, nullptr, ldb, ep, M, N, K, stream);
   }

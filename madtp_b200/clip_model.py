@@ -69,7 +69,7 @@ class MultiheadAttention(nn.Module):
 
     def _prepared(self):
         qkv = self._cache.get("in", [self.in_proj_weight, self.in_proj_bias],
-                              lambda: Fn.PreparedLinear(self.in_proj_weight, self.in_proj_bias, tf32=True))
+                              lambda: Fn.PreparedLinear(self.in_proj_weight, self.in_proj_bias, split=True))
         out = self._cache.get("out", [self.out_proj.weight, self.out_proj.bias],
                               lambda: Fn.PreparedLinear(self.out_proj.weight, self.out_proj.bias, f16=True))
         return qkv, out
@@ -79,7 +79,7 @@ class MultiheadAttention(nn.Module):
         C = self.embed_dim
         scale = self.head_dim ** -0.5        # q / sqrt(E) then q.k: exact for head_dim 64 (a power of two)
         if causal:
-            qkv = Fn.linear_tf32(y_hi, y_lo, qkv_w).view(B, N, 3 * C)
+            qkv = Fn.linear_split(y_hi, y_lo, qkv_w).view(B, N, 3 * C)
             ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_heads, scale,
                                              None, want_stats, causal=True)
         else:
@@ -114,7 +114,7 @@ class ResidualAttentionBlock(nn.Module):
         B, N, C = x.shape
         with_dict = space_dict is not None
         prune = with_dict and temperature > 0
-        ln1 = Fn.layernorm_rows(x.view(B * N, C), self.ln_1.weight, self.ln_1.bias, self.ln_1.eps, tf32=True,
+        ln1 = Fn.layernorm_rows(x.view(B * N, C), self.ln_1.weight, self.ln_1.bias, self.ln_1.eps, split=True,
                                 split_x=with_dict)
         token_attn = None
         if with_dict:                                                                    # :239-245
@@ -187,10 +187,10 @@ class VisionTransformer(nn.Module):
         B, _, Hh, Ww = x.shape
         P = self.patch_size
         conv = self._cache.get("conv1", [self.conv1.weight], lambda: Fn.PreparedLinear(
-            self.conv1.weight.reshape(self.conv1.weight.shape[0], -1), None, tf32=True))
+            self.conv1.weight.reshape(self.conv1.weight.shape[0], -1), None, split=True))
         hi, lo = L.patchify(x.contiguous(), P)
         n = (Hh // P) * (Ww // P)
-        patches = Fn.linear_tf32(hi, lo, conv)
+        patches = Fn.linear_split(hi, lo, conv)
         C = patches.shape[1]
         tok = L.assemble_tokens(patches, self.class_embedding.detach(), self.positional_embedding.detach(), B, n, C)
         y = self.ln_pre(tok)

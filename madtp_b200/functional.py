@@ -3,7 +3,8 @@ med.py / utils.py share. Everything here runs on the GPU through libmadtp_b200.s
 
 Precision lanes (hard part 1):
   scoring lane  LayerNorm -> q/k/v projection -> attention statistics, and token . codebook^T: fp32-accurate
-                (TF32x3 tensor-core GEMMs with chunk-drained fp32 accumulation, fp32 CUDA-core attention)
+                (error-compensated fp16 hi/lo tensor-core GEMMs and attention with chunk-drained fp32 accumulation;
+                fp32 CUDA-core attention for short text sequences)
   value lane    attention output projection, FFN, cross-attention: fp16 operands, fp32 accumulation
 """
 from __future__ import annotations
@@ -41,17 +42,17 @@ def pow2_scale(w: Tensor, target: float = 16384.0) -> float:
 
 
 class PreparedLinear:
-    """GEMM-ready copies of an nn.Linear: fp16 hi/lo split of scale * W (scoring lane; `tf32=True` for historical
+    """GEMM-ready copies of an nn.Linear: fp16 hi/lo split of scale * W (scoring lane; `split=True` for historical
     reasons selects this error-compensated lane) and/or plain fp16 (value lane)."""
     __slots__ = ("hi", "lo", "scale", "w16", "w32", "bias", "out_features", "in_features")
 
-    def __init__(self, weight: Tensor, bias: Optional[Tensor], tf32: bool = False, f16: bool = False,
+    def __init__(self, weight: Tensor, bias: Optional[Tensor], split: bool = False, f16: bool = False,
                  f32: bool = False, bias_scale: float = 1.0):
         w = weight.detach().to(torch.float32).contiguous()
         self.out_features, self.in_features = w.shape
         self.hi = self.lo = self.w16 = self.w32 = None
         self.scale = 1.0
-        if tf32:
+        if split:
             self.scale = pow2_scale(w)
             self.hi, self.lo = L.split_f16(w, self.scale)
         if f16:
@@ -87,7 +88,7 @@ class WeightCache:
 # ------------------------------------------------------------------------------------------------------------------
 # row operations
 # ------------------------------------------------------------------------------------------------------------------
-def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float, *, f32=False, tf32=False,
+def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float, *, f32=False, split=False,
                    f16=False, split_x=False):
     """LayerNorm over the rows of x2d [rows, d] with the requested operand copies.
     Returns dict with any of y, y_hi, y_lo, y16, x_hi, x_lo."""
@@ -99,7 +100,7 @@ def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor],
         return torch.empty(rows, d, dtype=dt, device=dev)
     if f32:
         out["y"] = new()
-    if tf32:
+    if split:
         out["y_hi"], out["y_lo"] = new(torch.float16), new(torch.float16)
     if f16:
         out["y16"] = new(torch.float16)
@@ -116,7 +117,7 @@ def split_rows(x2d: Tensor) -> Tuple[Tensor, Tensor]:
     return o["x_hi"], o["x_lo"]
 
 
-def linear_tf32(a_hi: Tensor, a_lo: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, residual=None,
+def linear_split(a_hi: Tensor, a_lo: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, residual=None,
                 act=L.ACT_NONE, alpha=1.0) -> Tensor:
     if out is None:
         out = torch.empty(a_hi.shape[0], lin.out_features, dtype=torch.float32, device=a_hi.device)

@@ -143,13 +143,13 @@ class BertLMPredictionHead(nn.Module):
         scoring lane (the ranking compares summed log-probabilities of candidates)."""
         t = self.transform
         dense = self._cache.get("dense", [t.dense.weight, t.dense.bias],
-                                lambda: Fn.PreparedLinear(t.dense.weight, t.dense.bias, tf32=True))
+                                lambda: Fn.PreparedLinear(t.dense.weight, t.dense.bias, split=True))
         dec = self._cache.get("dec", [self.decoder.weight, self.bias],
-                              lambda: Fn.PreparedLinear(self.decoder.weight, self.bias, tf32=True))
+                              lambda: Fn.PreparedLinear(self.decoder.weight, self.bias, split=True))
         hi, lo = Fn.split_rows(h2d)
-        y = Fn.linear_tf32(hi, lo, dense, act=Fn.L.ACT_GELU)
-        ln = Fn.layernorm_rows(y, t.LayerNorm.weight, t.LayerNorm.bias, t.LayerNorm.eps, tf32=True)
-        return Fn.linear_tf32(ln["y_hi"], ln["y_lo"], dec)
+        y = Fn.linear_split(hi, lo, dense, act=Fn.L.ACT_GELU)
+        ln = Fn.layernorm_rows(y, t.LayerNorm.weight, t.LayerNorm.bias, t.LayerNorm.eps, split=True)
+        return Fn.linear_split(ln["y_hi"], ln["y_lo"], dec)
 
     def forward(self, hidden_states):
         Fn.require_cuda(hidden_states, "hidden_states")

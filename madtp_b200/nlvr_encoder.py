@@ -139,11 +139,11 @@ class BertSelfAttention(nn.Module):
         return self.cls_attn
 
     # -- prepared operands ------------------------------------------------------------------------------------
-    def _qkv_tf32(self):
+    def _qkv_split(self):
         ps = [self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight, self.value.bias]
         return self._cache.get("qkv", ps, lambda: Fn.PreparedLinear(
             torch.cat([self.query.weight, self.key.weight, self.value.weight], 0),
-            torch.cat([self.query.bias, self.key.bias, self.value.bias], 0), tf32=True))
+            torch.cat([self.query.bias, self.key.bias, self.value.bias], 0), split=True))
 
     def _q_f16(self):
         return self._cache.get("q16", [self.query.weight, self.query.bias],
@@ -156,7 +156,7 @@ class BertSelfAttention(nn.Module):
             f16=True))
 
     # -- kernels ----------------------------------------------------------------------------------------------
-    def _qkv_book_tf32(self, space_dict):
+    def _qkv_book_split(self, space_dict):
         """[Wq; Wk; Wv; codebook (zero-padded to 128 rows)]: BERT's q/k/v and the Query_model dots share the operand
         h, so one GEMM produces both (the ViT cannot do this: its q/k/v read LayerNorm(x), its codebook dots read x)."""
         ps = [self.query.weight, self.query.bias, self.key.weight, self.key.bias, self.value.weight, self.value.bias,
@@ -168,13 +168,13 @@ class BertSelfAttention(nn.Module):
             w = torch.cat([self.query.weight, self.key.weight, self.value.weight, pad], 0)
             b = torch.cat([self.query.bias, self.key.bias, self.value.bias,
                            torch.zeros(Fn.TA_LD, dtype=torch.float32, device=space_dict.device)], 0)
-            return Fn.PreparedLinear(w, b, tf32=True)
+            return Fn.PreparedLinear(w, b, split=True)
         return self._cache.get("qkv_book", ps, build)
 
     def project_qkv_and_token_att(self, h_hi, h_lo, B, Ltok, space_dict):
-        """One TF32x3 GEMM -> (qkv view [B, L, 3C], token_att view [B, L, 128]) over the same rows."""
+        """One split-operand (fp16 hi/lo) GEMM -> (qkv view [B, L, 3C], token_att view [B, L, 128]) over the same rows."""
         C = self.all_head_size
-        out = Fn.linear_tf32(h_hi, h_lo, self._qkv_book_tf32(space_dict)).view(B, Ltok, 3 * C + Fn.TA_LD)
+        out = Fn.linear_split(h_hi, h_lo, self._qkv_book_split(space_dict)).view(B, Ltok, 3 * C + Fn.TA_LD)
         return out[..., :3 * C], out[..., 3 * C:]
 
     def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None, causal=False):
@@ -182,7 +182,7 @@ class BertSelfAttention(nn.Module):
         causal=True: decoder self-attention (key j visible to query i only if j <= i, models/med.py:749-771)."""
         C = self.all_head_size
         if qkv is None:
-            qkv = Fn.linear_tf32(h_hi, h_lo, self._qkv_tf32()).view(B, Ltok, 3 * C)
+            qkv = Fn.linear_split(h_hi, h_lo, self._qkv_split()).view(B, Ltok, 3 * C)
         ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_attention_heads,
                                          1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats, causal=causal)
         self.save_attention_map(stats)
@@ -260,7 +260,7 @@ class BertSelfOutput(nn.Module):
                              lambda: Fn.PreparedLinear(self.merge_layer.weight, self.merge_layer.bias, f16=True))
         return d0, d1, mg
 
-    def rows(self, ctx16, residual, *, f16=False, tf32=False):
+    def rows(self, ctx16, residual, *, f16=False, split=False):
         """ctx16 [rows, C] (or [rows, 2C] = [ctx0|ctx1] for the twin); residual fp32 [rows, C].
         Returns the layernorm_rows dict of LayerNorm(dense(ctx) + residual) (always with 'y')."""
         if not self.twin:
@@ -275,7 +275,7 @@ class BertSelfOutput(nn.Module):
             Fn.linear_f16(ctx16[:, C:], d1, out=d01[:, C:])
             pre = Fn.linear_f16(d01, mg, residual=residual)
         return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
-                                 f16=f16, tf32=tf32)
+                                 f16=f16, split=split)
 
     def forward(self, hidden_states, input_tensor):
         _eval_only(self)
@@ -603,7 +603,7 @@ class BertEncoder(nn.Module):
             Ltok, d = h.shape[1], h.shape[2]
             token_attn = qkv = None
             if space_dict is not None and not self.txt_query_model.map_func:
-                # q|k|v and the codebook dots share the operand h: one TF32x3 GEMM (see _qkv_book_tf32)
+                # q|k|v and the codebook dots share the operand h: one split-operand GEMM (see _qkv_book_split)
                 h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
                 qkv, ta_full = layer_module.attention.self.project_qkv_and_token_att(h_hi, h_lo, B, Ltok, space_dict)
                 token_attn, sd_txt_ft_all = Fn.query_model_from_token_att(ta_full, h, space_dict.shape[0],

@@ -56,14 +56,14 @@ class Query_model(nn.Module):
     def _qmap(self):
         lin = self.q_map[0]
         return self._cache.get("q_map", [lin.weight, lin.bias],
-                               lambda: Fn.PreparedLinear(lin.weight, lin.bias, tf32=True))
+                               lambda: Fn.PreparedLinear(lin.weight, lin.bias, split=True))
 
     def forward_rows(self, x3d, x_hi, x_lo, sd, sd_ft_acc=None, first_token=1):
-        """Fast path used by the encoders: x3d [B,N,d] with its tf32 split already produced by the LayerNorm kernel;
+        """Fast path used by the encoders: x3d [B,N,d] with its fp16 hi/lo split already produced by the LayerNorm kernel;
         tokens first_token.. are the prunable ones. Returns (token_att view [B,n,T], sd_ft (accumulated))."""
         if self.map_func:
             B, N, d = x3d.shape
-            q = Fn.linear_tf32(x_hi, x_lo, self._qmap())
+            q = Fn.linear_split(x_hi, x_lo, self._qmap())
             q_hi, q_lo = Fn.split_rows(q)
             return Fn.query_model_rows(q_hi, q_lo, q.view(B, N, -1), self._book(sd), self.att_dim, sd_ft_acc,
                                        first_token)

@@ -112,13 +112,13 @@ class Attention(nn.Module):
 
     def _prepared(self):
         qkv = self._cache.get("qkv", [self.qkv.weight, self.qkv.bias],
-                              lambda: Fn.PreparedLinear(self.qkv.weight, self.qkv.bias, tf32=True))
+                              lambda: Fn.PreparedLinear(self.qkv.weight, self.qkv.bias, split=True))
         proj = self._cache.get("proj", [self.proj.weight, self.proj.bias],
                                lambda: Fn.PreparedLinear(self.proj.weight, self.proj.bias, f16=True))
         return qkv, proj
 
     def forward_rows(self, y_hi, y_lo, B, N, residual=None, want_stats=True):
-        """y_hi/y_lo: tf32 split of the normalised input rows [B*N, C]. Returns fp32 [B*N, C] = proj(ctx) (+residual)
+        """y_hi/y_lo: fp16 hi/lo split of the normalised input rows [B*N, C]. Returns fp32 [B*N, C] = proj(ctx) (+residual)
         and stores the pruning statistics (models/vit.py:83,96-101)."""
         ctx16 = self.attend_rows(y_hi, y_lo, B, N, want_stats)
         return self.project_rows(ctx16, B, N, residual)
@@ -179,7 +179,7 @@ class Block(nn.Module):
         return res.x[:, 1:, :] if res.pruned else x
 
     def forward_rows(self, x, ln1, temperature=0, token_attn=None):
-        """x [B,N,C] fp32 contiguous; ln1 = functional.layernorm_rows(..., tf32=True) of norm1(x)."""
+        """x [B,N,C] fp32 contiguous; ln1 = functional.layernorm_rows(..., split=True) of norm1(x)."""
         B, N, C = x.shape
         prune = temperature > 0
         ctx16 = self.attn.attend_rows(ln1["y_hi"], ln1["y_lo"], B, N, want_stats=prune)
@@ -206,7 +206,7 @@ class Block(nn.Module):
             raise RuntimeError("madtp_b200: temperature > 0 needs token_attn (models/vit.py:131)")
         x = x.contiguous()
         B, N, C = x.shape
-        ln1 = Fn.layernorm_rows(x.view(B * N, C), self.norm1.weight, self.norm1.bias, self.norm1.eps, tf32=True)
+        ln1 = Fn.layernorm_rows(x.view(B * N, C), self.norm1.weight, self.norm1.bias, self.norm1.eps, split=True)
         return self.forward_rows(x, ln1, temperature, token_attn)
 
 
@@ -230,9 +230,9 @@ class PatchEmbed(nn.Module):
         P = self.patch_size[0]
         w = self._cache.get("proj", [self.proj.weight, self.proj.bias],
                             lambda: Fn.PreparedLinear(self.proj.weight.reshape(self.proj.weight.shape[0], -1),
-                                                      self.proj.bias, tf32=True))
+                                                      self.proj.bias, split=True))
         hi, lo = L.patchify(x, P)
-        return Fn.linear_tf32(hi, lo, w).view(B, (H // P) * (W // P), -1)
+        return Fn.linear_split(hi, lo, w).view(B, (H // P) * (W // P), -1)
 
 
 class VisionTransformer(nn.Module):
@@ -293,7 +293,7 @@ class VisionTransformer(nn.Module):
         for blk in self.blocks:
             N = x.shape[1]
             with_dict = space_dict is not None
-            ln1 = Fn.layernorm_rows(x.view(B * N, C), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, tf32=True,
+            ln1 = Fn.layernorm_rows(x.view(B * N, C), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, split=True,
                                     split_x=with_dict)
             if with_dict:
                 token_attn, sd_img_ft_all = self.img_query_model.forward_rows(x, ln1["x_hi"], ln1["x_lo"], space_dict,

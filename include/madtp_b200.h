@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MADTP_B200_ABI_VERSION 1
+#define MADTP_B200_ABI_VERSION 2   /* 2: fp16 hi/lo operand planes, persistent attention, cross-attention, read-back */
 
 /* GEMM operand precision */
 #define MADTP_GEMM_F16 0     /* fp16 operands, fp32 accumulate, tcgen05 kind::f16 */

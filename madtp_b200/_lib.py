@@ -17,6 +17,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
 _lib = None
 
+ABI_VERSION = 2                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
 GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
 QK_PLANE_SCALE, V_PLANE_SCALE = 8.0, 16.0     # include/madtp_b200.h MADTP_QK_PLANE_SCALE / MADTP_V_PLANE_SCALE
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
@@ -83,6 +84,9 @@ def load():
         fn.restype = C.c_int
     lib.madtp_last_error_string.restype = C.c_char_p
     lib.madtp_launch_count.restype = C.c_longlong
+    if int(lib.madtp_abi_version()) != ABI_VERSION:
+        raise RuntimeError(f"{_LIB_PATH} has ABI version {int(lib.madtp_abi_version())}, this binding needs {ABI_VERSION}: "
+                           "rebuild with `python -m madtp_b200.csrc.build --force`")
     _lib = lib
     _bind_fastcall(lib)
     return lib

@@ -387,7 +387,7 @@ def main():
               for b in model.visual_encoder.blocks]
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 scoring lane (tf32x3 tensor-core GEMMs, fp32 attention) + f16 value lane",
+                "vs_baseline": None, "dtype": "f32-accurate scoring lane (error-compensated fp16 hi/lo planes on tcgen05, fp32 accumulate) + f16 value lane",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "image_size": IMAGE, "text_len": TEXT_LEN,
                            "temperature": temp, "mac_ratio_oracle": cal["ratio"], "vit_topk_per_layer": ks,

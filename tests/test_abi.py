@@ -31,6 +31,19 @@ def test_ctypes_signatures_cover_the_header(lib):
     assert sorted(lib.SIGNATURES) == declared_functions()
 
 
+def test_binding_argument_counts_match_the_header(lib):
+    """Every entry of _lib.SIGNATURES lists exactly as many arguments as the prototype in include/madtp_b200.h (the
+    trampoline binding forwards whatever it is given, so a drifted signature would not fail at call time)."""
+    text = (ROOT / "include" / "madtp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(madtp_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert sorted(protos) == sorted(lib.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(lib.SIGNATURES[name]), f"{name}: header has {n} parameters, binding {len(lib.SIGNATURES[name])}"
+
+
 def test_argument_errors_are_reported_without_a_gpu(lib):
     cdll = lib.load()
     # invalid shapes are rejected before any CUDA call, so this is safe on a CPU-only host

@@ -158,22 +158,43 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (reference arm and cpu_baseline leg)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(sample_pairs: int, steps: int, warmup: int, temperature: float):
-    """images/s of the oracle forward on `sample_pairs` pairs (a bounded sample of the 32-pair workload)."""
+def cpu_reference_rate(sample_pairs: int, steps: int, warmup: int, temperature: float):
+    """images/s of the reference's own CPU forward on `sample_pairs` pairs of the workload. Returns
+    (rate, seconds per step, threads, kind): kind "reference" = the UNMODIFIED reference BLIP_NLVR.forward(train=False)
+    (models/blip_nlvr.py:63-100) imported from /root/reference or its byte-for-byte staging oracle/_ref (recipe:
+    oracle/make_ref.py) under the third-party import shims of oracle/ref_shims.py; kind "port" = oracle/dtp_oracle.py
+    when neither tree is present."""
     from madtp_b200 import synthetic
-    from oracle import dtp_oracle as O
+    from oracle import ref_shims
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synthetic.blip_nlvr_state_dict(1234, img_size=IMAGE)
     images, ids, mask = synthetic.nlvr_inputs(sample_pairs, IMAGE, TEXT_LEN, seed=0)
+    if ref_shims.available():
+        kind = "reference"
+        model, tok = ref_shims.build_blip_nlvr(IMAGE)
+        msg = model.load_state_dict(sd, strict=False)
+        assert not msg.unexpected_keys, msg.unexpected_keys
+        targets = torch.zeros(sample_pairs, dtype=torch.long)
+        text = ["x"] * sample_pairs
+
+        def fwd():
+            tok.next_ids = (ids, mask)
+            return model(images, text, targets, temperature, train=False)
+    else:
+        kind = "port"
+        from oracle import dtp_oracle as O
+
+        def fwd():
+            return O.blip_nlvr_forward(images, ids, mask, sd, temperature)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.blip_nlvr_forward(images, ids, mask, sd, temperature)
+            fwd()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
-    return 2 * sample_pairs * len(times) / total, total / len(times), torch.get_num_threads()
+    return 2 * sample_pairs * len(times) / total, total / len(times), torch.get_num_threads(), kind
 
 
 def run_reference_arm(args):
@@ -181,19 +202,34 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cal = calibration()
-    sample_pairs = 4
-    rate, sec, cores = cpu_oracle_rate(sample_pairs, args.steps, args.warmup, cal["temperature"])
-    sample = (f"{sample_pairs} pairs ({2 * sample_pairs} images) of the {PAIRS}-pair batch per step, "
-              f"oracle/dtp_oracle.py (PyTorch-CPU fp32 restatement of the reference forward; the Python reference "
-              f"itself does not travel to the GPU box), {cores} threads")
+    sample_pairs = args.sample_pairs or PAIRS
+    rate, sec, cores, kind = cpu_reference_rate(sample_pairs, args.steps, args.warmup, cal["temperature"])
+    what = ("the unmodified reference BLIP_NLVR.forward(train=False) (PyTorch-CPU fp32, staged by oracle/make_ref.py)"
+            if kind == "reference" else "oracle/dtp_oracle.py (PyTorch-CPU fp32 restatement; reference tree absent)")
+    sample = (f"{sample_pairs} pairs ({2 * sample_pairs} images) of the {PAIRS}-pair batch per step, {what}, "
+              f"{cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "temperature": cal["temperature"], "sample": sample},
-            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def cpu_baseline_subprocess(sample_pairs: int, steps: int, warmup: int):
+    """The cpu_baseline leg of the main arm: the reference arm in its OWN process (no CUDA context, no sampler thread
+    next to it -- round 1's in-process leg read 28 % low for that reason), on a bounded sample."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+           "--sample-pairs", str(sample_pairs)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"value": None, "unit": "images/s", "cores": None, "kind": "unavailable", "sample": r.stderr[-300:]}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -248,6 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="madtp_b200", choices=["madtp_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-pairs", type=int, default=0, help="reference arm: pairs per step (0 = the full batch)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "madtp_b200" else max(args.warmup, 1)
@@ -376,11 +413,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_pairs = 4
-        rate, sec, cores = cpu_oracle_rate(sample_pairs, 3, 1, temp)
-        cpu_baseline = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"oracle forward on {sample_pairs} pairs ({2 * sample_pairs} images) of the same "
-                                  f"batch, 1 warm-up + 3 timed, {sec:.2f} s each"}
+        cpu_baseline = cpu_baseline_subprocess(PAIRS, 3, 1)
 
     if rank == 0:
         ks = [(b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1)

@@ -93,6 +93,7 @@ def load():
 
 
 _fast = {}   # entry point name -> (trampoline, function address); empty when the _fastcall extension is unavailable
+_float_pos = {}   # entry point name -> positions of `float` parameters (the trampoline picks registers by Python type)
 
 
 def _bind_fastcall(lib):
@@ -107,8 +108,9 @@ def _bind_fastcall(lib):
         spec.loader.exec_module(mod)
     except Exception:
         return
-    for name in SIGNATURES:
+    for name, argtypes in SIGNATURES.items():
         _fast[name] = (mod.call, C.cast(getattr(lib, name), C.c_void_p).value)
+        _float_pos[name] = tuple(i for i, t in enumerate(argtypes) if t is _f32)
 
 
 def launch_count() -> int:
@@ -152,6 +154,19 @@ def _call(name, *args):
     fast = _fast.get(name)
     if fast is not None:
         tramp, addr = fast
+        # The trampoline chooses an integer or a float register from each argument's PYTHON type, so the arguments are
+        # brought in line with the C prototype here (what ctypes' argtypes would do): float parameters become float,
+        # everything else must be an int or None -- a float in an integer slot would shift every later argument.
+        fp = _float_pos[name]
+        if len(args) != len(SIGNATURES[name]):
+            raise TypeError(f"{name}: expected {len(SIGNATURES[name])} arguments, got {len(args)}")
+        if fp or any(type(a) is float for a in args):
+            args = list(args)
+            for i in fp:
+                args[i] = float(args[i])
+            for i, a in enumerate(args):
+                if type(a) is float and i not in fp:
+                    raise TypeError(f"{name}: argument {i} is a float but the C prototype takes an integer/pointer")
 
         def fn(*a):
             return tramp(addr, *a)
@@ -184,6 +199,11 @@ def _ptr(t, dtype=None, name="tensor"):
         raise RuntimeError(f"madtp_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError(f"madtp_b200: {name} must have dtype {dtype}, got {t.dtype}")
+    if _raw_device is not None and t.device.index != _raw_device():
+        # every launch goes to the CURRENT device's stream (one process per GPU): a tensor elsewhere would be an
+        # illegal address on the device, so fail here instead
+        raise RuntimeError(f"madtp_b200: {name} lives on cuda:{t.device.index} but the current device is "
+                           f"cuda:{_raw_device()} (use torch.cuda.set_device / torch.cuda.device)")
     return t.data_ptr()
 
 
@@ -567,9 +587,11 @@ def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, 
     ldo, bso = _qkv_strides(out_f16, "out_f16")
     if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Ltok):
         raise RuntimeError("madtp_b200.attn_small_self: key_mask must be contiguous [B, L]")
+    # the scratch tensor stays referenced until the launch has been enqueued (stream-ordered reuse after that is safe)
+    scratch = None if col_sum is None else torch.empty(B * H * Ltok * (Ltok + 1), dtype=torch.float32, device=q.device)
     st = _call("madtp_attn_small_self", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
                _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Ltok, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
-               _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(col_sum), _ptr(cls_attn),
-               _ptr(None if col_sum is None else torch.empty(B * H * Ltok * (Ltok + 1), dtype=torch.float32,
-                                                             device=q.device)), 1 if causal else 0, _stream())
+               _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(col_sum), _ptr(cls_attn), _ptr(scratch),
+               1 if causal else 0, _stream())
     _check(st, "madtp_attn_small_self")
+    del scratch

@@ -204,12 +204,20 @@ class VisionTransformer(nn.Module):
 
 
 class CLIP(nn.Module):
-    """The two encoders of clip/model.py:CLIP (ViT towers only) with `encode_image` / `encode_text` (:482-503)."""
+    """The two encoders of clip/model.py:CLIP (ViT towers only) with `encode_image` / `encode_text` (:482-503).
+    Constructor arguments and their order are the reference's (:317-332), including the positional `evaluate`; the
+    momentum twins, queues and the ResNet towers (:383-437, training only) are out of scope, so their state-dict keys
+    (`*_m.*`, `*_queue`) are reported as unexpected by `load_state_dict(strict=False)` exactly like any extra key."""
 
     def __init__(self, embed_dim: int, image_resolution: int, vision_layers: int, vision_width: int,
                  vision_patch_size: int, context_length: int, vocab_size: int, transformer_width: int,
-                 transformer_heads: int, transformer_layers: int, config=None):
+                 transformer_heads: int, transformer_layers: int, evaluate: bool = False, config=None):
         super().__init__()
+        if isinstance(evaluate, dict):
+            raise TypeError("madtp_b200.CLIP: the 11th positional argument is `evaluate` (clip/model.py:330); "
+                            "pass the config dict as `config=`")
+        if isinstance(vision_layers, (tuple, list)):
+            raise NotImplementedError("madtp_b200: the ModifiedResNet towers of clip/model.py are out of scope")
         self.sd_num, self.sd_dim = (100, 768) if config is None else (config['sd_num'], config['sd_dim'])
         self.space_dict = nn.Parameter(torch.randn(self.sd_num, self.sd_dim))
         self.context_length = context_length
@@ -220,12 +228,31 @@ class CLIP(nn.Module):
                                        attn_mask=self.build_attention_mask(), sd_dim=self.sd_dim)
         self.vocab_size = vocab_size
         self.token_embedding = nn.Embedding(vocab_size, transformer_width)
-        self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width).normal_(std=0.01))
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width))
         self.ln_final = LayerNorm(transformer_width)
-        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim).normal_(
-            std=transformer_width ** -0.5))
-        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
+        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)            # log(1 / 0.07), :381
+        if not evaluate:
+            self.initialize_parameters()
+        self.tokenize = None
+        self.vision_layers = vision_layers
+        self.transformer_layers = transformer_layers
+        self.embed_dim = embed_dim
         self._cache = Fn.WeightCache()
+
+    def initialize_parameters(self):
+        """clip/model.py:439-470 (ViT towers)."""
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        proj_std = (self.transformer.width ** -0.5) * ((2 * self.transformer.layers) ** -0.5)
+        attn_std = self.transformer.width ** -0.5
+        fc_std = (2 * self.transformer.width) ** -0.5
+        for block in self.transformer.resblocks:
+            nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=self.transformer.width ** -0.5)
 
     def build_attention_mask(self):
         mask = torch.empty(self.context_length, self.context_length)
@@ -257,3 +284,52 @@ class CLIP(nn.Module):
         proj = self._cache.get("tp", [self.text_projection],
                                lambda: Fn.PreparedLinear(self.text_projection.t(), None, f32=True))
         return Fn.linear_f32(eot, proj), sd_txt_ft_all
+
+
+def convert_weights(model: nn.Module):
+    """clip/model.py:655-676: Conv / Linear / attention in-projection weights and the two projection matrices to fp16.
+    `clip.load` (clip/clip.py:144-148) calls `.float()` on the result, so the net effect on a checkpoint is ONE fp16
+    rounding of those weights -- reproduced literally, because it changes the scores."""
+    def _convert(l):
+        if isinstance(l, (nn.Conv1d, nn.Conv2d, nn.Linear)):
+            l.weight.data = l.weight.data.half()
+            if l.bias is not None:
+                l.bias.data = l.bias.data.half()
+        if isinstance(l, (nn.MultiheadAttention, MultiheadAttention)):
+            for attr in ["in_proj_weight", "q_proj_weight", "k_proj_weight", "v_proj_weight", "in_proj_bias", "bias_k",
+                         "bias_v"]:
+                t = getattr(l, attr, None)
+                if t is not None:
+                    t.data = t.data.half()
+        for name in ["text_projection", "proj"]:
+            if hasattr(l, name):
+                attr = getattr(l, name)
+                if attr is not None and torch.is_tensor(attr):
+                    attr.data = attr.data.half()
+    model.apply(_convert)
+
+
+def build_model(state_dict: dict, evaluate: bool = False, config=None):
+    """clip/model.py:678-716: derive the architecture from a checkpoint's shapes, convert to fp16, load (strict=False).
+    The caller (clip/clip.py:144-148) moves the model to the device and calls `.float()`."""
+    if "visual.proj" not in state_dict:
+        raise NotImplementedError("madtp_b200: the ModifiedResNet towers of clip/model.py are out of scope")
+    vision_width = state_dict["visual.conv1.weight"].shape[0]
+    vision_layers = len([k for k in state_dict.keys() if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
+    vision_patch_size = state_dict["visual.conv1.weight"].shape[-1]
+    grid_size = round((state_dict["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+    image_resolution = vision_patch_size * grid_size
+    embed_dim = state_dict["text_projection"].shape[1]
+    context_length = state_dict["positional_embedding"].shape[0]
+    vocab_size = state_dict["token_embedding.weight"].shape[0]
+    transformer_width = state_dict["ln_final.weight"].shape[0]
+    transformer_heads = transformer_width // 64
+    transformer_layers = len(set(k.split(".")[2] for k in state_dict if k.startswith("transformer.resblocks")))
+    model = CLIP(embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size, context_length, vocab_size,
+                 transformer_width, transformer_heads, transformer_layers, evaluate, config)
+    for key in ["input_resolution", "context_length", "vocab_size"]:
+        if key in state_dict:
+            del state_dict[key]
+    convert_weights(model)
+    model.load_state_dict(state_dict, strict=False)
+    return model

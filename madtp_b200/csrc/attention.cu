@@ -349,14 +349,8 @@ int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream) {
                   "attn_fwd: row_max/row_sum/out_norm come together");
   if (a.B == 0) return kOk;
   const bool small_q = a.Nq <= 32 && a.row_max == nullptr;   // few queries: 32-row tiles waste far less
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (4 * T * LDS + T) * (int)sizeof(float)));
-    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    ((2 * 32 + 2 * T) * LDS + T) * (int)sizeof(float)));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE((4 * T * LDS + T) * (int)sizeof(float), attn_fwd_kernel<4>);
+  MADTP_SMEM_ATTR_ONCE(((2 * 32 + 2 * T) * LDS + T) * (int)sizeof(float), attn_fwd_kernel<2>);
   if (small_q) {
     const int smem = ((2 * 32 + 2 * T) * LDS + T) * sizeof(float);
     dim3 grid((a.Nq + 31) / 32, a.H, a.B);

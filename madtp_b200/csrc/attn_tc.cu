@@ -725,12 +725,7 @@ static int launch_fwd_kw(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, con
                          const CUtensorMap& tk_lo, const CUtensorMap& tv_hi, const CUtensorMap& tv_lo,
                          const AttnTcArgs& a, cudaStream_t stream) {
   using Cfg = FwdCfg<KW, NB>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<KW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::TOTAL));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(Cfg::TOTAL, attn_fwd_tc_kernel<KW, NB>);
   const long long items = static_cast<long long>((a.N + BM - 1) / BM) * a.H * a.B;
   const long long slots = static_cast<long long>(num_sms()) * Cfg::CTAS_PER_SM;
   const int grid = static_cast<int>(items < slots ? items : slots);
@@ -776,12 +771,7 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   CUtensorMap t_hi, t_lo;
   if ((st = make_tmap(&t_hi, a.qk_hi, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
   if ((st = make_tmap(&t_lo, a.qk_lo, false, rows, 2LL * a.H * 64, a.ld_qk, BM)) != kOk) return st;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(attn_stats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    StatsSmem::TOTAL));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(StatsSmem::TOTAL, attn_stats_tc_kernel);
   const long long items = static_cast<long long>(a.n_parts) * a.n_parts * a.B;
   const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   attn_stats_tc_kernel<<<grid, StatsSmem::THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);

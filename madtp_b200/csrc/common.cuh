@@ -55,6 +55,27 @@ const char* last_error();
 
 int num_sms();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per device index that it was set
+// (a process that touches a second GPU would otherwise launch with the default 48 KB limit there).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  // returns the current device index if the attribute still has to be set there, -1 if already done
+  int pending() const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;   // unknown: set it again (harmless)
+    return done[dev] ? -1 : dev;
+  }
+};
+#define MADTP_SMEM_ATTR_ONCE(bytes, ...)                                                              \
+  do {                                                                                                \
+    static ::madtp::PerDeviceOnce once_;                                                              \
+    const int dev_ = once_.pending();                                                                 \
+    if (dev_ >= 0) {                                                                                  \
+      MADTP_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      once_.done[dev_] = true;                                                                        \
+    }                                                                                                 \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // Warp helpers
 // ---------------------------------------------------------------------------------------------

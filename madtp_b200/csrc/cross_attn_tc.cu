@@ -240,12 +240,7 @@ int launch_cross_attn_tc(const CrossTcArgs& a, cudaStream_t stream) {
   if ((st = make_tmap(&tq, a.q, false, static_cast<long long>(a.B) * a.Lq, a.H * 64LL, a.ldq, 128)) != kOk) return st;
   if ((st = make_tmap(&tk, a.k, false, k_rows, a.H * 64LL, a.ldk, 64)) != kOk) return st;
   if ((st = make_tmap(&tv, a.vt, false, a.H * 64LL, v_cols, a.ld_vt, 64)) != kOk) return st;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(cross_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    CrossSmem::TOTAL));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(CrossSmem::TOTAL, cross_attn_tc_kernel);
   cross_attn_tc_kernel<<<dim3(a.H, a.B), CrossSmem::THREADS, CrossSmem::TOTAL, stream>>>(tq, tk, tv, a);
   MADTP_LAUNCH_CHECK();
   return kOk;

@@ -901,12 +901,7 @@ static int launch_tc(const void* a, const void* a_lo, long long lda, const void*
     tal = ta;
     tbl = tb;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, TF32X3, PAIR>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(Cfg::SMEM_BYTES, gemm_tcgen05_kernel<BLOCK_N, TF32X3, PAIR>);
   constexpr int CL = PAIR ? 2 : 1;
   const int m_tiles = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
@@ -940,12 +935,7 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   if ((st = make_tmap(&tb, b, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   if ((st = make_tmap(&tal, a_lo, !F16, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
   if ((st = make_tmap(&tbl, b_lo, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(Cfg::SMEM_BYTES, gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>);
   GemmEpilogue epc = ep;
   if (epc.chunk_kb <= 0) {
     static const int env_chunk = getenv("MADTP_CHUNK_KB") ? atoi(getenv("MADTP_CHUNK_KB")) : 0;

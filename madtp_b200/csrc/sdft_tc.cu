@@ -223,11 +223,7 @@ int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_t
   CUtensorMap tx;
   int st;
   if ((st = make_tmap(&tx, x, true, x_rows, d, d, TCH)) != kOk) return st;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(query_sdft_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(SMEM_TOTAL, query_sdft_tc_kernel);
   SdftArgs a;
   a.ta = token_att; a.ld_ta = ld_ta; a.bs_ta = bs_ta;
   a.col_max = col_max; a.col_sum = col_sum;

@@ -154,11 +154,7 @@ int launch_small_self_attn(const AttnArgs& g, float* col_sum, float* cls_attn, f
   a.p_scratch = scratch;
   a.n_scratch = scratch ? scratch + static_cast<long long>(g.B) * g.H * g.Nq * g.Nq : nullptr;
   const int smem = (4 * SL * SP + 3 * SL) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    MADTP_CUDA(cudaFuncSetAttribute(small_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  MADTP_SMEM_ATTR_ONCE(smem, small_self_attn_kernel);
   small_self_attn_kernel<<<dim3(g.H, g.B), 128, smem, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   if (col_sum != nullptr) {

@@ -40,18 +40,23 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0):
-    """Replicates rank `src`'s parameters and buffers with a single broadcast of one flat fp32 blob."""
+    """Replicates rank `src`'s parameters and buffers with a single broadcast of one flat fp32 blob. The copies go
+    through `param.detach()`, which shares the parameter's version counter (unlike `.data`), so the prepared-weight
+    caches (functional.WeightCache) see the update; they are cleared as well for good measure."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return 0
-    tensors: List[torch.Tensor] = [p.data for p in module.parameters()] + \
-        [b.data for b in module.buffers() if b.is_floating_point()]
+    tensors: List[torch.Tensor] = [p.detach() for p in module.parameters()] + \
+        [b.detach() for b in module.buffers() if b.is_floating_point()]
     flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
     dist.broadcast(flat, src=src)
     off = 0
-    for t in tensors:
-        n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
-        off += n
+    with torch.no_grad():
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+    from .functional import clear_caches
+    clear_caches(module)
     return flat.numel() * 4
 
 

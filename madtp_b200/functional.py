@@ -10,6 +10,7 @@ Precision lanes (hard part 1):
 from __future__ import annotations
 
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -63,7 +64,15 @@ class PreparedLinear:
 
 
 class WeightCache:
-    """Per-module cache of PreparedLinear objects, invalidated when any source parameter is modified or replaced."""
+    """Per-module cache of PreparedLinear objects, invalidated when any source tensor is modified in place (its
+    autograd version counter moves), replaced by another tensor object (checked through weak references, so a
+    temporary whose allocation is recycled by a later tensor of the same shape can never hit a stale entry) or
+    re-allocated.
+
+    One limitation is inherent to torch: writes through `param.data` (which carries its OWN version counter) are
+    invisible here. Code that updates weights that way after a first forward -- EMA, manual reloads -- must call
+    `clear_caches(module)` afterwards; `load_state_dict` and `madtp_b200.dist.broadcast_parameters` copy through
+    `param.detach()` / `param.copy_`, which share the counter, and need nothing."""
 
     def __init__(self):
         self._store = {}
@@ -76,13 +85,27 @@ class WeightCache:
         stamp = self._stamp(params)
         hit = self._store.get(key)
         if hit is not None and hit[0] == stamp:
-            return hit[1]
+            live = [p for p in params if p is not None]
+            if len(live) == len(hit[2]) and all(r() is p for r, p in zip(hit[2], live)):
+                return hit[1]
         val = build()
-        self._store[key] = (stamp, val)
+        self._store[key] = (stamp, val, [weakref.ref(p) for p in params if p is not None])
         return val
 
     def clear(self):
         self._store.clear()
+
+
+def clear_caches(module) -> int:
+    """Drops every prepared-weight cache below `module` (call after changing weights through `.data`). Returns the
+    number of caches cleared."""
+    n = 0
+    for m in module.modules():
+        for v in vars(m).values():
+            if isinstance(v, WeightCache):
+                v.clear()
+                n += 1
+    return n
 
 
 # ------------------------------------------------------------------------------------------------------------------

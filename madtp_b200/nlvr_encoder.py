@@ -84,6 +84,9 @@ class BertEmbeddings(nn.Module):
         if not input_ids.is_cuda:
             raise RuntimeError("madtp_b200: input_ids must be a CUDA tensor -- this package has no CPU fallback")
         B, Ltok = input_ids.shape
+        if Ltok > self.position_embeddings.weight.shape[0]:
+            raise RuntimeError(f"madtp_b200: sequence length {Ltok} exceeds max_position_embeddings "
+                               f"{self.position_embeddings.weight.shape[0]}")
         e = L.bert_embed(input_ids.to(torch.int64), self.word_embeddings.weight.detach(),
                          self.position_embeddings.weight.detach())
         d = e.shape[-1]
@@ -310,10 +313,11 @@ class BertAttention(nn.Module):
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, past_key_value=None, output_attentions=False, space_dict=None):
         if type(encoder_hidden_states) == list:
-            o0 = self.self0(hidden_states, attention_mask, head_mask, encoder_hidden_states[0],
-                            encoder_attention_mask[0], past_key_value, output_attentions)
-            o1 = self.self1(hidden_states, attention_mask, head_mask, encoder_hidden_states[1],
-                            encoder_attention_mask[1], past_key_value, output_attentions)
+            em = encoder_attention_mask if type(encoder_attention_mask) == list else [encoder_attention_mask] * 2
+            o0 = self.self0(hidden_states, attention_mask, head_mask, encoder_hidden_states[0], em[0],
+                            past_key_value, output_attentions)
+            o1 = self.self1(hidden_states, attention_mask, head_mask, encoder_hidden_states[1], em[1],
+                            past_key_value, output_attentions)
             attention_output = self.output([o0[0], o1[0]], hidden_states)
             return (attention_output,) + o0[1:]
         o = self.self(hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,

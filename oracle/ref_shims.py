@@ -20,7 +20,18 @@ import types
 import torch
 from torch import nn
 
-REFERENCE_ROOT = os.environ.get("MADTP_REFERENCE_ROOT", "/root/reference")
+def _resolve_root() -> str:
+    """$MADTP_REFERENCE_ROOT, else /root/reference (build container), else oracle/_ref (the byte-for-byte staging of the
+    hot-path files made by oracle/make_ref.py, which is what exists on the GPU box)."""
+    env = os.environ.get("MADTP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/models"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _resolve_root()
 _installed = False
 
 

@@ -104,25 +104,21 @@ class BLIP_NLVR(nn.Module):
 
 
 def load_state_dict_from_checkpoint(model: BLIP_NLVR, state_dict):
-    """models/blip_nlvr.py:143-158: pos-embed interpolation and self -> self0/self1, dense -> dense0/dense1 fan-out."""
-    state_dict = dict(state_dict)
-    state_dict['visual_encoder.pos_embed'] = interpolate_pos_embed(state_dict['visual_encoder.pos_embed'],
-                                                                   model.visual_encoder)
-    for key in list(state_dict.keys()):
-        if 'crossattention.self.' in key:
-            state_dict[key.replace('self', 'self0')] = state_dict[key]
-            state_dict[key.replace('self', 'self1')] = state_dict[key]
-        elif 'crossattention.output.dense.' in key:
-            state_dict[key.replace('dense', 'dense0')] = state_dict[key]
-            state_dict[key.replace('dense', 'dense1')] = state_dict[key]
-    return model.load_state_dict(state_dict, strict=False)
+    """models/blip_nlvr.py:143-158 over a state dict (see madtp_b200.checkpoint.load_nlvr_checkpoint)."""
+    from .checkpoint import load_nlvr_checkpoint
+    return load_nlvr_checkpoint(model, state_dict)[1]
+
+
+def load_checkpoint(model, url_or_filename, client=None):
+    """models/blip_nlvr.py:131-160 (local files / state dicts; the reference's URL and S3 branches are host I/O)."""
+    from .checkpoint import load_nlvr_checkpoint
+    return load_nlvr_checkpoint(model, url_or_filename)
 
 
 def blip_nlvr(pretrained='', **kwargs):
     model = BLIP_NLVR(**kwargs)
     if pretrained:
-        ckpt = torch.load(pretrained, map_location='cpu')
-        msg = load_state_dict_from_checkpoint(model, ckpt['model'])
+        model, msg = load_checkpoint(model, pretrained)
         print("missing keys:")
         print(msg.missing_keys)
     return model

@@ -173,3 +173,27 @@ class BLIP_VQA(nn.Module):
             raise NotImplementedError("madtp_b200: inference='generate' (beam search) is out of scope")
         q_states, _ = self.encode_question(image, question.input_ids, question.attention_mask, temperature)
         return self.rank_answer(q_states, question.attention_mask, answer.input_ids, answer.attention_mask, k_test)
+
+
+def load_checkpoint(model, url_or_filename, client=None):
+    """models/blip.py:254-278 (see madtp_b200.checkpoint.load_blip_checkpoint)."""
+    from .checkpoint import load_blip_checkpoint
+    return load_blip_checkpoint(model, url_or_filename)
+
+
+def blip_retrieval(pretrained='', **kwargs):
+    """models/blip_retrieval.py:285-291."""
+    model = BLIP_Retrieval(**kwargs)
+    if pretrained:
+        model, msg = load_checkpoint(model, pretrained)
+        print("missing keys:")
+        print(msg.missing_keys)
+    return model
+
+
+def blip_vqa(pretrained='', **kwargs):
+    """models/blip_vqa.py:206-211."""
+    model = BLIP_VQA(**kwargs)
+    if pretrained:
+        model, msg = load_checkpoint(model, pretrained)
+    return model

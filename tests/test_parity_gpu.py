@@ -34,17 +34,46 @@ def unpack(bits, n):
     return torch.from_numpy(np.unpackbits(bits, axis=1)[:, :n].astype(bool))
 
 
+AMBIGUOUS_GAP = 1e-8    # absolute score gap below which a top-k boundary decision is an fp32 tie (SURVEY.md 7-iii:
+                        # ~20x the measured fp32 noise floor of 4.7e-10 on scores of ~1.7e-3)
+
+
 def assert_masks_equal(keep_cuda, keep_ref, score_ref, k, what):
-    """Bit-exact keep-mask check that names the decision margin of any flipped token."""
+    """Bit-exact keep-mask check. Any flipped token is reported with its score and its distance to the top-k
+    boundary; a flip FAILS unless that distance is below AMBIGUOUS_GAP (an fp32 tie in the oracle itself), and every
+    such ambiguous row is printed so that a "tie" can never hide a real bug."""
     keep_cuda, keep_ref = keep_cuda.cpu().bool(), keep_ref.cpu().bool()
     if torch.equal(keep_cuda, keep_ref):
         return
     srt = score_ref.sort(dim=1, descending=True)[0]
-    msgs = []
+    hard, soft = [], []
     for b, j in (keep_cuda != keep_ref).nonzero().tolist():
-        gap = (srt[b, k - 1] - srt[b, k]).item()
-        msgs.append(f"row {b} token {j}: score {score_ref[b, j]:.9e}, boundary gap {gap:.3e}")
-    raise AssertionError(f"{what}: keep-mask differs from the oracle\n" + "\n".join(msgs[:20]))
+        lo, hi = srt[b, min(k, srt.shape[1] - 1)].item(), srt[b, k - 1].item()      # (k+1)-th and k-th largest
+        sj = score_ref[b, j].item()
+        margin = min(abs(sj - lo), abs(sj - hi))
+        msg = f"row {b} token {j}: score {sj:.9e}, distance to the top-k boundary {margin:.3e} (gap {hi - lo:.3e})"
+        (soft if margin < AMBIGUOUS_GAP else hard).append(msg)
+    if soft:
+        print(f"{what}: {len(soft)} AMBIGUOUS boundary decisions (below {AMBIGUOUS_GAP:g}):\n" + "\n".join(soft[:20]))
+    if hard:
+        raise AssertionError(f"{what}: keep-mask differs from the oracle\n" + "\n".join(hard[:20]))
+
+
+def assert_counts_equal(count_cuda, count_ref, score_ref, thr_ref, what):
+    """Per-row survivor counts #(score > threshold) must match; a row may differ only if one of its scores sits
+    within AMBIGUOUS_GAP of the oracle's threshold, and then it is printed."""
+    cc, cr = count_cuda.cpu().long(), count_ref.cpu().long()
+    if torch.equal(cc, cr):
+        return
+    hard, soft = [], []
+    for b in (cc != cr).nonzero().flatten().tolist():
+        margin = (score_ref[b] - thr_ref[b]).abs().min().item()
+        msg = f"row {b}: count {cc[b].item()} vs oracle {cr[b].item()}, closest score to the threshold {margin:.3e}"
+        (soft if margin < AMBIGUOUS_GAP else hard).append(msg)
+    if soft:
+        print(f"{what}: {len(soft)} AMBIGUOUS threshold decisions:\n" + "\n".join(soft[:20]))
+    if hard:
+        raise AssertionError(f"{what}: per-row counts differ\n" + "\n".join(hard[:20]))
 
 
 @pytest.fixture(scope="module")
@@ -131,7 +160,10 @@ def nlvr_setup(dev, image_size, pairs, text_len, temp, pad_to=0):
     return _NLVR_CACHE[key]
 
 
-NLVR_CASES = [(224, 2, 20, 1.0), (224, 2, 20, 8.0), (384, 2, 20, 3.5894)]
+CAL_TEMP = float(np.load(GOLDEN / "calib_nlvr_p50_b32.npz")["temperature"])
+# the last case is BASELINE configuration 2 at FULL size: 32 pairs = 64 images of 384 x 384 at the temperature calibrated
+# for p = 0.5 -- the shape bench.py times (the oracle runs it once per session on the host cores, ~10 s)
+NLVR_CASES = [(224, 2, 20, 1.0), (224, 2, 20, 8.0), (384, 2, 20, 3.5894), (384, 32, 20, CAL_TEMP)]
 
 
 @pytest.mark.parametrize("image_size,pairs,text_len,temp", NLVR_CASES)
@@ -146,8 +178,8 @@ def test_vit_layers_teacher_forced(dev, image_size, pairs, text_len, temp):
             token_attn, _, _ = vit.img_query_model(x[:, 1:, :], space, return_token_att=True)
             y = blk(x, False, 0, temp, token_attn)
         res = blk.last_prune
+        assert_counts_equal(res.count, t.count, t.score, t.threshold, f"ViT layer {i} (T={temp}, {pairs} pairs)")
         assert res.pruned == t.pruned, f"layer {i}: pruned {res.pruned} vs oracle {t.pruned}"
-        assert torch.equal(res.count.cpu().long(), t.count.long()), f"layer {i}: per-row counts differ"
         assert res.k == t.k, f"layer {i}: topk_num {res.k} vs oracle {t.k}"
         assert score_err(res.score, t.score) < SCORE_RTOL, f"layer {i}"
         if t.pruned:
@@ -157,7 +189,7 @@ def test_vit_layers_teacher_forced(dev, image_size, pairs, text_len, temp):
     assert worst < REL_TOL, f"hidden-state relative error {worst:.2e}"
 
 
-@pytest.mark.parametrize("image_size,pairs,text_len,temp", NLVR_CASES[:2])
+@pytest.mark.parametrize("image_size,pairs,text_len,temp", NLVR_CASES)
 def test_text_layers_teacher_forced(dev, image_size, pairs, text_len, temp):
     model, sd, _, tr, _ = nlvr_setup(dev, image_size, pairs, text_len, temp)
     enc = model.text_encoder.encoder
@@ -173,8 +205,8 @@ def test_text_layers_teacher_forced(dev, image_size, pairs, text_len, temp):
             out = layer(h, ext, space, None, enc_states, None, None, False, mode='multimodal', token_attn=token_attn,
                         temperature=temp)
         res = layer.last_prune
+        assert_counts_equal(res.count, t.count, t.score, t.threshold, f"text layer {i} (T={temp}, {pairs} pairs)")
         assert res.pruned == t.pruned and res.k == t.k, f"text layer {i}: k {res.k} vs oracle {t.k}"
-        assert torch.equal(res.count.cpu().long(), t.count.long())
         if t.pruned:
             assert_masks_equal(res.keep, t.keep, t.score, t.k, f"text layer {i} (T={temp})")
         assert out[0].shape == t.layer_output.shape
@@ -610,3 +642,51 @@ def test_dtp_edge_cases(lib, dev):
     empty = torch.empty(0, 16, device=dev)
     keep, dst, tail_w, tail_idx, _ = lib.dtp_select(empty, topk)
     assert keep.shape == (0, 16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# vector_gather (models/utils.py:13-33): the mirror and the C-ABI entry point behind it
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Ltok,K,D", [(3, 37, 11, 768), (64, 576, 410, 768), (2, 5, 5, 128), (4, 9, 0, 64)])
+def test_vector_gather_matches_torch_gather(lib, dev, B, Ltok, K, D):
+    from madtp_b200.utils import vector_gather
+    g = torch.Generator().manual_seed(B * 1000 + K)
+    x = torch.randn(B, Ltok, D, generator=g)
+    idx = torch.stack([torch.randperm(Ltok, generator=g)[:K] for _ in range(B)]) if K else torch.zeros(B, 0, dtype=torch.long)
+    out = vector_gather(x.to(dev), idx.to(dev))
+    ref = torch.gather(x, 1, idx[..., None].expand(-1, -1, D))          # what the reference's einops/gather computes
+    assert out.shape == ref.shape and torch.equal(out.cpu(), ref)       # a copy: bit-exact
+    if K:
+        # repeated and unsorted indices are legal for a gather
+        idx2 = torch.randint(0, Ltok, (B, K), generator=g)
+        out2 = lib.gather_rows(x.to(dev), idx2.to(torch.int32).to(dev))
+        assert torch.equal(out2.cpu(), torch.gather(x, 1, idx2[..., None].expand(-1, -1, D)))
+        with pytest.raises(IndexError):
+            vector_gather(x.to(dev), torch.full((B, 1), Ltok, dtype=torch.long, device=dev))
+    # non-contiguous input (a [:, 1:, :] slice, as Reduce_token passes it)
+    xs = x.to(dev)[:, 1:, :]
+    if K and Ltok > 2:
+        idx3 = torch.randint(0, Ltok - 1, (B, K), generator=g)
+        assert torch.equal(vector_gather(xs, idx3.to(dev)).cpu(), torch.gather(x[:, 1:], 1, idx3[..., None].expand(-1, -1, D)))
+
+
+def test_product_mac_counter_and_calibration_on_gpu(dev):
+    """SURVEY 8(f)-3 in the product: GMACs from the k trajectory of the forward that just ran (no tracing) and the
+    p -> temperature bisection built on it, against the oracle's counter on the same batch."""
+    from madtp_b200 import flops
+    from madtp_b200.blip_nlvr import TokenizedText
+    model, sd, (images, ids, mask), tr, _ = nlvr_setup(dev, 384, 2, 20, 3.5894)
+    text = TokenizedText(ids.to(dev), mask.to(dev))
+    img_d = images.to(dev)
+    full = flops.nlvr_macs_unpruned(577, 20)
+
+    def ratio_at(temp):
+        with torch.no_grad():
+            model(img_d, text, 2, temp, train=False)
+        return flops.nlvr_gmacs_of_last_forward(model, 384, 20) * 1e9 / full
+    r = ratio_at(3.5894)
+    r_oracle = O.nlvr_macs_from_trace(tr, 577, 20) / O.nlvr_macs_unpruned(577, 20)
+    assert abs(r - r_oracle) < 5e-3, (r, r_oracle)           # free-running k may differ by a token or two
+    temp, r50, probes = flops.calibrate_temperature(ratio_at, p=0.5, tol=0.01)
+    assert abs(r50 - 0.5) < 0.01 and 1.0 < temp < 16.0 and probes <= 16
+    assert ratio_at(0.0) == 1.0                              # temperature 0: nothing is pruned (models/vit.py:193)

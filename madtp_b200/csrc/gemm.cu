@@ -254,10 +254,11 @@ template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
-                    GemmEpilogue ep, int M, int N, int K) {
+                    GemmEpilogue ep, int M_cap, int N_cap, int K) {
   using Cfg = GemmCfg<BLOCK_N, TF32X3, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(!PAIR || !TF32X3, "the CTA-pair variant is fp16 only");
+  const int M = gemm_dyn_m(ep, M_cap), N = gemm_dyn_n(ep, N_cap);   // device-resident extents (gemm.cuh)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -513,11 +514,13 @@ template <int BLOCK_N, int CL, bool F16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
-                   GemmEpilogue ep, int M, int N, int K) {
+                   GemmEpilogue ep, int M_cap, int N_cap, int K) {
   using Cfg = Tf32Cfg<BLOCK_N, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CW = Cfg::COLS_PER_WARP;
   static_assert(!PAIR || (CL == 2 && F16), "the CTA-pair variant is the fp16-plane kernel on clusters of two");
+  const int M = gemm_dyn_m(ep, M_cap), N = gemm_dyn_n(ep, N_cap);   // device-resident extents (gemm.cuh)
+  const int n_tok = (ep.mode == 1 && ep.m_dev) ? __ldg(ep.m_dev) : ep.n_tok;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -717,8 +720,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                                                        m0 + quad * 32, col0, M, N, lane, rv);
             } else if (row < M) {
               // value projection: lane = token, so consecutive lanes write consecutive keys of one V^T row
-              const int b = static_cast<int>(row / ep.n_tok);
-              const int i = static_cast<int>(row - static_cast<long long>(b) * ep.n_tok);
+              const int b = static_cast<int>(row / n_tok);
+              const int i = static_cast<int>(row - static_cast<long long>(b) * n_tok);
               const int vc = col0 - ep.qk_cols;
               const long long off =
                   (static_cast<long long>(b * ep.heads + (vc >> 6)) * 64 + (vc & 63)) * ep.ld_vt + i;
@@ -766,7 +769,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
-                 GemmEpilogue ep, int M, int N, int K) {
+                 GemmEpilogue ep, int M_cap, int N_cap, int K) {
+  const int M = gemm_dyn_m(ep, M_cap), N = gemm_dyn_n(ep, N_cap);
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -818,7 +822,8 @@ gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __rest
 // a [32 x 2] output spreads over the machine instead of running as one 48-step dependent loop in a single CTA.
 __global__ void __launch_bounds__(256)
 gemm_rowdot_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B, long long ldb,
-                   GemmEpilogue ep, int M, int N, int K) {
+                   GemmEpilogue ep, int M_cap, int N_cap, int K) {
+  const int M = gemm_dyn_m(ep, M_cap), N = gemm_dyn_n(ep, N_cap);
   const long long o = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= static_cast<long long>(M) * N) return;

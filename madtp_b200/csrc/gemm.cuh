@@ -28,7 +28,23 @@ struct GemmEpilogue {
   int n_tok;
   int heads;
   int qk_cols;
+  // ---- dynamic extents (device-resident token counts; nullptr = the host value is exact) ----
+  // M = *m_dev * m_mult rows / N = *n_dev * n_mult columns are read at kernel start; the host M / N are then only
+  // CAPACITIES (grid size, tensor-map extents). Operand rows beyond the dynamic extent are read but feed only output
+  // rows / columns that are never stored. mode 1 additionally takes n_tok from *m_dev.
+  const int* m_dev;
+  int m_mult;
+  const int* n_dev;
+  int n_mult;
 };
+
+// Effective extents of a launch (device code).
+__device__ __forceinline__ int gemm_dyn_m(const GemmEpilogue& ep, int M) {
+  return ep.m_dev ? min(M, __ldg(ep.m_dev) * ep.m_mult) : M;
+}
+__device__ __forceinline__ int gemm_dyn_n(const GemmEpilogue& ep, int N) {
+  return ep.n_dev ? min(N, __ldg(ep.n_dev) * ep.n_mult) : N;
+}
 
 // Power-of-two scales of the q/k and v operand planes (keep the lo plane of typical activations a normal fp16 number;
 // the attention kernels fold them back into the softmax scale and the output normalisation).

@@ -22,7 +22,20 @@
 extern "C" {
 #endif
 
-#define MADTP_B200_ABI_VERSION 2   /* 2: fp16 hi/lo operand planes, persistent attention, cross-attention, read-back */
+#define MADTP_B200_ABI_VERSION 3   /* 3: device-resident token counts (`*_dev` arguments), cross-attention over any Nk */
+
+/*
+ * Device-resident lengths (ABI 3). The number of tokens a layer keeps (topk_num, vit.py:145) decides every later
+ * shape; the reference reads it back with `.item()` once per pruned layer. Every entry point whose work depends on a
+ * per-sequence token count therefore also accepts that count from DEVICE memory: an `int32_t*` argument named `*_dev`
+ * (NULL = the host value is exact, the ABI-2 behaviour). With a non-NULL `*_dev`
+ *   - the kernel reads the count when it starts; the host-side count is only a CAPACITY (>= the real one) used for
+ *     the grid size, tensor-map extents and argument checks;
+ *   - sequences are PACKED with the dynamic count: sequence b of a [B, N, ...] buffer starts at b * N_dynamic rows, and
+ *     every batch stride the signature carries is recomputed as N_dynamic * (row pitch) on the device;
+ *   - madtp_dtp_select writes the NEXT layer's count (and the per-layer trajectory) to device memory,
+ * so a whole pruned forward can be enqueued (or captured in a CUDA graph) without a single host read-back.
+ */
 
 /* GEMM operand precision */
 #define MADTP_GEMM_F16 0     /* fp16 operands, fp32 accumulate, tcgen05 kind::f16 */
@@ -52,7 +65,9 @@ long long madtp_launch_count(void);
  */
 int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, const void* b, const void* b_lo,
                int64_t ldb, void* c, int64_t ldc, int c_f16, const float* bias, const float* residual, int64_t ldr,
-               int act, float alpha, int M, int N, int K, void* stream);
+               int act, float alpha, int M, int N, int K, const int32_t* m_dev, int m_mult, const int32_t* n_dev,
+               int n_mult, void* stream);
+/* m_dev / n_dev (each may be NULL): M = *m_dev * m_mult rows, N = *n_dev * n_mult columns (sequences x tokens). */
 
 /*
  * Row LayerNorm with fused GEMM-operand preparation. Replaces nn.LayerNorm at vit.py:111,115,239 (eps 1e-6) and
@@ -63,7 +78,24 @@ int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, cons
  * gamma == beta == NULL: only x_hi/x_lo are produced. d must be a multiple of 128, <= 1024.
  */
 int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
-                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, void* stream);
+                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, const int32_t* n_dev,
+                    int n_mult, void* stream);
+/* n_dev: rows = *n_dev * n_mult. */
+
+/*
+ * Final LayerNorm of the image encoder written straight into the operand layout of the cross-attention K / V^T
+ * projections (vit.py:309 followed by nlvr_encoder.py:103-109 / med.py:103-109 with is_cross_attention): x is the packed
+ * stream [B * N, d]; sequence b is written as fp16 at y16 + (b / per_group) * group_stride + ((b % per_group) * P + t) * d
+ * with P = N rounded up to 8 rows (TMA box origins are 16-byte aligned), rows N..P-1 zero. per_group / group_stride
+ * (elements) split the batch into equal groups with their own base (BLIP-NLVR: image0 / image1 halves, blip_nlvr.py:67).
+ * y_f32 (optional): the packed fp32 result [B * N, d]. p_out_dev (optional) receives P. n_dev: dynamic N.
+ */
+int madtp_layernorm_pack(const float* x, int B, int N, int d, const float* gamma, const float* beta, float eps,
+                         float* y_f32, void* y16, int per_group, int64_t group_stride, int32_t* p_out_dev,
+                         const int32_t* n_dev, void* stream);
+/* out[b, :] = x[(b * N + token) * d ...]: one token of every sequence of a packed stream (`last_hidden_state[:, 0, :]`,
+ * blip_nlvr.py:80). n_dev: dynamic N. */
+int madtp_take_token(const float* x, int B, int N, int token, int d, float* out, const int32_t* n_dev, void* stream);
 
 /* hi = round_to_tf32(x), lo = x - hi (exact). Used once per weight at load time. */
 int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
@@ -82,8 +114,9 @@ int madtp_patchify(const float* img, void* rows_hi, void* rows_lo, int B, int C,
 int madtp_assemble_tokens(const float* patches, const float* cls, const float* pos, float* x, int B, int n, int d,
                           void* stream);
 /* out[b,l,:] = word[ids[b,l]] + position[l]   (nlvr_encoder.py:61-85; the LayerNorm is a madtp_layernorm call) */
+/* n_pos: rows of the position table; L > n_pos is an argument error (ids outside [0, vocab) are clamped). */
 int madtp_bert_embed(const int64_t* ids, const float* word, const float* position, float* out, int B, int L, int d,
-                     int vocab, void* stream);
+                     int vocab, int n_pos, void* stream);
 
 /*
  * Language-model head statistics per logits row (VQA answer ranking: models/med.py:1040-1047 CrossEntropyLoss with
@@ -117,7 +150,8 @@ int madtp_attn_fwd(const float* q, int64_t ldq, int64_t bsq, const float* k, int
 int madtp_attn_small_self(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk,
                           const float* v, int64_t ldv, int64_t bsv, int B, int H, int L, float scale,
                           const float* key_mask, void* out_f16, int64_t ldo, int64_t bso, float* col_sum,
-                          float* cls_attn, float* scratch, int causal, void* stream);
+                          float* cls_attn, float* scratch, int causal, const int32_t* l_dev, void* stream);
+/* l_dev: dynamic L (packed q / k / v / out / key_mask / col_sum / cls_attn). */
 
 /*
  * Pruning statistics of a self-attention (Nq == Nk == N), from the row statistics of madtp_attn_fwd:
@@ -134,18 +168,20 @@ int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, i
  *   colstats: col_max[b,t], col_sum[b,t] of softmax over tokens of token_att / divisor   (divisor = sqrt(sd_dim))
  *   sdft:     sd_ft[b,t,:] (+)= sum_j softmax_j(token_att[b,j,t] / divisor) * ft[b,j,:]
  * token_att row j of batch b is at token_att + b*bs_ta + j*ld_ta; ft row j at ft + b*bs_ft + j*ld_ft.
+ * n_dev / n_sub: *n_dev is the packed token count N INCLUDING the n_sub leading non-prunable tokens (n = N - n_sub).
  */
 int madtp_token_colstats(const float* token_att, int64_t ld_ta, int64_t bs_ta, int B, int n, int T, float divisor,
-                         float* col_max, float* col_sum, void* stream);
+                         float* col_max, float* col_sum, const int32_t* n_dev, int n_sub, void* stream);
 int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
                      const float* ft, int64_t ld_ft, int64_t bs_ft, int B, int n, int T, int d, float divisor,
-                     float* sd_ft, int accumulate, void* stream);
+                     float* sd_ft, int accumulate, const int32_t* n_dev, int n_sub, void* stream);
 
 /* madtp_query_sdft on the tensor cores: ft is the dense fp32 matrix x [x_rows, d] (token j of batch b at row
  * b*row_stride + first_row + j); both operands are re-laid out K-major in shared memory, nothing transposed touches HBM. */
 int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
                         const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
-                        float divisor, float* sd_ft, int accumulate, void* stream);
+                        float divisor, float* sd_ft, int accumulate, const int32_t* n_dev, void* stream);
+/* n_dev: *n_dev = tokens per sequence (row_stride = *n_dev, n = *n_dev - first_row). */
 
 /*
  * DTP scoring (vit.py:123-145 / nlvr_encoder.py:400-432 / med.py:345-369): Importance_score, threshold,
@@ -154,7 +190,9 @@ int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, co
  */
 int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
                     const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
-                    float* threshold, int32_t* count, int32_t* topk, void* stream);
+                    float* threshold, int32_t* count, int32_t* topk, const int32_t* n_dev, int parts_tile, void* stream);
+/* n_dev: *n_dev = n + 1 (packed col_part / cls_attn / token_att / score); parts_tile > 0: n_parts = ceil(N / parts_tile)
+ * (128 for madtp_attn_tc_stats, 64 for madtp_attn_stats), 0: n_parts as given. */
 
 /*
  * DTP selection (vit.py:153-158): exact top-k of score per row (k read from *topk on the device), survivors keep
@@ -167,7 +205,9 @@ int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, con
  */
 int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
                      int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
-                     void* stream);
+                     const int32_t* n_dev, int32_t* n_out_dev, int32_t* k_out_dev, void* stream);
+/* n_dev: *n_dev = n + 1; mask_in is then packed [B, N] and mask_out is written packed [B, N_out]. n_out_dev receives
+ * N_out = k + 2 (N when nothing is pruned) -- the next layer's `*_dev`; k_out_dev (optional) receives k or -1. */
 
 /*
  * DTP gather + merge (vit.py:154-161,202; models/utils.py:13-33 vector_gather): out[b] = [x[b,0], survivors in
@@ -176,7 +216,9 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
  */
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
                      const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* out_f16, int max_keep,
-                     void* stream);
+                     const int32_t* n_dev, void* stream);
+/* n_dev: *n_dev = n + 1; x is packed [B, N, d] and out is written packed [B, N_out, d] (a full copy when nothing is
+ * pruned, so that the next layer always reads `out`). */
 
 /*
  * Tensor-core self-attention for the scoring lane (vit.py:75-103 without materialising P). madtp_gemm_qkv is the
@@ -195,14 +237,17 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
 #define MADTP_V_PLANE_SCALE 16.0f
 int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
                    const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi, void* qk_lo,
-                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, void* stream);
+                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, const int32_t* n_dev, void* stream);
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      void* stream);
+                      const int32_t* n_dev, void* stream);
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, void* stream);
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max,
+                        const int32_t* n_dev, void* stream);
+/* n_dev (all three): dynamic n_tok / N; every [.., N] statistics buffer and the q/k planes are packed with it, V^T keeps
+ * its pitch ld_vt (>= the capacity). */
 
 /*
  * Asynchronous read-back of a few bytes (the per-layer topk_num, vit.py:145 `.item()`): begin records an event on
@@ -216,7 +261,8 @@ int madtp_readback_wait(int slot);
 
 /*
  * Tensor-core cross-attention of text queries over image tokens (nlvr_encoder.py:174-219, med.py:175-217 with
- * is_cross_attention; value lane, fp16 operands). Lq <= 128, Nk <= 256, head dim 64; larger problems use madtp_attn_fwd.
+ * is_cross_attention; value lane, fp16 operands). Lq <= 128, any Nk (walked in blocks of 128 keys with an online
+ * softmax), head dim 64.
  * q [B*Lq, ldq] and k [B*Nk, ldk] fp16 row-major (head h at column h*64); V^T [H*64, ld_vt] fp16 with the keys of
  * sequence b at columns b*vt_cols_per_batch + j (the value projection run as W_v . X^T); v_bias [H*64] is added to the
  * normalised output (rows of P sum to one). k_rows_per_batch / vt_cols_per_batch: per-sequence pitch (>= Nk; for V^T
@@ -226,7 +272,9 @@ int madtp_readback_wait(int slot);
 int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
                         const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
                         int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
-                        void* stream);
+                        const int32_t* lq_dev, const int32_t* nk_dev, void* stream);
+/* lq_dev / nk_dev: dynamic Lq (packed q / out) and Nk (packed key_mask; non-zero per-sequence pitches become Nk rounded
+ * up to 8, the layout madtp_layernorm_pack + the K / V^T projections produce). */
 
 /* vector_gather (models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :], x [B,L,d] with batch stride bsx, idx [B,K]
  * (indices are clamped to [0, L)), out [B,K,d] contiguous. */

@@ -17,7 +17,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
 _lib = None
 
-ABI_VERSION = 2                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
+ABI_VERSION = 3                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
 GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
 QK_PLANE_SCALE, V_PLANE_SCALE = 8.0, 16.0     # include/madtp_b200.h MADTP_QK_PLANE_SCALE / MADTP_V_PLANE_SCALE
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
@@ -30,11 +30,13 @@ SIGNATURES = {
     "madtp_last_error_string": [],
     "madtp_launch_count": [],
     "madtp_gemm": [_i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _i32,
-                   _i32, _vp],
-    "madtp_layernorm": [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                   _i32, _vp, _i32, _vp, _i32, _vp],
+    "madtp_layernorm": [_vp, _i64, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "madtp_layernorm_pack": [_vp, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _i32, _i64, _vp, _vp, _vp],
+    "madtp_take_token": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
     "madtp_attn_cross_tc": [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
-                            _i64, _vp],
+                            _i64, _vp, _vp, _vp],
     "madtp_readback_begin": [_vp, _vp, _i64, _i32, _vp],
     "madtp_readback_wait": [_i32],
     "madtp_lm_nll": [_vp, _i64, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
@@ -42,25 +44,27 @@ SIGNATURES = {
     "madtp_cast_f16": [_vp, _vp, _i64, _vp],
     "madtp_patchify": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "madtp_assemble_tokens": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
-    "madtp_bert_embed": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "madtp_bert_embed": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "madtp_attn_fwd": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
                        _i64, _i64, _vp, _vp, _vp, _i32, _vp],
     "madtp_attn_stats": [_vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
                          _vp],
     "madtp_attn_small_self": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
-                              _i64, _vp, _vp, _vp, _i32, _vp],
-    "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
-    "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
-    "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp],
-    "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp],
-    "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp],
-    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
+                              _i64, _vp, _vp, _vp, _i32, _vp, _vp],
+    "madtp_token_colstats": [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i32, _vp],
+    "madtp_query_sdft": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp, _i32,
+                         _vp],
+    "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp,
+                            _vp],
+    "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+    "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
-                       _vp],
+                       _vp, _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
-                          _vp],
-    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+                          _vp, _vp],
+    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp],
 }
 
 
@@ -226,10 +230,83 @@ def _rowmajor(t, name):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# buffers: plain torch allocations, or an Arena of persistent buffers for the device-resident-length (graph) mode
+# ------------------------------------------------------------------------------------------------------------------
+class Arena:
+    """Persistent buffers handed out in CALL ORDER. The launch sequence of a forward with device-resident lengths does
+    not depend on the data, so the i-th allocation of every pass is the same buffer: the first pass creates it
+    (zero-initialised), later passes -- the CUDA-graph capture among them -- get the same memory back. Three things
+    follow: no allocator call is left on the hot path; every kernel argument is stable across passes (what a CUDA
+    graph needs); and the region of a capacity-sized buffer BEYOND the dynamic length only ever holds zeros or finite
+    values written by an earlier pass through the same role -- which is what makes it safe for the tensor cores to
+    read it (P = 0 times a stale V is 0, never NaN)."""
+
+    def __init__(self):
+        self.bufs = []
+        self.i = 0
+        self.frozen = False
+
+    def begin(self):
+        self.i = 0
+
+    def take(self, shape, dtype, device):
+        shape = tuple(int(x) for x in shape)
+        if self.i < len(self.bufs):
+            t = self.bufs[self.i]
+            if tuple(t.shape) != shape or t.dtype != dtype:
+                raise RuntimeError(f"madtp_b200.Arena: allocation {self.i} changed from {tuple(t.shape)} {t.dtype} to "
+                                   f"{shape} {dtype}: the launch sequence must not depend on the data")
+        else:
+            if self.frozen:
+                raise RuntimeError("madtp_b200.Arena: new allocation after the arena was frozen")
+            t = torch.zeros(shape, dtype=dtype, device=device)
+            self.bufs.append(t)
+        self.i += 1
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs)
+
+
+_arena = None
+
+
+def set_arena(arena):
+    """Route every buffer the wrappers below (and functional.py) allocate through `arena` (None: plain torch)."""
+    global _arena
+    prev = _arena
+    _arena = arena
+    return prev
+
+
+def empty(shape, dtype, device):
+    if _arena is not None:
+        return _arena.take(shape, dtype, device)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def zeros(shape, dtype, device):
+    if _arena is not None:
+        return _arena.take(shape, dtype, device).zero_()
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+def _dyn(t):
+    """Device pointer of an int32 device scalar holding a dynamic token count (None: the host value is exact)."""
+    if t is None:
+        return None
+    if t.dtype != torch.int32 or not t.is_cuda or t.numel() < 1:
+        raise RuntimeError("madtp_b200: a dynamic length must be an int32 CUDA tensor")
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # thin functional wrappers
 # ------------------------------------------------------------------------------------------------------------------
-def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None, act=ACT_NONE, alpha=1.0):
-    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual. out may be a column slice of a wider buffer."""
+def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None, act=ACT_NONE, alpha=1.0,
+         m_dev=None, m_mult=1, n_dev=None, n_mult=1):
+    """out[M,N] = act(alpha * a[M,K] @ b[N,K]^T + bias) + residual. out may be a column slice of a wider buffer.
+    m_dev / n_dev: device-resident extents M = *m_dev * m_mult, N = *n_dev * n_mult (the tensor shapes are capacities)."""
     lda, ldb, ldc = _rowmajor(a, "a"), _rowmajor(b, "b"), _rowmajor(out, "out")
     M, K = a.shape
     N = b.shape[0]
@@ -251,12 +328,14 @@ def gemm(precision, a, b, out, *, a_lo=None, b_lo=None, bias=None, residual=None
     st = _call("madtp_gemm", precision, _ptr(a, op_dtype, "a"), _ptr(a_lo, lo_dtype, "a_lo"), lda,
                            _ptr(b, op_dtype, "b"), _ptr(b_lo, lo_dtype, "b_lo"), ldb, _ptr(out, None, "out"),
                            ldc, 1 if out.dtype == torch.float16 else 0, _ptr(bias, torch.float32, "bias"),
-                           _ptr(residual, torch.float32, "residual"), ldr, act, float(alpha), M, N, K, _stream())
+                           _ptr(residual, torch.float32, "residual"), ldr, act, float(alpha), M, N, K, _dyn(m_dev),
+                           int(m_mult), _dyn(n_dev), int(n_mult), _stream())
     _check(st, "madtp_gemm")
     return out
 
 
-def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=None, x_hi=None, x_lo=None):
+def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=None, x_hi=None, x_lo=None, n_dev=None,
+              n_mult=1):
     """x: [rows, d] fp32 (row stride free). Every output is optional and contiguous [rows, d]."""
     ldx = _rowmajor(x, "x")
     rows, d = x.shape
@@ -266,8 +345,28 @@ def layernorm(x, gamma, beta, eps, *, y_f32=None, y_hi=None, y_lo=None, y_f16=No
             raise RuntimeError(f"madtp_b200.layernorm: bad output {nm}")
     st = _call("madtp_layernorm", _ptr(x, torch.float32, "x"), ldx, rows, d, _ptr(gamma, torch.float32, "gamma"),
                                 _ptr(beta, torch.float32, "beta"), float(eps), _ptr(y_f32), _ptr(y_hi), _ptr(y_lo),
-                                _ptr(y_f16), _ptr(x_hi), _ptr(x_lo), _stream())
+                                _ptr(y_f16), _ptr(x_hi), _ptr(x_lo), _dyn(n_dev), int(n_mult), _stream())
     _check(st, "madtp_layernorm")
+
+
+def layernorm_pack(x2d, B, N, gamma, beta, eps, y16, per_group, group_stride, *, y_f32=None, p_out=None, n_dev=None):
+    """LayerNorm of the packed stream x2d [B * N, d] -> fp16 cross-attention operand layout (madtp_layernorm_pack)."""
+    d = x2d.shape[1]
+    if not x2d.is_contiguous():
+        raise RuntimeError("madtp_b200.layernorm_pack: x must be dense")
+    st = _call("madtp_layernorm_pack", _ptr(x2d, torch.float32, "x"), B, N, d, _ptr(gamma, torch.float32, "gamma"),
+               _ptr(beta, torch.float32, "beta"), float(eps), _ptr(y_f32, torch.float32, "y_f32"),
+               _ptr(y16, torch.float16, "y16"), int(per_group), int(group_stride), _dyn(p_out), _dyn(n_dev), _stream())
+    _check(st, "madtp_layernorm_pack")
+
+
+def take_token(x2d, B, N, token, *, n_dev=None):
+    """x2d: packed stream [B * N, d] -> [B, d] = row `token` of every sequence."""
+    d = x2d.shape[1]
+    out = empty((B, d), torch.float32, x2d.device)
+    _check(_call("madtp_take_token", _ptr(x2d, torch.float32, "x"), B, N, int(token), d, _ptr(out), _dyn(n_dev),
+                 _stream()), "madtp_take_token")
+    return out
 
 
 def split_tf32(x):
@@ -299,15 +398,15 @@ def patchify(img, P):
     B, Cc, H, W = img.shape
     img = img.contiguous()
     rows = B * (H // P) * (W // P)
-    hi = torch.empty(rows, Cc * P * P, dtype=torch.float16, device=img.device)
-    lo = torch.empty_like(hi)
+    hi = empty((rows, Cc * P * P), torch.float16, img.device)
+    lo = empty((rows, Cc * P * P), torch.float16, img.device)
     _check(_call("madtp_patchify", _ptr(img, torch.float32, "img"), _ptr(hi), _ptr(lo), B, Cc, H, W, P, _stream()),
            "madtp_patchify")
     return hi, lo
 
 
 def assemble_tokens(patches, cls, pos, B, n, d):
-    x = torch.empty(B, n + 1, d, dtype=torch.float32, device=patches.device)
+    x = empty((B, n + 1, d), torch.float32, patches.device)
     _check(_call("madtp_assemble_tokens", _ptr(patches, torch.float32, "patches"), _ptr(cls, torch.float32, "cls"),
                                         _ptr(pos, torch.float32, "pos"), _ptr(x), B, n, d, _stream()),
            "madtp_assemble_tokens")
@@ -318,10 +417,10 @@ def bert_embed(ids, word, position):
     B, L = ids.shape
     ids = ids.contiguous()
     d = word.shape[1]
-    out = torch.empty(B, L, d, dtype=torch.float32, device=word.device)
+    out = empty((B, L, d), torch.float32, word.device)
     _check(_call("madtp_bert_embed", _ptr(ids, torch.int64, "ids"), _ptr(word, torch.float32, "word"),
                                    _ptr(position, torch.float32, "position"), _ptr(out), B, L, d, word.shape[0],
-                                   _stream()), "madtp_bert_embed")
+                                   position.shape[0], _stream()), "madtp_bert_embed")
     return out
 
 
@@ -392,10 +491,11 @@ def lm_nll(logits, labels=None, label_smoothing=0.0):
 
 
 def cross_tc_supported(Lq, Nk):
-    return Lq <= 128 and Nk <= 256
+    return Lq <= 128
 
 
-def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_bias=None, key_mask=None):
+def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_bias=None, key_mask=None, lq_dev=None,
+                  nk_dev=None):
     """Tensor-core cross-attention (value lane). q16 [B,Lq,H*64] fp16 view of a row-major matrix (batch stride =
     Lq * row stride). keys_per_batch = P > 0 (a multiple of 8, default: Nk rounded up): k16 [B,Nk,H*64] fp16 view with
     batch stride P rows, vt16 [H*64, >= B*P] fp16 (V^T, keys of sequence b at columns b*P ..). keys_per_batch = 0:
@@ -420,7 +520,7 @@ def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_b
     st = _call("madtp_attn_cross_tc", _ptr(q16, torch.float16, "q"), q16.stride(1), _ptr(k16, torch.float16, "k"), ldk,
                per, _ptr(vt16, torch.float16, "vt"), vt16.stride(0), per, _ptr(v_bias, torch.float32, "v_bias"), B, H, Lq,
                Nk, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
-               bso, _stream())
+               bso, _dyn(lq_dev), _dyn(nk_dev), _stream())
     _check(st, "madtp_attn_cross_tc")
 
 
@@ -436,74 +536,80 @@ def attn_stats(q, k, H, scale, stats, col_part, cls_attn, *, key_mask=None, caus
     _check(st, "madtp_attn_stats")
 
 
-def token_colstats(token_att, n, T, divisor):
-    """token_att: [B, rows>=n, ld] fp32 view whose row j is prunable token j. Returns (col_max, col_sum) [B, T]."""
+def token_colstats(token_att, n, T, divisor, *, n_dev=None, n_sub=0):
+    """token_att: [B, rows>=n, ld] fp32 view whose row j is prunable token j. Returns (col_max, col_sum) [B, T].
+    n_dev: device-resident tokens per sequence INCLUDING the n_sub leading tokens the view skips (packed sequences)."""
     B = token_att.shape[0]
     ld, bs = token_att.stride(1), token_att.stride(0)
-    cm = torch.empty(B, T, dtype=torch.float32, device=token_att.device)
-    cs = torch.empty_like(cm)
+    cm = empty((B, T), torch.float32, token_att.device)
+    cs = empty((B, T), torch.float32, token_att.device)
     _check(_call("madtp_token_colstats", _ptr(token_att, torch.float32, "token_att"), ld, bs, B, n, T, float(divisor),
-                                       _ptr(cm), _ptr(cs), _stream()), "madtp_token_colstats")
+                                       _ptr(cm), _ptr(cs), _dyn(n_dev), int(n_sub), _stream()), "madtp_token_colstats")
     return cm, cs
 
 
-def query_sdft(token_att, col_max, col_sum, ft, n, T, divisor, sd_ft, accumulate):
+def query_sdft(token_att, col_max, col_sum, ft, n, T, divisor, sd_ft, accumulate, *, n_dev=None, n_sub=0):
     B = token_att.shape[0]
     d = ft.shape[-1]
     st = _call("madtp_query_sdft", _ptr(token_att, torch.float32, "token_att"), token_att.stride(1), token_att.stride(0),
                                  _ptr(col_max), _ptr(col_sum), _ptr(ft, torch.float32, "ft"), ft.stride(1),
                                  ft.stride(0), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
-                                 1 if accumulate else 0, _stream())
+                                 1 if accumulate else 0, _dyn(n_dev), int(n_sub), _stream())
     _check(st, "madtp_query_sdft")
 
 
-def dtp_score(col_part, cls_attn, token_att, n, T, temperature):
-    """Returns (score [B,n], threshold [B], count [B] int32, topk [1] int32)."""
+def dtp_score(col_part, cls_attn, token_att, n, T, temperature, *, n_dev=None, parts_tile=0):
+    """Returns (score [B,n], threshold [B], count [B] int32, topk [1] int32). n_dev: device-resident N = n + 1
+    (packed buffers); parts_tile: query-tile height of the col_part producer (n_parts = ceil(N / parts_tile)), 0 = fixed."""
     B, n_parts, N = col_part.shape
     assert N == n + 1
     dev = col_part.device
-    score = torch.empty(B, n, dtype=torch.float32, device=dev)
-    thr = torch.empty(B, dtype=torch.float32, device=dev)
-    cnt = torch.empty(B, dtype=torch.int32, device=dev)
-    topk = torch.zeros(1, dtype=torch.int32, device=dev)
+    score = empty((B, n), torch.float32, dev)
+    thr = empty((B,), torch.float32, dev)
+    cnt = empty((B,), torch.int32, dev)
+    topk = zeros((1,), torch.int32, dev)
     st = _call("madtp_dtp_score", B, n, T, _ptr(col_part, torch.float32, "col_part"), n_parts,
                                 _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(token_att, torch.float32, "token_att"),
                                 token_att.stride(1), token_att.stride(0), float(temperature), _ptr(score), _ptr(thr),
-                                _ptr(cnt), _ptr(topk), _stream())
+                                _ptr(cnt), _ptr(topk), _dyn(n_dev), int(parts_tile), _stream())
     _check(st, "madtp_dtp_score")
     return score, thr, cnt, topk
 
 
-def dtp_select(score, topk, *, mask_mode=0, mask_in=None, max_keep=0):
+def dtp_select(score, topk, *, mask_mode=0, mask_in=None, max_keep=0, n_dev=None, n_out=None, k_out=None):
+    """n_dev / n_out / k_out: device-resident lengths -- *n_dev = n + 1 in, the next layer's length and the trajectory
+    entry out (see madtp_dtp_select)."""
     B, n = score.shape
     dev = score.device
-    keep = torch.empty(B, n, dtype=torch.uint8, device=dev)
-    dst = torch.empty(B, n, dtype=torch.int32, device=dev)
-    tail_w = torch.empty(B, n, dtype=torch.float32, device=dev)
-    tail_idx = torch.empty(B, n, dtype=torch.int32, device=dev)
+    keep = empty((B, n), torch.uint8, dev)
+    dst = empty((B, n), torch.int32, dev)
+    tail_w = empty((B, n), torch.float32, dev)
+    tail_idx = empty((B, n), torch.int32, dev)
     mask_out = None
     if mask_mode:
         if mask_in is None or not mask_in.is_contiguous() or mask_in.numel() != B * (n + 1):
             raise RuntimeError("madtp_b200.dtp_select: mask_in must be contiguous [B, n+1]")
-        mask_out = torch.empty(B, n + 1, dtype=torch.float32, device=dev)
+        mask_out = empty((B, n + 1), torch.float32, dev)
     st = _call("madtp_dtp_select", B, n, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"), _ptr(keep),
                                  _ptr(dst), _ptr(tail_w), _ptr(tail_idx), mask_mode,
-                                 _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), int(max_keep), _stream())
+                                 _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), int(max_keep), _dyn(n_dev),
+                                 _dyn(n_out), _dyn(k_out), _stream())
     _check(st, "madtp_dtp_select")
     return keep, dst, tail_w, tail_idx, mask_out
 
 
-def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0, want_f16=False):
-    """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d] (and its fp16 copy if want_f16)."""
+def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0, want_f16=False, n_dev=None):
+    """x: [B, n+1, d] fp32 (unit inner stride, dense rows). Returns [B, k+2, d] (and its fp16 copy if want_f16).
+    n_dev: device-resident N = n + 1; pass k = n - 1 so that the output has the capacity of the input."""
     B, N, d = x.shape
     if x.stride(2) != 1 or x.stride(1) != d:
         raise RuntimeError("madtp_b200.dtp_gather: x rows must be dense")
-    out = torch.empty(B, k + 2, d, dtype=torch.float32, device=x.device)
-    out16 = torch.empty(B, k + 2, d, dtype=torch.float16, device=x.device) if want_f16 else None
+    out = empty((B, k + 2, d), torch.float32, x.device)
+    out16 = empty((B, k + 2, d), torch.float16, x.device) if want_f16 else None
     st = _call("madtp_dtp_gather", B, N - 1, d, _ptr(x, torch.float32, "x"), x.stride(0), _ptr(topk, torch.int32, "topk"),
                                  _ptr(dst, torch.int32, "dst"), _ptr(tail_w, torch.float32, "tail_w"),
                                  _ptr(tail_idx, torch.int32, "tail_idx"), _ptr(out), out.stride(0), _ptr(out16),
-                                 int(max_keep), _stream())
+                                 int(max_keep), _dyn(n_dev), _stream())
     _check(st, "madtp_dtp_gather")
     return (out, out16) if want_f16 else out
 
@@ -521,7 +627,7 @@ def gather_rows(x, idx):
 
 
 
-def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
+def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0, n_dev=None):
     """Fused q|k|v projection for the tensor-core attention: returns fp16 planes (qk_hi, qk_lo [M, 2*heads*64] of
     QK_PLANE_SCALE * value, vt_hi, vt_lo [B*heads*64, n_pad] of V_PLANE_SCALE * value) -- see madtp_gemm_qkv in
     include/madtp_b200.h."""
@@ -529,20 +635,20 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0):
     B = M // n_tok
     n_pad = (n_tok + 7) // 8 * 8
     dev = a_hi.device
-    qk_hi = torch.empty(M, 2 * heads * 64, dtype=torch.float16, device=dev)
-    qk_lo = torch.empty_like(qk_hi)
-    vt_hi = torch.empty(B * heads * 64, n_pad, dtype=torch.float16, device=dev)
-    vt_lo = torch.empty_like(vt_hi)
+    qk_hi = empty((M, 2 * heads * 64), torch.float16, dev)
+    qk_lo = empty((M, 2 * heads * 64), torch.float16, dev)
+    vt_hi = empty((B * heads * 64, n_pad), torch.float16, dev)
+    vt_lo = empty((B * heads * 64, n_pad), torch.float16, dev)
     st = _call("madtp_gemm_qkv", _ptr(a_hi, torch.float16, "a_hi"), _ptr(a_lo, torch.float16, "a_lo"),
                _rowmajor(a_hi, "a_hi"), _ptr(w_hi, torch.float16, "w_hi"), _ptr(w_lo, torch.float16, "w_lo"),
                _rowmajor(w_hi, "w_hi"), _ptr(bias, torch.float32, "bias"), float(alpha), M, K, n_tok, heads, _ptr(qk_hi),
-               _ptr(qk_lo), qk_hi.stride(0), _ptr(vt_hi), _ptr(vt_lo), n_pad, _stream())
+               _ptr(qk_lo), qk_hi.stride(0), _ptr(vt_hi), _ptr(vt_lo), n_pad, _dyn(n_dev), _stream())
     _check(st, "madtp_gemm_qkv")
     return qk_hi, qk_lo, vt_hi, vt_lo
 
 
 def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None, cls_p=None,
-                cls_tile_max=None):
+                cls_tile_max=None, n_dev=None):
     """cls_p [B,H,N] / cls_tile_max [B,H,ceil(N/64)] fp32 (both or neither): the CLS query row for attn_tc_stats."""
     ldo, bso = _qkv_strides(out_f16, "out_f16")
     st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
@@ -550,21 +656,22 @@ def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, ou
                vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
                _ptr(out_norm, torch.float32, "out_norm"), _ptr(cls_p, torch.float32, "cls_p"),
-               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _stream())
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _dyn(n_dev), _stream())
     _check(st, "madtp_attn_tc_fwd")
 
 
 def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, cls_p, cls_tile_max, *,
-                  key_mask=None):
+                  key_mask=None, n_dev=None):
     st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
                _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
                _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(cls_p, torch.float32, "cls_p"),
-               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _stream())
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _dyn(n_dev), _stream())
     _check(st, "madtp_attn_tc_stats")
 
 
-def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T, divisor, sd_ft, accumulate):
+def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T, divisor, sd_ft, accumulate, *,
+                  n_dev=None):
     """Tensor-core sd_ft: x2d is the dense fp32 matrix [rows, d] of ALL token rows (token j of batch b at row
     b*row_stride + first_row + j)."""
     B = token_att.shape[0]
@@ -574,11 +681,12 @@ def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T,
     st = _call("madtp_query_sdft_tc", _ptr(token_att, torch.float32, "token_att"), token_att.stride(1),
                token_att.stride(0), _ptr(col_max), _ptr(col_sum), _ptr(x2d, torch.float32, "x"), x2d.shape[0],
                int(row_stride), int(first_row), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
-               1 if accumulate else 0, _stream())
+               1 if accumulate else 0, _dyn(n_dev), _stream())
     _check(st, "madtp_query_sdft_tc")
 
 
-def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, cls_attn=None, causal=False):
+def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, cls_attn=None, causal=False,
+                    l_dev=None):
     """Self-attention of a short sequence (L <= 64) with optional fused pruning statistics (col_sum, cls_attn [B, L])."""
     B, Ltok, _ = q.shape
     ldq, bsq = _qkv_strides(q, "q")
@@ -588,10 +696,10 @@ def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, 
     if key_mask is not None and (not key_mask.is_contiguous() or key_mask.numel() != B * Ltok):
         raise RuntimeError("madtp_b200.attn_small_self: key_mask must be contiguous [B, L]")
     # the scratch tensor stays referenced until the launch has been enqueued (stream-ordered reuse after that is safe)
-    scratch = None if col_sum is None else torch.empty(B * H * Ltok * (Ltok + 1), dtype=torch.float32, device=q.device)
+    scratch = None if col_sum is None else empty((B * H * Ltok * (Ltok + 1),), torch.float32, q.device)
     st = _call("madtp_attn_small_self", _ptr(q, torch.float32, "q"), ldq, bsq, _ptr(k, torch.float32, "k"), ldk, bsk,
                _ptr(v, torch.float32, "v"), ldv, bsv, B, H, Ltok, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(col_sum), _ptr(cls_attn), _ptr(scratch),
-               1 if causal else 0, _stream())
+               1 if causal else 0, _dyn(l_dev), _stream())
     _check(st, "madtp_attn_small_self")
     del scratch

@@ -67,6 +67,42 @@ class BLIP_NLVR(nn.Module):
         hs = cfg.hidden_size
         self.cls_head = nn.Sequential(nn.Linear(hs, hs), nn.ReLU(), nn.Linear(hs, 2))
         self._cache = Fn.WeightCache()
+        self.record_states = False      # keep fp32 copies of image_embeds / last_hidden_state in self.last (tests)
+        self._graphs = None             # shape key -> graphs.GraphedCall, when enable_cuda_graphs(True)
+        self.last = {}
+
+    def enable_cuda_graphs(self, enable: bool = True):
+        """Capture the pruned forward (device-resident lengths) in a CUDA graph per input shape and temperature and
+        replay it on later calls. The graph bakes in the addresses of the weights and of their GEMM-ready copies: call
+        `reset_cuda_graphs()` after loading or changing weights."""
+        self._graphs = {} if enable else None
+        return self
+
+    def reset_cuda_graphs(self):
+        if self._graphs is not None:
+            self._graphs = {}
+
+    def _cls_head(self, hidden_state):
+        from . import _lib as L
+        l0, l2 = self.cls_head[0], self.cls_head[2]
+        w0 = self._cache.get("c0", [l0.weight, l0.bias], lambda: Fn.PreparedLinear(l0.weight, l0.bias, f32=True))
+        w2 = self._cache.get("c2", [l2.weight, l2.bias], lambda: Fn.PreparedLinear(l2.weight, l2.bias, f32=True))
+        return Fn.linear_f32(Fn.linear_f32(hidden_state, w0, act=L.ACT_RELU), w2)
+
+    def _forward_device(self, image, input_ids, attention_mask, temperature):
+        """blip_nlvr.py:63-81 with device-resident lengths from the first ViT layer to the logits: nothing is read
+        back, every launch argument is data-independent. Returns (logits [P, 2], [image trajectory, text trajectory])."""
+        from . import _lib as L
+        enc_id = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        input_ids[:, 0] = enc_id                                                            # blip_nlvr.py:69
+        keep = self.record_states
+        enc = self.visual_encoder.forward_device(image, self.space_dict, temperature, pack_groups=2, keep_f32=keep)
+        h, sd_txt_ft, traj, l_dev = self.text_encoder.forward_device(input_ids, attention_mask, enc, self.space_dict,
+                                                                     temperature)
+        B, Lcap, d = h.shape
+        hidden_state = L.take_token(h.view(B * Lcap, d), B, Lcap, 0, n_dev=l_dev)           # last_hidden_state[:, 0, :]
+        self.last = _LazyStates(enc, h, traj, sd_txt_ft) if keep else {"sd_img_ft": enc.sd_ft, "sd_txt_ft": sd_txt_ft}
+        return self._cls_head(hidden_state), [enc.traj, traj]
 
     def _tokenize(self, text, device):
         if hasattr(text, "input_ids"):
@@ -82,6 +118,21 @@ class BLIP_NLVR(nn.Module):
     def forward(self, image, text, targets, temperature=0, train=True):
         if train:
             raise NotImplementedError("madtp_b200 implements the evaluation forward (train=False) only")
+        from .vit import device_lengths_enabled
+        if temperature > 0 and device_lengths_enabled():
+            Fn.require_cuda(image, "image")
+            input_ids, attention_mask = self._tokenize(text, image.device)
+            if input_ids.shape[1] <= 64 and image.shape[0] == 2 * input_ids.shape[0]:
+                if self._graphs is None:
+                    return self._forward_device(image.contiguous(), input_ids, attention_mask, float(temperature))[0]
+                from .graphs import GraphedCall
+                key = (tuple(image.shape), tuple(input_ids.shape), float(temperature))
+                g = self._graphs.get(key)
+                if g is None:
+                    t = float(temperature)
+                    g = self._graphs[key] = GraphedCall(lambda im, ids, m: self._forward_device(im, ids, m, t),
+                                                        [image.contiguous(), input_ids, attention_mask])
+                return g(image, input_ids, attention_mask)
         image_embeds, sd_img_ft = self.visual_encoder(image, space_dict=self.space_dict, temperature=temperature)
         P = targets.size(0) if torch.is_tensor(targets) else int(targets)
         image0_embeds, image1_embeds = image_embeds[:P], image_embeds[P:]                   # blip_nlvr.py:67
@@ -94,13 +145,29 @@ class BLIP_NLVR(nn.Module):
                                               encoder_attention_mask=None, return_dict=True,
                                               space_dict=self.space_dict, temperature=temperature)
         hidden_state = output.last_hidden_state[:, 0, :].contiguous()
-        l0, l2 = self.cls_head[0], self.cls_head[2]
-        w0 = self._cache.get("c0", [l0.weight, l0.bias], lambda: Fn.PreparedLinear(l0.weight, l0.bias, f32=True))
-        w2 = self._cache.get("c2", [l2.weight, l2.bias], lambda: Fn.PreparedLinear(l2.weight, l2.bias, f32=True))
-        from . import _lib as L
         self.last = {"image_embeds": image_embeds, "last_hidden_state": output.last_hidden_state,
                      "sd_img_ft": sd_img_ft, "sd_txt_ft": sd_txt_ft}
-        return Fn.linear_f32(Fn.linear_f32(hidden_state, w0, act=L.ACT_RELU), w2)
+        return self._cls_head(hidden_state)
+
+
+class _LazyStates:
+    """`model.last` of a device-resident-length forward: narrowed views materialise on first access (one read-back)."""
+
+    def __init__(self, enc, h, traj, sd_txt_ft):
+        self._enc, self._h, self._traj, self._sd_txt = enc, h, traj, sd_txt_ft
+
+    def __getitem__(self, key):
+        if key == "image_embeds":
+            return self._enc.narrowed()
+        if key == "last_hidden_state":
+            B, _, d = self._h.shape
+            n = self._traj.host()[0][-1]
+            return self._h.reshape(-1)[:B * n * d].view(B, n, d)
+        if key == "sd_img_ft":
+            return self._enc.sd_ft
+        if key == "sd_txt_ft":
+            return self._sd_txt
+        raise KeyError(key)
 
 
 def load_state_dict_from_checkpoint(model: BLIP_NLVR, state_dict):

@@ -40,6 +40,8 @@ struct AttnTcArgs {
   float* cls_attn;                       // [B, N]
   float* cls_p;                          // [B, H, N] CLS query row: 256 * exp(logit - max of its 64-key tile)
   float* cls_tile_max;                   // [B, H, ceil(N/64)] those maxima (running row maximum at each key tile)
+  const int* n_dev;                      // dynamic N read on the device (N above is then the capacity): the sequences are
+                                         // packed with the dynamic N in every buffer, V^T keeps its pitch ld_vt
 };
 int launch_attn_fwd_tc(const AttnTcArgs& a, cudaStream_t stream);
 int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream);
@@ -57,13 +59,16 @@ struct CrossTcArgs {
   float scale;
   const float* key_mask;                 // additive [B, Nk] or nullptr
   __half* out_f16; long long ldo, bso;
+  const int* lq_dev;                     // dynamic Lq (queries and output packed with it)
+  const int* nk_dev;                     // dynamic Nk; per-sequence pitches become Nk rounded up to 8 (when not 0)
 };
 int launch_cross_attn_tc(const CrossTcArgs& a, cudaStream_t stream);
 
 int launch_attn_fwd(const AttnArgs& a, cudaStream_t stream);
 // Short-sequence self-attention (small_attn.cu): Nq == Nk <= 64, context + (optionally) col_sum[B,L] =
 // sum_{i>=1} max_h P and cls_attn[B,L]; scratch holds B*H*L*(L+1) floats when statistics are requested.
-int launch_small_self_attn(const AttnArgs& a, float* col_sum, float* cls_attn, float* scratch, cudaStream_t stream);
+int launch_small_self_attn(const AttnArgs& a, float* col_sum, float* cls_attn, float* scratch, const int* n_dev,
+                           cudaStream_t stream);
 int launch_attn_stats(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace madtp

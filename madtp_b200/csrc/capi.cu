@@ -53,8 +53,12 @@ long long madtp_launch_count(void) { return g_launches.load(std::memory_order_re
 
 int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, const void* b, const void* b_lo,
                int64_t ldb, void* c, int64_t ldc, int c_f16, const float* bias, const float* residual, int64_t ldr,
-               int act, float alpha, int M, int N, int K, void* stream) {
+               int act, float alpha, int M, int N, int K, const int32_t* m_dev, int m_mult, const int32_t* n_dev,
+               int n_mult, void* stream) {
   GemmEpilogue ep = {};
+  ep.m_dev = m_dev; ep.m_mult = m_mult;
+  ep.n_dev = n_dev; ep.n_mult = n_mult;
+  MADTP_CHECK_ARG((m_dev == nullptr || m_mult > 0) && (n_dev == nullptr || n_mult > 0), "gemm: m_mult / n_mult must be > 0");
   ep.c = c;
   ep.ldc = ldc;
   ep.c_f16 = c_f16;
@@ -68,8 +72,11 @@ int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, cons
 }
 
 int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* gamma, const float* beta, float eps,
-                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, void* stream) {
+                    float* y_f32, void* y_hi, void* y_lo, void* y_f16, void* x_hi, void* x_lo, const int32_t* n_dev,
+                    int n_mult, void* stream) {
   LayerNormArgs a;
+  a.n_dev = n_dev;
+  a.n_mult = n_mult;
   a.x = x;
   a.ldx = ldx;
   a.rows = rows;
@@ -84,6 +91,20 @@ int madtp_layernorm(const float* x, int64_t ldx, int rows, int d, const float* g
   a.x_hi = static_cast<__half*>(x_hi);
   a.x_lo = static_cast<__half*>(x_lo);
   return counted(launch_layernorm(a, as_stream(stream)), rows > 0 ? 1 : 0);
+}
+
+int madtp_layernorm_pack(const float* x, int B, int N, int d, const float* gamma, const float* beta, float eps,
+                         float* y_f32, void* y16, int per_group, int64_t group_stride, int32_t* p_out_dev,
+                         const int32_t* n_dev, void* stream) {
+  LayerNormPackArgs a;
+  a.x = x; a.B = B; a.N = N; a.d = d; a.n_dev = n_dev;
+  a.gamma = gamma; a.beta = beta; a.eps = eps;
+  a.y_f32 = y_f32; a.y16 = static_cast<__half*>(y16);
+  a.per_group = per_group; a.group_stride = group_stride; a.p_out = p_out_dev;
+  return counted(launch_layernorm_pack(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+int madtp_take_token(const float* x, int B, int N, int token, int d, float* out, const int32_t* n_dev, void* stream) {
+  return counted(launch_take_token(x, B, N, n_dev, token, d, out, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
 int madtp_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
@@ -104,8 +125,8 @@ int madtp_assemble_tokens(const float* patches, const float* cls, const float* p
   return counted(launch_assemble_tokens(patches, cls, pos, x, B, n, d, as_stream(stream)), B > 0 ? 1 : 0);
 }
 int madtp_bert_embed(const int64_t* ids, const float* word, const float* position, float* out, int B, int L, int d,
-                     int vocab, void* stream) {
-  return counted(launch_bert_embed(reinterpret_cast<const long long*>(ids), word, position, out, B, L, d, vocab,
+                     int vocab, int n_pos, void* stream) {
+  return counted(launch_bert_embed(reinterpret_cast<const long long*>(ids), word, position, out, B, L, d, vocab, n_pos,
                                    as_stream(stream)),
                  B > 0 ? 1 : 0);
 }
@@ -156,7 +177,7 @@ int madtp_attn_stats(const float* q, int64_t ldq, int64_t bsq, const float* k, i
 int madtp_attn_small_self(const float* q, int64_t ldq, int64_t bsq, const float* k, int64_t ldk, int64_t bsk,
                           const float* v, int64_t ldv, int64_t bsv, int B, int H, int L, float scale,
                           const float* key_mask, void* out_f16, int64_t ldo, int64_t bso, float* col_sum,
-                          float* cls_attn, float* scratch, int causal, void* stream) {
+                          float* cls_attn, float* scratch, int causal, const int32_t* l_dev, void* stream) {
   AttnArgs a = {};
   a.q = q; a.ldq = ldq; a.bsq = bsq;
   a.k = k; a.ldk = ldk; a.bsk = bsk;
@@ -166,35 +187,38 @@ int madtp_attn_small_self(const float* q, int64_t ldq, int64_t bsq, const float*
   a.key_mask = key_mask;
   a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
   a.causal = causal;
-  return counted(launch_small_self_attn(a, col_sum, cls_attn, scratch, as_stream(stream)),
+  return counted(launch_small_self_attn(a, col_sum, cls_attn, scratch, l_dev, as_stream(stream)),
                  B > 0 ? (col_sum ? 2 : 1) : 0);
 }
 
 int madtp_token_colstats(const float* token_att, int64_t ld_ta, int64_t bs_ta, int B, int n, int T, float divisor,
-                         float* col_max, float* col_sum, void* stream) {
-  return counted(launch_token_colstats(token_att, ld_ta, bs_ta, B, n, T, divisor, col_max, col_sum, as_stream(stream)),
+                         float* col_max, float* col_sum, const int32_t* n_dev, int n_sub, void* stream) {
+  return counted(launch_token_colstats(token_att, ld_ta, bs_ta, B, n, T, divisor, col_max, col_sum, n_dev, n_sub,
+                                       as_stream(stream)),
                  B > 0 ? 1 : 0);
 }
 int madtp_query_sdft(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
                      const float* ft, int64_t ld_ft, int64_t bs_ft, int B, int n, int T, int d, float divisor,
-                     float* sd_ft, int accumulate, void* stream) {
+                     float* sd_ft, int accumulate, const int32_t* n_dev, int n_sub, void* stream) {
   return counted(launch_query_sdft(token_att, ld_ta, bs_ta, col_max, col_sum, ft, ld_ft, bs_ft, B, n, T, d, divisor,
-                                   sd_ft, accumulate, as_stream(stream)),
+                                   sd_ft, accumulate, n_dev, n_sub, as_stream(stream)),
                  B > 0 ? 1 : 0);
 }
 
 int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max, const float* col_sum,
                         const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
-                        float divisor, float* sd_ft, int accumulate, void* stream) {
+                        float divisor, float* sd_ft, int accumulate, const int32_t* n_dev, void* stream) {
   return counted(launch_query_sdft_tc(token_att, ld_ta, bs_ta, col_max, col_sum, x, x_rows, row_stride,
-                                      first_row, B, n, T, d, divisor, sd_ft, accumulate, as_stream(stream)),
+                                      first_row, B, n, T, d, divisor, sd_ft, accumulate, n_dev, as_stream(stream)),
                  B > 0 ? 1 : 0);
 }
 
 int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
                     const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
-                    float* threshold, int32_t* count, int32_t* topk, void* stream) {
+                    float* threshold, int32_t* count, int32_t* topk, const int32_t* n_dev, int parts_tile,
+                    void* stream) {
   DtpScoreArgs a;
+  a.n_dev = n_dev; a.parts_tile = parts_tile;
   a.B = B; a.n = n; a.T = T;
   a.col_part = col_part; a.n_parts = n_parts;
   a.cls_attn = cls_attn;
@@ -206,8 +230,10 @@ int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, con
 
 int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint8_t* keep, int32_t* dst, float* tail_w,
                      int32_t* tail_idx, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
-                     void* stream) {
+                     const int32_t* n_dev, int32_t* n_out_dev, int32_t* k_out_dev, void* stream) {
   DtpSelectArgs a;
+  a.n_dev = n_dev; a.n_out = n_out_dev; a.k_out = k_out_dev;
+  MADTP_CHECK_ARG(n_dev == nullptr || n_out_dev != nullptr, "dtp_select: n_dev needs n_out_dev");
   a.B = B; a.n = n;
   a.score = score; a.topk = topk;
   a.keep = keep; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
@@ -218,8 +244,9 @@ int madtp_dtp_select(int B, int n, const float* score, const int32_t* topk, uint
 
 int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int32_t* topk, const int32_t* dst,
                      const float* tail_w, const int32_t* tail_idx, float* out, int64_t bso, void* out_f16, int max_keep,
-                     void* stream) {
+                     const int32_t* n_dev, void* stream) {
   DtpGatherArgs a;
+  a.n_dev = n_dev;
   a.B = B; a.n = n; a.d = d;
   a.x = x; a.bsx = bsx;
   a.topk = topk; a.dst = dst; a.tail_w = tail_w; a.tail_idx = tail_idx;
@@ -231,17 +258,18 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
 
 int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
                    const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi, void* qk_lo,
-                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, void* stream) {
+                   int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, const int32_t* n_dev, void* stream) {
   return counted(launch_gemm_qkv(a_hi, a_lo, lda, w_hi, w_lo, ldb, bias, alpha, M, K, n_tok, heads, qk_hi, qk_lo, ld_qk, vt_hi,
-                                 vt_lo, ld_vt, as_stream(stream)),
+                                 vt_lo, ld_vt, n_dev, as_stream(stream)),
                  M > 0 ? 1 : 0);
 }
 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      void* stream) {
+                      const int32_t* n_dev, void* stream) {
   AttnTcArgs a = {};
+  a.n_dev = n_dev;
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.vt_hi = static_cast<const __half*>(vt_hi); a.vt_lo = static_cast<const __half*>(vt_lo); a.ld_vt = ld_vt;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
@@ -253,8 +281,10 @@ int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const
 
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, void* stream) {
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max,
+                        const int32_t* n_dev, void* stream) {
   AttnTcArgs a = {};
+  a.n_dev = n_dev;
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.row_lse = const_cast<float*>(row_lse); a.out_norm = const_cast<float*>(out_norm);
@@ -266,8 +296,9 @@ int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int
 int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
                         const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
                         int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
-                        void* stream) {
+                        const int32_t* lq_dev, const int32_t* nk_dev, void* stream) {
   CrossTcArgs a = {};
+  a.lq_dev = lq_dev; a.nk_dev = nk_dev;
   a.q = static_cast<const __half*>(q_f16); a.ldq = ldq;
   a.k = static_cast<const __half*>(k_f16); a.ldk = ldk; a.k_rows_per_batch = k_rows_per_batch;
   a.vt = static_cast<const __half*>(vt_f16); a.ld_vt = ld_vt; a.vt_cols_per_batch = vt_cols_per_batch;

@@ -48,9 +48,15 @@ __device__ __forceinline__ int block_sum_i(int v, int* red) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 token_colstats_kernel(const float* __restrict__ ta, long long ld, long long bs, int n, int T, float divisor,
-                      float* __restrict__ col_max, float* __restrict__ col_sum) {
+                      float* __restrict__ col_max, float* __restrict__ col_sum, const int* __restrict__ n_dev,
+                      int n_sub) {
   __shared__ float smax[8][32];
   __shared__ float ssum[8][32];
+  if (n_dev != nullptr) {
+    const int N = __ldg(n_dev);
+    n = min(n, N - n_sub);
+    bs = N * ld;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * 32 + lane, b = blockIdx.y;
   const float* base = ta + b * bs;
@@ -82,12 +88,13 @@ token_colstats_kernel(const float* __restrict__ ta, long long ld, long long bs, 
 }
 
 int launch_token_colstats(const float* token_att, long long ld_ta, long long bs_ta, int B, int n, int T, float divisor,
-                          float* col_max, float* col_sum, cudaStream_t stream) {
+                          float* col_max, float* col_sum, const int* n_dev, int n_sub, cudaStream_t stream) {
   MADTP_CHECK_ARG(token_att && col_max && col_sum, "token_colstats: null pointer");
   MADTP_CHECK_ARG(B >= 0 && n > 0 && T > 0 && divisor > 0.f && B <= 65535, "token_colstats: bad shape");
   if (B == 0) return kOk;
   dim3 grid((T + 31) / 32, B);
-  token_colstats_kernel<<<grid, 256, 0, stream>>>(token_att, ld_ta, bs_ta, n, T, divisor, col_max, col_sum);
+  token_colstats_kernel<<<grid, 256, 0, stream>>>(token_att, ld_ta, bs_ta, n, T, divisor, col_max, col_sum, n_dev,
+                                                  n_sub);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }
@@ -99,7 +106,14 @@ int launch_token_colstats(const float* token_att, long long ld_ta, long long bs_
 __global__ void __launch_bounds__(256)
 query_sdft_kernel(const float* __restrict__ ta, long long ld_ta, long long bs_ta, const float* __restrict__ col_max,
                   const float* __restrict__ col_sum, const float* __restrict__ x, long long ldx, long long bsx, int n,
-                  int T, int d, float divisor, float* __restrict__ out, int accumulate) {
+                  int T, int d, float divisor, float* __restrict__ out, int accumulate,
+                  const int* __restrict__ n_dev, int n_sub) {
+  if (n_dev != nullptr) {
+    const int N = __ldg(n_dev);
+    n = min(n, N - n_sub);
+    bs_ta = N * ld_ta;
+    bsx = N * ldx;
+  }
   __shared__ float Ws[32][128 + 4];
   __shared__ float Xs[32][64];
   __shared__ float cmx[128], cinv[128];
@@ -164,14 +178,14 @@ query_sdft_kernel(const float* __restrict__ ta, long long ld_ta, long long bs_ta
 
 int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
                       const float* col_sum, const float* x, long long ldx, long long bsx, int B, int n, int T, int d,
-                      float divisor, float* sd_ft, int accumulate, cudaStream_t stream) {
+                      float divisor, float* sd_ft, int accumulate, const int* n_dev, int n_sub, cudaStream_t stream) {
   MADTP_CHECK_ARG(token_att && col_max && col_sum && x && sd_ft, "query_sdft: null pointer");
   MADTP_CHECK_ARG(B >= 0 && n > 0 && T > 0 && T <= 128 && d % 4 == 0 && ldx % 4 == 0 && bsx % 4 == 0 && B <= 65535,
                   "query_sdft: unsupported shape (T=%d must be <= 128, d=%d multiple of 4)", T, d);
   if (B == 0) return kOk;
   dim3 grid((d + 63) / 64, B);
   query_sdft_kernel<<<grid, 256, 0, stream>>>(token_att, ld_ta, bs_ta, col_max, col_sum, x, ldx, bsx, n, T, d, divisor,
-                                              sd_ft, accumulate);
+                                              sd_ft, accumulate, n_dev, n_sub);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }
@@ -191,6 +205,12 @@ dtp_score_kernel(DtpScoreArgs a) {
   __shared__ float thr_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.n_dev != nullptr) {          // device-resident token count: packed sequences
+    const int Nd = min(a.n + 1, __ldg(a.n_dev));
+    a.n = Nd - 1;
+    a.bs_ta = Nd * a.ld_ta;
+    if (a.parts_tile > 0) a.n_parts = (Nd + a.parts_tile - 1) / a.parts_tile;
+  }
   const int b = blockIdx.x, n = a.n, N = n + 1;
   const float* ta = a.token_att + b * a.bs_ta;
 
@@ -308,10 +328,18 @@ dtp_select_kernel(DtpSelectArgs a) {
   __shared__ int wsum[8];
   __shared__ double red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x, n = a.n;
+  const bool dyn = a.n_dev != nullptr;
+  const int b = blockIdx.x, n = dyn ? min(a.n, __ldg(a.n_dev) - 1) : a.n;
   const int k_in = *a.topk;
   const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);   // reference early-out: nothing is pruned
   const int k = identity ? n : k_in;
+  // packed mask rows: the input holds n + 1 entries per sequence; the output k + 2 in dynamic mode (the next layer's
+  // packed length), n + 1 (worst case, narrowed by the host) otherwise
+  const int mo_pitch = dyn ? (identity ? n + 1 : k + 2) : a.n + 1;
+  if (dyn && b == 0 && tid == 0) {
+    if (a.n_out) *a.n_out = identity ? n + 1 : k + 2;
+    if (a.k_out) *a.k_out = identity ? -1 : k;
+  }
 
   for (int j = tid; j < n; j += 256) S[j] = a.score[static_cast<long long>(b) * n + j];
   __syncthreads();
@@ -374,7 +402,7 @@ dtp_select_kernel(DtpSelectArgs a) {
       if (!flags[u]) a.tail_idx[static_cast<long long>(b) * n + (j - run)] = j;  // pruned tokens, ascending
       if (a.mask_mode != 0 && !identity) {
         const float mj = a.mask_in[static_cast<long long>(b) * (n + 1) + 1 + j];
-        float* mo = a.mask_out + static_cast<long long>(b) * (n + 1);
+        float* mo = a.mask_out + static_cast<long long>(b) * mo_pitch;
         if (a.mask_mode == 1) {
           if (R[j] <= k) mo[1 + R[j]] = mj;           // slot r <- mask of the r-th ranked token, r = 0..k
         } else {
@@ -386,7 +414,7 @@ dtp_select_kernel(DtpSelectArgs a) {
     }
   }
   if (a.mask_mode != 0) {
-    float* mo = a.mask_out + static_cast<long long>(b) * (n + 1);
+    float* mo = a.mask_out + static_cast<long long>(b) * mo_pitch;
     const float* mi = a.mask_in + static_cast<long long>(b) * (n + 1);
     if (identity) {
       for (int j = tid; j < n + 1; j += 256) mo[j] = mi[j];
@@ -417,10 +445,15 @@ int launch_dtp_select(const DtpSelectArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 dtp_gather_kernel(DtpGatherArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, n = a.n, d4 = a.d >> 2;
+  const bool dyn = a.n_dev != nullptr;
+  const int b = blockIdx.y, n = dyn ? min(a.n, __ldg(a.n_dev) - 1) : a.n, d4 = a.d >> 2;
   const int k_in = *a.topk;
   const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);
   const int k = identity ? n : k_in;
+  if (dyn) {                       // packed input [B, n + 1, d] and packed output [B, N_out, d]
+    a.bsx = static_cast<long long>(n + 1) * a.d;
+    a.bso = static_cast<long long>(identity ? n + 1 : k + 2) * a.d;
+  }
   const float4* xb = reinterpret_cast<const float4*>(a.x + b * a.bsx);
   float4* ob = reinterpret_cast<float4*>(a.out + b * a.bso);
   uint2* ob16 = a.out_f16 ? reinterpret_cast<uint2*>(a.out_f16 + b * a.bso) : nullptr;

@@ -8,20 +8,25 @@ constexpr int kDtpMaxTokens = 1024;  // n = N-1 prunable tokens per sequence han
 
 // Column (over-token) softmax statistics of token_att / divisor, per codebook entry t:
 //   col_max[b,t] = max_j x[b,j,t],  col_sum[b,t] = sum_j exp(x[b,j,t] - col_max[b,t]),  x = token_att / divisor
+// Dynamic lengths (every launcher below): `n_dev` (may be nullptr) points to the device-resident token count N of the
+// packed sequences INCLUDING the n_sub leading tokens that are not prunable (CLS / [ENC]); the kernel then uses
+// n = N - n_sub, recomputes every per-sequence stride as N * (row pitch), and the host-side n / strides are only
+// capacities.
 int launch_token_colstats(const float* token_att, long long ld_ta, long long bs_ta, int B, int n, int T, float divisor,
-                          float* col_max, float* col_sum, cudaStream_t stream);
+                          float* col_max, float* col_sum, const int* n_dev, int n_sub, cudaStream_t stream);
 
 // Query_model's aggregated feature (reference models/utils.py:174-178):
 //   sd_ft[b,t,:] (+)= sum_j softmax_j(token_att[b,j,t] / divisor) * x[b,j,:]
 int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
                       const float* col_sum, const float* x, long long ldx, long long bsx, int B, int n, int T, int d,
-                      float divisor, float* sd_ft, int accumulate, cudaStream_t stream);
+                      float divisor, float* sd_ft, int accumulate, const int* n_dev, int n_sub, cudaStream_t stream);
 
 // Tensor-core variant (sdft_tc.cu): x is the dense fp32 matrix [x_rows, d]; token j of batch b sits at row
 // b*row_stride + first_row + j.
 int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
                          const float* col_sum, const float* x, long long x_rows, int row_stride, int first_row, int B,
-                         int n, int T, int d, float divisor, float* sd_ft, int accumulate, cudaStream_t stream);
+                         int n, int T, int d, float divisor, float* sd_ft, int accumulate, const int* n_dev,
+                         cudaStream_t stream);
 
 struct DtpScoreArgs {
   int B, n, T;                // n prunable tokens (sequence position 1..n), T codebook entries
@@ -35,6 +40,8 @@ struct DtpScoreArgs {
   float* threshold;           // [B]
   int* count;                 // [B]     #(score > threshold)
   int* topk;                  // [1]     max_b count, must be zeroed before the launch (atomicMax)
+  const int* n_dev;           // dynamic N = n + 1 (see above); sequences are then packed: strides N * ld_ta, N
+  int parts_tile;             // with n_dev: n_parts = ceil(N / parts_tile) (0: n_parts as given)
 };
 int launch_dtp_score(const DtpScoreArgs& a, cudaStream_t stream);
 
@@ -52,6 +59,9 @@ struct DtpSelectArgs {
   const float* mask_in;       // [B, n+1] additive mask incl. position 0
   float* mask_out;            // [B, n+1] worst case; entries [0, k+2) are written
   int max_keep;               // nothing is pruned when k <= max_keep (0 everywhere but CLIP, clip/model.py:220)
+  const int* n_dev;           // dynamic N = n + 1; mask_in is packed [B, N] and mask_out is written packed [B, N_out]
+  int* n_out;                 // with n_dev: receives N_out = k + 2 (or N when nothing is pruned) -- the next layer's N
+  int* k_out;                 // optional trajectory record: k, or -1 when nothing is pruned
 };
 int launch_dtp_select(const DtpSelectArgs& a, cudaStream_t stream);
 
@@ -67,6 +77,7 @@ struct DtpGatherArgs {
   long long bso;              // batch stride of out (elements) -- the caller sizes it with the k it read back
   __half* out_f16;            // optional fp16 copy of out with the same batch stride (operand of the next GEMM)
   int max_keep;
+  const int* n_dev;           // dynamic N = n + 1: x is packed [B, N, d], out is written packed [B, N_out, d]
 };
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);
 

@@ -992,7 +992,8 @@ static int launch_tf32(const void* a, const void* a_lo, long long lda, const voi
 
 int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                     long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi,
-                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, cudaStream_t stream) {
+                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, const int* n_dev,
+                    cudaStream_t stream) {
   MADTP_CHECK_ARG(a_hi && a_lo && w_hi && w_lo && qk_hi && qk_lo && vt_hi && vt_lo, "gemm_qkv: null pointer");
   MADTP_CHECK_ARG(M >= 0 && K > 0 && n_tok > 0 && heads > 0 && M % n_tok == 0, "gemm_qkv: bad shape M=%d n_tok=%d", M,
                   n_tok);
@@ -1015,6 +1016,8 @@ int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const voi
   ep.n_tok = n_tok;
   ep.heads = heads;
   ep.qk_cols = 2 * heads * 64;
+  ep.m_dev = n_dev;              // dynamic tokens per sequence: M = *n_dev * (number of sequences)
+  ep.m_mult = M / n_tok;
   return launch_tf32<256, true>(a_hi, a_lo, lda, w_hi, w_lo, ldb, ep, M, 3 * heads * 64, K, stream);
 }
 

@@ -102,7 +102,8 @@ int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long 
 // Fused q|k|v projection (F16x3) with the split / transposed epilogue described at GemmEpilogue::mode.
 int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                     long long ldb, const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi,
-                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, cudaStream_t stream);
+                    void* qk_lo, long long ld_qk, void* vt_hi, void* vt_lo, long long ld_vt, const int* n_dev,
+                    cudaStream_t stream);
 
 int launch_gemm(int precision, const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo,
                 long long ldb, const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream);

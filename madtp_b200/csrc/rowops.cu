@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(LayerNormArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= a.rows) return;
+  const int rows = a.n_dev ? min(a.rows, __ldg(a.n_dev) * a.n_mult) : a.rows;
+  if (warp >= rows) return;
   const long long row = warp;
   const float4* xin = reinterpret_cast<const float4*>(a.x + row * a.ldx);
   float4 v[V];
@@ -94,6 +95,103 @@ int launch_layernorm(const LayerNormArgs& a, cudaStream_t stream) {
     MADTP_LN_CASE(7) MADTP_LN_CASE(8)
 #undef MADTP_LN_CASE
   }
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+// LayerNorm -> fp16, repacked per sequence with the row padding the cross-attention operands need (see rowops.cuh).
+template <int V>
+__global__ void __launch_bounds__(256)
+layernorm_pack_kernel(LayerNormPackArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = a.n_dev ? min(a.N, __ldg(a.n_dev)) : a.N;
+  const int P = (N + 7) & ~7;
+  if (warp == 0 && lane == 0 && a.p_out) *a.p_out = P;
+  const int Pcap = (a.N + 7) & ~7;
+  const int b = warp / Pcap, t = warp - b * Pcap;
+  if (b >= a.B || t >= P) return;
+  __half* dst = a.y16 + (b / a.per_group) * a.group_stride + (static_cast<long long>(b % a.per_group) * P + t) * a.d;
+  if (t >= N) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) reinterpret_cast<uint2*>(dst)[lane + 32 * i] = make_uint2(0u, 0u);
+    return;
+  }
+  const long long row = static_cast<long long>(b) * N + t;
+  const float4* xin = reinterpret_cast<const float4*>(a.x + row * a.d);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xin[lane + 32 * i];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / static_cast<float>(a.d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(a.d) + a.eps);
+  const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = lane + 32 * i;
+    const float4 g = __ldg(g4 + c), be = __ldg(b4 + c);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + be.x;
+    y.y = (v[i].y - mean) * rstd * g.y + be.y;
+    y.z = (v[i].z - mean) * rstd * g.z + be.z;
+    y.w = (v[i].w - mean) * rstd * g.w + be.w;
+    if (a.y_f32) reinterpret_cast<float4*>(a.y_f32 + row * a.d)[c] = y;
+    __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(dst)[c] = pk;
+  }
+}
+
+int launch_layernorm_pack(const LayerNormPackArgs& a, cudaStream_t stream) {
+  MADTP_CHECK_ARG(a.x && a.gamma && a.beta && a.y16, "layernorm_pack: null pointer");
+  MADTP_CHECK_ARG(a.B >= 0 && a.N > 0 && a.d > 0 && a.d % 128 == 0 && a.d <= 1024 && a.per_group > 0 &&
+                      a.group_stride % 8 == 0,
+                  "layernorm_pack: bad shape (d=%d must be a multiple of 128, <= 1024)", a.d);
+  if (a.B == 0) return kOk;
+  const long long warps = static_cast<long long>(a.B) * ((a.N + 7) & ~7);
+  const int blocks = static_cast<int>((warps + 7) / 8);
+  switch (a.d / 128) {
+#define MADTP_LNP_CASE(V)                                     \
+  case V:                                                     \
+    layernorm_pack_kernel<V><<<blocks, 256, 0, stream>>>(a);  \
+    break;
+    MADTP_LNP_CASE(1) MADTP_LNP_CASE(2) MADTP_LNP_CASE(3) MADTP_LNP_CASE(4) MADTP_LNP_CASE(5) MADTP_LNP_CASE(6)
+    MADTP_LNP_CASE(7) MADTP_LNP_CASE(8)
+#undef MADTP_LNP_CASE
+  }
+  MADTP_LAUNCH_CHECK();
+  return kOk;
+}
+
+__global__ void __launch_bounds__(256)
+take_token_kernel(const float* __restrict__ x, int B, int N_cap, const int* __restrict__ n_dev, int token, int d4,
+                  float* __restrict__ out) {
+  const int N = n_dev ? min(N_cap, __ldg(n_dev)) : N_cap;
+  const long long total = static_cast<long long>(B) * d4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / d4;
+    const int c = static_cast<int>(i - b * d4);
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(x)[(b * N + token) * d4 + c];
+  }
+}
+
+int launch_take_token(const float* x, int B, int N, const int* n_dev, int token, int d, float* out, cudaStream_t stream) {
+  MADTP_CHECK_ARG(x && out && B >= 0 && N > 0 && token >= 0 && token < N && d > 0 && d % 4 == 0, "take_token: bad arguments");
+  if (B == 0) return kOk;
+  const long long total = static_cast<long long>(B) * (d / 4);
+  take_token_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(x, B, N, n_dev, token, d / 4, out);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }
@@ -252,8 +350,9 @@ bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ w
 }
 
 int launch_bert_embed(const long long* ids, const float* word, const float* posemb, float* out, int B, int L, int d,
-                      int vocab, cudaStream_t stream) {
+                      int vocab, int n_pos, cudaStream_t stream) {
   MADTP_CHECK_ARG(ids && word && posemb && out && d % 4 == 0 && vocab > 0, "bert_embed: bad arguments");
+  MADTP_CHECK_ARG(L <= n_pos, "bert_embed: sequence length %d exceeds the position table (%d rows)", L, n_pos);
   const long long total = static_cast<long long>(B) * L * (d / 4);
   if (total == 0) return kOk;
   long long blocks = (total + 255) / 256;

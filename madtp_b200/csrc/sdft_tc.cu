@@ -41,6 +41,7 @@ struct SdftArgs {
   int n, T, d, row_stride, first_row;        // x row of token j of batch b = b*row_stride + first_row + j
   float divisor;
   float* out; int accumulate;
+  const int* n_dev;                          // dynamic tokens per sequence N: row_stride = N, n = N - first_row
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -55,6 +56,12 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d0 = blockIdx.x * DN, b = blockIdx.y;
+  if (a.n_dev != nullptr) {                  // device-resident token count: packed sequences
+    const int Nd = __ldg(a.n_dev);
+    a.n = min(a.n, Nd - a.first_row);
+    a.row_stride = Nd;
+    a.bs_ta = Nd * a.ld_ta;
+  }
   const int chunks = (a.n + TCH - 1) / TCH;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
@@ -215,7 +222,8 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
 // x: fp32 rows [x_rows, d] (dense) holding token j of batch b at row b*row_stride + first_row + j.
 int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
                          const float* col_sum, const float* x, long long x_rows, int row_stride, int first_row, int B,
-                         int n, int T, int d, float divisor, float* sd_ft, int accumulate, cudaStream_t stream) {
+                         int n, int T, int d, float divisor, float* sd_ft, int accumulate, const int* n_dev,
+                         cudaStream_t stream) {
   MADTP_CHECK_ARG(token_att && col_max && col_sum && x && sd_ft, "query_sdft_tc: null pointer");
   MADTP_CHECK_ARG(B >= 0 && n > 0 && T > 0 && T <= TM && d > 0 && d % 32 == 0 && B <= 65535,
                   "query_sdft_tc: unsupported shape (T=%d must be <= 128, d=%d a multiple of 32)", T, d);
@@ -229,6 +237,7 @@ int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_t
   a.col_max = col_max; a.col_sum = col_sum;
   a.n = n; a.T = T; a.d = d; a.row_stride = row_stride; a.first_row = first_row;
   a.divisor = divisor; a.out = sd_ft; a.accumulate = accumulate;
+  a.n_dev = n_dev;
   dim3 grid((d + DN - 1) / DN, B);
   query_sdft_tc_kernel<<<grid, 320, SMEM_TOTAL, stream>>>(tx, a);
   MADTP_LAUNCH_CHECK();

@@ -27,7 +27,18 @@ struct SmallSelfArgs {
   float* cls_attn;           // [B, L]
   float* p_scratch;          // [B, H, L, L] probabilities of every head (statistics only)
   float* n_scratch;          // [B, H, L]    ||context[b,h,i]||
+  const int* n_dev;          // dynamic L (packed sequences: every batch stride becomes L * row pitch)
 };
+
+__device__ __forceinline__ void small_self_dyn(SmallSelfArgs& a) {
+  if (a.n_dev == nullptr) return;
+  const int L = min(a.L, __ldg(a.n_dev));
+  a.L = L;
+  a.bsq = L * a.ldq;
+  a.bsk = L * a.ldk;
+  a.bsv = L * a.ldv;
+  a.bso = L * a.ldo;
+}
 
 // grid (H, B), block 128: one head of one sequence
 __global__ void __launch_bounds__(128)
@@ -40,6 +51,7 @@ small_self_attn_kernel(SmallSelfArgs a) {
   float* Msk = Ps + SL * SP;
   float* Nsq = Msk + SL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  small_self_dyn(a);
   const int h = blockIdx.x, b = blockIdx.y, L = a.L, H = a.H;
   const bool stats = a.col_sum != nullptr;
   if (tid < SL) Msk[tid] = (a.key_mask != nullptr && tid < L) ? a.key_mask[static_cast<long long>(b) * L + tid] : 0.f;
@@ -111,6 +123,7 @@ small_self_attn_kernel(SmallSelfArgs a) {
 __global__ void __launch_bounds__(256)
 small_self_stats_kernel(SmallSelfArgs a) {
   __shared__ float part[4][SL];
+  small_self_dyn(a);
   const int j = threadIdx.x & 63, sl = threadIdx.x >> 6, b = blockIdx.x, L = a.L, H = a.H;
   const float* P = a.p_scratch + static_cast<long long>(b) * H * L * L;
   const float* Nr = a.n_scratch + static_cast<long long>(b) * H * L;
@@ -134,7 +147,8 @@ small_self_stats_kernel(SmallSelfArgs a) {
   a.cls_attn[static_cast<long long>(b) * L + j] = acc;
 }
 
-int launch_small_self_attn(const AttnArgs& g, float* col_sum, float* cls_attn, float* scratch, cudaStream_t stream) {
+int launch_small_self_attn(const AttnArgs& g, float* col_sum, float* cls_attn, float* scratch, const int* n_dev,
+                           cudaStream_t stream) {
   MADTP_CHECK_ARG(g.q && g.k && g.v && g.out_f16, "small_self_attn: null pointer");
   MADTP_CHECK_ARG(g.Nq == g.Nk && g.Nq >= 1 && g.Nq <= SL && g.H >= 1 && g.H <= 65535 && g.B <= 65535,
                   "small_self_attn: needs Nq == Nk <= %d", SL);
@@ -153,6 +167,7 @@ int launch_small_self_attn(const AttnArgs& g, float* col_sum, float* cls_attn, f
   a.col_sum = col_sum; a.cls_attn = cls_attn;
   a.p_scratch = scratch;
   a.n_scratch = scratch ? scratch + static_cast<long long>(g.B) * g.H * g.Nq * g.Nq : nullptr;
+  a.n_dev = n_dev;
   const int smem = (4 * SL * SP + 3 * SL) * sizeof(float);
   MADTP_SMEM_ATTR_ONCE(smem, small_self_attn_kernel);
   small_self_attn_kernel<<<dim3(g.H, g.B), 128, smem, stream>>>(a);

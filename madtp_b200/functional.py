@@ -112,15 +112,16 @@ def clear_caches(module) -> int:
 # row operations
 # ------------------------------------------------------------------------------------------------------------------
 def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float, *, f32=False, split=False,
-                   f16=False, split_x=False):
+                   f16=False, split_x=False, n_dev: Optional[Tensor] = None, n_mult: int = 1):
     """LayerNorm over the rows of x2d [rows, d] with the requested operand copies.
-    Returns dict with any of y, y_hi, y_lo, y16, x_hi, x_lo."""
+    Returns dict with any of y, y_hi, y_lo, y16, x_hi, x_lo. n_dev / n_mult: device-resident row count
+    rows = *n_dev * n_mult (x2d.shape[0] is then the capacity)."""
     rows, d = x2d.shape
     dev = x2d.device
     out = {}
 
     def new(dt=torch.float32):
-        return torch.empty(rows, d, dtype=dt, device=dev)
+        return L.empty((rows, d), dt, dev)
     if f32:
         out["y"] = new()
     if split:
@@ -130,34 +131,35 @@ def layernorm_rows(x2d: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor],
     if split_x:
         out["x_hi"], out["x_lo"] = new(torch.float16), new(torch.float16)
     L.layernorm(x2d, gamma, beta, eps, y_f32=out.get("y"), y_hi=out.get("y_hi"), y_lo=out.get("y_lo"),
-                y_f16=out.get("y16"), x_hi=out.get("x_hi"), x_lo=out.get("x_lo"))
+                y_f16=out.get("y16"), x_hi=out.get("x_hi"), x_lo=out.get("x_lo"), n_dev=n_dev, n_mult=n_mult)
     return out
 
 
-def split_rows(x2d: Tensor) -> Tuple[Tensor, Tensor]:
+def split_rows(x2d: Tensor, n_dev: Optional[Tensor] = None, n_mult: int = 1) -> Tuple[Tensor, Tensor]:
     """fp16 hi/lo split of fp32 rows (the operand format of the F16x3 GEMM)."""
-    o = layernorm_rows(x2d, None, None, 0.0, split_x=True)
+    o = layernorm_rows(x2d, None, None, 0.0, split_x=True, n_dev=n_dev, n_mult=n_mult)
     return o["x_hi"], o["x_lo"]
 
 
 def linear_split(a_hi: Tensor, a_lo: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, residual=None,
-                act=L.ACT_NONE, alpha=1.0) -> Tensor:
+                act=L.ACT_NONE, alpha=1.0, m_dev: Optional[Tensor] = None, m_mult: int = 1) -> Tensor:
     if out is None:
-        out = torch.empty(a_hi.shape[0], lin.out_features, dtype=torch.float32, device=a_hi.device)
+        out = L.empty((a_hi.shape[0], lin.out_features), torch.float32, a_hi.device)
     return L.gemm(L.GEMM_F16X3, a_hi, lin.hi, out, a_lo=a_lo, b_lo=lin.lo, bias=lin.bias, residual=residual, act=act,
-                  alpha=alpha / lin.scale)
+                  alpha=alpha / lin.scale, m_dev=m_dev, m_mult=m_mult)
 
 
 def linear_f16(a16: Tensor, lin: PreparedLinear, out: Optional[Tensor] = None, *, out_dtype=torch.float32,
-               residual=None, act=L.ACT_NONE, alpha=1.0) -> Tensor:
+               residual=None, act=L.ACT_NONE, alpha=1.0, m_dev: Optional[Tensor] = None, m_mult: int = 1) -> Tensor:
     if out is None:
-        out = torch.empty(a16.shape[0], lin.out_features, dtype=out_dtype, device=a16.device)
-    return L.gemm(L.GEMM_F16, a16, lin.w16, out, bias=lin.bias, residual=residual, act=act, alpha=alpha)
+        out = L.empty((a16.shape[0], lin.out_features), out_dtype, a16.device)
+    return L.gemm(L.GEMM_F16, a16, lin.w16, out, bias=lin.bias, residual=residual, act=act, alpha=alpha, m_dev=m_dev,
+                  m_mult=m_mult)
 
 
 def linear_f32(a: Tensor, lin: PreparedLinear, *, act=L.ACT_NONE) -> Tensor:
     """fp32 CUDA-core GEMM for tiny heads (cls_head)."""
-    out = torch.empty(a.shape[0], lin.out_features, dtype=torch.float32, device=a.device)
+    out = L.empty((a.shape[0], lin.out_features), torch.float32, a.device)
     return L.gemm(L.GEMM_SIMT, a, lin.w32, out, bias=lin.bias, act=act)
 
 
@@ -178,32 +180,34 @@ def prepare_codebook(space_dict: Tensor):
 
 
 def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int, sd_ft: Optional[Tensor],
-                     first_token: int = 1):
+                     first_token: int = 1, n_dev: Optional[Tensor] = None):
     """token_att for EVERY row of x3d [B,N,d] (one GEMM over the flat rows), then the over-token softmax
-    aggregation over tokens first_token..N-1.  Returns (token_att view [B, N-first_token, T], sd_ft [B,T,d])."""
+    aggregation over tokens first_token..N-1.  Returns (token_att view [B, N-first_token, T], sd_ft [B,T,d]).
+    n_dev: device-resident N (x3d is then a capacity-sized buffer holding B packed sequences)."""
     B, N, d = x3d.shape
     hi, lo, T, scale = book
-    ta = torch.empty(B * N, TA_LD, dtype=torch.float32, device=x3d.device)
-    L.gemm(L.GEMM_F16X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo, alpha=1.0 / scale)
-    return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token)
+    ta = L.empty((B * N, TA_LD), torch.float32, x3d.device)
+    L.gemm(L.GEMM_F16X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo, alpha=1.0 / scale, m_dev=n_dev, m_mult=B)
+    return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token, n_dev=n_dev)
 
 
 def query_model_from_token_att(ta_full: Tensor, x3d: Tensor, T: int, sd_dim: int, sd_ft: Optional[Tensor],
-                               first_token: int = 1):
+                               first_token: int = 1, n_dev: Optional[Tensor] = None):
     """Second half of Query_model given token_att for every row (ta_full [B, N, >=T] view, unit inner stride):
     over-token softmax statistics and the aggregated feature. Returns (token_att view [B, n, T], sd_ft)."""
     B, N, d = x3d.shape
     ta3 = ta_full[:, first_token:, :]
     n = N - first_token
     div = math.sqrt(sd_dim)
-    cm, cs = L.token_colstats(ta3, n, T, div)
+    cm, cs = L.token_colstats(ta3, n, T, div, n_dev=n_dev, n_sub=first_token)
     accumulate = sd_ft is not None
     if sd_ft is None:
-        sd_ft = torch.empty(B, T, d, dtype=torch.float32, device=x3d.device)
+        sd_ft = L.empty((B, T, d), torch.float32, x3d.device)
     if n >= 64 and x3d.is_contiguous() and d % 32 == 0:     # tensor-core path over the dense rows of x3d
-        L.query_sdft_tc(ta3, cm, cs, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate)
+        L.query_sdft_tc(ta3, cm, cs, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate, n_dev=n_dev)
     else:
-        L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate)
+        L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate, n_dev=n_dev,
+                     n_sub=first_token)
     return ta3[:, :, :T], sd_ft
 
 
@@ -216,24 +220,30 @@ class AttnStats:
     (reference models/vit.py:83,101): per-query-tile partial column sums of max_h P, and cls_attn."""
     col_part: Tensor   # [B, n_parts, N]
     cls_attn: Tensor   # [B, N]  (entry 0 unused)
+    parts_tile: int = 0   # query-tile height of the producer (n_parts = ceil(N / parts_tile)); 0: one part
 
 
 def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_mask: Optional[Tensor],
-                   want_stats: bool, ctx16: Optional[Tensor] = None, causal: bool = False):
-    """q,k,v: [B,N,H*64] fp32 views. Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
+                   want_stats: bool, ctx16: Optional[Tensor] = None, causal: bool = False,
+                   l_dev: Optional[Tensor] = None):
+    """q,k,v: [B,N,H*64] fp32 views. Returns (ctx16 [B,N,H*64] fp16, AttnStats or None).
+    l_dev: device-resident N (short-sequence path only: packed q / k / v / mask / outputs)."""
     B, N, C = q.shape
     dev = q.device
     if ctx16 is None:
-        ctx16 = torch.empty(B, N, C, dtype=torch.float16, device=dev)
+        ctx16 = L.empty((B, N, C), torch.float16, dev)
     if N <= 64:     # short text sequences: per-(head, sequence) CTAs + one statistics pass
         if not want_stats:
-            L.attn_small_self(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal)
+            L.attn_small_self(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal, l_dev=l_dev)
             return ctx16, None
-        col_part = torch.empty(B, 1, N, dtype=torch.float32, device=dev)
-        cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
+        col_part = L.empty((B, 1, N), torch.float32, dev)
+        cls_attn = L.empty((B, N), torch.float32, dev)
         L.attn_small_self(q, k, v, H, scale, ctx16, key_mask=key_mask, col_sum=col_part, cls_attn=cls_attn,
-                          causal=causal)
-        return ctx16, AttnStats(col_part, cls_attn)
+                          causal=causal, l_dev=l_dev)
+        return ctx16, AttnStats(col_part, cls_attn, 0)
+    if l_dev is not None:
+        raise RuntimeError("madtp_b200: device-resident lengths need the short-sequence (N <= 64) or the tensor-core "
+                           "self-attention path")
     if not want_stats:
         L.attn_fwd(q, k, v, H, scale, ctx16, key_mask=key_mask, causal=causal)
         return ctx16, None
@@ -244,29 +254,31 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
     col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
     cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
     L.attn_stats(q, k, H, scale, stats, col_part, cls_attn, key_mask=key_mask, causal=causal)
-    return ctx16, AttnStats(col_part, cls_attn)
+    return ctx16, AttnStats(col_part, cls_attn, 64)
 
 
 def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N: int, H: int, scale: float,
-                      want_stats: bool):
+                      want_stats: bool, n_dev: Optional[Tensor] = None):
     """Tensor-core scoring-lane self-attention from the fp16 hi/lo planes of the normalised rows [B*N, C]:
     fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
-    Returns (ctx16 [B,N,H*64] fp16, AttnStats or None)."""
+    Returns (ctx16 [B,N,H*64] fp16, AttnStats or None). n_dev: device-resident N (N is then the capacity)."""
     dev = y_hi.device
-    qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H, alpha=1.0 / qkv.scale)
-    ctx16 = torch.empty(B, N, H * 64, dtype=torch.float16, device=dev)
-    rows = torch.empty(3 if want_stats else 2, B, H, N, dtype=torch.float32, device=dev)
+    qk_hi, qk_lo, vt_hi, vt_lo = L.gemm_qkv(y_hi, y_lo, qkv.hi, qkv.lo, qkv.bias, N, H, alpha=1.0 / qkv.scale,
+                                            n_dev=n_dev)
+    ctx16 = L.empty((B, N, H * 64), torch.float16, dev)
+    rows = L.empty((3 if want_stats else 2, B, H, N), torch.float32, dev)
     if not want_stats:
-        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1])
+        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], n_dev=n_dev)
         return ctx16, None
-    cls_tile_max = torch.empty(B, H, (N + 63) // 64, dtype=torch.float32, device=dev)
+    cls_tile_max = L.empty((B, H, (N + 63) // 64), torch.float32, dev)
     L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], cls_p=rows[2],
-                  cls_tile_max=cls_tile_max)
+                  cls_tile_max=cls_tile_max, n_dev=n_dev)
     n_parts = (N + 127) // 128
-    col_part = torch.empty(B, n_parts, N, dtype=torch.float32, device=dev)
-    cls_attn = torch.empty(B, N, dtype=torch.float32, device=dev)
-    L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn, rows[2], cls_tile_max)
-    return ctx16, AttnStats(col_part, cls_attn)
+    col_part = L.empty((B, n_parts, N), torch.float32, dev)
+    cls_attn = L.empty((B, N), torch.float32, dev)
+    L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn, rows[2], cls_tile_max,
+                    n_dev=n_dev)
+    return ctx16, AttnStats(col_part, cls_attn, 128)
 
 
 @dataclass
@@ -290,22 +302,35 @@ class PendingPrune:
         self.score, self.thr, self.cnt, self.topk, self.handle = score, thr, cnt, topk, handle
 
 
-def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: int) -> PendingPrune:
+def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: int,
+                    n_dev: Optional[Tensor] = None) -> PendingPrune:
     """First half of Reduce_token: importance score, threshold, survivor counts and their batch maximum (reference
     models/vit.py:126-145), plus an asynchronous read-back of that maximum. Launch work that does not depend on the
-    pruning decision between this and dtp_finish: it runs while the host waits for topk_num."""
+    pruning decision between this and dtp_finish: it runs while the host waits for topk_num.
+    n_dev: device-resident N = n + 1 -- nothing is read back, dtp_finish consumes topk_num on the device."""
     T = token_att.shape[2]
-    score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature)
+    score, thr, cnt, topk = L.dtp_score(stats.col_part, stats.cls_attn, token_att, n, T, temperature, n_dev=n_dev,
+                                        parts_tile=stats.parts_tile)
     _dist.allreduce_topk_(topk)         # no-op unless madtp_b200.dist.global_topk(True) (strict multi-GPU mode)
-    return PendingPrune(score, thr, cnt, topk, L.readback_begin(topk))
+    return PendingPrune(score, thr, cnt, topk, None if n_dev is not None else L.readback_begin(topk))
 
 
 def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Optional[Tensor] = None,
-               max_keep: int = 0, want_f16: bool = False) -> PruneResult:
-    """Second half of Reduce_token on x [B, n+1, d] (position 0 always survives): select, gather, merge."""
+               max_keep: int = 0, want_f16: bool = False, n_dev: Optional[Tensor] = None,
+               n_out: Optional[Tensor] = None, k_out: Optional[Tensor] = None) -> PruneResult:
+    """Second half of Reduce_token on x [B, n+1, d] (position 0 always survives): select, gather, merge.
+    n_dev / n_out / k_out (device-resident lengths): x is a capacity-sized buffer of packed sequences; the kernels read
+    topk_num and N on the device, write the next layer's N to n_out and the trajectory entry to k_out, and the result
+    is again capacity-sized (`pruned` and `k` of the returned record are unknown to the host: None / -1)."""
     B, N, d = x.shape
     n = N - 1
     score, thr, cnt, topk = pend.score, pend.thr, pend.cnt, pend.topk
+    if n_dev is not None:
+        keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
+                                                             max_keep=max_keep, n_dev=n_dev, n_out=n_out, k_out=k_out)
+        out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, n - 1, max_keep=max_keep, want_f16=want_f16, n_dev=n_dev)
+        out, out16 = out if want_f16 else (out, None)
+        return PruneResult(out, None, -1, score, thr, cnt, keep, mask_out, out16)
     k = L.readback_wait(pend.handle)        # the reference's one host sync per pruned layer (models/vit.py:145)
     if k <= max_keep or n - k <= 1:         # models/vit.py:148-149 (max_keep = 0); clip/model.py:220
         return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
@@ -314,6 +339,77 @@ def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Op
     out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep, want_f16=want_f16)
     out, out16 = out if want_f16 else (out, None)
     return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2], out16)
+
+
+class Trajectory:
+    """Device-resident lengths of one encoder pass: dims[i] = tokens per sequence (incl. CLS / [ENC]) entering layer i
+    (dims[depth] = leaving the last layer), ks[i] = topk_num of layer i or -1 when it did not prune. `host()` copies
+    both to the host ONCE (the only device -> host transfer of such a pass) and caches them."""
+
+    def __init__(self, dims: Tensor, ks: Tensor):
+        self.dims, self.ks = dims, ks
+        self._host = None
+
+    def invalidate(self):
+        self._host = None
+
+    def host(self):
+        if self._host is None:
+            v = torch.cat([self.dims, self.ks]).cpu().tolist()
+            nd = self.dims.numel()
+            self._host = (v[:nd], v[nd:])
+        return self._host
+
+
+class LazyPrune:
+    """PruneResult of one layer of a device-resident-length pass. The buffers are capacity-sized and packed with the
+    dynamic lengths; attribute access narrows them with the trajectory read from the device on first use."""
+
+    def __init__(self, traj: Trajectory, layer: int, res: PruneResult, B: int):
+        self._traj, self._layer, self._res, self._B = traj, layer, res, B
+
+    def _packed(self, t, per_seq, tail=()):
+        return t.reshape(-1)[:self._B * per_seq * int(math.prod(tail))].view(self._B, per_seq, *tail)
+
+    @property
+    def k(self):
+        return self._traj.host()[1][self._layer]
+
+    @property
+    def pruned(self):
+        return self.k >= 0
+
+    @property
+    def n_in(self):
+        return self._traj.host()[0][self._layer] - 1
+
+    @property
+    def n_out_tokens(self):
+        return self._traj.host()[0][self._layer + 1]
+
+    @property
+    def score(self):
+        return self._packed(self._res.score, self.n_in)
+
+    @property
+    def keep(self):
+        return self._packed(self._res.keep, self.n_in) if self.pruned else None
+
+    @property
+    def threshold(self):
+        return self._res.threshold
+
+    @property
+    def count(self):
+        return self._res.count
+
+    @property
+    def x(self):
+        return self._packed(self._res.x, self.n_out_tokens, (self._res.x.shape[-1],))
+
+    @property
+    def mask(self):
+        return None if self._res.mask is None else self._packed(self._res.mask, self.n_out_tokens)
 
 
 def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,

@@ -1,0 +1,62 @@
+"""CUDA-graph execution of a forward with device-resident lengths.
+
+With the pruned token counts kept on the device (functional.dtp_finish, include/madtp_b200.h "Device-resident lengths")
+the launch sequence of a forward no longer depends on the data: the same ~400 kernel launches, with the same arguments,
+for every batch of a given shape. `GraphedCall` runs such a forward twice for warm-up inside an `_lib.Arena` (every
+buffer the wrappers allocate becomes a persistent, zero-initialised buffer handed out in call order), captures the third
+run in a torch.cuda.CUDAGraph and replays it from then on: one graph launch per forward instead of 400 Python-issued
+launches and 24 blocking read-backs (the reference: one `.item()` per pruned layer, models/vit.py:145).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+class GraphedCall:
+    """fn(*static_inputs) -> (outputs, trajectories): captured once, replayed on fresh inputs of the same shapes."""
+
+    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 2):
+        self.static_inputs = [t.clone() for t in example_inputs]
+        self.arena = L.Arena()
+        self.fn = fn
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.arena.frozen = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs, self.trajectories = self._run()
+        self.launches = None
+
+    def _run(self):
+        self.arena.begin()
+        prev = L.set_arena(self.arena)
+        try:
+            return self.fn(*self.static_inputs)
+        finally:
+            L.set_arena(prev)
+
+    def matches(self, inputs: Sequence[torch.Tensor]) -> bool:
+        return len(inputs) == len(self.static_inputs) and all(
+            a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+            for a, b in zip(inputs, self.static_inputs))
+
+    def __call__(self, *inputs: torch.Tensor):
+        """Copies `inputs` into the captured buffers (device or pinned-host sources, asynchronously) and replays.
+        Returns the captured output tensors: they are overwritten by the next replay."""
+        for dst, src in zip(self.static_inputs, inputs):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for t in self.trajectories:
+            t.invalidate()
+        return self.outputs

@@ -84,14 +84,14 @@ class BertEncoder(_ne.BertEncoder):
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, past_key_values=None, use_cache=None, output_attentions=False,
                 output_hidden_states=False, return_dict=True, mode='multimodal', space_dict=None, temperature=0,
-                _causal=False):
+                _causal=False, _device=False):
         return _ne.BertEncoder.forward(self, hidden_states, attention_mask=attention_mask, space_dict=space_dict,
                                        temperature=temperature, head_mask=head_mask,
                                        encoder_hidden_states=encoder_hidden_states,
                                        encoder_attention_mask=encoder_attention_mask, past_key_values=past_key_values,
                                        use_cache=use_cache, output_attentions=output_attentions,
                                        output_hidden_states=output_hidden_states, return_dict=return_dict, mode=mode,
-                                       _causal=_causal)
+                                       _causal=_causal, _device=_device)
 
 
 class BertModel(_ne.BertModel):

@@ -64,6 +64,16 @@ class CrossKV:
         self.k16, self.vt16, self.v_bias, self.keys_per_batch = k16, vt16, v_bias, keys_per_batch
 
 
+class LayerLengths:
+    """Device-resident lengths of one text layer (see functional.dtp_finish): tokens per sequence entering the layer,
+    where the layer writes the count it leaves and its topk_num, and the (device-resident) number of image tokens the
+    cross-attention reads, if that is dynamic too."""
+    __slots__ = ("l_in", "l_out", "k_out", "nk_dev")
+
+    def __init__(self, l_in, l_out, k_out, nk_dev=None):
+        self.l_in, self.l_out, self.k_out, self.nk_dev = l_in, l_out, k_out, nk_dev
+
+
 class BertEmbeddings(nn.Module):
     """word + position embeddings -> LayerNorm (models/nlvr_encoder.py:43-85)."""
 
@@ -174,20 +184,23 @@ class BertSelfAttention(nn.Module):
             return Fn.PreparedLinear(w, b, split=True)
         return self._cache.get("qkv_book", ps, build)
 
-    def project_qkv_and_token_att(self, h_hi, h_lo, B, Ltok, space_dict):
+    def project_qkv_and_token_att(self, h_hi, h_lo, B, Ltok, space_dict, l_dev=None):
         """One split-operand (fp16 hi/lo) GEMM -> (qkv view [B, L, 3C], token_att view [B, L, 128]) over the same rows."""
         C = self.all_head_size
-        out = Fn.linear_split(h_hi, h_lo, self._qkv_book_split(space_dict)).view(B, Ltok, 3 * C + Fn.TA_LD)
+        out = Fn.linear_split(h_hi, h_lo, self._qkv_book_split(space_dict), m_dev=l_dev,
+                              m_mult=B).view(B, Ltok, 3 * C + Fn.TA_LD)
         return out[..., :3 * C], out[..., 3 * C:]
 
-    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None, causal=False):
+    def self_rows(self, h_hi, h_lo, B, Ltok, key_mask, want_stats=True, qkv=None, causal=False, l_dev=None):
         """Self-attention on the scoring lane. Returns ctx16 [B,L,C]; stores AttnStats + cls_attn (:213-235).
-        causal=True: decoder self-attention (key j visible to query i only if j <= i, models/med.py:749-771)."""
+        causal=True: decoder self-attention (key j visible to query i only if j <= i, models/med.py:749-771).
+        l_dev: device-resident L (packed sequences in capacity-sized buffers)."""
         C = self.all_head_size
         if qkv is None:
-            qkv = Fn.linear_split(h_hi, h_lo, self._qkv_split()).view(B, Ltok, 3 * C)
+            qkv = Fn.linear_split(h_hi, h_lo, self._qkv_split(), m_dev=l_dev, m_mult=B).view(B, Ltok, 3 * C)
         ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_attention_heads,
-                                         1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats, causal=causal)
+                                         1.0 / math.sqrt(self.attention_head_size), key_mask, want_stats, causal=causal,
+                                         l_dev=l_dev)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return ctx16
@@ -263,22 +276,24 @@ class BertSelfOutput(nn.Module):
                              lambda: Fn.PreparedLinear(self.merge_layer.weight, self.merge_layer.bias, f16=True))
         return d0, d1, mg
 
-    def rows(self, ctx16, residual, *, f16=False, split=False):
+    def rows(self, ctx16, residual, *, f16=False, split=False, m_dev=None, m_mult=1):
         """ctx16 [rows, C] (or [rows, 2C] = [ctx0|ctx1] for the twin); residual fp32 [rows, C].
-        Returns the layernorm_rows dict of LayerNorm(dense(ctx) + residual) (always with 'y')."""
+        Returns the layernorm_rows dict of LayerNorm(dense(ctx) + residual) (always with 'y').
+        m_dev / m_mult: device-resident row count rows = *m_dev * m_mult."""
+        dyn = dict(m_dev=m_dev, m_mult=m_mult)
         if not self.twin:
-            pre = Fn.linear_f16(ctx16, self._dense(), residual=residual)
+            pre = Fn.linear_f16(ctx16, self._dense(), residual=residual, **dyn)
         elif not self.merge:
-            pre = Fn.linear_f16(ctx16, self._twin_avg(), residual=residual, alpha=0.5)
+            pre = Fn.linear_f16(ctx16, self._twin_avg(), residual=residual, alpha=0.5, **dyn)
         else:
             d0, d1, mg = self._twin_sep()
             C = d0.out_features
-            d01 = torch.empty(ctx16.shape[0], 2 * C, dtype=torch.float16, device=ctx16.device)
-            Fn.linear_f16(ctx16[:, :C], d0, out=d01[:, :C])
-            Fn.linear_f16(ctx16[:, C:], d1, out=d01[:, C:])
-            pre = Fn.linear_f16(d01, mg, residual=residual)
+            d01 = L.empty((ctx16.shape[0], 2 * C), torch.float16, ctx16.device)
+            Fn.linear_f16(ctx16[:, :C], d0, out=d01[:, :C], **dyn)
+            Fn.linear_f16(ctx16[:, C:], d1, out=d01[:, C:], **dyn)
+            pre = Fn.linear_f16(d01, mg, residual=residual, **dyn)
         return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
-                                 f16=f16, split=split)
+                                 f16=f16, split=split, n_dev=m_dev, n_mult=m_mult)
 
     def forward(self, hidden_states, input_tensor):
         _eval_only(self)
@@ -336,10 +351,10 @@ class BertIntermediate(nn.Module):
         self.intermediate_act_fn = nn.GELU() if act == "gelu" else nn.ReLU()
         self._cache = Fn.WeightCache()
 
-    def rows(self, y16):
+    def rows(self, y16, m_dev=None, m_mult=1):
         w = self._cache.get("dense", [self.dense.weight, self.dense.bias],
                             lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
-        return Fn.linear_f16(y16, w, out_dtype=torch.float16, act=self.act_code)
+        return Fn.linear_f16(y16, w, out_dtype=torch.float16, act=self.act_code, m_dev=m_dev, m_mult=m_mult)
 
     def forward(self, hidden_states):
         _eval_only(self)
@@ -355,11 +370,12 @@ class BertOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
         self._cache = Fn.WeightCache()
 
-    def rows(self, inter16, residual):
+    def rows(self, inter16, residual, m_dev=None, m_mult=1):
         w = self._cache.get("dense", [self.dense.weight, self.dense.bias],
                             lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
-        pre = Fn.linear_f16(inter16, w, residual=residual)
-        return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True)["y"]
+        pre = Fn.linear_f16(inter16, w, residual=residual, m_dev=m_dev, m_mult=m_mult)
+        return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
+                                 n_dev=m_dev, n_mult=m_mult)["y"]
 
     def forward(self, hidden_states, input_tensor):
         _eval_only(self)
@@ -413,7 +429,7 @@ class BertLayer(nn.Module):
 
     def _forward_impl(self, hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
                       past_key_value, output_attentions, mode, token_attn, temperature, _kv, _qkv=None,
-                      _causal=False):
+                      _causal=False, _dyn: Optional[LayerLengths] = None):
         Fn.require_cuda(hidden_states, "hidden_states")
         _eval_only(self)
         _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
@@ -424,27 +440,36 @@ class BertLayer(nn.Module):
         if prune and token_attn is None:
             raise RuntimeError("madtp_b200: temperature > 0 needs token_attn")
 
+        # device-resident lengths (functional.dtp_finish): h / key_mask are capacity-sized buffers of packed sequences
+        l_dev = None if _dyn is None else _dyn.l_in
         # self-attention + output LayerNorm (:501-509)
         sa = self.attention.self
         if _qkv is not None:      # BertEncoder already projected q|k|v together with the codebook dots
-            ctx16 = sa.self_rows(None, None, B, Ltok, key_mask, want_stats=prune, qkv=_qkv, causal=_causal)
+            ctx16 = sa.self_rows(None, None, B, Ltok, key_mask, want_stats=prune, qkv=_qkv, causal=_causal, l_dev=l_dev)
         else:
-            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
-            ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune, causal=_causal)
+            h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d), n_dev=l_dev, n_mult=B)
+            ctx16 = sa.self_rows(h_hi, h_lo, B, Ltok, key_mask, want_stats=prune, causal=_causal, l_dev=l_dev)
         # score kernel + read-back of topk_num first: the output dense + LayerNorm below do not depend on them
-        pend = Fn.dtp_score_async(sa.get_attention_map(), token_attn, float(temperature), Ltok - 1) if prune else None
-        att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=True)
+        pend = Fn.dtp_score_async(sa.get_attention_map(), token_attn, float(temperature), Ltok - 1,
+                                  n_dev=l_dev) if prune else None
+        att = self.attention.output.rows(ctx16.view(B * Ltok, d), h.view(B * Ltok, d), f16=True, m_dev=l_dev, m_mult=B)
         att_f32, att16 = att["y"].view(B, Ltok, d), att.get("y16")
 
         # dynamic token pruning between self- and cross-attention (:519-533)
         self.last_prune = None
         if prune:
             if key_mask is None:
-                key_mask = torch.zeros(B, Ltok, dtype=torch.float32, device=h.device)
-            res = Fn.dtp_finish(att_f32, pend, mask_mode=self.MASK_MODE, mask_in=key_mask, want_f16=True)
+                key_mask = L.zeros((B, Ltok), torch.float32, h.device)
+            res = Fn.dtp_finish(att_f32, pend, mask_mode=self.MASK_MODE, mask_in=key_mask, want_f16=True,
+                                n_dev=l_dev, n_out=None if _dyn is None else _dyn.l_out,
+                                k_out=None if _dyn is None else _dyn.k_out)
             self.last_prune = res
             att_f32 = res.x
-            if res.pruned:          # the gather kernel also wrote the fp16 operand of the next GEMM
+            if _dyn is not None:    # capacity-sized results, packed with the length the select kernel wrote to l_out
+                key_mask = res.mask
+                att16 = res.x16.view(B * Ltok, d)
+                l_dev = _dyn.l_out
+            elif res.pruned:        # the gather kernel also wrote the fp16 operand of the next GEMM
                 key_mask = res.mask.contiguous()
                 Ltok = att_f32.shape[1]
                 att16 = res.x16.view(B * Ltok, d)
@@ -453,13 +478,14 @@ class BertLayer(nn.Module):
 
         if mode == 'multimodal':
             assert encoder_hidden_states is not None, "encoder_hidden_states must be given for cross-attention layers"
-            att_rows, att16 = self._cross(att_rows, att16, B, Ltok, encoder_hidden_states, encoder_attention_mask, _kv)
+            att_rows, att16 = self._cross(att_rows, att16, B, Ltok, encoder_hidden_states, encoder_attention_mask, _kv,
+                                          l_dev=l_dev, nk_dev=None if _dyn is None else _dyn.nk_dev)
 
-        inter16 = self.intermediate.rows(att16)
-        out = self.output.rows(inter16, att_rows).view(B, Ltok, d)
+        inter16 = self.intermediate.rows(att16, m_dev=l_dev, m_mult=B)
+        out = self.output.rows(inter16, att_rows, m_dev=l_dev, m_mult=B).view(B, Ltok, d)
         return (out, None, attention_mask)
 
-    def _cross(self, att_rows, att16, B, Ltok, enc, enc_mask, kv):
+    def _cross(self, att_rows, att16, B, Ltok, enc, enc_mask, kv, l_dev=None, nk_dev=None):
         """Twin (list-valued encoder states, :312-335) or single cross-attention + output LayerNorm."""
         ca = self.crossattention
         d = att_rows.shape[1]
@@ -470,24 +496,28 @@ class BertLayer(nn.Module):
             selfs, enc, masks = [ca.self], [enc], [enc_mask]
         C = selfs[0].all_head_size
         nb = len(selfs)
-        ctx = torch.empty(B, Ltok, nb * C, dtype=torch.float16, device=att_rows.device)
+        ctx = L.empty((B, Ltok, nb * C), torch.float16, att_rows.device)
         use_tc = kv is not None and all(isinstance(kv[i], CrossKV) for i in range(nb))   # tensor-core kernel operands
+        if (l_dev is not None or nk_dev is not None) and not use_tc:
+            raise RuntimeError("madtp_b200: device-resident lengths need the tensor-core cross-attention operands")
+        dyn = dict(m_dev=l_dev, m_mult=B)
         qdt = torch.float16 if use_tc else torch.float32
         if nb == 2:   # both query projections read the same rows: one GEMM over [Wq0; Wq1]
             ps = [p for s in selfs for p in (s.query.weight, s.query.bias)]
             wq = ca._qcache.get("q01", ps, lambda: Fn.PreparedLinear(
                 torch.cat([s.query.weight for s in selfs], 0), torch.cat([s.query.bias for s in selfs], 0), f16=True))
-            q_all = Fn.linear_f16(att16, wq, out_dtype=qdt).view(B, Ltok, nb * C)
+            q_all = Fn.linear_f16(att16, wq, out_dtype=qdt, **dyn).view(B, Ltok, nb * C)
         for i, s in enumerate(selfs):
-            q = q_all[..., i * C:(i + 1) * C] if nb == 2 else Fn.linear_f16(att16, s._q_f16(),
-                                                                             out_dtype=qdt).view(B, Ltok, C)
+            q = q_all[..., i * C:(i + 1) * C] if nb == 2 else Fn.linear_f16(att16, s._q_f16(), out_dtype=qdt,
+                                                                             **dyn).view(B, Ltok, C)
             em = masks[i] if s.CROSS_ATTENTION_MASK else None
             out = ctx[..., i * C:(i + 1) * C]
             if use_tc:
                 ckv = kv[i]
                 Nk = ckv.k16.shape[-2]
                 L.attn_cross_tc(q, ckv.k16, ckv.vt16, s.num_attention_heads, 1.0 / math.sqrt(s.attention_head_size), out,
-                                keys_per_batch=ckv.keys_per_batch, v_bias=ckv.v_bias, key_mask=_key_mask(em, B, Nk))
+                                keys_per_batch=ckv.keys_per_batch, v_bias=ckv.v_bias, key_mask=_key_mask(em, B, Nk),
+                                lq_dev=l_dev, nk_dev=nk_dev)
                 continue
             Nk = enc[i].shape[1]
             if kv is not None:
@@ -497,7 +527,7 @@ class BertLayer(nn.Module):
                 kvp = s.project_kv(e16).view(B, Nk, 2 * C)
                 k, v = kvp[..., :C], kvp[..., C:]
             s.cross_rows(q, k, v, _key_mask(em, B, Nk), out)
-        o = ca.output.rows(ctx.view(B * Ltok, nb * C), att_rows, f16=True)
+        o = ca.output.rows(ctx.view(B * Ltok, nb * C), att_rows, f16=True, **dyn)
         return o["y"], o["y16"]
 
     def feed_forward_chunk(self, attention_output):
@@ -586,10 +616,34 @@ class BertEncoder(nn.Module):
                 per_layer[i].append((allkv[..., o:o + C], allkv[..., o + C:o + 2 * C]))
         return per_layer
 
+    def _project_encoder_states_device(self, enc):
+        """The same operands from a vit.DeviceEncoded record whose final LayerNorm was written by madtp_layernorm_pack:
+        fp16 image tokens [groups, per_group * P, w] with P = the DEVICE-RESIDENT token count rounded up to 8. One
+        group per cross-attention branch (BLIP-NLVR: image0 -> self0, image1 -> self1); the K and V^T projections of
+        all layers run as one GEMM each over the dynamic row count."""
+        names = ["self0", "self1"] if enc.y16.shape[0] == 2 else ["self"]
+        if enc.y16.shape[0] != len(names):
+            raise RuntimeError("madtp_b200: one group of image tokens per cross-attention branch")
+        C = self.config.hidden_size
+        per, Pcap = enc.per_group, enc.P
+        per_layer = [[] for _ in self.layer]
+        for gi, name in enumerate(names):
+            wk, wv16, vb = self._all_k_vt_weights(name)
+            e16 = enc.y16[gi]                                                                  # [per * Pcap, w]
+            allk = Fn.linear_f16(e16, wk, out_dtype=torch.float16, m_dev=enc.p_dev, m_mult=per).view(per, Pcap, -1)
+            allvt = L.empty((wv16.shape[0], per * Pcap), torch.float16, e16.device)
+            L.gemm(L.GEMM_F16, wv16, e16, allvt, n_dev=enc.p_dev, n_mult=per)
+            for i in range(len(self.layer)):
+                per_layer[i].append(CrossKV(allk[:, :enc.cap, i * C:(i + 1) * C], allvt[i * C:(i + 1) * C], vb[i], Pcap))
+        return per_layer
+
     def forward(self, hidden_states, attention_mask=None, space_dict=None, temperature=0, head_mask=None,
                 encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None, use_cache=None,
                 output_attentions=False, output_hidden_states=False, return_dict=True, mode='multimodal',
-                _causal=False):
+                _causal=False, _device=False):
+        """_device=True (internal): device-resident lengths -- `hidden_states` stays a capacity-sized buffer of packed
+        sequences, nothing is read back, and the return value is (final states [B, L_cap, d], sd_txt_ft, Trajectory,
+        device scalar with the final length). `encoder_hidden_states` may then be a vit.DeviceEncoded record."""
         _unsupported(past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
                      output_hidden_states=output_hidden_states)
         Fn.require_cuda(hidden_states, "hidden_states")
@@ -599,29 +653,50 @@ class BertEncoder(nn.Module):
         token_num = hidden_states.shape[-2]
         reduce_num = int((token_num - 1) // self.config.num_hidden_layers)
         kv = None
-        if mode == 'multimodal' and encoder_hidden_states is not None:
+        nk_dev = None
+        enc_dev = encoder_hidden_states if hasattr(encoder_hidden_states, "y16") else None
+        if mode == 'multimodal' and enc_dev is not None:
+            kv = self._project_encoder_states_device(enc_dev)
+            nk_dev = enc_dev.n_dev
+        elif mode == 'multimodal' and encoder_hidden_states is not None:
             kv = self._project_encoder_states(encoder_hidden_states, hidden_states.shape[1])
+        dims = ks = traj = None
+        depth = len(self.layer)
+        if _device:
+            lens = L.empty((2 * depth + 1,), torch.int32, hidden_states.device)
+            dims, ks = lens[:depth + 1], lens[depth + 1:]
+            dims[:1].fill_(token_num)
+            ks.fill_(-1)
+            traj = Fn.Trajectory(dims, ks)
         sd_txt_ft_all = None
         for i, layer_module in enumerate(self.layer):
             h = hidden_states.contiguous()
             Ltok, d = h.shape[1], h.shape[2]
             token_attn = qkv = None
+            dyn = LayerLengths(dims[i:i + 1], dims[i + 1:i + 2], ks[i:i + 1], nk_dev) if _device else None
+            l_dev = None if dyn is None else dyn.l_in
             if space_dict is not None and not self.txt_query_model.map_func:
                 # q|k|v and the codebook dots share the operand h: one split-operand GEMM (see _qkv_book_split)
-                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
-                qkv, ta_full = layer_module.attention.self.project_qkv_and_token_att(h_hi, h_lo, B, Ltok, space_dict)
+                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d), n_dev=l_dev, n_mult=B)
+                qkv, ta_full = layer_module.attention.self.project_qkv_and_token_att(h_hi, h_lo, B, Ltok, space_dict,
+                                                                                     l_dev=l_dev)
                 token_attn, sd_txt_ft_all = Fn.query_model_from_token_att(ta_full, h, space_dict.shape[0],
-                                                                          self.txt_query_model.att_dim, sd_txt_ft_all)
+                                                                          self.txt_query_model.att_dim, sd_txt_ft_all,
+                                                                          n_dev=l_dev)
             elif space_dict is not None:
-                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d))
+                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d), n_dev=l_dev, n_mult=B)
                 token_attn, sd_txt_ft_all = self.txt_query_model.forward_rows(h, h_hi, h_lo, space_dict,
-                                                                              sd_txt_ft_all)
+                                                                              sd_txt_ft_all, n_dev=l_dev)
             layer_outputs = layer_module._forward_impl(h, attention_mask, None, encoder_hidden_states,
                                                        encoder_attention_mask, None, False, mode, token_attn,
                                                        temperature, None if kv is None else kv[i], _qkv=qkv,
-                                                       _causal=_causal)
+                                                       _causal=_causal, _dyn=dyn)
+            if _device:
+                layer_module.last_prune = Fn.LazyPrune(traj, i, layer_module.last_prune, B)
             hidden_states = layer_outputs[0]
             attention_mask = layer_outputs[-1]
+        if _device:
+            return hidden_states, sd_txt_ft_all, traj, dims[depth:depth + 1]
         if not return_dict:
             return (hidden_states,), sd_txt_ft_all
         return EncoderOutput(hidden_states), sd_txt_ft_all
@@ -684,7 +759,32 @@ class BertModel(nn.Module):
             if enc_ext is not None and type(encoder_hidden_states) == list and type(enc_ext) != list:
                 enc_ext = [enc_ext] * len(encoder_hidden_states)
         emb = self.embeddings(input_ids=input_ids) if encoder_embeds is None else encoder_embeds
+        from .vit import device_lengths_enabled
+        prunes = temperature > 0 and (space_dict is not None or self.encoder.REQUIRE_SPACE_DICT)
+        if prunes and not is_decoder and device_lengths_enabled() and Ltok <= 64:
+            # device-resident lengths: ONE host read-back (the final length, to shape the returned tensor) instead of
+            # one per layer (models/nlvr_encoder.py:432 / models/med.py:369)
+            h, sd_txt_ft, traj, l_dev = self.encoder(emb, attention_mask=ext, space_dict=space_dict,
+                                                     temperature=temperature,
+                                                     encoder_hidden_states=encoder_hidden_states,
+                                                     encoder_attention_mask=enc_ext, mode=mode, _device=True)
+            n = traj.host()[0][-1]
+            d = h.shape[-1]
+            return EncoderOutput(h.reshape(-1)[:B * n * d].view(B, n, d)), sd_txt_ft
         out, sd_txt_ft = self.encoder(emb, attention_mask=ext, space_dict=space_dict, temperature=temperature,
                                       encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=enc_ext,
                                       mode=mode, _causal=bool(is_decoder))
         return out, sd_txt_ft
+
+    @torch.no_grad()
+    def forward_device(self, input_ids, attention_mask, enc, space_dict, temperature, mode='multimodal'):
+        """Pruned text encoder with device-resident lengths end to end: `enc` is the vit.DeviceEncoded record of the
+        image encoder (packed fp16 image tokens + their device-resident count). Nothing is read back. Returns
+        (final states [B, L_cap, d] packed, sd_txt_ft, Trajectory, device scalar with the final length)."""
+        _eval_only(self)
+        if attention_mask is None:
+            attention_mask = torch.ones(input_ids.shape, device=input_ids.device)
+        ext = self.get_extended_attention_mask(attention_mask)
+        emb = self.embeddings(input_ids=input_ids)
+        return self.encoder(emb, attention_mask=ext, space_dict=space_dict, temperature=temperature,
+                            encoder_hidden_states=enc, encoder_attention_mask=None, mode=mode, _device=True)

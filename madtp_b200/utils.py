@@ -58,16 +58,16 @@ class Query_model(nn.Module):
         return self._cache.get("q_map", [lin.weight, lin.bias],
                                lambda: Fn.PreparedLinear(lin.weight, lin.bias, split=True))
 
-    def forward_rows(self, x3d, x_hi, x_lo, sd, sd_ft_acc=None, first_token=1):
+    def forward_rows(self, x3d, x_hi, x_lo, sd, sd_ft_acc=None, first_token=1, n_dev=None):
         """Fast path used by the encoders: x3d [B,N,d] with its fp16 hi/lo split already produced by the LayerNorm kernel;
         tokens first_token.. are the prunable ones. Returns (token_att view [B,n,T], sd_ft (accumulated))."""
         if self.map_func:
             B, N, d = x3d.shape
-            q = Fn.linear_split(x_hi, x_lo, self._qmap())
-            q_hi, q_lo = Fn.split_rows(q)
+            q = Fn.linear_split(x_hi, x_lo, self._qmap(), m_dev=n_dev, m_mult=B)
+            q_hi, q_lo = Fn.split_rows(q, n_dev=n_dev, n_mult=B)
             return Fn.query_model_rows(q_hi, q_lo, q.view(B, N, -1), self._book(sd), self.att_dim, sd_ft_acc,
-                                       first_token)
-        return Fn.query_model_rows(x_hi, x_lo, x3d, self._book(sd), self.att_dim, sd_ft_acc, first_token)
+                                       first_token, n_dev=n_dev)
+        return Fn.query_model_rows(x_hi, x_lo, x3d, self._book(sd), self.att_dim, sd_ft_acc, first_token, n_dev=n_dev)
 
     def forward(self, ft, sd, mask=None, return_token_att=False, temperature=1):
         """ft [B, n, ft_dim], sd [T, sd_dim] -> (token_att [B,n,T] | att_weight [B,T,n], att_ft [B,T,sd_dim], sd)."""

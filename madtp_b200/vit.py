@@ -11,6 +11,7 @@ Differences that are part of the contract:
 """
 from __future__ import annotations
 
+import os
 from functools import partial
 
 import torch
@@ -59,11 +60,12 @@ class Mlp(nn.Module):
                               lambda: Fn.PreparedLinear(self.fc2.weight, self.fc2.bias, f16=True))
         return fc1, fc2
 
-    def forward_rows(self, y16, residual=None):
-        """y16 [rows, C] fp16 (already normalised) -> fp32 [rows, C] (+ residual)."""
+    def forward_rows(self, y16, residual=None, m_dev=None, m_mult=1):
+        """y16 [rows, C] fp16 (already normalised) -> fp32 [rows, C] (+ residual). m_dev / m_mult: device-resident
+        row count rows = *m_dev * m_mult."""
         fc1, fc2 = self._prepared()
-        h = Fn.linear_f16(y16, fc1, out_dtype=torch.float16, act=_act_code(self.act))
-        return Fn.linear_f16(h, fc2, residual=residual)
+        h = Fn.linear_f16(y16, fc1, out_dtype=torch.float16, act=_act_code(self.act), m_dev=m_dev, m_mult=m_mult)
+        return Fn.linear_f16(h, fc2, residual=residual, m_dev=m_dev, m_mult=m_mult)
 
     def forward(self, x):
         Fn.require_cuda(x, "x")
@@ -123,17 +125,18 @@ class Attention(nn.Module):
         ctx16 = self.attend_rows(y_hi, y_lo, B, N, want_stats)
         return self.project_rows(ctx16, B, N, residual)
 
-    def attend_rows(self, y_hi, y_lo, B, N, want_stats=True):
+    def attend_rows(self, y_hi, y_lo, B, N, want_stats=True, n_dev=None):
         """q|k|v projection, attention and (optionally) the pruning statistics; returns the fp16 context [B,N,C]."""
         qkv_w, _ = self._prepared()
-        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, self.scale, want_stats)
+        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, self.scale, want_stats,
+                                            n_dev=n_dev)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return ctx16
 
-    def project_rows(self, ctx16, B, N, residual=None):
+    def project_rows(self, ctx16, B, N, residual=None, n_dev=None):
         _, proj_w = self._prepared()
-        return Fn.linear_f16(ctx16.view(B * N, self.dim), proj_w, residual=residual)
+        return Fn.linear_f16(ctx16.view(B * N, self.dim), proj_w, residual=residual, m_dev=n_dev, m_mult=B)
 
     def forward(self, x, register_hook=False):
         Fn.require_cuda(x, "x")
@@ -178,24 +181,30 @@ class Block(nn.Module):
         self.last_prune = res
         return res.x[:, 1:, :] if res.pruned else x
 
-    def forward_rows(self, x, ln1, temperature=0, token_attn=None):
-        """x [B,N,C] fp32 contiguous; ln1 = functional.layernorm_rows(..., split=True) of norm1(x)."""
+    def forward_rows(self, x, ln1, temperature=0, token_attn=None, n_dev=None, n_out=None, k_out=None):
+        """x [B,N,C] fp32 contiguous; ln1 = functional.layernorm_rows(..., split=True) of norm1(x).
+        n_dev / n_out / k_out: device-resident lengths (x is a capacity-sized buffer of packed sequences, *n_dev tokens
+        each; the layer writes the next length to n_out and its topk_num to k_out -- see functional.dtp_finish)."""
         B, N, C = x.shape
         prune = temperature > 0
-        ctx16 = self.attn.attend_rows(ln1["y_hi"], ln1["y_lo"], B, N, want_stats=prune)
+        ctx16 = self.attn.attend_rows(ln1["y_hi"], ln1["y_lo"], B, N, want_stats=prune, n_dev=n_dev)
         # the score kernel and the read-back of topk_num go first; the output projection does not depend on them and
         # runs while the host waits for the four bytes
-        pend = Fn.dtp_score_async(self.attn.get_attention_map(), token_attn, float(temperature), N - 1) if prune else None
-        x1 = self.attn.project_rows(ctx16, B, N, residual=x.view(B * N, C)).view(B, N, C)
+        pend = Fn.dtp_score_async(self.attn.get_attention_map(), token_attn, float(temperature), N - 1,
+                                  n_dev=n_dev) if prune else None
+        x1 = self.attn.project_rows(ctx16, B, N, residual=x.view(B * N, C), n_dev=n_dev).view(B, N, C)
         self.last_prune = None
+        nd2 = n_dev
         if prune:
-            res = Fn.dtp_finish(x1, pend)
+            res = Fn.dtp_finish(x1, pend, n_dev=n_dev, n_out=n_out, k_out=k_out)
             self.last_prune = res
             x1 = res.x
+            if n_dev is not None:
+                nd2 = n_out
         N2 = x1.shape[1]
         x2d = x1.view(B * N2, C)
-        ln2 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, f16=True)
-        return self.mlp.forward_rows(ln2["y16"], residual=x2d).view(B, N2, C)
+        ln2 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, f16=True, n_dev=nd2, n_mult=B)
+        return self.mlp.forward_rows(ln2["y16"], residual=x2d, m_dev=nd2, m_mult=B).view(B, N2, C)
 
     def forward(self, x, register_hook=False, reduce_num=0, temperature=0, token_attn=None):
         Fn.require_cuda(x, "x")
@@ -277,11 +286,70 @@ class VisionTransformer(nn.Module):
         return {'pos_embed', 'cls_token'}
 
     @torch.no_grad()
+    def forward_device(self, x, space_dict, temperature, pack_groups=0, keep_f32=False):
+        """The pruned forward with DEVICE-RESIDENT token counts: no host read-back anywhere (the reference syncs once
+        per layer, models/vit.py:145), so the whole pass can be enqueued ahead or captured in a CUDA graph. Every
+        buffer is sized for the unpruned token count and holds B packed sequences of the current, device-side length.
+        Returns a DeviceEncoded record; pack_groups > 0 writes the final LayerNorm straight into the fp16 operand
+        layout of the cross-attention K / V^T projections (madtp_layernorm_pack), split into that many equal groups of
+        sequences (BLIP-NLVR: 2 = image0 / image1)."""
+        Fn.require_cuda(x, "image")
+        _eval_only(self)
+        if not (temperature > 0) or space_dict is None:
+            raise RuntimeError("madtp_b200: forward_device is the PRUNED path (temperature > 0 with a codebook)")
+        B = x.shape[0]
+        patches = self.patch_embed(x.contiguous())
+        n, C = patches.shape[1], patches.shape[2]
+        if n + 1 > self.pos_embed.shape[1]:
+            raise RuntimeError("madtp_b200: image has more patches than pos_embed rows")
+        x = L.assemble_tokens(patches, self.cls_token.detach().reshape(-1), self.pos_embed.detach().reshape(-1, C),
+                              B, n, C)
+        N = n + 1
+        depth = len(self.blocks)
+        lens = L.empty((2 * depth + 2,), torch.int32, x.device)     # dims [depth + 1] | ks [depth] | P
+        dims, ks = lens[:depth + 1], lens[depth + 1:2 * depth + 1]
+        dims[:1].fill_(N)
+        ks.fill_(-1)
+        traj = Fn.Trajectory(dims, ks)
+        sd_img_ft_all = None
+        for i, blk in enumerate(self.blocks):
+            n_dev, n_out, k_out = dims[i:i + 1], dims[i + 1:i + 2], ks[i:i + 1]
+            ln1 = Fn.layernorm_rows(x.view(B * N, C), blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, split=True,
+                                    split_x=True, n_dev=n_dev, n_mult=B)
+            token_attn, sd_img_ft_all = self.img_query_model.forward_rows(x, ln1["x_hi"], ln1["x_lo"], space_dict,
+                                                                          sd_img_ft_all, n_dev=n_dev)
+            x = blk.forward_rows(x, ln1, temperature, token_attn, n_dev=n_dev, n_out=n_out, k_out=k_out)
+            blk.last_prune = Fn.LazyPrune(traj, i, blk.last_prune, B)
+        n_dev = dims[depth:depth + 1]
+        enc = DeviceEncoded(B, N, C, n_dev, traj, sd_img_ft_all)
+        if pack_groups:
+            if B % pack_groups:
+                raise RuntimeError("madtp_b200: the batch does not split into equal groups")
+            P = (N + 7) // 8 * 8
+            per = B // pack_groups
+            enc.y16 = L.empty((pack_groups, per * P, C), torch.float16, x.device)
+            enc.p_dev = lens[2 * depth + 1:2 * depth + 2]
+            enc.per_group, enc.P = per, P
+            if keep_f32:
+                enc.y = L.empty((B * N, C), torch.float32, x.device)
+            L.layernorm_pack(x.view(B * N, C), B, N, self.norm.weight, self.norm.bias, self.norm.eps, enc.y16, per,
+                             per * P * C, y_f32=enc.y, p_out=enc.p_dev, n_dev=n_dev)
+        else:
+            enc.y = Fn.layernorm_rows(x.view(B * N, C), self.norm.weight, self.norm.bias, self.norm.eps, f32=True,
+                                      n_dev=n_dev, n_mult=B)["y"]
+        return enc
+
+    @torch.no_grad()
     def forward(self, x, register_blk=-1, space_dict=None, temperature=0):
         Fn.require_cuda(x, "image")
         _eval_only(self)
         if register_blk >= 0:
             raise NotImplementedError("madtp_b200: register_blk needs the materialised attention map")
+        if temperature > 0 and space_dict is not None and device_lengths_enabled():
+            # device-resident lengths: ONE host read-back (the final token count, to shape the returned tensor)
+            # instead of one per layer
+            enc = self.forward_device(x, space_dict, temperature)
+            return enc.narrowed(), enc.sd_ft
         B = x.shape[0]
         patches = self.patch_embed(x.contiguous())
         n, C = patches.shape[1], patches.shape[2]
@@ -304,6 +372,35 @@ class VisionTransformer(nn.Module):
         N = x.shape[1]
         x = Fn.layernorm_rows(x.view(B * N, C), self.norm.weight, self.norm.bias, self.norm.eps, f32=True)["y"]
         return x.view(B, N, C), sd_img_ft_all
+
+
+class DeviceEncoded:
+    """Result of an encoder pass with device-resident lengths: capacity-sized buffers of B packed sequences, the device
+    scalar holding the final tokens-per-sequence, and the trajectory."""
+
+    def __init__(self, B, cap, C, n_dev, traj, sd_ft):
+        self.B, self.cap, self.C, self.n_dev, self.traj, self.sd_ft = B, cap, C, n_dev, traj, sd_ft
+        self.y = None          # packed fp32 final states [B * cap, C]
+        self.y16 = None        # or: fp16 cross-attention operand layout [groups, per_group * P, C] (layernorm_pack)
+        self.p_dev = None      # device scalar P = final length rounded up to 8
+        self.per_group = self.P = 0
+
+    def narrowed(self):
+        """[B, N_final, C] view of the packed final states (one device -> host read of the trajectory)."""
+        n = self.traj.host()[0][-1]
+        return self.y.reshape(-1)[:self.B * n * self.C].view(self.B, n, self.C)
+
+
+_DEVICE_LENGTHS = [os.environ.get("MADTP_HOST_LENGTHS", "0") != "1"]
+
+
+def device_lengths_enabled(enable=None) -> bool:
+    """Module-level switch: encoders keep the pruned token counts on the device (default) or read them back once per
+    layer like the reference does (MADTP_HOST_LENGTHS=1 / device_lengths_enabled(False): the round-1 path, kept as a
+    cross-check -- both produce bit-identical results)."""
+    if enable is not None:
+        _DEVICE_LENGTHS[0] = bool(enable)
+    return _DEVICE_LENGTHS[0]
 
 
 def interpolate_pos_embed(pos_embed_checkpoint, visual_encoder):

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
     cdll = lib.load()
     for name in declared_functions():
         assert hasattr(cdll, name), f"{name} is declared in include/madtp_b200.h but not exported"
-    assert cdll.madtp_abi_version() == lib.ABI_VERSION == 2
+    assert cdll.madtp_abi_version() == lib.ABI_VERSION == 3
 
 
 def test_ctypes_signatures_cover_the_header(lib):
@@ -47,11 +47,11 @@ def test_binding_argument_counts_match_the_header(lib):
 def test_argument_errors_are_reported_without_a_gpu(lib):
     cdll = lib.load()
     # invalid shapes are rejected before any CUDA call, so this is safe on a CPU-only host
-    st = cdll.madtp_dtp_select(1, 0, None, None, None, None, None, None, 0, None, None, 0, None)
+    st = cdll.madtp_dtp_select(1, 0, None, None, None, None, None, None, 0, None, None, 0, None, None, None, None)
     assert st == 1
     assert b"null pointer" in cdll.madtp_last_error_string() or b"out of range" in cdll.madtp_last_error_string()
     st = cdll.madtp_gemm(7, None, None, 0, None, None, 0, None, 0, 0, None, None, 0, 0, ctypes.c_float(1.0), 1, 1, 1,
-                         None)
+                         None, 1, None, 1, None)
     assert st == 1
 
 

@@ -279,6 +279,42 @@ def set_arena(arena):
     return prev
 
 
+class arena_for:
+    """`with arena_for(owner, key):` -- run a forward with device-resident lengths inside the persistent Arena that
+    `owner` (a module) keeps for `key` (the input shapes). Such a forward NEEDS one: its buffers are capacity-sized and
+    the tensor cores read past the dynamic length, so that region must hold zeros or stale finite values, never the
+    arbitrary bits of a fresh allocation. Nested scopes reuse the outer arena. Results that must survive the owner's
+    next call with the same key have to be cloned by the caller."""
+
+    def __init__(self, owner, key):
+        self.owner, self.key, self.own, self.prev = owner, key, False, None
+
+    def __enter__(self):
+        if _arena is not None:
+            return _arena
+        arenas = self.owner.__dict__.setdefault("_madtp_arenas", {})
+        a = arenas.get(self.key)
+        if a is None:
+            a = arenas[self.key] = Arena()
+        a.begin()
+        self.prev = set_arena(a)
+        self.own = True
+        return a
+
+    def __exit__(self, *exc):
+        if self.own:
+            set_arena(self.prev)
+        return False
+
+
+def release_arenas(module) -> int:
+    """Frees the persistent buffers every sub-module of `module` keeps for its device-resident-length forwards."""
+    n = 0
+    for m in module.modules():
+        n += len(m.__dict__.pop("_madtp_arenas", {}))
+    return n
+
+
 def empty(shape, dtype, device):
     if _arena is not None:
         return _arena.take(shape, dtype, device)

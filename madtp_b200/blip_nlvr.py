@@ -124,9 +124,12 @@ class BLIP_NLVR(nn.Module):
             input_ids, attention_mask = self._tokenize(text, image.device)
             if input_ids.shape[1] <= 64 and image.shape[0] == 2 * input_ids.shape[0]:
                 if self._graphs is None:
-                    return self._forward_device(image.contiguous(), input_ids, attention_mask, float(temperature))[0]
+                    from . import _lib as L
+                    with L.arena_for(self, (tuple(image.shape), tuple(input_ids.shape), self.record_states)):
+                        return self._forward_device(image.contiguous(), input_ids, attention_mask,
+                                                    float(temperature))[0].clone()
                 from .graphs import GraphedCall
-                key = (tuple(image.shape), tuple(input_ids.shape), float(temperature))
+                key = (tuple(image.shape), tuple(input_ids.shape), float(temperature), self.record_states)
                 g = self._graphs.get(key)
                 if g is None:
                     t = float(temperature)

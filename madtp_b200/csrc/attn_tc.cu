@@ -133,7 +133,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
   float* cls_stage = reinterpret_cast<float*>(smem + Cfg::CLS_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.n_dev ? min(a.N, __ldg(a.n_dev)) : a.N, HD = a.H * 64;   // device-resident token count (packed)
+  const int N = a.n_dev ? min(a.N, load_len(a.n_dev)) : a.N, HD = a.H * 64;   // device-resident token count (packed)
   if (a.n_dev) a.bso = static_cast<long long>(N) * a.ldo;
   const int T = (N + 63) / 64;           // key tiles per item
   const int QT = (N + BM - 1) / BM;      // query tiles per (sequence, head)
@@ -545,7 +545,7 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   float* part = reinterpret_cast<float*>(smem + StatsSmem::PART_OFF);      // [item parity][quadrant][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.n_dev ? min(a.N, __ldg(a.n_dev)) : a.N, H = a.H, HD = a.H * 64;
+  const int N = a.n_dev ? min(a.N, load_len(a.n_dev)) : a.N, H = a.H, HD = a.H * 64;
   if (a.n_dev) a.n_parts = (N + BM - 1) / BM;    // packed col_part [B, ceil(N/128), N] with the dynamic N
   const int NT = a.n_parts;                      // tiles per side
   const int items = NT * NT * a.B;
@@ -694,7 +694,7 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_cls_combine_kernel(AttnTcArgs a) {
-  const int N = a.n_dev ? min(a.N, __ldg(a.n_dev)) : a.N, H = a.H, T = (N + 63) / 64;
+  const int N = a.n_dev ? min(a.N, load_len(a.n_dev)) : a.N, H = a.H, T = (N + 63) / 64;
   const int j = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
   if (j >= N) return;
   const long long base = static_cast<long long>(b) * H * N + j;

@@ -76,6 +76,11 @@ struct PerDeviceOnce {
     }                                                                                                 \
   } while (0)
 
+// Device-resident length (the `*_dev` arguments of the C ABI): written by an earlier kernel of the same stream (the
+// DTP select kernel, or a fill). Read with a plain coherent load -- NOT __ldg: the non-coherent path may serve a line
+// that was cached before the producer kernel wrote it.
+__device__ __forceinline__ int load_len(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
 // ---------------------------------------------------------------------------------------------
 // Warp helpers
 // ---------------------------------------------------------------------------------------------

@@ -59,8 +59,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int Lq = a.lq_dev ? min(a.Lq, __ldg(a.lq_dev)) : a.Lq;
-  const int Nk = a.nk_dev ? min(a.Nk, __ldg(a.nk_dev)) : a.Nk;
+  const int Lq = a.lq_dev ? min(a.Lq, load_len(a.lq_dev)) : a.Lq;
+  const int Nk = a.nk_dev ? min(a.Nk, load_len(a.nk_dev)) : a.Nk;
   if (a.lq_dev) a.bso = static_cast<long long>(Lq) * a.ldo;             // packed output
   if (a.nk_dev && a.k_rows_per_batch != 0) a.k_rows_per_batch = a.vt_cols_per_batch = (Nk + 7) & ~7;
   const int NB = (Nk + CrossSmem::KB - 1) / CrossSmem::KB;              // key blocks

@@ -53,7 +53,7 @@ token_colstats_kernel(const float* __restrict__ ta, long long ld, long long bs, 
   __shared__ float smax[8][32];
   __shared__ float ssum[8][32];
   if (n_dev != nullptr) {
-    const int N = __ldg(n_dev);
+    const int N = load_len(n_dev);
     n = min(n, N - n_sub);
     bs = N * ld;
   }
@@ -109,7 +109,7 @@ query_sdft_kernel(const float* __restrict__ ta, long long ld_ta, long long bs_ta
                   int T, int d, float divisor, float* __restrict__ out, int accumulate,
                   const int* __restrict__ n_dev, int n_sub) {
   if (n_dev != nullptr) {
-    const int N = __ldg(n_dev);
+    const int N = load_len(n_dev);
     n = min(n, N - n_sub);
     bs_ta = N * ld_ta;
     bsx = N * ldx;
@@ -206,7 +206,7 @@ dtp_score_kernel(DtpScoreArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.n_dev != nullptr) {          // device-resident token count: packed sequences
-    const int Nd = min(a.n + 1, __ldg(a.n_dev));
+    const int Nd = min(a.n + 1, load_len(a.n_dev));
     a.n = Nd - 1;
     a.bs_ta = Nd * a.ld_ta;
     if (a.parts_tile > 0) a.n_parts = (Nd + a.parts_tile - 1) / a.parts_tile;
@@ -329,7 +329,7 @@ dtp_select_kernel(DtpSelectArgs a) {
   __shared__ double red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dyn = a.n_dev != nullptr;
-  const int b = blockIdx.x, n = dyn ? min(a.n, __ldg(a.n_dev) - 1) : a.n;
+  const int b = blockIdx.x, n = dyn ? min(a.n, load_len(a.n_dev) - 1) : a.n;
   const int k_in = *a.topk;
   const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);   // reference early-out: nothing is pruned
   const int k = identity ? n : k_in;
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256)
 dtp_gather_kernel(DtpGatherArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dyn = a.n_dev != nullptr;
-  const int b = blockIdx.y, n = dyn ? min(a.n, __ldg(a.n_dev) - 1) : a.n, d4 = a.d >> 2;
+  const int b = blockIdx.y, n = dyn ? min(a.n, load_len(a.n_dev) - 1) : a.n, d4 = a.d >> 2;
   const int k_in = *a.topk;
   const bool identity = (k_in <= a.max_keep) || (n - k_in <= 1);
   const int k = identity ? n : k_in;

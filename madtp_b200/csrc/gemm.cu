@@ -520,7 +520,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   constexpr int CW = Cfg::COLS_PER_WARP;
   static_assert(!PAIR || (CL == 2 && F16), "the CTA-pair variant is the fp16-plane kernel on clusters of two");
   const int M = gemm_dyn_m(ep, M_cap), N = gemm_dyn_n(ep, N_cap);   // device-resident extents (gemm.cuh)
-  const int n_tok = (ep.mode == 1 && ep.m_dev) ? __ldg(ep.m_dev) : ep.n_tok;
+  const int n_tok = (ep.mode == 1 && ep.m_dev) ? load_len(ep.m_dev) : ep.n_tok;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -40,10 +40,10 @@ struct GemmEpilogue {
 
 // Effective extents of a launch (device code).
 __device__ __forceinline__ int gemm_dyn_m(const GemmEpilogue& ep, int M) {
-  return ep.m_dev ? min(M, __ldg(ep.m_dev) * ep.m_mult) : M;
+  return ep.m_dev ? min(M, load_len(ep.m_dev) * ep.m_mult) : M;
 }
 __device__ __forceinline__ int gemm_dyn_n(const GemmEpilogue& ep, int N) {
-  return ep.n_dev ? min(N, __ldg(ep.n_dev) * ep.n_mult) : N;
+  return ep.n_dev ? min(N, load_len(ep.n_dev) * ep.n_mult) : N;
 }
 
 // Power-of-two scales of the q/k and v operand planes (keep the lo plane of typical activations a normal fp16 number;

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(LayerNormArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int rows = a.n_dev ? min(a.rows, __ldg(a.n_dev) * a.n_mult) : a.rows;
+  const int rows = a.n_dev ? min(a.rows, load_len(a.n_dev) * a.n_mult) : a.rows;
   if (warp >= rows) return;
   const long long row = warp;
   const float4* xin = reinterpret_cast<const float4*>(a.x + row * a.ldx);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256)
 layernorm_pack_kernel(LayerNormPackArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int N = a.n_dev ? min(a.N, __ldg(a.n_dev)) : a.N;
+  const int N = a.n_dev ? min(a.N, load_len(a.n_dev)) : a.N;
   const int P = (N + 7) & ~7;
   if (warp == 0 && lane == 0 && a.p_out) *a.p_out = P;
   const int Pcap = (a.N + 7) & ~7;
@@ -177,7 +177,7 @@ int launch_layernorm_pack(const LayerNormPackArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 take_token_kernel(const float* __restrict__ x, int B, int N_cap, const int* __restrict__ n_dev, int token, int d4,
                   float* __restrict__ out) {
-  const int N = n_dev ? min(N_cap, __ldg(n_dev)) : N_cap;
+  const int N = n_dev ? min(N_cap, load_len(n_dev)) : N_cap;
   const long long total = static_cast<long long>(B) * d4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {

@@ -57,7 +57,7 @@ query_sdft_tc_kernel(const __grid_constant__ CUtensorMap tm_x, SdftArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d0 = blockIdx.x * DN, b = blockIdx.y;
   if (a.n_dev != nullptr) {                  // device-resident token count: packed sequences
-    const int Nd = __ldg(a.n_dev);
+    const int Nd = load_len(a.n_dev);
     a.n = min(a.n, Nd - a.first_row);
     a.row_stride = Nd;
     a.bs_ta = Nd * a.ld_ta;

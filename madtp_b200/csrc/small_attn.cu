@@ -32,7 +32,7 @@ struct SmallSelfArgs {
 
 __device__ __forceinline__ void small_self_dyn(SmallSelfArgs& a) {
   if (a.n_dev == nullptr) return;
-  const int L = min(a.L, __ldg(a.n_dev));
+  const int L = min(a.L, load_len(a.n_dev));
   a.L = L;
   a.bsq = L * a.ldq;
   a.bsk = L * a.ldk;

@@ -33,9 +33,11 @@ class GraphedCall:
         torch.cuda.synchronize()
         self.arena.frozen = True
         self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(self.graph):
             self.outputs, self.trajectories = self._run()
-        self.launches = None
+        self.launches = L.launch_count() - n0      # kernels of libmadtp_b200.so inside one replay of the graph
+        self.replays = 0
 
     def _run(self):
         self.arena.begin()
@@ -57,6 +59,7 @@ class GraphedCall:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        self.replays += 1
         for t in self.trajectories:
             t.invalidate()
         return self.outputs

@@ -489,7 +489,10 @@ class BertLayer(nn.Module):
         """Twin (list-valued encoder states, :312-335) or single cross-attention + output LayerNorm."""
         ca = self.crossattention
         d = att_rows.shape[1]
-        if type(enc) == list:
+        if hasattr(enc, "y16"):     # vit.DeviceEncoded: one group of packed image tokens per branch, no encoder mask
+            selfs = [ca.self0, ca.self1] if enc.y16.shape[0] == 2 else [ca.self]
+            enc, masks = [None] * len(selfs), [None] * len(selfs)
+        elif type(enc) == list:
             selfs = [ca.self0, ca.self1]
             masks = enc_mask if type(enc_mask) == list else [enc_mask, enc_mask]
         else:
@@ -764,13 +767,21 @@ class BertModel(nn.Module):
         if prunes and not is_decoder and device_lengths_enabled() and Ltok <= 64:
             # device-resident lengths: ONE host read-back (the final length, to shape the returned tensor) instead of
             # one per layer (models/nlvr_encoder.py:432 / models/med.py:369)
-            h, sd_txt_ft, traj, l_dev = self.encoder(emb, attention_mask=ext, space_dict=space_dict,
-                                                     temperature=temperature,
-                                                     encoder_hidden_states=encoder_hidden_states,
-                                                     encoder_attention_mask=enc_ext, mode=mode, _device=True)
-            n = traj.host()[0][-1]
-            d = h.shape[-1]
-            return EncoderOutput(h.reshape(-1)[:B * n * d].view(B, n, d)), sd_txt_ft
+            enc_shape = None
+            if torch.is_tensor(encoder_hidden_states):
+                enc_shape = tuple(encoder_hidden_states.shape)
+            elif type(encoder_hidden_states) == list:
+                enc_shape = tuple(tuple(e.shape) for e in encoder_hidden_states)
+            with L.arena_for(self, (B, Ltok, mode, enc_shape, enc_ext is None)):
+                h, sd_txt_ft, traj, l_dev = self.encoder(emb, attention_mask=ext, space_dict=space_dict,
+                                                         temperature=temperature,
+                                                         encoder_hidden_states=encoder_hidden_states,
+                                                         encoder_attention_mask=enc_ext, mode=mode, _device=True)
+                n = traj.host()[0][-1]
+                d = h.shape[-1]
+                # clones: the arena's buffers are reused by the next call with the same shapes
+                return (EncoderOutput(h.reshape(-1)[:B * n * d].view(B, n, d).clone()),
+                        None if sd_txt_ft is None else sd_txt_ft.clone())
         out, sd_txt_ft = self.encoder(emb, attention_mask=ext, space_dict=space_dict, temperature=temperature,
                                       encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=enc_ext,
                                       mode=mode, _causal=bool(is_decoder))

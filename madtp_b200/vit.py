@@ -348,8 +348,9 @@ class VisionTransformer(nn.Module):
         if temperature > 0 and space_dict is not None and device_lengths_enabled():
             # device-resident lengths: ONE host read-back (the final token count, to shape the returned tensor)
             # instead of one per layer
-            enc = self.forward_device(x, space_dict, temperature)
-            return enc.narrowed(), enc.sd_ft
+            with L.arena_for(self, tuple(x.shape)):
+                enc = self.forward_device(x, space_dict, temperature)
+                return enc.narrowed().clone(), enc.sd_ft.clone()      # the arena's buffers are reused by the next call
         B = x.shape[0]
         patches = self.patch_embed(x.contiguous())
         n, C = patches.shape[1], patches.shape[2]

@@ -36,12 +36,7 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-PAIRS = 32            # BASELINE config 2: batch = 32 pairs = 64 images per GPU
-IMAGE = 384
-TEXT_LEN = 20
-CALIB = ROOT / "tests" / "golden" / "calib_nlvr_p50_b32.npz"
-METRIC = "BLIP-NLVR p=0.5 forward images/sec"
-WORKLOAD = f"BLIP-NLVR forward (vit.py + nlvr_encoder.py), {IMAGE}x{IMAGE} synthetic pairs, p=0.5, batch={PAIRS} pairs/GPU"
+from bench_workloads import WORKLOADS  # noqa: E402
 
 
 def load_peaks():
@@ -51,13 +46,6 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
                 "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
-
-
-def calibration():
-    c = np.load(CALIB)
-    return {"temperature": float(c["temperature"]), "ratio": float(c["ratio"]),
-            "macs_pruned": int(c["macs_pruned"]), "macs_unpruned": int(c["macs_unpruned"]),
-            "vit_k": c["vit_k"].tolist()}
 
 
 class NvmlClockSampler:
@@ -156,76 +144,41 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle on the host cores (reference arm and cpu_baseline leg)
+# CPU arm: the reference's own forward on the host cores (reference arm and cpu_baseline leg)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(sample_pairs: int, steps: int, warmup: int, temperature: float):
-    """images/s of the reference's own CPU forward on `sample_pairs` pairs of the workload. Returns
-    (rate, seconds per step, threads, kind): kind "reference" = the UNMODIFIED reference BLIP_NLVR.forward(train=False)
-    (models/blip_nlvr.py:63-100) imported from /root/reference or its byte-for-byte staging oracle/_ref (recipe:
-    oracle/make_ref.py) under the third-party import shims of oracle/ref_shims.py; kind "port" = oracle/dtp_oracle.py
-    when neither tree is present."""
-    from madtp_b200 import synthetic
-    from oracle import ref_shims
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = synthetic.blip_nlvr_state_dict(1234, img_size=IMAGE)
-    images, ids, mask = synthetic.nlvr_inputs(sample_pairs, IMAGE, TEXT_LEN, seed=0)
-    if ref_shims.available():
-        kind = "reference"
-        model, tok = ref_shims.build_blip_nlvr(IMAGE)
-        msg = model.load_state_dict(sd, strict=False)
-        assert not msg.unexpected_keys, msg.unexpected_keys
-        targets = torch.zeros(sample_pairs, dtype=torch.long)
-        text = ["x"] * sample_pairs
-
-        def fwd():
-            tok.next_ids = (ids, mask)
-            return model(images, text, targets, temperature, train=False)
-    else:
-        kind = "port"
-        from oracle import dtp_oracle as O
-
-        def fwd():
-            return O.blip_nlvr_forward(images, ids, mask, sd, temperature)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            fwd()
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    total = sum(times)
-    return 2 * sample_pairs * len(times) / total, total / len(times), torch.get_num_threads(), kind
-
-
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    """`--impl reference`: the UNMODIFIED reference modules of the chosen configuration (staged byte for byte in
+    oracle/_ref by oracle/make_ref.py, imported under the third-party shims of oracle/ref_shims.py) on all host threads;
+    the oracle port when the reference tree is absent. Rank 0 only."""
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    cal = calibration()
-    sample_pairs = args.sample_pairs or PAIRS
-    rate, sec, cores, kind = cpu_reference_rate(sample_pairs, args.steps, args.warmup, cal["temperature"])
-    what = ("the unmodified reference BLIP_NLVR.forward(train=False) (PyTorch-CPU fp32, staged by oracle/make_ref.py)"
-            if kind == "reference" else "oracle/dtp_oracle.py (PyTorch-CPU fp32 restatement; reference tree absent)")
-    sample = (f"{sample_pairs} pairs ({2 * sample_pairs} images) of the {PAIRS}-pair batch per step, {what}, "
-              f"{cores} threads")
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = WORKLOADS[args.config]()
+    rate, sec, kind, sample = w.cpu_reference(args.sample, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    sample = f"{sample}, PyTorch-CPU fp32, {cores} threads"
+    line = {"impl": "reference", "metric": w.metric, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "temperature": cal["temperature"], "sample": sample},
+            "config": {"workload": w.workload, "baseline_config": w.config, "temperature": w.temperature,
+                       "sample": sample},
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def cpu_baseline_subprocess(sample_pairs: int, steps: int, warmup: int):
+def cpu_baseline_subprocess(config: int, sample: int, steps: int, warmup: int):
     """The cpu_baseline leg of the main arm: the reference arm in its OWN process (no CUDA context, no sampler thread
-    next to it -- round 1's in-process leg read 28 % low for that reason), on a bounded sample."""
-    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
-           "--sample-pairs", str(sample_pairs)]
+    next to it -- round 1's in-process leg read 28 % low for that reason)."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--config", str(config), "--steps", str(steps),
+           "--warmup", str(warmup), "--sample", str(sample)]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
     env["CUDA_VISIBLE_DEVICES"] = ""
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": "images/s", "cores": None, "kind": "unavailable", "sample": "timed out"}
     for ln in reversed(r.stdout.strip().splitlines()):
         if ln.startswith("{"):
             return json.loads(ln)["cpu_baseline"]
@@ -258,36 +211,17 @@ def algorithmic_flops(name, meta):
     return 0.0
 
 
-def parity_report(keeps_gpu, ks_gpu, pred_gpu, fixture_path=None):
-    """Free-running agreement of the GPU forward with the oracle trajectory stored in the calibration fixture
-    (rank 0's batch is the fixture's batch): per ViT layer, the fraction of the oracle's surviving ORIGINAL patches that
-    the GPU run also kept (tokens are tracked back to their patch index through every prune; merged tokens are not
-    counted), both k trajectories and the largest logit difference. The bit-exact, teacher-forced gates live in
-    tests/test_parity_gpu.py; this is the end-to-end number SURVEY.md section 7 (iv) asks to be reported with them."""
-    c = np.load(fixture_path or CALIB)
-    B = int(c["pairs"]) * 2
-    n0 = (int(c["image_size"]) // 16) ** 2
-    ids_o = np.tile(np.arange(n0), (B, 1))
-    ids_g = ids_o.copy()
-    agree = []
-    for i, k_o in enumerate(c["vit_k"].tolist()):
-        if k_o >= 0:
-            ko = np.unpackbits(c[f"vit{i}_keep"], axis=1)[:, :ids_o.shape[1]].astype(bool)
-            ids_o = np.stack([np.concatenate([ids_o[b][ko[b]], [-1]]) for b in range(B)])
-        kg = keeps_gpu[i]
-        if kg is not None:
-            kg = kg.astype(bool)
-            ids_g = np.stack([np.concatenate([ids_g[b][kg[b]], [-1]]) for b in range(B)])
-        fr = []
-        for b in range(B):
-            so, sg = set(ids_o[b].tolist()) - {-1}, set(ids_g[b].tolist()) - {-1}
-            fr.append(len(so & sg) / max(len(so), 1))
-        agree.append(round(float(np.mean(fr)), 5))
-    return {"mask_agreement_per_layer": agree, "k_gpu": list(ks_gpu), "k_oracle": c["vit_k"].tolist(),
-            "logit_max_abs": float(np.abs(pred_gpu - c["pred"]).max()),
-            "argmax_agreement": float((pred_gpu.argmax(1) == c["pred"].argmax(1)).mean()),
-            "what": "free-running (no teacher forcing) vs tests/golden/calib_nlvr_p50_b32.npz; layer 0 sees identical "
-                    "inputs and must read 1.0"}
+
+def ncu_traffic(kernel_key: str):
+    """DRAM bytes per launch of the dominant kernel class from the kept `ncu --set full` summary (profiles/
+    ncu_traffic.json, written by profiles/summarize.py from the capture of this same command), or None."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    try:
+        return json.loads(p.read_text()).get(kernel_key)
+    except Exception:
+        return None
 
 
 _JSON_OUT = None
@@ -315,8 +249,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="madtp_b200", choices=["madtp_b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (2 = the headline BLIP-NLVR forward)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sample-pairs", type=int, default=0, help="reference arm: pairs per step (0 = the full batch)")
+    ap.add_argument("--sample", "--sample-pairs", type=int, default=0, dest="sample",
+                    help="reference arm: pairs / images per step (0 = the full batch)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the "
+                                                            "captured CUDA graph (device-resident lengths either way)")
+    ap.add_argument("--host-lengths", action="store_true", help="round-1 path: read topk_num back once per layer")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "madtp_b200" else max(args.warmup, 1)
@@ -324,8 +264,8 @@ def main():
         run_reference_arm(args)
         return
 
-    from madtp_b200 import _lib, dist as mdist, synthetic
-    from madtp_b200.blip_nlvr import BLIP_NLVR, TokenizedText
+    from madtp_b200 import _lib, dist as mdist, vit as mvit
+    from madtp_b200.pipeline import InputPrefetcher
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: madtp_b200 has no CPU fallback")
     _lib.load()
@@ -334,58 +274,65 @@ def main():
         raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    cal = calibration()
-    temp = cal["temperature"]
     peaks = load_peaks()
+    w = WORKLOADS[args.config]()
 
     # weights: rank 0 draws the seeded state dict, everyone else receives it over NCCL
-    model = BLIP_NLVR(image_size=IMAGE, evaluate=True)
-    if rank == 0:
-        msg = model.load_state_dict(synthetic.blip_nlvr_state_dict(1234, img_size=IMAGE), strict=False)
-        assert not msg.missing_keys and not msg.unexpected_keys
-    model = model.to(dev).eval()
+    model = w.build(dev, rank)
     mdist.broadcast_parameters(model, src=0)
+    mvit.device_lengths_enabled(not args.host_lengths)
+    use_graph = w.graphable and not (args.no_graph or args.host_lengths)
+    w.enable_graphs(use_graph)
 
-    images, ids, mask = synthetic.nlvr_inputs(PAIRS, IMAGE, TEXT_LEN, seed=rank)       # this rank's own pairs
-    images_h, ids_h, mask_h = images.pin_memory(), ids.pin_memory(), mask.pin_memory()
-    images_d, ids_d, mask_d = images_h.to(dev), ids_h.to(dev), mask_h.to(dev)
-    text_d = TokenizedText(ids_d, mask_d)
-    logits_h = torch.empty(PAIRS * world, 2).pin_memory()
+    host = tuple(t.pin_memory() for t in w.host_inputs(rank))          # this rank's own batch
+    resident = tuple(t.to(dev) for t in host)
+    result_shape = None
 
     def step_resident():
-        pred = model(images_d, text_d, PAIRS, temp, train=False)
-        return mdist.all_gather_rows(pred)
+        return mdist.all_gather_rows(w.step(resident))
 
-    from madtp_b200.pipeline import InputPrefetcher
-    feeder = InputPrefetcher(dev, (images_h, ids_h, mask_h))
-    e2e_state = {"i": 0, "end": 0}
+    feeder = InputPrefetcher(dev, host)
+    e2e_state = {"i": 0, "start": 0, "end": 0, "out_h": None}
 
     def step_e2e():
         """Public API with HOST inputs: every step's pinned-host -> HBM copy (issued one step ahead on a side stream,
-        inside the timed region) and the device -> host read of the logits."""
+        inside the timed region) and the device -> host read of the result."""
         i = e2e_state["i"]
         if i == e2e_state["start"]:
-            feeder.submit(i, (images_h, ids_h, mask_h))
+            feeder.submit(i, host)
         if i + 1 < e2e_state["end"]:
-            feeder.submit(i + 1, (images_h, ids_h, mask_h))
-        im, ids_g, mask_g = feeder.acquire(i)
-        pred = mdist.all_gather_rows(model(im, TokenizedText(ids_g, mask_g), PAIRS, temp, train=False))
+            feeder.submit(i + 1, host)
+        out = mdist.all_gather_rows(w.step(feeder.acquire(i)))
         feeder.release(i)
-        logits_h.copy_(pred, non_blocking=True)
+        if e2e_state["out_h"] is None:
+            e2e_state["out_h"] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        e2e_state["out_h"].copy_(out, non_blocking=True)
         e2e_state["i"] = i + 1
-        return pred
+        return out
 
-    # ---- warm-up; the first warm-up step is fully instrumented to find the dominant kernel ----
-    step_resident()                       # first call also prepares the GEMM-ready weight copies (one-off)
-    torch.cuda.synchronize()
-    timer = _lib.LaunchTimer()
-    _lib.set_launch_timer(timer)
-    step_resident()
-    torch.cuda.synchronize()
-    _lib.set_launch_timer(None)
+    class per_kernel_mode:
+        """Per-kernel CUDA-event timing needs every launch to come from Python with its exact shape arguments: the
+        instrumented passes run the SAME kernels with host-side lengths (one read-back per layer, the round-1 path;
+        results are bit-identical, tests/test_device_lengths_gpu.py) instead of replaying the graph."""
+
+        def __enter__(self):
+            mvit.device_lengths_enabled(False)
+
+        def __exit__(self, *exc):
+            mvit.device_lengths_enabled(not args.host_lengths)
+
+    # ---- warm-up; one warm-up step is fully instrumented to find the dominant kernel ----
+    with per_kernel_mode():
+        step_resident()                   # first call also prepares the GEMM-ready weight copies (one-off)
+        torch.cuda.synchronize()
+        timer = _lib.LaunchTimer()
+        _lib.set_launch_timer(timer)
+        step_resident()
+        torch.cuda.synchronize()
+        _lib.set_launch_timer(None)
     prof = timer.summary()
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
-    for _ in range(max(args.warmup - 2, 1)):
+    for _ in range(max(args.warmup, 3)):  # graph mode: two passes inside the arena, the capture, then replays
         step_resident()
     torch.cuda.synchronize()
 
@@ -393,7 +340,7 @@ def main():
         t = _lib.LaunchTimer(only=only) if only else None
         mdist.barrier()
         torch.cuda.synchronize()
-        l0 = _lib.launch_count()
+        l0 = _lib.launch_count() + w.graph_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _lib.set_launch_timer(t)
         e0.record()
@@ -404,15 +351,16 @@ def main():
         torch.cuda.synchronize()
         mdist.barrier()
         ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
-        return ms, _lib.launch_count() - l0, t
+        return ms, _lib.launch_count() + w.graph_launches() - l0, t
 
     sampler = make_clock_sampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms, launches, _ = timed(step_resident, args.steps)
     # the same K steps once more with CUDA events around every launch of the dominant kernel (kept out of the pass
-    # that produces `value`: ~250 extra event records per step are not free on the host side of a 27 ms step)
-    ms_instr, _, t_top = timed(step_resident, args.steps, only=[top])
+    # that produces `value`)
+    with per_kernel_mode():
+        ms_instr, _, t_top = timed(step_resident, args.steps, only=[top])
     clocks = sampler.stop() if sampler else None
     e2e_state.update(i=0, start=0, end=1)
     step_e2e()
@@ -420,23 +368,30 @@ def main():
     e2e_state.update(start=e2e_state["i"], end=e2e_state["i"] + args.steps)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
-    images_per_step = 2 * PAIRS * world
-    value = images_per_step * args.steps / (ms / 1e3)
-    e2e_value = images_per_step * args.steps / (ms_e2e / 1e3)
+    units_per_step = w.units * world
+    value = units_per_step * args.steps / (ms / 1e3)
+    e2e_value = units_per_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel, from the events recorded INSIDE the timed region ----
+    # ---- roofline of the dominant kernel, from CUDA events around each of its launches ----
     rec = t_top.summary()[top]
     flops = sum(algorithmic_flops(top, m) for m in rec["meta"])
     achieved = flops / (rec["ms"] / 1e3) / 1e12 if rec["ms"] > 0 else 0.0
     share = rec["ms"] / ms_instr
+    traffic = ncu_traffic(top) if args.config == 2 else None
     roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "traffic_detail": traffic,
                 "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
                 "launches_per_step": rec["launches"] // args.steps, "ms_per_step": rec["ms"] / args.steps,
                 "share_of_step": share, "instrumented_ms_per_step": ms_instr / args.steps,
+                "algorithmic_tflop_per_launch": flops / max(rec["launches"], 1) / 1e12,
+                "timed_in": "a second pass of the same K steps with CUDA events around every launch of this kernel, "
+                            "launched from Python with host-side lengths (the kernels inside the CUDA graph of the "
+                            "`value` pass cannot be bracketed by events; same kernels, bit-identical results)",
                 "note": "algorithmic FLOPs per launch as in DESIGN.md section 5 (error-compensation passes and the "
                         "second QK^T pass are not credited)"}
-    step_flops = 2.0 * cal["macs_pruned"] * PAIRS          # oracle trajectory, per rank
+    step_flops = w.step_flops()                               # oracle trajectory, per rank
     step_roofline = {"algorithmic_tflop_per_step": step_flops / 1e12,
                      "achieved": step_flops / (ms / args.steps / 1e3) / 1e12, "peak": peaks["tflops_sustained"],
                      "unit": "TFLOP/s", "frac": step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tflops_sustained"]}
@@ -445,29 +400,28 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_subprocess(PAIRS, 3, 1)
+        cpu_baseline = cpu_baseline_subprocess(args.config, 0, 3, 1)
 
     parity = None
     if rank == 0:
-        pred = step_resident()
+        out = step_resident()
         torch.cuda.synchronize()
-        ks = [(b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1)
-              for b in model.visual_encoder.blocks]
-        keeps = [(b.last_prune.keep.cpu().numpy() if b.last_prune is not None and b.last_prune.pruned else None)
-                 for b in model.visual_encoder.blocks]
-        parity = parity_report(keeps, ks, pred[:PAIRS].float().cpu().numpy())
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        parity = w.parity(out)
+        execution = ("CUDA graph replay, device-resident token counts (0 host read-backs per step)" if use_graph else
+                     "Python-issued launches, " + ("one read-back per pruned layer" if args.host_lengths or args.config == 4
+                                                   else "device-resident token counts, one read-back per encoder call"))
+        cfg = {"workload": w.workload, "baseline_config": w.config, "temperature": w.temperature,
+               "parallelism": f"batch-shard x{world}", "execution": execution,
+               "l2": "per-step working set (weights + activations) exceeds the 126 MB L2; no flush"}
+        cfg.update(w.config_extra())
+        line = {"metric": w.metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32-accurate scoring lane (error-compensated fp16 hi/lo planes on tcgen05, fp32 accumulate) + f16 value lane",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS, "image_size": IMAGE, "text_len": TEXT_LEN,
-                           "temperature": temp, "mac_ratio_oracle": cal["ratio"], "vit_topk_per_layer": ks,
-                           "vit_topk_oracle": cal["vit_k"], "parallelism": f"batch-shard x{world}",
-                           "l2": "per-step working set (weights 1.9 GB + activations) exceeds the 126 MB L2; no flush"},
-                "clocks": clocks,
+                "vs_baseline": None,
+                "dtype": "f32-accurate scoring lane (error-compensated fp16 hi/lo planes on tcgen05, fp32 accumulate) + f16 value lane",
+                "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": int(images_h.numel() * 4 + ids_h.numel() * 8 + mask_h.numel() * 8),
-                        "d2h_bytes_per_step": int(logits_h.numel() * 4)},
+                        "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
+                        "d2h_bytes_per_step": int(e2e_state["out_h"].numel() * e2e_state["out_h"].element_size())},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roofline, "kernel_ms_one_step": breakdown,
                 "parity": parity, "cpu_baseline": cpu_baseline}

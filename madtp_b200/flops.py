@@ -107,3 +107,37 @@ def calibrate_temperature(ratio_at: Callable[[float], float], p: float, lo: floa
         else:
             hi = mid
     return best[0], best[1], max_iter
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configurations 3-5: BLIP retrieval evaluation path, CLIP ViT-B/16 towers, BLIP-VQA question encoder
+# ---------------------------------------------------------------------------------------------------------------
+def retrieval_macs(n0: int, vit_ks: Sequence[int], text_len: int, text_ks: Sequence[int], mm_ks: Sequence[int],
+                   d: int = D) -> int:
+    """One image-text pair through the evaluation path of compress_retrieval_dtp.py:104,120,170-177: pruned ViT, text
+    encoder in mode 'text', one multimodal (ITM) pass over the pruned image tokens, itm_head."""
+    n_img = trajectory(n0, vit_ks)[-1][1] if len(vit_ks) else n0
+    return (vit_macs(n0, vit_ks, d) + text_macs(text_len, text_ks, 0, 0, d) + text_macs(text_len, mm_ks, n_img, 1, d)
+            + 2 * d)
+
+
+def vqa_encoder_macs(n0: int, vit_ks: Sequence[int], text_len: int, mm_ks: Sequence[int], d: int = D) -> int:
+    """One (image, question) pair through models/blip_vqa.py:60,119-125: pruned ViT and the question encoder with
+    cross-attention over the pruned image tokens (the answer decoder is not part of this count)."""
+    n_img = trajectory(n0, vit_ks)[-1][1] if len(vit_ks) else n0
+    return vit_macs(n0, vit_ks, d) + text_macs(text_len, mm_ks, n_img, 1, d)
+
+
+def clip_layer_macs(n_in: int, n_out: int, d: int, sd_dim: int = 768, T: int = T_BOOK) -> int:
+    """clip/model.py:236-261: q_map Linear(d -> sd_dim) and the codebook products on the prunable tokens, attention on
+    n_in tokens, the 4x QuickGELU MLP on n_out."""
+    return (n_in - 1) * (d * sd_dim + 2 * sd_dim * T) + 4 * n_in * d * d + 2 * n_in * n_in * d + 8 * n_out * d * d
+
+
+def clip_macs(n0: int, vision_ks: Sequence[int], text_ks: Sequence[int], context: int = 77, vision_width: int = 768,
+              text_width: int = 512, embed_dim: int = 512, patch: int = 16) -> int:
+    """One (image, caption) pair through CLIP.encode_image + CLIP.encode_text (clip/model.py:482-503), ViT-B/16."""
+    total = (n0 - 1) * 3 * patch * patch * vision_width + vision_width * embed_dim + text_width * embed_dim
+    total += sum(clip_layer_macs(a, b, vision_width) for a, b in trajectory(n0, vision_ks))
+    total += sum(clip_layer_macs(a, b, text_width) for a, b in trajectory(context, text_ks))
+    return total

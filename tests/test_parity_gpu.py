@@ -248,8 +248,12 @@ def test_nlvr_small_end_to_end_against_golden(dev, ti):
     model, sd, (images, ids, mask), tr, pred_or = nlvr_setup(dev, 224, 2, 20, temp)
     assert weights.tensor_digest(images, ids, mask) == str(gold["input_digest"])
     from madtp_b200.blip_nlvr import TokenizedText
-    with torch.no_grad():
-        pred = model(images.to(dev), TokenizedText(ids.to(dev), mask.to(dev)), 2, temp, train=False)
+    model.record_states = True          # keep fp32 copies of image_embeds / last_hidden_state in model.last
+    try:
+        with torch.no_grad():
+            pred = model(images.to(dev), TokenizedText(ids.to(dev), mask.to(dev)), 2, temp, train=False)
+    finally:
+        model.record_states = False
     ks = [(b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1)
           for b in model.visual_encoder.blocks]
     tks = [(l.last_prune.k if l.last_prune is not None and l.last_prune.pruned else -1)

@@ -768,10 +768,10 @@ class BertModel(nn.Module):
             # device-resident lengths: ONE host read-back (the final length, to shape the returned tensor) instead of
             # one per layer (models/nlvr_encoder.py:432 / models/med.py:369)
             enc_shape = None
-            if torch.is_tensor(encoder_hidden_states):
-                enc_shape = tuple(encoder_hidden_states.shape)
+            if torch.is_tensor(encoder_hidden_states):      # a zero batch stride (ITM rerank broadcast) changes the launches
+                enc_shape = (tuple(encoder_hidden_states.shape), encoder_hidden_states.stride(0) == 0)
             elif type(encoder_hidden_states) == list:
-                enc_shape = tuple(tuple(e.shape) for e in encoder_hidden_states)
+                enc_shape = tuple((tuple(e.shape), e.stride(0) == 0) for e in encoder_hidden_states)
             with L.arena_for(self, (B, Ltok, mode, enc_shape, enc_ext is None)):
                 h, sd_txt_ft, traj, l_dev = self.encoder(emb, attention_mask=ext, space_dict=space_dict,
                                                          temperature=temperature,

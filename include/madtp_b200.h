@@ -241,11 +241,13 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      const int32_t* n_dev, void* stream);
+                      int causal, const int32_t* n_dev, void* stream);
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max,
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, int causal,
                         const int32_t* n_dev, void* stream);
+/* causal != 0 (both passes): key j is visible to query i only if j <= i -- the CLIP text tower's mask (clip/model.py:
+ * 452-457, cropped to the current length by clip/mock.py:309-310). */
 /* n_dev (all three): dynamic n_tok / N; every [.., N] statistics buffer and the q/k planes are packed with it, V^T keeps
  * its pitch ld_vt (>= the capacity). */
 
@@ -272,7 +274,14 @@ int madtp_readback_wait(int slot);
 int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
                         const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
                         int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
-                        const int32_t* lq_dev, const int32_t* nk_dev, void* stream);
+                        const int32_t* lq_dev, const int32_t* nk_dev, const int32_t* k_start_dev,
+                        const int32_t* k_len_dev, const float* key0_bias_dev, void* stream);
+/* Ragged keys (k_start_dev / k_len_dev [B], both or neither; key0_bias_dev [B] optional): sequence b attends to
+ * k_len[b] keys that start at row / V^T column k_start[b] (a multiple of 8) of a PACKED K / V^T -- the t2i ITM rerank of
+ * one caption against k_test images whose pruned lengths differ (compress_retrieval_dtp.py:186-200). k_rows_per_batch /
+ * vt_cols_per_batch then carry the packed totals and Nk = max_b k_len[b]. key0_bias[b] is added to the logit of key 0:
+ * ln(1 + pad_b) evaluates "pad the shorter image with pad_b copies of its CLS token" (:142-154) exactly, without the
+ * copies. */
 /* lq_dev / nk_dev: dynamic Lq (packed q / out) and Nk (packed key_mask; non-zero per-sequence pitches become Nk rounded
  * up to 8, the layout madtp_layernorm_pack + the K / V^T projections produce). */
 

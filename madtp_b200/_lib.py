@@ -36,7 +36,7 @@ SIGNATURES = {
     "madtp_take_token": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "madtp_split_tf32": [_vp, _vp, _vp, _i64, _vp],
     "madtp_attn_cross_tc": [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
-                            _i64, _vp, _vp, _vp],
+                            _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "madtp_readback_begin": [_vp, _vp, _i64, _i32, _vp],
     "madtp_readback_wait": [_i32],
     "madtp_lm_nll": [_vp, _i64, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
@@ -63,8 +63,9 @@ SIGNATURES = {
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
                        _vp, _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
-                          _vp, _vp],
-    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp],
+                          _i32, _vp, _vp],
+    "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp,
+                            _vp],
 }
 
 
@@ -530,6 +531,29 @@ def cross_tc_supported(Lq, Nk):
     return Lq <= 128
 
 
+def attn_cross_tc_ragged(q16, k16, vt16, H, scale, out_f16, k_start, k_len, max_len, *, v_bias=None, key0_bias=None,
+                         lq_dev=None):
+    """Cross-attention over RAGGED keys: q16 [B, Lq, H*64] fp16 view; k16 [rows, H*64] fp16 and vt16 [H*64, >= rows] fp16
+    hold the keys / values of all sequences packed back to back; sequence b owns k_len[b] of them from row k_start[b]
+    (int32 device tensors [B], starts multiples of 8); max_len >= max(k_len). key0_bias [B] fp32: extra logit of key 0."""
+    B, Lq, C = q16.shape
+    if q16.stride(2) != 1 or (B > 1 and q16.stride(0) != Lq * q16.stride(1)):
+        raise RuntimeError("madtp_b200.attn_cross_tc_ragged: q must be a [B*Lq, ld] row-major view")
+    if k16.dim() != 2 or k16.stride(1) != 1 or vt16.dim() != 2 or vt16.stride(1) != 1 or vt16.shape[1] < k16.shape[0]:
+        raise RuntimeError("madtp_b200.attn_cross_tc_ragged: k [rows, C] and vt [C, >= rows] with unit inner stride")
+    for t in (k_start, k_len):
+        if t.dtype != torch.int32 or t.numel() != B or not t.is_contiguous():
+            raise RuntimeError("madtp_b200.attn_cross_tc_ragged: k_start / k_len must be contiguous int32 [B]")
+    ldo, bso = _qkv_strides(out_f16, "out_f16")
+    rows = k16.shape[0]
+    st = _call("madtp_attn_cross_tc", _ptr(q16, torch.float16, "q"), q16.stride(1), _ptr(k16, torch.float16, "k"),
+               k16.stride(0), rows, _ptr(vt16, torch.float16, "vt"), vt16.stride(0), rows,
+               _ptr(v_bias, torch.float32, "v_bias"), B, H, Lq, int(max_len), float(scale), None,
+               _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _dyn(lq_dev), None, _ptr(k_start, torch.int32),
+               _ptr(k_len, torch.int32), _ptr(key0_bias, torch.float32, "key0_bias"), _stream())
+    _check(st, "madtp_attn_cross_tc")
+
+
 def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_bias=None, key_mask=None, lq_dev=None,
                   nk_dev=None):
     """Tensor-core cross-attention (value lane). q16 [B,Lq,H*64] fp16 view of a row-major matrix (batch stride =
@@ -556,7 +580,7 @@ def attn_cross_tc(q16, k16, vt16, H, scale, out_f16, *, keys_per_batch=None, v_b
     st = _call("madtp_attn_cross_tc", _ptr(q16, torch.float16, "q"), q16.stride(1), _ptr(k16, torch.float16, "k"), ldk,
                per, _ptr(vt16, torch.float16, "vt"), vt16.stride(0), per, _ptr(v_bias, torch.float32, "v_bias"), B, H, Lq,
                Nk, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(out_f16, torch.float16, "out_f16"), ldo,
-               bso, _dyn(lq_dev), _dyn(nk_dev), _stream())
+               bso, _dyn(lq_dev), _dyn(nk_dev), None, None, None, _stream())
     _check(st, "madtp_attn_cross_tc")
 
 
@@ -684,7 +708,7 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0, n_dev=None):
 
 
 def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None, cls_p=None,
-                cls_tile_max=None, n_dev=None):
+                cls_tile_max=None, n_dev=None, causal=False):
     """cls_p [B,H,N] / cls_tile_max [B,H,ceil(N/64)] fp32 (both or neither): the CLS query row for attn_tc_stats."""
     ldo, bso = _qkv_strides(out_f16, "out_f16")
     st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
@@ -692,17 +716,17 @@ def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, ou
                vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
                _ptr(out_norm, torch.float32, "out_norm"), _ptr(cls_p, torch.float32, "cls_p"),
-               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _dyn(n_dev), _stream())
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), 1 if causal else 0, _dyn(n_dev), _stream())
     _check(st, "madtp_attn_tc_fwd")
 
 
 def attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, row_lse, out_norm, col_part, cls_attn, cls_p, cls_tile_max, *,
-                  key_mask=None, n_dev=None):
+                  key_mask=None, n_dev=None, causal=False):
     st = _call("madtp_attn_tc_stats", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"), _ptr(row_lse),
                _ptr(out_norm), _ptr(col_part, torch.float32, "col_part"), col_part.shape[1],
                _ptr(cls_attn, torch.float32, "cls_attn"), _ptr(cls_p, torch.float32, "cls_p"),
-               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), _dyn(n_dev), _stream())
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), 1 if causal else 0, _dyn(n_dev), _stream())
     _check(st, "madtp_attn_tc_stats")
 
 

@@ -89,6 +89,23 @@ class BLIP_Retrieval(nn.Module):
         return self.itm_score(input_ids, attention_mask, feats, temperature)
 
     @torch.no_grad()
+    def itm_rerank_t2i(self, image_feats, input_ids_row, attention_mask_row, temperature=0, pad_to=None):
+        """ITM rerank of ONE caption against k_test candidate images (compress_retrieval_dtp.py:186-200). The candidates
+        come from different evaluation batches, so their pruned lengths differ: `image_feats` is a list of [N_i, d]
+        tensors. The reference pads them with CLS copies to the longest image of the whole set (:142-154, `pad_to`) and
+        repeats the caption k_test times; here the images stay packed (nlvr_encoder.RaggedImageFeatures: `cu_seqlens`
+        layout, the CLS padding evaluated in closed form) and only the caption is repeated. Returns ITM logits [k_test, 2]."""
+        from .nlvr_encoder import RaggedImageFeatures
+        k = len(image_feats)
+        enc = RaggedImageFeatures(image_feats, pad_to)
+        ids = input_ids_row.reshape(1, -1).repeat(k, 1)
+        ids[:, 0] = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        mask = attention_mask_row.reshape(1, -1).repeat(k, 1)
+        out, _ = self.text_encoder(ids, attention_mask=mask, encoder_hidden_states=enc, encoder_attention_mask=None,
+                                   return_dict=True, space_dict=self.space_dict, temperature=temperature)
+        return Fn.linear_f32(out.last_hidden_state[:, 0, :].contiguous(), self._lin("itm_head"))
+
+    @torch.no_grad()
     def forward(self, image, caption, alpha=0.0, idx=None, temperature=0, train=True):
         """Evaluation-path forward (BASELINE config 3): image encoder + text-only encoder + one multimodal ITM pass
         over the matched pairs. `caption` is pre-tokenised (input_ids, attention_mask) or text for `tokenizer`."""

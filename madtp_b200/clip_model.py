@@ -78,12 +78,8 @@ class MultiheadAttention(nn.Module):
         qkv_w, out_w = self._prepared()
         C = self.embed_dim
         scale = self.head_dim ** -0.5        # q / sqrt(E) then q.k: exact for head_dim 64 (a power of two)
-        if causal:
-            qkv = Fn.linear_split(y_hi, y_lo, qkv_w).view(B, N, 3 * C)
-            ctx16, stats = Fn.self_attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], self.num_heads, scale,
-                                             None, want_stats, causal=True)
-        else:
-            ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, scale, want_stats)
+        # image tower and the causal text tower (clip/mock.py:302-340) both run the tensor-core scoring-lane attention
+        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, scale, want_stats, causal=causal)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return Fn.linear_f16(ctx16.view(B * N, C), out_w, residual=residual)

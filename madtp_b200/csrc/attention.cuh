@@ -40,6 +40,7 @@ struct AttnTcArgs {
   float* cls_attn;                       // [B, N]
   float* cls_p;                          // [B, H, N] CLS query row: 256 * exp(logit - max of its 64-key tile)
   float* cls_tile_max;                   // [B, H, ceil(N/64)] those maxima (running row maximum at each key tile)
+  int causal;                            // 1: key j visible to query i only if j <= i (CLIP text tower, clip/model.py:452-457)
   const int* n_dev;                      // dynamic N read on the device (N above is then the capacity): the sequences are
                                          // packed with the dynamic N in every buffer, V^T keeps its pitch ld_vt
 };
@@ -61,6 +62,11 @@ struct CrossTcArgs {
   __half* out_f16; long long ldo, bso;
   const int* lq_dev;                     // dynamic Lq (queries and output packed with it)
   const int* nk_dev;                     // dynamic Nk; per-sequence pitches become Nk rounded up to 8 (when not 0)
+  // ragged keys (all three or none): sequence b attends to k_len[b] keys starting at row / V^T column k_start[b] (a
+  // multiple of 8) of the packed K / V^T, and key 0 carries the extra logit key0_bias[b] -- ln(multiplicity) of the
+  // first key, which is how "pad the shorter image with copies of its CLS token" (compress_retrieval_dtp.py:142-154)
+  // is evaluated without materialising the copies. Nk is then the capacity (max_b k_len[b]).
+  const int* k_start; const int* k_len; const float* key0_bias;
 };
 int launch_cross_attn_tc(const CrossTcArgs& a, cudaStream_t stream);
 

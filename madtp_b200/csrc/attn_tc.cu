@@ -356,6 +356,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
 #pragma unroll
           for (int k = 0; k < KW; ++k) s[k] = (j0 + k < N) ? s[k] : -INFINITY;
         }
+        if (a.causal && j0 + KW - 1 > i) {           // causal: keys after the query (key 0 is always visible)
+#pragma unroll
+          for (int k = 0; k < KW; ++k) s[k] = (j0 + k <= i) ? s[k] : -INFINITY;
+        }
         float mx = s[0];
 #pragma unroll
         for (int k = 1; k < KW; ++k) mx = fmaxf(mx, s[k]);
@@ -650,12 +654,23 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[hb]);
+        if (a.causal && j0 + BM - 1 > i) {   // warp-divergent only on the diagonal tiles
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float t0 = fmaf(__uint_as_float(v0[k]), sc, cm[half * 64 + k]) - lse;
-          const float t1 = fmaf(__uint_as_float(v1[k]), sc, cm[half * 64 + 32 + k]) - lse;
-          mx[k] = fmaxf(mx[k], t0);
-          mx[32 + k] = fmaxf(mx[32 + k], t1);
+          for (int k = 0; k < 32; ++k) {
+            const int jj = j0 + half * 64 + k;
+            const float t0 = fmaf(__uint_as_float(v0[k]), sc, cm[half * 64 + k]) - lse;
+            const float t1 = fmaf(__uint_as_float(v1[k]), sc, cm[half * 64 + 32 + k]) - lse;
+            mx[k] = fmaxf(mx[k], jj <= i ? t0 : -INFINITY);
+            mx[32 + k] = fmaxf(mx[32 + k], jj + 32 <= i ? t1 : -INFINITY);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float t0 = fmaf(__uint_as_float(v0[k]), sc, cm[half * 64 + k]) - lse;
+            const float t1 = fmaf(__uint_as_float(v1[k]), sc, cm[half * 64 + 32 + k]) - lse;
+            mx[k] = fmaxf(mx[k], t0);
+            mx[32 + k] = fmaxf(mx[32 + k], t1);
+          }
         }
       }
       // column sums over this warp's 32 query rows (lane l ends up with columns l and 32 + l of its half), then over

@@ -267,9 +267,10 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      const int32_t* n_dev, void* stream) {
+                      int causal, const int32_t* n_dev, void* stream) {
   AttnTcArgs a = {};
   a.n_dev = n_dev;
+  a.causal = causal;
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.vt_hi = static_cast<const __half*>(vt_hi); a.vt_lo = static_cast<const __half*>(vt_lo); a.ld_vt = ld_vt;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
@@ -281,10 +282,11 @@ int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const
 
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
-                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max,
+                        int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, int causal,
                         const int32_t* n_dev, void* stream) {
   AttnTcArgs a = {};
   a.n_dev = n_dev;
+  a.causal = causal;
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
   a.row_lse = const_cast<float*>(row_lse); a.out_norm = const_cast<float*>(out_norm);
@@ -296,9 +298,11 @@ int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int
 int madtp_attn_cross_tc(const void* q_f16, int64_t ldq, const void* k_f16, int64_t ldk, int k_rows_per_batch,
                         const void* vt_f16, int64_t ld_vt, int vt_cols_per_batch, const float* v_bias, int B, int H,
                         int Lq, int Nk, float scale, const float* key_mask, void* out_f16, int64_t ldo, int64_t bso,
-                        const int32_t* lq_dev, const int32_t* nk_dev, void* stream) {
+                        const int32_t* lq_dev, const int32_t* nk_dev, const int32_t* k_start_dev,
+                        const int32_t* k_len_dev, const float* key0_bias_dev, void* stream) {
   CrossTcArgs a = {};
   a.lq_dev = lq_dev; a.nk_dev = nk_dev;
+  a.k_start = k_start_dev; a.k_len = k_len_dev; a.key0_bias = key0_bias_dev;
   a.q = static_cast<const __half*>(q_f16); a.ldq = ldq;
   a.k = static_cast<const __half*>(k_f16); a.ldk = ldk; a.k_rows_per_batch = k_rows_per_batch;
   a.vt = static_cast<const __half*>(vt_f16); a.ld_vt = ld_vt; a.vt_cols_per_batch = vt_cols_per_batch;

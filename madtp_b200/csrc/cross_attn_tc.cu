@@ -60,7 +60,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int Lq = a.lq_dev ? min(a.Lq, load_len(a.lq_dev)) : a.Lq;
-  const int Nk = a.nk_dev ? min(a.Nk, load_len(a.nk_dev)) : a.Nk;
+  const int Nk = a.k_len ? min(a.Nk, __ldg(a.k_len + b)) : (a.nk_dev ? min(a.Nk, load_len(a.nk_dev)) : a.Nk);
   if (a.lq_dev) a.bso = static_cast<long long>(Lq) * a.ldo;             // packed output
   if (a.nk_dev && a.k_rows_per_batch != 0) a.k_rows_per_batch = a.vt_cols_per_batch = (Nk + 7) & ~7;
   const int NB = (Nk + CrossSmem::KB - 1) / CrossSmem::KB;              // key blocks
@@ -99,7 +99,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tma_load_2d(&tm_q, q_full, q_s, h * 64, b * Lq);
     }
     __syncwarp();
-    const int krow0 = b * a.k_rows_per_batch, vcol0 = b * a.vt_cols_per_batch;
+    const int krow0 = a.k_start ? __ldg(a.k_start + b) : b * a.k_rows_per_batch;
+    const int vcol0 = a.k_start ? krow0 : b * a.vt_cols_per_batch;
     for (int blk = 0; blk < NB; ++blk) {
       const int st = blk & 1;
       mbar_wait(&kv_empty[st], ((blk >> 1) & 1) ^ 1);
@@ -158,6 +159,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const float c1 = a.scale * kLog2e;
       const float mask_to_raw = kLog2e / c1;
       const float* mask = a.key_mask ? a.key_mask + static_cast<long long>(b) * Nk : nullptr;
+      const float k0_raw = a.key0_bias ? __ldg(a.key0_bias + b) / a.scale : 0.f;   // extra logit of key 0, raw units
       const int col0 = half * 64;                // this thread's 64 keys of the block: S columns [col0, col0 + 64)
       float m = -INFINITY, l = 0.f;              // running maximum (log2 domain) and sum of 256 p
       float o[32];
@@ -173,12 +175,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           tmem_ld_32x32b_x32(tmem_base + lane_off + col0 + c * 32, v);
           tmem_ld_wait();
           const int j0 = jb + c * 32;
-          if (mask != nullptr || j0 + 32 > Nk) {
+          if (mask != nullptr || j0 + 32 > Nk || j0 == 0) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
               const int j = j0 + k;
               float x = __uint_as_float(v[k]);
               if (mask != nullptr && j < Nk) x = fmaf(__ldg(mask + j), mask_to_raw, x);
+              if (j == 0) x += k0_raw;
               s[k] = (j < Nk) ? x : -INFINITY;
             }
           } else {
@@ -278,17 +281,25 @@ int launch_cross_attn_tc(const CrossTcArgs& a, cudaStream_t stream) {
                   "cross_attn_tc: needs 1 <= Lq <= 128 and Nk >= 1 (Lq=%d Nk=%d)", a.Lq, a.Nk);
   MADTP_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ld_vt % 8 == 0 && a.ldo % 8 == 0 && a.bso % 8 == 0,
                   "cross_attn_tc: leading dimensions must be multiples of 8 halves");
-  MADTP_CHECK_ARG(a.k_rows_per_batch == 0 || a.k_rows_per_batch >= a.Nk, "cross_attn_tc: k rows per batch is >= Nk or 0");
+  MADTP_CHECK_ARG(a.k_rows_per_batch == 0 || a.k_rows_per_batch >= a.Nk || a.k_start != nullptr,
+                  "cross_attn_tc: k rows per batch is >= Nk or 0");
   // TMA box origins must be 16-byte aligned in global memory: a sequence's keys start at a multiple of 8 columns
   MADTP_CHECK_ARG(a.vt_cols_per_batch == 0 || (a.vt_cols_per_batch >= a.Nk && a.vt_cols_per_batch % 8 == 0),
                   "cross_attn_tc: V^T columns per batch must be 0 or a multiple of 8 that is >= Nk (got %d)",
                   a.vt_cols_per_batch);
   MADTP_CHECK_ARG(a.B <= 65535, "cross_attn_tc: B must fit the grid limits");
+  MADTP_CHECK_ARG((a.k_start == nullptr) == (a.k_len == nullptr) && (a.key0_bias == nullptr || a.k_start != nullptr),
+                  "cross_attn_tc: k_start / k_len come together (key0_bias only with them)");
+  MADTP_CHECK_ARG(a.k_start == nullptr || (a.key_mask == nullptr && a.nk_dev == nullptr),
+                  "cross_attn_tc: ragged keys exclude key_mask and nk_dev");
   if (a.B == 0) return kOk;
   CUtensorMap tq, tk, tv;
   int st;
-  const long long k_rows = a.k_rows_per_batch ? static_cast<long long>(a.B) * a.k_rows_per_batch : a.Nk;
-  const long long v_cols = a.vt_cols_per_batch ? static_cast<long long>(a.B) * a.vt_cols_per_batch : a.Nk;
+  // ragged: k_rows_per_batch / vt_cols_per_batch carry the TOTAL packed rows / columns
+  const long long k_rows = a.k_start ? a.k_rows_per_batch
+                                     : (a.k_rows_per_batch ? static_cast<long long>(a.B) * a.k_rows_per_batch : a.Nk);
+  const long long v_cols = a.k_start ? a.vt_cols_per_batch
+                                     : (a.vt_cols_per_batch ? static_cast<long long>(a.B) * a.vt_cols_per_batch : a.Nk);
   if ((st = make_tmap(&tq, a.q, false, static_cast<long long>(a.B) * a.Lq, a.H * 64LL, a.ldq, 128)) != kOk) return st;
   if ((st = make_tmap(&tk, a.k, false, k_rows, a.H * 64LL, a.ldk, 64)) != kOk) return st;
   if ((st = make_tmap(&tv, a.vt, false, a.H * 64LL, v_cols, a.ld_vt, 64)) != kOk) return st;

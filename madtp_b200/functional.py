@@ -258,7 +258,7 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
 
 
 def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N: int, H: int, scale: float,
-                      want_stats: bool, n_dev: Optional[Tensor] = None):
+                      want_stats: bool, n_dev: Optional[Tensor] = None, causal: bool = False):
     """Tensor-core scoring-lane self-attention from the fp16 hi/lo planes of the normalised rows [B*N, C]:
     fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
     Returns (ctx16 [B,N,H*64] fp16, AttnStats or None). n_dev: device-resident N (N is then the capacity)."""
@@ -268,16 +268,16 @@ def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N
     ctx16 = L.empty((B, N, H * 64), torch.float16, dev)
     rows = L.empty((3 if want_stats else 2, B, H, N), torch.float32, dev)
     if not want_stats:
-        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], n_dev=n_dev)
+        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], n_dev=n_dev, causal=causal)
         return ctx16, None
     cls_tile_max = L.empty((B, H, (N + 63) // 64), torch.float32, dev)
     L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], cls_p=rows[2],
-                  cls_tile_max=cls_tile_max, n_dev=n_dev)
+                  cls_tile_max=cls_tile_max, n_dev=n_dev, causal=causal)
     n_parts = (N + 127) // 128
     col_part = L.empty((B, n_parts, N), torch.float32, dev)
     cls_attn = L.empty((B, N), torch.float32, dev)
     L.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, rows[0], rows[1], col_part, cls_attn, rows[2], cls_tile_max,
-                    n_dev=n_dev)
+                    n_dev=n_dev, causal=causal)
     return ctx16, AttnStats(col_part, cls_attn, 128)
 
 

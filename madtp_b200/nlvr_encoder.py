@@ -57,11 +57,47 @@ def _key_mask(ext_mask: Optional[torch.Tensor], B: int, N: int) -> Optional[torc
 class CrossKV:
     """Operands of the tensor-core cross-attention for one layer and branch: k16 [B,Nk,C] (or [Nk,C] when broadcast)
     fp16 view, vt16 [C, >= B*P] fp16 (V^T, keys contiguous, P = keys_per_batch columns per sequence, 0 = broadcast),
-    v_bias [C] fp32."""
-    __slots__ = ("k16", "vt16", "v_bias", "keys_per_batch")
+    v_bias [C] fp32. `ragged` = (k_start, k_len, key0_bias, max_len): sequences of DIFFERENT key counts packed back to
+    back in k16 [rows, C] / vt16 [C, rows] (see RaggedImageFeatures)."""
+    __slots__ = ("k16", "vt16", "v_bias", "keys_per_batch", "ragged")
 
-    def __init__(self, k16, vt16, v_bias, keys_per_batch):
-        self.k16, self.vt16, self.v_bias, self.keys_per_batch = k16, vt16, v_bias, keys_per_batch
+    def __init__(self, k16, vt16, v_bias, keys_per_batch, ragged=None):
+        self.k16, self.vt16, self.v_bias, self.keys_per_batch, self.ragged = k16, vt16, v_bias, keys_per_batch, ragged
+
+
+class RaggedImageFeatures:
+    """Pruned image features of DIFFERENT lengths as ONE packed tensor -- the encoder states of the t2i ITM rerank (one
+    caption against k_test images from different evaluation batches, compress_retrieval_dtp.py:186-200). The reference
+    pads every image to the longest one of the whole evaluation set with copies of its CLS token (:142-154) and runs a
+    dense cross-attention; here the images stay packed (`cu_seqlens` layout, rows aligned to 8) and the padding is
+    evaluated in closed form: `pad` copies of key 0 are the same as key 0 with ln(1 + pad) added to its logit.
+
+    feats: list of [N_i, d] fp32 CUDA tensors (token 0 = CLS); pad_to: the length the reference would pad to (default:
+    the longest of the list)."""
+
+    def __init__(self, feats, pad_to=None):
+        if not feats:
+            raise RuntimeError("madtp_b200: RaggedImageFeatures needs at least one image")
+        lens = [int(f.shape[0]) for f in feats]
+        self.pad_to = max(lens) if pad_to is None else int(pad_to)
+        if self.pad_to < max(lens):
+            raise RuntimeError("madtp_b200: pad_to is shorter than the longest image")
+        dev, d = feats[0].device, feats[0].shape[1]
+        starts, total = [], 0
+        for n in lens:
+            starts.append(total)
+            total += (n + 7) // 8 * 8
+        self.rows = total
+        self.max_len = max(lens)
+        packed = torch.zeros(total, d, dtype=torch.float32, device=dev)
+        for s, n, f in zip(starts, lens, feats):
+            Fn.require_cuda(f, "image feature")
+            packed[s:s + n] = f
+        self.e16 = L.cast_f16(packed)
+        self.k_start = torch.tensor(starts, dtype=torch.int32, device=dev)
+        self.k_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+        self.key0_bias = torch.tensor([math.log(1 + self.pad_to - n) for n in lens], dtype=torch.float32, device=dev)
+        self.B = len(feats)
 
 
 class LayerLengths:
@@ -489,7 +525,9 @@ class BertLayer(nn.Module):
         """Twin (list-valued encoder states, :312-335) or single cross-attention + output LayerNorm."""
         ca = self.crossattention
         d = att_rows.shape[1]
-        if hasattr(enc, "y16"):     # vit.DeviceEncoded: one group of packed image tokens per branch, no encoder mask
+        if isinstance(enc, RaggedImageFeatures):
+            selfs, enc, masks = [ca.self], [None], [None]
+        elif hasattr(enc, "y16"):   # vit.DeviceEncoded: one group of packed image tokens per branch, no encoder mask
             selfs = [ca.self0, ca.self1] if enc.y16.shape[0] == 2 else [ca.self]
             enc, masks = [None] * len(selfs), [None] * len(selfs)
         elif type(enc) == list:
@@ -515,6 +553,13 @@ class BertLayer(nn.Module):
                                                                              **dyn).view(B, Ltok, C)
             em = masks[i] if s.CROSS_ATTENTION_MASK else None
             out = ctx[..., i * C:(i + 1) * C]
+            if use_tc and kv[i].ragged is not None:
+                ckv = kv[i]
+                k_start, k_len, key0_bias, max_len = ckv.ragged
+                L.attn_cross_tc_ragged(q, ckv.k16, ckv.vt16, s.num_attention_heads,
+                                       1.0 / math.sqrt(s.attention_head_size), out, k_start, k_len, max_len,
+                                       v_bias=ckv.v_bias, key0_bias=key0_bias, lq_dev=l_dev)
+                continue
             if use_tc:
                 ckv = kv[i]
                 Nk = ckv.k16.shape[-2]
@@ -619,6 +664,17 @@ class BertEncoder(nn.Module):
                 per_layer[i].append((allkv[..., o:o + C], allkv[..., o + C:o + 2 * C]))
         return per_layer
 
+    def _project_encoder_states_ragged(self, enc: "RaggedImageFeatures"):
+        """K / V^T of every layer over the packed rows of a RaggedImageFeatures (one GEMM each)."""
+        C = self.config.hidden_size
+        wk, wv16, vb = self._all_k_vt_weights("self")
+        allk = Fn.linear_f16(enc.e16, wk, out_dtype=torch.float16)                         # [rows, layers * C]
+        allvt = L.empty((wv16.shape[0], enc.rows), torch.float16, enc.e16.device)
+        L.gemm(L.GEMM_F16, wv16, enc.e16, allvt)
+        rag = (enc.k_start, enc.k_len, enc.key0_bias, enc.max_len)
+        return [[CrossKV(allk[:, i * C:(i + 1) * C], allvt[i * C:(i + 1) * C], vb[i], 0, rag)]
+                for i in range(len(self.layer))]
+
     def _project_encoder_states_device(self, enc):
         """The same operands from a vit.DeviceEncoded record whose final LayerNorm was written by madtp_layernorm_pack:
         fp16 image tokens [groups, per_group * P, w] with P = the DEVICE-RESIDENT token count rounded up to 8. One
@@ -658,7 +714,9 @@ class BertEncoder(nn.Module):
         kv = None
         nk_dev = None
         enc_dev = encoder_hidden_states if hasattr(encoder_hidden_states, "y16") else None
-        if mode == 'multimodal' and enc_dev is not None:
+        if mode == 'multimodal' and isinstance(encoder_hidden_states, RaggedImageFeatures):
+            kv = self._project_encoder_states_ragged(encoder_hidden_states)
+        elif mode == 'multimodal' and enc_dev is not None:
             kv = self._project_encoder_states_device(enc_dev)
             nk_dev = enc_dev.n_dev
         elif mode == 'multimodal' and encoder_hidden_states is not None:
@@ -772,6 +830,8 @@ class BertModel(nn.Module):
                 enc_shape = (tuple(encoder_hidden_states.shape), encoder_hidden_states.stride(0) == 0)
             elif type(encoder_hidden_states) == list:
                 enc_shape = tuple((tuple(e.shape), e.stride(0) == 0) for e in encoder_hidden_states)
+            elif isinstance(encoder_hidden_states, RaggedImageFeatures):
+                enc_shape = ("ragged", encoder_hidden_states.rows, encoder_hidden_states.B)
             with L.arena_for(self, (B, Ltok, mode, enc_shape, enc_ext is None)):
                 h, sd_txt_ft, traj, l_dev = self.encoder(emb, attention_mask=ext, space_dict=space_dict,
                                                          temperature=temperature,

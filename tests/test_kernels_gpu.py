@@ -396,6 +396,48 @@ def test_attention_tensor_core_path(lib, dev, monkeypatch, B, H, N, masked, vari
     assert ((a - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 3e-6
 
 
+@pytest.mark.parametrize("B,H,N", [(3, 8, 77), (2, 8, 27), (2, 4, 130), (1, 2, 300)])
+def test_attention_tensor_core_causal(lib, dev, B, H, N):
+    """causal = 1: the CLIP text tower (clip/model.py:452-457, mock.py:309-310; 77 tokens, 8 heads) on the tensor-core
+    scoring-lane kernels -- context, log-sum-exp, norms and both pruning statistics against fp64."""
+    g = torch.Generator(device="cpu").manual_seed(N * 7 + B)
+    K, HD = 128, H * 64
+    x = torch.randn(B * N, K, generator=g).to(dev)
+    w = (torch.randn(3 * HD, K, generator=g) * 0.1).to(dev)
+    bias = (torch.randn(3 * HD, generator=g) * 0.1).to(dev)
+    x_hi, x_lo = lib.split_f16(x)
+    w_hi, w_lo = lib.split_f16(w, 2.0 ** 14)
+    qk_hi, qk_lo, vt_hi, vt_lo = lib.gemm_qkv(x_hi, x_lo, w_hi, w_lo, bias, N, H, alpha=2.0 ** -14)
+    qk = (qk_hi.double() + qk_lo.double()) / lib.QK_PLANE_SCALE
+    vt = ((vt_hi.double() + vt_lo.double()) / lib.V_PLANE_SCALE)[:, :N].reshape(B, H, 64, N)
+    scale = 0.125
+    out = torch.empty(B, N, HD, device=dev, dtype=torch.float16)
+    lse = torch.empty(B, H, N, device=dev)
+    norm = torch.empty(B, H, N, device=dev)
+    cls_p = torch.zeros(B, H, N, device=dev)
+    cls_m = torch.zeros(B, H, (N + 63) // 64, device=dev)
+    lib.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out, lse, norm, cls_p=cls_p, cls_tile_max=cls_m, causal=True)
+    col_part = torch.zeros(B, (N + 127) // 128, N, device=dev)
+    cls_attn = torch.zeros(B, N, device=dev)
+    lib.attn_tc_stats(qk_hi, qk_lo, B, H, N, scale, lse, norm, col_part, cls_attn, cls_p, cls_m, causal=True)
+    q = qk[:, :HD].reshape(B, N, H, 64).permute(0, 2, 1, 3).double()
+    k = qk[:, HD:].reshape(B, N, H, 64).permute(0, 2, 1, 3).double()
+    v = vt.permute(0, 1, 3, 2).double()
+    s = q @ k.transpose(-1, -2) * scale + torch.full((N, N), float("-inf"), dtype=torch.float64, device=dev).triu_(1)
+    p = torch.softmax(s, dim=-1)
+    o = p @ v
+    assert _rel(out, o.permute(0, 2, 1, 3).reshape(B, N, HD)) < 6e-4
+    assert (lse.double() - torch.logsumexp(s, dim=-1)).abs().max().item() < 2e-5
+    assert (norm.double() - o.norm(dim=-1)).abs().max().item() < 1e-5 * max(1.0, o.norm(dim=-1).max().item())
+    hi = o[..., 1:, :].norm(dim=-1)
+    hi = hi / (hi.sum(dim=1, keepdim=True) + 1e-8)
+    cls_ref = (p[:, :, 0, 1:] * hi).sum(dim=1)               # identically zero: the CLS query only sees itself
+    a_ref = p[:, :, 1:, 1:].max(dim=1)[0].sum(dim=1)
+    assert (cls_attn[:, 1:].double() - cls_ref).abs().max().item() < 1e-6
+    a = col_part.double().sum(dim=1)[:, 1:]
+    assert ((a - a_ref).abs() / a_ref.abs().clamp_min(1e-3)).max().item() < 3e-6
+
+
 @pytest.mark.parametrize("B,n,T,d", [(3, 196, 100, 768), (2, 576, 100, 768), (4, 19, 100, 768), (2, 76, 100, 512)])
 def test_query_sdft_tensor_core(lib, dev, B, n, T, d):
     """sd_ft = softmax_tokens(token_att / sqrt(d))^T . x on tcgen05 (operands re-laid out K-major in shared memory)."""

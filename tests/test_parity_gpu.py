@@ -694,3 +694,32 @@ def test_product_mac_counter_and_calibration_on_gpu(dev):
     temp, r50, probes = flops.calibrate_temperature(ratio_at, p=0.5, tol=0.01)
     assert abs(r50 - 0.5) < 0.01 and 1.0 < temp < 16.0 and probes <= 16
     assert ratio_at(0.0) == 1.0                              # temperature 0: nothing is pruned (models/vit.py:193)
+
+
+def test_itm_rerank_t2i_ragged_matches_cls_padded(dev):
+    """SURVEY 8(f)-1, t2i direction (compress_retrieval_dtp.py:142-154,186-200): one caption against k_test images whose
+    pruned lengths differ. The packed `cu_seqlens` path (CLS padding evaluated in closed form as a logit bias on key 0)
+    must agree with the reference's computation -- images padded with CLS copies to the longest, caption repeated --
+    both through the mirror's dense path and through the oracle."""
+    from madtp_b200.blip_retrieval import BLIP_Retrieval
+    sd = weights.retrieval_state_dict(4321, img_size=224)
+    model = BLIP_Retrieval(image_size=224, evaluate=True)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(21)
+    lens, pad_to, temp = [37, 150, 41, 60, 33, 129], 160, 8.0
+    feats = [torch.randn(n, 768, generator=g) for n in lens]
+    _, ids, mask = weights.retrieval_inputs(1, 32, 35, seed=4)
+    dense = torch.stack([torch.cat([f, f[:1].repeat(pad_to - f.shape[0], 1)], 0) for f in feats])      # :142-154
+    k = len(lens)
+    with torch.no_grad():
+        got = model.itm_rerank_t2i([f.to(dev) for f in feats], ids[0].to(dev), mask[0].to(dev), temp, pad_to=pad_to)
+        want = model.itm_score(ids.repeat(k, 1).to(dev), mask.repeat(k, 1).to(dev), dense.to(dev), temp)
+        ids2 = ids.repeat(k, 1)
+        ids2[:, 0] = 30523
+        mm, _ = O.med_text_encoder(ids2, mask.repeat(k, 1), sd, "text_encoder.", dense, sd["space_dict"], temp, "multimodal")
+        oracle = O.linear(mm[:, 0, :], sd, "itm_head")
+    assert got.shape == (k, 2)
+    assert (got - want).abs().max().item() < 5e-3, (got - want).abs().max().item()       # same lane, different key layout
+    assert (got.cpu() - oracle).abs().max().item() < 2e-2
+    assert (want.cpu() - oracle).abs().max().item() < 2e-2

@@ -221,6 +221,19 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
  * pruned, so that the next layer always reads `out`). */
 
 /*
+ * madtp_dtp_select + madtp_dtp_gather + the LayerNorm that follows the pruning (vit.py:205 norm2) as ONE kernel:
+ * radix select of the k-th largest score (ties -> lower token index), stream compaction in ascending token order, merged
+ * token, and -- when ln_gamma / ln_beta / ln_out_f16 are given -- LayerNorm(out) written as fp16 (the operand of the
+ * GEMM that follows), computed while the row is in registers. keep (optional) [B, n]. out_f16 (optional): fp16 copy of
+ * out. Everything else as madtp_dtp_select / madtp_dtp_gather; results are bit-identical to that pair + madtp_layernorm.
+ * d must be a multiple of 128, <= 1024; n <= 1024 (mask modes: n <= 256).
+ */
+int madtp_dtp_apply(int B, int n, int d, const float* score, const int32_t* topk, const float* x, int64_t bsx, float* out,
+                    int64_t bso, void* out_f16, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                    void* ln_out_f16, uint8_t* keep, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
+                    const int32_t* n_dev, int32_t* n_out_dev, int32_t* k_out_dev, void* stream);
+
+/*
  * Tensor-core self-attention for the scoring lane (vit.py:75-103 without materialising P). madtp_gemm_qkv is the
  * fused q|k|v projection (vit.py:77; a_hi/a_lo and w_hi/w_lo are fp16 hi/lo planes as for MADTP_GEMM_F16X3, alpha
  * removes the weight's scale) with an epilogue that writes q and k as fp16 hi/lo planes of MADTP_QK_PLANE_SCALE * value,

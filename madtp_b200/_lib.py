@@ -59,6 +59,8 @@ SIGNATURES = {
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp],
+    "madtp_dtp_apply": [_i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _f32, _vp, _vp, _i32, _vp, _vp,
+                        _i32, _vp, _vp, _vp, _vp],
     "madtp_gather_rows": [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
                        _vp, _vp],
@@ -672,6 +674,36 @@ def dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=0, want_f16=False, n_
                                  int(max_keep), _dyn(n_dev), _stream())
     _check(st, "madtp_dtp_gather")
     return (out, out16) if want_f16 else out
+
+
+def dtp_apply(x, score, topk, k, *, mask_mode=0, mask_in=None, max_keep=0, want_f16=False, ln=None, n_dev=None,
+              n_out=None, k_out=None):
+    """Fused select + gather + merged token (+ LayerNorm): x [B, n+1, d] fp32 dense rows, score [B, n], topk device
+    scalar. k: the host's copy of topk (output rows = k + 2), or n - 1 with device-resident lengths (capacity-sized
+    output). ln = (gamma, beta, eps): also LayerNorm(out) as fp16. Returns (out, out16 | None, ln16 | None, keep,
+    mask_out | None)."""
+    B, N, d = x.shape
+    n = N - 1
+    if x.stride(2) != 1 or x.stride(1) != d:
+        raise RuntimeError("madtp_b200.dtp_apply: x rows must be dense")
+    dev = x.device
+    out = empty((B, k + 2, d), torch.float32, dev)
+    out16 = empty((B, k + 2, d), torch.float16, dev) if want_f16 else None
+    ln16 = empty((B, k + 2, d), torch.float16, dev) if ln is not None else None
+    keep = empty((B, n), torch.uint8, dev)
+    mask_out = None
+    if mask_mode:
+        if mask_in is None or not mask_in.is_contiguous() or mask_in.numel() != B * (n + 1):
+            raise RuntimeError("madtp_b200.dtp_apply: mask_in must be contiguous [B, n+1]")
+        mask_out = empty((B, n + 1), torch.float32, dev)
+    g, bt, eps = ln if ln is not None else (None, None, 0.0)
+    st = _call("madtp_dtp_apply", B, n, d, _ptr(score, torch.float32, "score"), _ptr(topk, torch.int32, "topk"),
+               _ptr(x, torch.float32, "x"), x.stride(0), _ptr(out), out.stride(0), _ptr(out16),
+               _ptr(g, torch.float32, "ln_gamma"), _ptr(bt, torch.float32, "ln_beta"), float(eps), _ptr(ln16), _ptr(keep),
+               int(mask_mode), _ptr(mask_in, torch.float32, "mask_in"), _ptr(mask_out), int(max_keep), _dyn(n_dev),
+               _dyn(n_out), _dyn(k_out), _stream())
+    _check(st, "madtp_dtp_apply")
+    return out, out16, ln16, keep, mask_out
 
 
 def gather_rows(x, idx):

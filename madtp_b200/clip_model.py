@@ -120,13 +120,16 @@ class ResidualAttentionBlock(nn.Module):
         self.last_prune = None
         if prune:                                                                        # :254-258
             res = Fn.dtp_prune(x1, self.attn.get_attention_map(), token_attn, float(temperature),
-                               max_keep=int(max_keep))
+                               max_keep=int(max_keep), ln=(self.ln_2.weight, self.ln_2.bias, self.ln_2.eps))
             self.last_prune = res
             x1 = res.x
         N2 = x1.shape[1]
         x2d = x1.view(B * N2, C)
         fc, pj = self._mlp()
-        y16 = Fn.layernorm_rows(x2d, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, f16=True)["y16"]
+        if prune and res.ln16 is not None:      # ln_2 came out of the fused select + gather kernel
+            y16 = res.ln16.view(B * N2, C)
+        else:
+            y16 = Fn.layernorm_rows(x2d, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, f16=True)["y16"]
         h = Fn.linear_f16(y16, fc, out_dtype=torch.float16, act=L.ACT_QUICKGELU)
         return Fn.linear_f16(h, pj, residual=x2d).view(B, N2, C), sd_ft_all
 

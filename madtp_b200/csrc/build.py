@@ -19,7 +19,7 @@ CSRC = Path(__file__).resolve().parent
 REPO = CSRC.parent.parent
 LIB = CSRC.parent / "libmadtp_b200.so"
 BUILD = CSRC / "build"
-SOURCES = ["capi.cu", "gemm.cu", "rowops.cu", "attention.cu", "small_attn.cu", "attn_tc.cu", "cross_attn_tc.cu", "sdft_tc.cu", "dtp.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "rowops.cu", "attention.cu", "small_attn.cu", "attn_tc.cu", "cross_attn_tc.cu", "sdft_tc.cu", "dtp.cu", "dtp_apply.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "rowops.cuh", "attention.cuh", "dtp.cuh", "../../include/madtp_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

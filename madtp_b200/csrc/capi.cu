@@ -256,6 +256,22 @@ int madtp_dtp_gather(int B, int n, int d, const float* x, int64_t bsx, const int
   return counted(launch_dtp_gather(a, as_stream(stream)), B > 0 ? 1 : 0);
 }
 
+int madtp_dtp_apply(int B, int n, int d, const float* score, const int32_t* topk, const float* x, int64_t bsx, float* out,
+                    int64_t bso, void* out_f16, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                    void* ln_out_f16, uint8_t* keep, int mask_mode, const float* mask_in, float* mask_out, int max_keep,
+                    const int32_t* n_dev, int32_t* n_out_dev, int32_t* k_out_dev, void* stream) {
+  DtpApplyArgs a;
+  a.B = B; a.n = n; a.d = d;
+  a.score = score; a.topk = topk;
+  a.x = x; a.bsx = bsx; a.out = out; a.bso = bso;
+  a.out_f16 = static_cast<__half*>(out_f16);
+  a.ln_gamma = ln_gamma; a.ln_beta = ln_beta; a.ln_eps = ln_eps; a.ln_out = static_cast<__half*>(ln_out_f16);
+  a.keep = keep;
+  a.mask_mode = mask_mode; a.mask_in = mask_in; a.mask_out = mask_out; a.max_keep = max_keep;
+  a.n_dev = n_dev; a.n_out = n_out_dev; a.k_out = k_out_dev;
+  return counted(launch_dtp_apply(a, as_stream(stream)), B > 0 ? 1 : 0);
+}
+
 int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo, int64_t ldb,
                    const float* bias, float alpha, int M, int K, int n_tok, int heads, void* qk_hi, void* qk_lo,
                    int64_t ld_qk, void* vt_hi, void* vt_lo, int64_t ld_vt, const int32_t* n_dev, void* stream) {

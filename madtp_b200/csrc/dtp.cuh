@@ -81,6 +81,32 @@ struct DtpGatherArgs {
 };
 int launch_dtp_gather(const DtpGatherArgs& a, cudaStream_t stream);
 
+// Fused selection + compaction + merged token + LayerNorm (dtp_apply.cu): what dtp_select + dtp_gather + the following
+// layernorm launch do, in one kernel with a radix select.
+struct DtpApplyArgs {
+  int B, n, d;
+  const float* score;         // [B, n]
+  const int* topk;            // device scalar k (batch max count)
+  const float* x;             // [B, n+1, d] tokens incl. position 0 (always survives)
+  long long bsx;              // batch stride of x (elements, a multiple of d)
+  float* out;                 // [B, k+2, d]: [position 0, survivors ascending, merged]
+  long long bso;
+  __half* out_f16;            // optional fp16 copy of out
+  const float* ln_gamma;      // optional LayerNorm applied to every output row, written as fp16 to ln_out
+  const float* ln_beta;
+  float ln_eps;
+  __half* ln_out;             // [B, k+2, d] fp16, same batch stride as out
+  unsigned char* keep;        // optional [B, n]: 1 = survivor
+  int mask_mode;              // as DtpSelectArgs
+  const float* mask_in;
+  float* mask_out;
+  int max_keep;
+  const int* n_dev;           // device-resident N = n + 1 (packed input / output), as DtpSelectArgs / DtpGatherArgs
+  int* n_out;
+  int* k_out;
+};
+int launch_dtp_apply(const DtpApplyArgs& a, cudaStream_t stream);
+
 // vector_gather (reference models/utils.py:13-33): out[b,i,:] = x[b, idx[b,i], :]; one warp per output row.
 int launch_gather_rows(const float* x, long long bsx, const int* idx, float* out, int B, int L, int K, int d,
                        cudaStream_t stream);

@@ -292,6 +292,7 @@ class PruneResult:
     keep: Optional[Tensor] = None   # [B, n] uint8
     mask: Optional[Tensor] = None   # [B, k+2] additive mask (text)
     x16: Optional[Tensor] = None    # fp16 copy of x when the caller asked for it (dtp_finish(want_f16=True))
+    ln16: Optional[Tensor] = None   # fp16 LayerNorm(x) when the caller passed ln=(gamma, beta, eps)
 
 
 class PendingPrune:
@@ -317,7 +318,7 @@ def dtp_score_async(stats: AttnStats, token_att: Tensor, temperature: float, n: 
 
 def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Optional[Tensor] = None,
                max_keep: int = 0, want_f16: bool = False, n_dev: Optional[Tensor] = None,
-               n_out: Optional[Tensor] = None, k_out: Optional[Tensor] = None) -> PruneResult:
+               n_out: Optional[Tensor] = None, k_out: Optional[Tensor] = None, ln=None) -> PruneResult:
     """Second half of Reduce_token on x [B, n+1, d] (position 0 always survives): select, gather, merge.
     n_dev / n_out / k_out (device-resident lengths): x is a capacity-sized buffer of packed sequences; the kernels read
     topk_num and N on the device, write the next layer's N to n_out and the trajectory entry to k_out, and the result
@@ -325,20 +326,19 @@ def dtp_finish(x: Tensor, pend: PendingPrune, *, mask_mode: int = 0, mask_in: Op
     B, N, d = x.shape
     n = N - 1
     score, thr, cnt, topk = pend.score, pend.thr, pend.cnt, pend.topk
+    # select + gather + merged token (+ the LayerNorm that follows, ln = (gamma, beta, eps)) are ONE kernel: dtp_apply.cu
     if n_dev is not None:
-        keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
-                                                             max_keep=max_keep, n_dev=n_dev, n_out=n_out, k_out=k_out)
-        out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, n - 1, max_keep=max_keep, want_f16=want_f16, n_dev=n_dev)
-        out, out16 = out if want_f16 else (out, None)
-        return PruneResult(out, None, -1, score, thr, cnt, keep, mask_out, out16)
+        out, out16, ln16, keep, mask_out = L.dtp_apply(x, score, topk, n - 1, mask_mode=mask_mode, mask_in=mask_in,
+                                                       max_keep=max_keep, want_f16=want_f16, ln=ln, n_dev=n_dev,
+                                                       n_out=n_out, k_out=k_out)
+        return PruneResult(out, None, -1, score, thr, cnt, keep, mask_out, out16, ln16)
     k = L.readback_wait(pend.handle)        # the reference's one host sync per pruned layer (models/vit.py:145)
     if k <= max_keep or n - k <= 1:         # models/vit.py:148-149 (max_keep = 0); clip/model.py:220
         return PruneResult(x, False, k, score, thr, cnt, None, mask_in)
-    keep, dst, tail_w, tail_idx, mask_out = L.dtp_select(score, topk, mask_mode=mask_mode, mask_in=mask_in,
-                                                         max_keep=max_keep)
-    out = L.dtp_gather(x, topk, dst, tail_w, tail_idx, k, max_keep=max_keep, want_f16=want_f16)
-    out, out16 = out if want_f16 else (out, None)
-    return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2], out16)
+    out, out16, ln16, keep, mask_out = L.dtp_apply(x, score, topk, k, mask_mode=mask_mode, mask_in=mask_in,
+                                                   max_keep=max_keep, want_f16=want_f16, ln=ln)
+    return PruneResult(out, True, k, score, thr, cnt, keep, None if mask_out is None else mask_out[:, :k + 2], out16,
+                       ln16)
 
 
 class Trajectory:
@@ -413,8 +413,8 @@ class LazyPrune:
 
 
 def dtp_prune(x: Tensor, stats: AttnStats, token_att: Tensor, temperature: float, *, mask_mode: int = 0,
-              mask_in: Optional[Tensor] = None, max_keep: int = 0) -> PruneResult:
+              mask_in: Optional[Tensor] = None, max_keep: int = 0, ln=None) -> PruneResult:
     """Reduce_token on x [B, n+1, d] (position 0 always survives). reference models/vit.py:123-163,
     models/nlvr_encoder.py:400-454 (mask_mode 1), models/med.py:345-391 (mask_mode 2)."""
     pend = dtp_score_async(stats, token_att, temperature, x.shape[1] - 1)
-    return dtp_finish(x, pend, mask_mode=mask_mode, mask_in=mask_in, max_keep=max_keep)
+    return dtp_finish(x, pend, mask_mode=mask_mode, mask_in=mask_in, max_keep=max_keep, ln=ln)

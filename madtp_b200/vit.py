@@ -195,16 +195,22 @@ class Block(nn.Module):
         x1 = self.attn.project_rows(ctx16, B, N, residual=x.view(B * N, C), n_dev=n_dev).view(B, N, C)
         self.last_prune = None
         nd2 = n_dev
-        if prune:
-            res = Fn.dtp_finish(x1, pend, n_dev=n_dev, n_out=n_out, k_out=k_out)
+        y16 = None
+        if prune:   # select + gather + merged token + norm2 in one kernel (dtp_apply.cu)
+            res = Fn.dtp_finish(x1, pend, n_dev=n_dev, n_out=n_out, k_out=k_out,
+                                ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps))
             self.last_prune = res
             x1 = res.x
+            if res.ln16 is not None:
+                y16 = res.ln16.view(-1, C)
             if n_dev is not None:
                 nd2 = n_out
         N2 = x1.shape[1]
         x2d = x1.view(B * N2, C)
-        ln2 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, f16=True, n_dev=nd2, n_mult=B)
-        return self.mlp.forward_rows(ln2["y16"], residual=x2d, m_dev=nd2, m_mult=B).view(B, N2, C)
+        if y16 is None:     # nothing was pruned (host-side early-out) or pruning is off
+            y16 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, f16=True, n_dev=nd2,
+                                    n_mult=B)["y16"]
+        return self.mlp.forward_rows(y16, residual=x2d, m_dev=nd2, m_mult=B).view(B, N2, C)
 
     def forward(self, x, register_hook=False, reduce_num=0, temperature=0, token_attn=None):
         Fn.require_cuda(x, "x")

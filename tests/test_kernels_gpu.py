@@ -539,3 +539,43 @@ def test_cross_attention_tensor_core(lib, dev, B, H, Lq, Nk, masked, broadcast):
     ref = (torch.softmax(s, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(B, Lq, C) + v_bias.double()
     assert not torch.isnan(out).any()
     assert _rel(out, ref) < 1.5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused DTP apply (radix select + compaction + merged token + LayerNorm) against the three kernels it replaces
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,n,d,mode", [(64, 576, 768, 0), (3, 196, 768, 0), (5, 1023, 512, 0), (4, 34, 768, 1),
+                                        (4, 34, 768, 2), (2, 5, 128, 0), (32, 19, 768, 1)])
+def test_dtp_apply_matches_select_gather_layernorm(lib, dev, B, n, d, mode):
+    g = torch.Generator(device="cpu").manual_seed(n * 11 + B + mode)
+    x = torch.randn(B, n + 1, d, generator=g).to(dev)
+    score = (torch.rand(B, n, generator=g) * 1e-3 + 1e-3)
+    score[:, ::7] = score[:, :1]                      # exact ties: the lower token index wins
+    if n > 20:
+        score[1 % B, 3] = -score[1 % B, 3]            # a negative score (vit.py:131-132 can produce them)
+    score = score.to(dev)
+    gamma, beta = torch.randn(d, generator=g).to(dev), torch.randn(d, generator=g).to(dev)
+    mask_in = None
+    if mode:
+        mask_in = torch.where(torch.rand(B, n + 1, generator=g) < 0.3, -10000.0, 0.0).to(dev)
+    for k in sorted({1, max(1, n // 3), max(1, n - 2)}):
+        if n - k <= 1:
+            continue
+        topk = torch.tensor([k], dtype=torch.int32, device=dev)
+        keep, dst, tw, ti, mo = lib.dtp_select(score, topk, mask_mode=mode, mask_in=mask_in)
+        ref = lib.dtp_gather(x, topk, dst, tw, ti, k, want_f16=True)
+        ref_out, ref16 = ref
+        ref_ln = torch.empty(B * (k + 2), d, dtype=torch.float16, device=dev)
+        lib.layernorm(ref_out.view(B * (k + 2), d), gamma, beta, 1e-6, y_f16=ref_ln)
+        out, out16, ln16, keep2, mo2 = lib.dtp_apply(x, score, topk, k, mask_mode=mode, mask_in=mask_in, want_f16=True,
+                                                     ln=(gamma, beta, 1e-6))
+        assert torch.equal(keep2, keep), f"k={k}: keep flags"
+        assert torch.equal(out, ref_out), f"k={k}: survivors / merged token differ by {(out - ref_out).abs().max().item():.3e}"
+        assert torch.equal(out16, ref16)
+        assert torch.equal(ln16.view(B * (k + 2), d), ref_ln), f"k={k}: fused LayerNorm"
+        if mode:
+            assert torch.equal(mo2[:, :k + 2], mo[:, :k + 2]), f"k={k}: pruned mask (mode {mode})"
+        # exact top-k set against torch (ties -> lower index first = a stable descending sort)
+        order = torch.sort(score.cpu(), dim=1, descending=True, stable=True)[1][:, :k]
+        want = torch.zeros(B, n, dtype=torch.bool).scatter_(1, order, True)
+        assert torch.equal(keep2.cpu().bool(), want), f"k={k}: not the exact top-k set"

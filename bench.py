@@ -391,6 +391,19 @@ def main():
                             "`value` pass cannot be bracketed by events; same kernels, bit-identical results)",
                 "note": "algorithmic FLOPs per launch as in DESIGN.md section 5 (error-compensation passes and the "
                         "second QK^T pass are not credited)"}
+    # the dominant kernel class by launch shape (events of the instrumented pass): where inside the class the time goes
+    by_shape = {}
+    for (name, e0, e1, meta) in t_top.records:
+        d = by_shape.setdefault(tuple(meta), [0, 0.0])
+        d[0] += 1
+        d[1] += e0.elapsed_time(e1)
+    shapes = []
+    for meta, (cnt, tms) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:10]:
+        fl = algorithmic_flops(top, meta) * cnt
+        shapes.append({"shape": list(meta), "launches_per_step": cnt / args.steps, "us_per_launch": 1e3 * tms / cnt,
+                       "tflops": fl / (tms / 1e3) / 1e12 if tms > 0 else 0.0,
+                       "share_of_class": tms / rec["ms"]})
+    roofline["by_shape"] = shapes
     step_flops = w.step_flops()                               # oracle trajectory, per rank
     step_roofline = {"algorithmic_tflop_per_step": step_flops / 1e12,
                      "achieved": step_flops / (ms / args.steps / 1e3) / 1e12, "peak": peaks["tflops_sustained"],

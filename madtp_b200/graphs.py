@@ -34,7 +34,9 @@ class GraphedCall:
         self.arena.frozen = True
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count()
-        with torch.cuda.graph(self.graph):
+        # thread-local capture mode: other threads of the process (NCCL's watchdog, bench.py's NVML clock sampler) may
+        # keep calling the CUDA API while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.outputs, self.trajectories = self._run()
         self.launches = L.launch_count() - n0      # kernels of libmadtp_b200.so inside one replay of the graph
         self.replays = 0

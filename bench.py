@@ -416,9 +416,9 @@ def main():
         cpu_baseline = cpu_baseline_subprocess(args.config, 0, 3, 1)
 
     parity = None
+    out = step_resident()             # every rank: the step contains the logits all-gather
+    torch.cuda.synchronize()
     if rank == 0:
-        out = step_resident()
-        torch.cuda.synchronize()
         parity = w.parity(out)
         execution = ("CUDA graph replay, device-resident token counts (0 host read-backs per step)" if use_graph else
                      "Python-issued launches, " + ("one read-back per pruned layer" if args.host_lengths or args.config == 4

@@ -48,6 +48,8 @@ extern "C" {
 #define MADTP_ACT_GELU 1       /* erf GELU: nn.GELU (vit.py:18) / ACT2FN["gelu"] (med.py:308) */
 #define MADTP_ACT_RELU 2       /* cls_head ReLU (blip_nlvr.py:58) */
 #define MADTP_ACT_QUICKGELU 3  /* clip/model.py QuickGELU */
+#define MADTP_ACT_GELU_FAST 4  /* the same erf GELU through one tanh.approx: |error| <= 2.6e-5 + 2^-11 relative (the fp16
+                                  rounding of the value lane); half the epilogue instructions of MADTP_ACT_GELU */
 
 int madtp_abi_version(void);
 const char* madtp_last_error_string(void);

@@ -20,7 +20,10 @@ _lib = None
 ABI_VERSION = 3                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
 GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
 QK_PLANE_SCALE, V_PLANE_SCALE = 8.0, 16.0     # include/madtp_b200.h MADTP_QK_PLANE_SCALE / MADTP_V_PLANE_SCALE
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU, ACT_GELU_FAST = 0, 1, 2, 3, 4
+# erf GELU of the FFNs: MADTP_ACT_GELU_FAST (one tanh.approx; error below the fp16 rounding of its own output) unless
+# MADTP_EXACT_GELU=1 asks for the 1.5e-7-accurate erfc form
+FFN_GELU = ACT_GELU if os.environ.get("MADTP_EXACT_GELU") else ACT_GELU_FAST
 
 _i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 

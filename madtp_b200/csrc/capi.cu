@@ -67,7 +67,7 @@ int madtp_gemm(int precision, const void* a, const void* a_lo, int64_t lda, cons
   ep.ldr = ldr;
   ep.act = act;
   ep.alpha = alpha;
-  MADTP_CHECK_ARG(act >= 0 && act <= 3, "gemm: unknown activation %d", act);
+  MADTP_CHECK_ARG(act >= 0 && act <= 4, "gemm: unknown activation %d", act);
   return counted(launch_gemm(precision, a, a_lo, lda, b, b_lo, ldb, ep, M, N, K, as_stream(stream)), M > 0 ? 1 : 0);
 }
 

@@ -129,6 +129,7 @@ __device__ __forceinline__ void load_residual(const GemmEpilogue& ep, long long 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
   if (ACT == 1) return gelu_erf(x);
+  if (ACT == 4) return gelu_tanh5(x);
   if (ACT == 2) return fmaxf(x, 0.0f);
   if (ACT == 3) return x / (1.0f + __expf(-1.702f * x));
   return x;
@@ -428,6 +429,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           case 1: epilogue_chunks_tmem<1, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
           case 2: epilogue_chunks_tmem<2, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
           case 3: epilogue_chunks_tmem<3, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
+          case 4: epilogue_chunks_tmem<4, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
           default: epilogue_chunks_tmem<0, NCH>(ep, taddr, stage, row_base, col_begin, M, N, lane); break;
         }
       } else {

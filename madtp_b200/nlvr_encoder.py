@@ -383,7 +383,7 @@ class BertIntermediate(nn.Module):
         act = config.hidden_act
         if act not in ("gelu", "relu"):
             raise NotImplementedError(f"madtp_b200: hidden_act {act!r}")
-        self.act_code = L.ACT_GELU if act == "gelu" else L.ACT_RELU
+        self.act_code = L.FFN_GELU if act == "gelu" else L.ACT_RELU
         self.intermediate_act_fn = nn.GELU() if act == "gelu" else nn.ReLU()
         self._cache = Fn.WeightCache()
 

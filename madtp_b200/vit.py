@@ -24,7 +24,7 @@ from .utils import Query_model, vector_gather  # noqa: F401  (models/vit.py does
 
 def _act_code(act: nn.Module) -> int:
     if isinstance(act, nn.GELU):
-        return L.ACT_GELU
+        return L.FFN_GELU
     if isinstance(act, nn.ReLU):
         return L.ACT_RELU
     if isinstance(act, nn.Identity):

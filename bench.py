@@ -257,6 +257,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the "
                                                             "captured CUDA graph (device-resident lengths either way)")
     ap.add_argument("--host-lengths", action="store_true", help="round-1 path: read topk_num back once per layer")
+    ap.add_argument("--streams", type=int, default=2, help="batches in flight: consecutive steps alternate between this "
+                    "many CUDA streams, each with its own captured graph and buffers (madtp_b200.pipeline.StreamPool); "
+                    "1 = every step on the current stream")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "madtp_b200" else max(args.warmup, 1)
@@ -265,7 +268,7 @@ def main():
         return
 
     from madtp_b200 import _lib, dist as mdist, vit as mvit
-    from madtp_b200.pipeline import InputPrefetcher
+    from madtp_b200.pipeline import InputPrefetcher, StreamPool
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: madtp_b200 has no CPU fallback")
     _lib.load()
@@ -288,10 +291,29 @@ def main():
     resident = tuple(t.to(dev) for t in host)
     result_shape = None
 
-    def step_resident():
-        return mdist.all_gather_rows(w.step(resident))
+    n_streams = args.streams if (w.graphable and not (args.no_graph or args.host_lengths)) else 1
+    pool = StreamPool(dev, n_streams) if n_streams > 1 else None
+    step_no = [0]
 
-    feeder = InputPrefetcher(dev, host)
+    def step_resident():
+        if pool is None:
+            return mdist.all_gather_rows(w.step(resident))
+        i = step_no[0]
+        step_no[0] += 1
+        with pool.stream(i, wait_current=False):     # the whole step (graph replay + logits all-gather) on its own stream
+            return mdist.all_gather_rows(w.step(resident))
+
+    def join_streams():
+        if pool is not None:
+            pool.join()
+
+    def fork_streams():
+        if pool is not None:
+            cur = torch.cuda.current_stream()
+            for s in pool.streams:
+                s.wait_stream(cur)
+
+    feeder = InputPrefetcher(dev, host, depth=args.streams + 1)
     e2e_state = {"i": 0, "start": 0, "end": 0, "out_h": None}
 
     def step_e2e():
@@ -302,11 +324,19 @@ def main():
             feeder.submit(i, host)
         if i + 1 < e2e_state["end"]:
             feeder.submit(i + 1, host)
-        out = mdist.all_gather_rows(w.step(feeder.acquire(i)))
-        feeder.release(i)
-        if e2e_state["out_h"] is None:
-            e2e_state["out_h"] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        e2e_state["out_h"].copy_(out, non_blocking=True)
+
+        def body():
+            out = mdist.all_gather_rows(w.step(feeder.acquire(i)))
+            feeder.release(i)
+            if e2e_state["out_h"] is None:
+                e2e_state["out_h"] = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(max(1, n_streams))]
+            e2e_state["out_h"][i % max(1, n_streams)].copy_(out, non_blocking=True)
+            return out
+        if pool is None:
+            out = body()
+        else:
+            with pool.stream(i, wait_current=False):   # H2D wait, forward, all-gather and D2H of step i on stream i % n
+                out = body()
         e2e_state["i"] = i + 1
         return out
 
@@ -332,7 +362,7 @@ def main():
         _lib.set_launch_timer(None)
     prof = timer.summary()
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
-    for _ in range(max(args.warmup, 3)):  # graph mode: two passes inside the arena, the capture, then replays
+    for _ in range(max(args.warmup, 3) * max(1, args.streams)):   # graph mode: arena passes, the capture, then replays
         step_resident()
     torch.cuda.synchronize()
 
@@ -344,8 +374,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _lib.set_launch_timer(t)
         e0.record()
+        fork_streams()
         for _ in range(steps):
             fn()
+        join_streams()
         e1.record()
         _lib.set_launch_timer(None)
         torch.cuda.synchronize()
@@ -417,10 +449,13 @@ def main():
 
     parity = None
     out = step_resident()             # every rank: the step contains the logits all-gather
+    join_streams()
     torch.cuda.synchronize()
     if rank == 0:
         parity = w.parity(out)
-        execution = ("CUDA graph replay, device-resident token counts (0 host read-backs per step)" if use_graph else
+        execution = ("CUDA graph replay, device-resident token counts (0 host read-backs per step)" +
+                     (f", {n_streams} batches in flight on {n_streams} CUDA streams (pipeline.StreamPool)" if pool else "")
+                     if use_graph else
                      "Python-issued launches, " + ("one read-back per pruned layer" if args.host_lengths or args.config == 4
                                                    else "device-resident token counts, one read-back per encoder call"))
         cfg = {"workload": w.workload, "baseline_config": w.config, "temperature": w.temperature,
@@ -434,7 +469,7 @@ def main():
                 "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
-                        "d2h_bytes_per_step": int(e2e_state["out_h"].numel() * e2e_state["out_h"].element_size())},
+                        "d2h_bytes_per_step": int(e2e_state["out_h"][0].numel() * e2e_state["out_h"][0].element_size())},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "step_roofline": step_roofline, "kernel_ms_one_step": breakdown,
                 "parity": parity, "cpu_baseline": cpu_baseline}

@@ -129,7 +129,10 @@ class BLIP_NLVR(nn.Module):
                         return self._forward_device(image.contiguous(), input_ids, attention_mask,
                                                     float(temperature))[0].clone()
                 from .graphs import GraphedCall
-                key = (tuple(image.shape), tuple(input_ids.shape), float(temperature), self.record_states)
+                # one captured graph (with its own buffers) per input shape, temperature AND stream: forwards issued on
+                # different streams may overlap on the device (two batches in flight, bench.py --streams 2)
+                key = (tuple(image.shape), tuple(input_ids.shape), float(temperature), self.record_states,
+                       torch.cuda.current_stream().cuda_stream)
                 g = self._graphs.get(key)
                 if g is None:
                     t = float(temperature)

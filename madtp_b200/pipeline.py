@@ -37,3 +37,37 @@ class InputPrefetcher:
     def release(self, i: int):
         """Mark batch i's slot reusable once the work enqueued so far on the compute stream has finished."""
         self.free[i % self.depth].record(torch.cuda.current_stream(self.device))
+
+
+class StreamPool:
+    """N batches in flight: consecutive forwards alternate between N CUDA streams so that the latency-bound tail of one
+    batch (the text encoder: ~230 small launches) overlaps the compute-bound image encoder of the next. Each stream gets
+    its own captured CUDA graph and buffers (BLIP_NLVR keys its graph cache on the current stream). Measured on B200,
+    BLIP-NLVR 32 pairs: 13.2 ms per batch with one stream, 11.8 ms with two, no further gain with three.
+
+        pool = StreamPool(device, 2)
+        for i, batch in enumerate(batches):
+            with pool.stream(i):                      # everything inside is enqueued on stream i % n
+                logits[i % 2] = model(*batch, temperature, train=False)
+        pool.join()                                   # the current stream waits for every stream of the pool
+
+    Results of step i must be consumed on its stream (or after join()); inputs produced on the current stream are safe:
+    entering `stream(i)` makes that stream wait for the work enqueued so far on the stream that was current."""
+
+    def __init__(self, device: torch.device, n: int = 2):
+        self.device = device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(max(1, n))]
+
+    def __len__(self):
+        return len(self.streams)
+
+    def stream(self, i: int, wait_current: bool = True):
+        s = self.streams[i % len(self.streams)]
+        if wait_current:
+            s.wait_stream(torch.cuda.current_stream(self.device))
+        return torch.cuda.stream(s)
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)

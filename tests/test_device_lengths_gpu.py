@@ -242,3 +242,32 @@ def test_gemm_dynamic_extents_and_layernorm_pack(lib, dev):
         assert not blk[:, Nd:].any(), "padding rows are zero"
     tok = lib.take_token(y32, B, Ncap2, 2, n_dev=torch.tensor([Nd], dtype=torch.int32, device=dev))
     assert torch.equal(tok, y32[:B * Nd].view(B, Nd, d)[:, 2])
+
+
+def test_two_batches_in_flight_match_sequential(dev):
+    """pipeline.StreamPool: consecutive forwards on alternating streams (own graph + buffers per stream) give exactly the
+    logits of the sequential run, whatever the interleaving."""
+    from madtp_b200.blip_nlvr import TokenizedText
+    from madtp_b200.pipeline import StreamPool
+    model = nlvr_model(dev, 224)
+    temp, pairs = 8.0, 2
+    batches = [weights.nlvr_inputs(pairs, 224, 20, seed=s) for s in (11, 12, 13, 14, 15)]
+    dev_batches = [(im.to(dev), TokenizedText(ids.to(dev), mask.to(dev))) for im, ids, mask in batches]
+    with torch.no_grad():
+        want = [model(im, tx, pairs, temp, train=False).clone() for im, tx in dev_batches]
+    model.enable_cuda_graphs(True)
+    try:
+        pool = StreamPool(dev, 2)
+        got = [None] * len(batches)
+        with torch.no_grad():
+            for rep in range(3):
+                for i, (im, tx) in enumerate(dev_batches):
+                    with pool.stream(i):
+                        got[i] = model(im, tx, pairs, temp, train=False).clone()
+                pool.join()
+                torch.cuda.synchronize()
+                for i in range(len(batches)):
+                    assert torch.equal(got[i], want[i]), f"rep {rep}, batch {i}"
+        assert len(model._graphs) == 2       # one captured graph per stream
+    finally:
+        model.enable_cuda_graphs(False)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MADTP_B200_ABI_VERSION 3   /* 3: device-resident token counts (`*_dev` arguments), cross-attention over any Nk */
+#define MADTP_B200_ABI_VERSION 4   /* 3: device-resident token counts (`*_dev` arguments), cross-attention over any Nk; 4: madtp_query_sdft_planes */
 
 /*
  * Device-resident lengths (ABI 3). The number of tokens a layer keeps (topk_num, vit.py:145) decides every later
@@ -184,6 +184,14 @@ int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, co
                         const float* x, int64_t x_rows, int row_stride, int first_row, int B, int n, int T, int d,
                         float divisor, float* sd_ft, int accumulate, const int32_t* n_dev, void* stream);
 /* n_dev: *n_dev = tokens per sequence (row_stride = *n_dev, n = *n_dev - first_row). */
+
+/* The same aggregation from the fp16 hi/lo planes of ft (x = x_unscale * (x_hi + x_lo), dense [x_rows, d]; the planes
+ * the LayerNorm entry point writes for the codebook product): the tensor core reads both operands MN-major, i.e. with
+ * the token index as the row index they have in HBM, so nothing is transposed anywhere (models/utils.py:174-178). */
+int madtp_query_sdft_planes(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max,
+                            const float* col_sum, const void* x_hi, const void* x_lo, float x_unscale, int64_t x_rows,
+                            int row_stride, int first_row, int B, int n, int T, int d, float divisor, float* sd_ft,
+                            int accumulate, const int32_t* n_dev, void* stream);
 
 /*
  * DTP scoring (vit.py:123-145 / nlvr_encoder.py:400-432 / med.py:345-369): Importance_score, threshold,

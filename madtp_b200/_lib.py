@@ -17,7 +17,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / "libmadtp_b200.so"
 _lib = None
 
-ABI_VERSION = 3                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
+ABI_VERSION = 4                                # include/madtp_b200.h MADTP_B200_ABI_VERSION
 GEMM_F16, GEMM_TF32X3, GEMM_SIMT, GEMM_F16X3 = 0, 1, 2, 3
 QK_PLANE_SCALE, V_PLANE_SCALE = 8.0, 16.0     # include/madtp_b200.h MADTP_QK_PLANE_SCALE / MADTP_V_PLANE_SCALE
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_QUICKGELU, ACT_GELU_FAST = 0, 1, 2, 3, 4
@@ -59,6 +59,8 @@ SIGNATURES = {
                          _vp],
     "madtp_query_sdft_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _i32, _vp,
                             _vp],
+    "madtp_query_sdft_planes": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32,
+                                _vp, _i32, _vp, _vp],
     "madtp_dtp_score": [_i32, _i32, _i32, _vp, _i32, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "madtp_dtp_select": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "madtp_dtp_gather": [_i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp],
@@ -778,6 +780,21 @@ def query_sdft_tc(token_att, col_max, col_sum, x2d, row_stride, first_row, n, T,
                int(row_stride), int(first_row), B, n, T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"),
                1 if accumulate else 0, _dyn(n_dev), _stream())
     _check(st, "madtp_query_sdft_tc")
+
+
+def query_sdft_planes(token_att, col_max, col_sum, x_hi, x_lo, row_stride, first_row, n, T, divisor, sd_ft, accumulate, *,
+                      x_unscale=1.0, n_dev=None):
+    """Tensor-core sd_ft from the fp16 hi/lo planes [rows, d] of ALL token rows (x = x_unscale * (x_hi + x_lo); token j
+    of batch b at row b*row_stride + first_row + j): MN-major operands, nothing transposed (madtp_query_sdft_planes)."""
+    B = token_att.shape[0]
+    d = x_hi.shape[1]
+    if not (x_hi.is_contiguous() and x_lo.is_contiguous()) or x_hi.shape != x_lo.shape:
+        raise RuntimeError("madtp_b200.query_sdft_planes: x_hi / x_lo must be dense [rows, d] planes of the same shape")
+    st = _call("madtp_query_sdft_planes", _ptr(token_att, torch.float32, "token_att"), token_att.stride(1),
+               token_att.stride(0), _ptr(col_max), _ptr(col_sum), _ptr(x_hi, torch.float16, "x_hi"),
+               _ptr(x_lo, torch.float16, "x_lo"), float(x_unscale), x_hi.shape[0], int(row_stride), int(first_row), B, n,
+               T, d, float(divisor), _ptr(sd_ft, torch.float32, "sd_ft"), 1 if accumulate else 0, _dyn(n_dev), _stream())
+    _check(st, "madtp_query_sdft_planes")
 
 
 def attn_small_self(q, k, v, H, scale, out_f16, *, key_mask=None, col_sum=None, cls_attn=None, causal=False,

@@ -213,6 +213,16 @@ int madtp_query_sdft_tc(const float* token_att, int64_t ld_ta, int64_t bs_ta, co
                  B > 0 ? 1 : 0);
 }
 
+int madtp_query_sdft_planes(const float* token_att, int64_t ld_ta, int64_t bs_ta, const float* col_max,
+                            const float* col_sum, const void* x_hi, const void* x_lo, float x_unscale, int64_t x_rows,
+                            int row_stride, int first_row, int B, int n, int T, int d, float divisor, float* sd_ft,
+                            int accumulate, const int32_t* n_dev, void* stream) {
+  return counted(launch_query_sdft_planes(token_att, ld_ta, bs_ta, col_max, col_sum, static_cast<const __half*>(x_hi),
+                                          static_cast<const __half*>(x_lo), x_unscale, x_rows, row_stride, first_row, B,
+                                          n, T, d, divisor, sd_ft, accumulate, n_dev, as_stream(stream)),
+                 B > 0 ? 1 : 0);
+}
+
 int madtp_dtp_score(int B, int n, int T, const float* col_part, int n_parts, const float* cls_attn,
                     const float* token_att, int64_t ld_ta, int64_t bs_ta, float temperature, float* score,
                     float* threshold, int32_t* count, int32_t* topk, const int32_t* n_dev, int parts_tile,

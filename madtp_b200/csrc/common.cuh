@@ -199,6 +199,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D TMA tile load (coordinates innermost first).
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // Thread-block clusters: rank of this CTA, cluster-wide barrier, TMA tile load multicast to the CTAs in `mask` (the
 // data lands at the same shared-memory offset in every destination CTA and signals the mbarrier at the same offset
 // there), and a tcgen05.commit that arrives on the mbarrier of every CTA in `mask`.

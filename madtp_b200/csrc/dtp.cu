@@ -6,7 +6,11 @@
 // All reductions run in a fixed order (no floating-point atomics). Sums that feed a comparison (normalisers, the
 // softmax-weighted threshold, the tail weight sum) are accumulated in fp64 and rounded once, so the only
 // discrepancy against the fp32 reference is the reference's own rounding.
+#include <cooperative_groups.h>
+
 #include "dtp.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace madtp {
 
@@ -44,12 +48,113 @@ __device__ __forceinline__ int block_sum_i(int v, int* red) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// Column softmax statistics over tokens. grid = (ceil(T/32), B), block = 256 (8 warps split the rows).
+// Column softmax statistics over tokens. grid = (ceil(T/32), B), block = 512: one CTA owns 32 codebook columns of one
+// sequence. Its [n x 32] slab of token_att is read from global memory ONCE (lane = column, warp = row split, four
+// independent row loads in flight per warp) into shared memory; the maximum and the exponential sum run from there.
+// max_j (x_j / divisor) = (max_j x_j) / divisor because IEEE division by a positive number is monotone, so the
+// maximum is taken on the raw values and divided once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+namespace {
+constexpr int kStatThreads = 512, kStatWarps = kStatThreads / 32, kStatInflight = 4;
+constexpr int kSlabMaxRows = 1024;   // 128 KB of dynamic shared memory at most
+
+// Loads this CTA's 32 columns (t = 32 * group + lane, valid when `tok`) of rows 0..n-1 into slab[j * 32 + lane]
+// (-inf where t >= T); returns the running column maximum over the rows this warp owns (j = warp mod 16).
+// row_fn(j, v) sees every row (warp-uniform j, v = this lane's column).
+//   vec: rows are 16-byte aligned and T is a multiple of 4 -> the whole slab is requested with 16-byte cp.async
+//        copies before anything waits (one memory round trip); otherwise four scalar row loads in flight per warp.
+template <typename RowFn>
+__device__ __forceinline__ float load_slab(const float* __restrict__ ta, long long ld, int n, int T, int group,
+                                           bool vec, float* __restrict__ slab, RowFn row_fn) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = group * 32 + lane;
+  const bool tok = t < T;
+  float cmx = -INFINITY;
+  if (vec) {
+    const int g4 = (threadIdx.x & 7) * 4;                 // eight threads per row, 64 rows per sweep
+    const int tt = group * 32 + g4;
+    for (int j = threadIdx.x >> 3; j < n; j += kStatThreads / 8) {
+      float* dst = slab + j * 32 + g4;
+      if (tt < T) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(ta + j * ld + tt) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    for (int j = warp; j < n; j += kStatWarps) {
+      const float v = slab[j * 32 + lane];
+      cmx = fmaxf(cmx, v);
+      row_fn(j, v);
+    }
+    return cmx;
+  }
+  for (int j0 = warp; j0 < n; j0 += kStatWarps * kStatInflight) {
+    float v[kStatInflight];
+#pragma unroll
+    for (int u = 0; u < kStatInflight; ++u) {
+      const int j = j0 + u * kStatWarps;
+      v[u] = (tok && j < n) ? ta[j * ld + t] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < kStatInflight; ++u) {
+      const int j = j0 + u * kStatWarps;
+      if (j < n) {
+        slab[j * 32 + lane] = v[u];
+        cmx = fmaxf(cmx, v[u]);
+        row_fn(j, v[u]);
+      }
+    }
+  }
+  return cmx;
+}
+
+__host__ inline bool slab_vec_ok(const float* ta, long long ld, long long bs, int T) {
+  return (reinterpret_cast<uintptr_t>(ta) % 16 == 0) && ld % 4 == 0 && bs % 4 == 0 && T % 4 == 0;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kStatThreads)
 token_colstats_kernel(const float* __restrict__ ta, long long ld, long long bs, int n, int T, float divisor,
                       float* __restrict__ col_max, float* __restrict__ col_sum, const int* __restrict__ n_dev,
-                      int n_sub) {
+                      int n_sub, int vec) {
+  extern __shared__ __align__(16) float slab[];
+  __shared__ float pmax[kStatWarps][32];
+  __shared__ float psum[kStatWarps][32];
+  if (n_dev != nullptr) {
+    const int N = load_len(n_dev);
+    n = min(n, N - n_sub);
+    bs = N * ld;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 32 + lane, b = blockIdx.y;
+  const bool ok = t < T;
+  pmax[warp][lane] = load_slab(ta + b * bs, ld, n, T, blockIdx.x, vec != 0, slab, [](int, float) {});
+  __syncthreads();
+  float raw = pmax[0][lane];
+#pragma unroll
+  for (int w = 1; w < kStatWarps; ++w) raw = fmaxf(raw, pmax[w][lane]);
+  const float gmx = __fdiv_rn(raw, divisor);
+  float s = 0.f;
+  if (ok)
+    for (int j = warp; j < n; j += kStatWarps) s += expf(__fdiv_rn(slab[j * 32 + lane], divisor) - gmx);
+  psum[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kStatWarps; ++w) tot += psum[w][lane];   // fixed order
+    col_max[b * T + t] = gmx;
+    col_sum[b * T + t] = tot;
+  }
+}
+
+// Sequences longer than the shared-memory slab: the same statistics streamed twice from global memory.
+__global__ void __launch_bounds__(256)
+token_colstats_stream_kernel(const float* __restrict__ ta, long long ld, long long bs, int n, int T, float divisor,
+                             float* __restrict__ col_max, float* __restrict__ col_sum,
+                             const int* __restrict__ n_dev, int n_sub) {
   __shared__ float smax[8][32];
   __shared__ float ssum[8][32];
   if (n_dev != nullptr) {
@@ -62,15 +167,13 @@ token_colstats_kernel(const float* __restrict__ ta, long long ld, long long bs, 
   const float* base = ta + b * bs;
   const bool ok = t < T;
   float mx = -INFINITY;
-  for (int j = warp; j < n; j += 8) {
-    const float x = ok ? __fdiv_rn(base[j * ld + t], divisor) : 0.f;
-    mx = fmaxf(mx, x);
-  }
+  for (int j = warp; j < n; j += 8) mx = fmaxf(mx, ok ? base[j * ld + t] : 0.f);
   smax[warp][lane] = mx;
   __syncthreads();
-  float gmx = smax[0][lane];
+  float raw = smax[0][lane];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) gmx = fmaxf(gmx, smax[w][lane]);
+  for (int w = 1; w < 8; ++w) raw = fmaxf(raw, smax[w][lane]);
+  const float gmx = __fdiv_rn(raw, divisor);
   float s = 0.f;
   for (int j = warp; j < n; j += 8) {
     const float x = ok ? __fdiv_rn(base[j * ld + t], divisor) : 0.f;
@@ -93,8 +196,15 @@ int launch_token_colstats(const float* token_att, long long ld_ta, long long bs_
   MADTP_CHECK_ARG(B >= 0 && n > 0 && T > 0 && divisor > 0.f && B <= 65535, "token_colstats: bad shape");
   if (B == 0) return kOk;
   dim3 grid((T + 31) / 32, B);
-  token_colstats_kernel<<<grid, 256, 0, stream>>>(token_att, ld_ta, bs_ta, n, T, divisor, col_max, col_sum, n_dev,
-                                                  n_sub);
+  if (n <= kSlabMaxRows) {
+    MADTP_SMEM_ATTR_ONCE(kSlabMaxRows * 32 * 4, token_colstats_kernel);
+    token_colstats_kernel<<<grid, kStatThreads, static_cast<size_t>(n) * 32 * 4, stream>>>(
+        token_att, ld_ta, bs_ta, n, T, divisor, col_max, col_sum, n_dev, n_sub,
+        slab_vec_ok(token_att, ld_ta, bs_ta, T) ? 1 : 0);
+  } else {
+    token_colstats_stream_kernel<<<grid, 256, 0, stream>>>(token_att, ld_ta, bs_ta, n, T, divisor, col_max, col_sum,
+                                                           n_dev, n_sub);
+  }
   MADTP_LAUNCH_CHECK();
   return kOk;
 }
@@ -191,32 +301,49 @@ int launch_query_sdft(const float* token_att, long long ld_ta, long long bs_ta, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Importance score, threshold and survivor count. grid = B, block = 1024 (32 warps): one CTA per sequence is all the
-// parallelism there is across CTAs (B = 64 on 148 SMs), so the block is as wide as the hardware allows.
+// Importance score, threshold and survivor count (reference models/vit.py:126-145).
+// grid = (4, B) in clusters of four CTAs, block = 512: the four CTAs of a sequence own 32 codebook columns each (cluster
+// rank = column group). Every CTA stages its [n x 32] slab of token_att in shared memory with ONE pass over global
+// memory; the row maxima (over all T columns) are exchanged through distributed shared memory, the cheap per-token
+// work (a, b, score) is computed redundantly by the four CTAs, the threshold sum -- the only O(n T) exponential pass
+// -- is split by columns and its per-CTA minima are exchanged the same way. Rank 0 writes the results.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-dtp_score_kernel(DtpScoreArgs a) {
-  __shared__ float S[kDtpMaxTokens];      // a_j, then the score
-  __shared__ float Bm[kDtpMaxTokens];     // max_t token_att[j,t]
+constexpr int kScoreCluster = 4;
+
+__global__ void __cluster_dims__(kScoreCluster, 1, 1) __launch_bounds__(kStatThreads, 1)
+dtp_score_kernel(DtpScoreArgs a, int vec) {
+  extern __shared__ __align__(16) float slab[];            // [n][32]: columns 32*rank .. 32*rank+31 of every token
+  __shared__ float S[kDtpMaxTokens];                       // a_j, then the score
+  __shared__ float Rpart[kDtpMaxTokens];                   // max over THIS CTA's columns of token j (peers read it)
+  __shared__ float Bm[kDtpMaxTokens];                      // b_j = max over all columns
   __shared__ double red[32];
   __shared__ int redi[32];
-  __shared__ float pmax[8][128];
-  __shared__ double pnum[8][128], pden[8][128];
-  __shared__ float thr_s;
+  __shared__ float pmax[kStatWarps][32];
+  __shared__ double pnum[kStatWarps][32], pden[kStatWarps][32];
+  __shared__ float thr_part[kScoreCluster];
 
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = blockIdx.x;                             // == cluster.block_rank(): gridDim.x is the cluster width
   if (a.n_dev != nullptr) {          // device-resident token count: packed sequences
     const int Nd = min(a.n + 1, load_len(a.n_dev));
     a.n = Nd - 1;
     a.bs_ta = Nd * a.ld_ta;
     if (a.parts_tile > 0) a.n_parts = (Nd + a.parts_tile - 1) / a.parts_tile;
   }
-  const int b = blockIdx.x, n = a.n, N = n + 1;
-  const float* ta = a.token_att + b * a.bs_ta;
+  const int b = blockIdx.y, n = a.n, N = n + 1;
+  const int t = rank * 32 + lane;
+  const bool tok = t < a.T;
+
+  // (B, first half) slab + this column group's share of b_j = max_t token_att[j,t]
+  pmax[warp][lane] = load_slab(a.token_att + b * a.bs_ta, a.ld_ta, n, a.T, rank, vec != 0, slab, [&](int j, float v) {
+    const float m = warp_max(v);
+    if (lane == 0) Rpart[j] = m;
+  });
 
   // (A) self-attention statistic: a_j = sum over query tiles (fixed order)
   double part = 0.0;
-  for (int j = tid; j < n; j += blockDim.x) {
+  for (int j = tid; j < n; j += kStatThreads) {
     float s = 0.f;
     for (int p = 0; p < a.n_parts; ++p) s += a.col_part[(static_cast<long long>(b) * a.n_parts + p) * N + 1 + j];
     S[j] = s;
@@ -224,76 +351,68 @@ dtp_score_kernel(DtpScoreArgs a) {
   }
   const float a_den = static_cast<float>(block_sum_d(part, red)) + 1e-8f;
 
-  // (B) alignment statistic: b_j = max_t token_att[j,t]
+  cluster.sync();                    // all four CTAs run and their partial row maxima are complete
+
+  // (B, second half): combine the four column groups through distributed shared memory
+  const float* r0 = cluster.map_shared_rank(Rpart, 0);
+  const float* r1 = cluster.map_shared_rank(Rpart, 1);
+  const float* r2 = cluster.map_shared_rank(Rpart, 2);
+  const float* r3 = cluster.map_shared_rank(Rpart, 3);
   part = 0.0;
-  for (int j = warp; j < n; j += 32) {
-    float mx = -INFINITY;
-    for (int t = lane; t < a.T; t += 32) mx = fmaxf(mx, ta[j * a.ld_ta + t]);
-    mx = warp_max(mx);
-    if (lane == 0) {
-      Bm[j] = mx;
-      part += static_cast<double>(mx);
-    }
+  for (int j = tid; j < n; j += kStatThreads) {
+    const float m = fmaxf(fmaxf(r0[j], r1[j]), fmaxf(r2[j], r3[j]));
+    Bm[j] = m;                       // the same thread reads it back in (C)
+    part += static_cast<double>(m);
   }
   const float b_den = static_cast<float>(block_sum_d(part, red)) + 1e-8f;
 
   // (C) Importance_score = (a' + b' + cls_attn) / 3
-  for (int j = tid; j < n; j += blockDim.x) {
+  for (int j = tid; j < n; j += kStatThreads) {
     const float av = __fdiv_rn(S[j], a_den);
     const float bv = __fdiv_rn(Bm[j], b_den);
     const float cv = a.cls_attn[static_cast<long long>(b) * N + 1 + j];
     const float sc = __fdiv_rn((av + bv) + cv, 3.0f);
     S[j] = sc;
-    a.score[static_cast<long long>(b) * n + j] = sc;
+    if (rank == 0) a.score[static_cast<long long>(b) * n + j] = sc;
   }
   __syncthreads();
 
-  // (D) threshold = min_t  sum_j softmax_j(token_att[j,t] / temperature) * score_j
-  //     warp w: column group g = w % 4 (t = 32 g + lane), row split q = w / 4 (eight splits)
-  const int g = warp & 3, qd = warp >> 2;
-  const int ngroups = (a.T + 31) / 32;  // <= 4
-  const int t = g * 32 + lane;
-  const bool tok = (g < ngroups) && (t < a.T);
-  float mx = -INFINITY;
-  if (tok)
-    for (int j = qd; j < n; j += 8) mx = fmaxf(mx, __fdiv_rn(ta[j * a.ld_ta + t], a.temperature));
-  pmax[qd][g * 32 + lane] = mx;
-  __syncthreads();
-  float gmx = pmax[0][g * 32 + lane];
+  // (D) threshold = min_t  sum_j softmax_j(token_att[j,t] / temperature) * score_j   over this CTA's 32 columns
+  float raw = pmax[0][lane];
 #pragma unroll
-  for (int q = 1; q < 8; ++q) gmx = fmaxf(gmx, pmax[q][g * 32 + lane]);
+  for (int w = 1; w < kStatWarps; ++w) raw = fmaxf(raw, pmax[w][lane]);
+  const float gmx = __fdiv_rn(raw, a.temperature);
   double num = 0.0, den = 0.0;
   if (tok)
-    for (int j = qd; j < n; j += 8) {
-      const float e = expf(__fdiv_rn(ta[j * a.ld_ta + t], a.temperature) - gmx);
+    for (int j = warp; j < n; j += kStatWarps) {
+      const float e = expf(__fdiv_rn(slab[j * 32 + lane], a.temperature) - gmx);
       den += static_cast<double>(e);
       num += static_cast<double>(e) * static_cast<double>(S[j]);
     }
-  pnum[qd][g * 32 + lane] = num;
-  pden[qd][g * 32 + lane] = den;
+  pnum[warp][lane] = num;
+  pden[warp][lane] = den;
   __syncthreads();
-  if (warp < 4) {
+  if (warp == 0) {
     float v = INFINITY;
     if (tok) {
       double nn = 0.0, dd = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {   // fixed order
-        nn += pnum[q][t];
-        dd += pden[q][t];
+      for (int q = 0; q < kStatWarps; ++q) {   // fixed order
+        nn += pnum[q][lane];
+        dd += pden[q][lane];
       }
       v = static_cast<float>(nn / dd);
     }
     v = warp_min(v);
-    if (lane == 0) pmax[0][warp] = v;
+    if (lane < kScoreCluster) *cluster.map_shared_rank(&thr_part[rank], lane) = v;
   }
-  __syncthreads();
-  if (tid == 0) thr_s = fminf(fminf(pmax[0][0], pmax[0][1]), fminf(pmax[0][2], pmax[0][3]));
-  __syncthreads();
-  const float thr = thr_s;
+  cluster.sync();                    // the last remote access precedes this barrier: CTAs may exit independently after it
+  if (rank != 0) return;
+  const float thr = fminf(fminf(thr_part[0], thr_part[1]), fminf(thr_part[2], thr_part[3]));
 
   // (E) count
   int c = 0;
-  for (int j = tid; j < n; j += blockDim.x) c += (S[j] > thr) ? 1 : 0;
+  for (int j = tid; j < n; j += kStatThreads) c += (S[j] > thr) ? 1 : 0;
   c = block_sum_i(c, redi);
   if (tid == 0) {
     a.threshold[b] = thr;
@@ -306,13 +425,15 @@ int launch_dtp_score(const DtpScoreArgs& a, cudaStream_t stream) {
   if (a.B == 0) return kOk;   // empty batch: nothing to do (and torch hands out null pointers for empty tensors)
   MADTP_CHECK_ARG(a.col_part && a.cls_attn && a.token_att && a.score && a.threshold && a.count && a.topk,
                   "dtp_score: null pointer");
-  MADTP_CHECK_ARG(a.B >= 0 && a.n > 0 && a.n <= kDtpMaxTokens, "dtp_score: n=%d out of range (1..%d)", a.n,
-                  kDtpMaxTokens);
+  MADTP_CHECK_ARG(a.B >= 0 && a.B <= 65535 && a.n > 0 && a.n <= kDtpMaxTokens,
+                  "dtp_score: n=%d out of range (1..%d)", a.n, kDtpMaxTokens);
   MADTP_CHECK_ARG(a.T > 0 && a.T <= 128, "dtp_score: codebook size T=%d must be in 1..128", a.T);
   MADTP_CHECK_ARG(a.temperature > 0.f, "dtp_score: temperature must be > 0");
   MADTP_CHECK_ARG(a.n_parts > 0, "dtp_score: n_parts must be > 0");
-  if (a.B == 0) return kOk;
-  dtp_score_kernel<<<a.B, 1024, 0, stream>>>(a);
+  static_assert(kDtpMaxTokens <= kSlabMaxRows, "the score kernel stages every token of the sequence");
+  MADTP_SMEM_ATTR_ONCE(kSlabMaxRows * 32 * 4, dtp_score_kernel);
+  dtp_score_kernel<<<dim3(kScoreCluster, a.B), kStatThreads, static_cast<size_t>(a.n) * 32 * 4, stream>>>(
+      a, slab_vec_ok(a.token_att, a.ld_ta, a.bs_ta, a.T) ? 1 : 0);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

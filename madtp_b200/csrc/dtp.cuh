@@ -28,6 +28,12 @@ int launch_query_sdft_tc(const float* token_att, long long ld_ta, long long bs_t
                          int n, int T, int d, float divisor, float* sd_ft, int accumulate, const int* n_dev,
                          cudaStream_t stream);
 
+// MN-major tensor-core variant (sdft_tc.cu): x as fp16 hi/lo planes [x_rows, d] of x / x_unscale, no transposition.
+int launch_query_sdft_planes(const float* token_att, long long ld_ta, long long bs_ta, const float* col_max,
+                             const float* col_sum, const __half* x_hi, const __half* x_lo, float x_unscale,
+                             long long x_rows, int row_stride, int first_row, int B, int n, int T, int d, float divisor,
+                             float* sd_ft, int accumulate, const int* n_dev, cudaStream_t stream);
+
 struct DtpScoreArgs {
   int B, n, T;                // n prunable tokens (sequence position 1..n), T codebook entries
   const float* col_part;      // [B, n_parts, n+1] partial column sums from attn_stats (index 0 = CLS, unused)

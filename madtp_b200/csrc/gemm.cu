@@ -893,6 +893,33 @@ int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long 
   return kOk;
 }
 
+// Row-major fp16 [rows, cols] matrix (cols a multiple of 64) seen as [cols / 64 column groups][rows][64 columns]:
+// one box = `box_groups` column groups x `box_rows` rows x 128 bytes, written to shared memory group after group, each
+// group a [box_rows x 128 bytes] tile with the 128-byte swizzle -- an MN-major tensor-core operand in ONE copy.
+int make_tmap_colgroups(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                        int box_groups) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return kCudaError;
+  }
+  MADTP_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "operand pointer must be 16-byte aligned");
+  MADTP_CHECK_ARG((ld * 2) % 16 == 0 && cols % 64 == 0, "operand row pitch / width unsupported (ld=%lld cols=%lld)", ld, cols);
+  cuuint64_t gdim[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 64)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_groups)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (column groups) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows,
+              cols, ld);
+    return kCudaError;
+  }
+  return kOk;
+}
+
 template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 static int launch_tc(const void* a, const void* a_lo, long long lda, const void* b, const void* b_lo, long long ldb,
                      const GemmEpilogue& ep, int M, int N, int K, cudaStream_t stream) {

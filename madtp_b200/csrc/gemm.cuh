@@ -114,6 +114,8 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // 2-D TMA descriptor of a row-major [rows, cols] matrix (leading dimension ld elements, fp32 or fp16) with a
 // box of box_rows x 128 bytes and the 128-byte swizzle; out-of-bounds elements read as zero.
 int make_tmap(CUtensorMap* map, const void* ptr, bool f32, long long rows, long long cols, long long ld, int box_rows);
+int make_tmap_colgroups(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                        int box_groups);
 
 // Fused q|k|v projection (F16x3) with the split / transposed epilogue described at GemmEpilogue::mode.
 int launch_gemm_qkv(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,

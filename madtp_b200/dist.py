@@ -77,6 +77,16 @@ def max_over_ranks(value: float, device) -> float:
     return float(t.item())
 
 
+def gather_over_ranks(value: float, device) -> List[float]:
+    """Every rank's scalar, in rank order (diagnostics: which GPU of the node set the max-over-ranks time)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [value]
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    out = torch.empty(dist.get_world_size(), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, t)
+    return [float(v) for v in out.tolist()]
+
+
 # ---- optional strict mode: the pruning of a sharded batch matches the single-process run on the whole batch ---------
 # topk_num is a maximum over the batch (models/vit.py:145), so sharding the batch changes how many tokens each sample
 # keeps. The reference's multi-GPU evaluation lives with that (every rank takes the max over its LOCAL batch); with

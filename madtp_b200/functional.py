@@ -10,6 +10,7 @@ Precision lanes (hard part 1):
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -20,6 +21,8 @@ from . import _lib as L
 from . import dist as _dist
 
 Tensor = torch.Tensor
+# MADTP_SDFT_PLANES=0 keeps the round-1 aggregation kernel (fp32 x re-laid out K-major by builder warps)
+SDFT_PLANES = os.environ.get("MADTP_SDFT_PLANES", "1") != "0"
 TA_LD = 128  # row pitch of token_att buffers (T = 100 codebook entries padded to a 16-byte multiple of columns)
 
 
@@ -188,11 +191,12 @@ def query_model_rows(x_hi: Tensor, x_lo: Tensor, x3d: Tensor, book, sd_dim: int,
     hi, lo, T, scale = book
     ta = L.empty((B * N, TA_LD), torch.float32, x3d.device)
     L.gemm(L.GEMM_F16X3, x_hi, hi, ta, a_lo=x_lo, b_lo=lo, alpha=1.0 / scale, m_dev=n_dev, m_mult=B)
-    return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token, n_dev=n_dev)
+    return query_model_from_token_att(ta.view(B, N, TA_LD), x3d, T, sd_dim, sd_ft, first_token, n_dev=n_dev,
+                                      planes=(x_hi, x_lo))
 
 
 def query_model_from_token_att(ta_full: Tensor, x3d: Tensor, T: int, sd_dim: int, sd_ft: Optional[Tensor],
-                               first_token: int = 1, n_dev: Optional[Tensor] = None):
+                               first_token: int = 1, n_dev: Optional[Tensor] = None, planes=None):
     """Second half of Query_model given token_att for every row (ta_full [B, N, >=T] view, unit inner stride):
     over-token softmax statistics and the aggregated feature. Returns (token_att view [B, n, T], sd_ft)."""
     B, N, d = x3d.shape
@@ -203,7 +207,10 @@ def query_model_from_token_att(ta_full: Tensor, x3d: Tensor, T: int, sd_dim: int
     accumulate = sd_ft is not None
     if sd_ft is None:
         sd_ft = L.empty((B, T, d), torch.float32, x3d.device)
-    if n >= 64 and x3d.is_contiguous() and d % 32 == 0:     # tensor-core path over the dense rows of x3d
+    if n >= 64 and planes is not None and d % 64 == 0 and SDFT_PLANES:
+        # tensor-core path over the fp16 hi/lo planes the LayerNorm kernel wrote (MN-major operands, no transposition)
+        L.query_sdft_planes(ta3, cm, cs, planes[0], planes[1], N, first_token, n, T, div, sd_ft, accumulate, n_dev=n_dev)
+    elif n >= 64 and x3d.is_contiguous() and d % 32 == 0:     # tensor-core path over the dense fp32 rows of x3d
         L.query_sdft_tc(ta3, cm, cs, x3d.view(B * N, d), N, first_token, n, T, div, sd_ft, accumulate, n_dev=n_dev)
     else:
         L.query_sdft(ta3, cm, cs, x3d[:, first_token:, :], n, T, div, sd_ft, accumulate, n_dev=n_dev,

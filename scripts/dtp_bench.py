@@ -9,16 +9,25 @@ dev = torch.device("cuda:0")
 
 
 def t(fn, n=20):
+    """us per launch inside a CUDA graph of n back-to-back launches (no host launch cost in the number)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        fn()
-    e1.record()
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(5):
+            g.replay()
+        e1.record(s)
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
+    return e0.elapsed_time(e1) / (5 * n) * 1e3
 
 
 for B, n in ((64, 576), (64, 345), (64, 255), (32, 19)):
@@ -32,3 +41,18 @@ for B, n in ((64, 576), (64, 345), (64, 255), (32, 19)):
     c = t(lambda: lib.token_colstats(ta_p, n, T, math.sqrt(768)))
     s = t(lambda: lib.dtp_score(col_part, cls_attn, ta_p[:, :, :T], n, T, 3.5894))
     print(f"B={B} n={n}: token_colstats {c:.1f} us, dtp_score {s:.1f} us")
+
+# Query_model aggregation: fp32-x kernel (builder warps transpose) against the MN-major plane kernel
+for B, n in ((64, 576), (64, 345), (64, 255)):
+    g = torch.Generator().manual_seed(1)
+    N, T, d = n + 1, 100, 768
+    x = torch.randn(B, N, d, generator=g).to(dev)
+    ta = (torch.randn(B, N, 128, generator=g) * 5).to(dev)
+    ta_p = ta[:, 1:, :]
+    div = math.sqrt(d)
+    cm, cs = lib.token_colstats(ta_p, n, T, div)
+    hi, lo = lib.split_f16(x.view(B * N, d))
+    sd = torch.zeros(B, T, d, device=dev)
+    a = t(lambda: lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, False))
+    p = t(lambda: lib.query_sdft_planes(ta_p, cm, cs, hi, lo, N, 1, n, T, div, sd, False))
+    print(f"B={B} n={n}: query_sdft_tc {a:.1f} us, query_sdft_planes {p:.1f} us")

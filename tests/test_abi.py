@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(lib):
     cdll = lib.load()
     for name in declared_functions():
         assert hasattr(cdll, name), f"{name} is declared in include/madtp_b200.h but not exported"
-    assert cdll.madtp_abi_version() == lib.ABI_VERSION == 3
+    assert cdll.madtp_abi_version() == lib.ABI_VERSION == 4
 
 
 def test_ctypes_signatures_cover_the_header(lib):

@@ -457,6 +457,43 @@ def test_query_sdft_tensor_core(lib, dev, B, n, T, d):
     assert _rel(sd, 2 * ref) < 5e-6
 
 
+@pytest.mark.parametrize("B,n,T,d", [(3, 196, 100, 768), (2, 576, 100, 768), (4, 19, 100, 768), (2, 76, 100, 512),
+                                     (2, 345, 100, 768), (1, 64, 128, 384)])
+def test_query_sdft_planes(lib, dev, B, n, T, d):
+    """The same aggregation from the fp16 hi/lo planes of x with MN-major tensor-core operands (no transposition)."""
+    g = torch.Generator(device="cpu").manual_seed(n + d + 1)
+    N = n + 1
+    x = (torch.randn(B, N, d, generator=g) * 3).to(dev)
+    ta = (torch.randn(B, N, 128, generator=g) * 20).to(dev)
+    ta_p = ta[:, 1:, :]
+    div = math.sqrt(d)
+    cm, cs = lib.token_colstats(ta_p, n, T, div)
+    x_hi, x_lo = lib.split_f16(x.view(B * N, d))
+    sd = torch.full((B, T, d), float("nan"), device=dev)
+    lib.query_sdft_planes(ta_p, cm, cs, x_hi, x_lo, N, 1, n, T, div, sd, False)
+    w = torch.softmax(ta_p[..., :T].double() / div, dim=1)
+    ref = w.transpose(1, 2) @ x[:, 1:, :].double()
+    assert _rel(sd, ref) < 5e-6
+    lib.query_sdft_planes(ta_p, cm, cs, x_hi, x_lo, N, 1, n, T, div, sd, True)
+    assert _rel(sd, 2 * ref) < 5e-6
+    # device-resident length: a capacity-sized buffer holding B packed sequences of N_dyn tokens
+    Nd = N - 5
+    if Nd - 1 >= 8:
+        xp = torch.zeros(B * N, d, device=dev)
+        xp[:B * Nd] = x[:, :Nd].reshape(B * Nd, d)
+        tap = torch.zeros(B * N, 128, device=dev)
+        tap[:B * Nd] = ta[:, :Nd].reshape(B * Nd, 128)
+        n_dev = torch.tensor([Nd], dtype=torch.int32, device=dev)
+        ta_v = tap.view(B, N, 128)[:, 1:, :]
+        cm2, cs2 = lib.token_colstats(ta_v, n, T, div, n_dev=n_dev, n_sub=1)
+        h2, l2 = lib.split_f16(xp)
+        sd2 = torch.full((B, T, d), float("nan"), device=dev)
+        lib.query_sdft_planes(ta_v, cm2, cs2, h2, l2, N, 1, n, T, div, sd2, False, n_dev=n_dev)
+        w2 = torch.softmax(ta[:, 1:Nd, :T].double() / div, dim=1)
+        ref2 = w2.transpose(1, 2) @ x[:, 1:Nd, :].double()
+        assert _rel(sd2, ref2) < 5e-6
+
+
 @pytest.mark.parametrize("B,H,L,masked,causal", [(3, 12, 20, True, False), (2, 12, 35, True, False), (2, 8, 64, False, True),
                                                  (4, 12, 7, False, False), (1, 12, 1, False, False)])
 def test_small_self_attention_fused_stats(lib, dev, B, H, L, masked, causal):

@@ -353,7 +353,7 @@ def main():
         def __exit__(self, *exc):
             mvit.device_lengths_enabled(not args.host_lengths)
 
-    # ---- warm-up; one warm-up step is fully instrumented to find the dominant kernel ----
+    # ---- warm-up; one warm-up step is fully instrumented: it records every launch's exact shape arguments ----
     with per_kernel_mode():
         step_resident()                   # first call also prepares the GEMM-ready weight copies (one-off)
         torch.cuda.synchronize()
@@ -362,8 +362,7 @@ def main():
         step_resident()
         torch.cuda.synchronize()
         _lib.set_launch_timer(None)
-    prof = timer.summary()
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
+    shapes_pass = timer.records            # (kernel, e0, e1, shape arguments) in launch order, host-side lengths
     for _ in range(max(args.warmup, 3) * max(1, args.streams)):   # graph mode: arena passes, the capture, then replays
         step_resident()
     torch.cuda.synchronize()
@@ -392,15 +391,43 @@ def main():
         ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
         return ms, _lib.launch_count() + w.graph_launches() - l0, t
 
+    def backlogged_pass(steps):
+        mdist.barrier()
+        torch.cuda.synchronize()
+        recs, total = [], 0.0
+        held = w.suspend_graphs()          # device-resident lengths stay on: no read-back drains the queue mid-step
+        try:
+            for _ in range(2):             # arena passes of the un-graphed path
+                w.step(resident)
+            torch.cuda.synchronize()
+            for _ in range(steps):
+                t = _lib.LaunchTimer()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(60_000_000)          # ~30 ms: the host needs ~10 ms to queue 410 launches + events
+                _lib.set_launch_timer(t)
+                e0.record()
+                w.step(resident)
+                e1.record()
+                _lib.set_launch_timer(None)
+                torch.cuda.synchronize()
+                recs.append([(n, a.elapsed_time(b)) for (n, a, b, _) in t.records])
+                total += e0.elapsed_time(e1)
+        finally:
+            _lib.set_launch_timer(None)
+            w.resume_graphs(held)
+        return recs, total
+
     sampler = make_clock_sampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     ms, launches, _ = timed(step_resident, args.steps)
-    # the same K steps once more with CUDA events around every launch of the dominant kernel (kept out of the pass
-    # that produces `value`)
-    with per_kernel_mode():
-        ms_instr, _, t_top = timed(step_resident, args.steps, only=[top])
+    # (the clock sampler covers exactly the timed region above)
+    # Per-kernel device times: the same steps once more, launched from Python with CUDA events around every launch
+    # (kept out of the pass that produces `value`). The GPU is held back by a spin kernel at the start of each step so
+    # that the host has queued the whole step before the first kernel runs: the events then bracket kernel time, not
+    # the host's launch gaps (which dominate the ~5 us text-encoder kernels otherwise).
     clocks = sampler.stop() if sampler else None
+    timed_records, ms_instr = backlogged_pass(min(args.steps, 10))
     e2e_state.update(i=0, start=0, end=1)
     step_e2e()
     torch.cuda.synchronize()
@@ -411,37 +438,64 @@ def main():
     value = units_per_step * args.steps / (ms / 1e3)
     e2e_value = units_per_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel, from CUDA events around each of its launches ----
-    rec = t_top.summary()[top]
-    flops = sum(algorithmic_flops(top, m) for m in rec["meta"])
-    achieved = flops / (rec["ms"] / 1e3) / 1e12 if rec["ms"] > 0 else 0.0
-    share = rec["ms"] / ms_instr
+    # ---- roofline of the dominant kernel class: shapes from the host-length pass, times from the backlogged pass ----
+    def per_name(records, field):
+        d = {}
+        for r in records:
+            d.setdefault(r[0], []).append(r[field])
+        return d
+    metas = per_name(shapes_pass, 3)
+    times = {}                                                   # kernel -> per-launch ms summed over the timed steps
+    for step_recs in timed_records:
+        for name, lst in per_name(step_recs, 1).items():
+            acc = times.setdefault(name, [0.0] * len(lst))
+            if len(acc) == len(lst):
+                for i, v in enumerate(lst):
+                    acc[i] += v
+    n_timed = max(len(timed_records), 1)
+    prof = {k: {"launches": len(v), "ms": sum(v) / n_timed} for k, v in times.items()}
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
+    busy_ms = sum(v["ms"] for v in prof.values())                # GPU-busy time of one step: the sum of its kernels
+    matched = top in metas and len(metas[top]) == len(times[top])
+    if matched:
+        top_meta, top_ms = metas[top], [v / n_timed for v in times[top]]
+        timed_in = ("a second pass of the same K steps, launched from Python with CUDA events around every launch and "
+                    "the GPU held back at the start of each step until the host has queued it (events bracket kernel "
+                    "time, not host launch gaps); shape arguments from an instrumented warm-up step with host-side "
+                    "lengths (same kernels in the same order, bit-identical results); the kernels inside the CUDA graph "
+                    "of the `value` pass cannot be bracketed by events")
+    else:   # the two passes launched this kernel a different number of times: fall back to the host-length pass alone
+        top_meta = metas.get(top, [])
+        top_ms = [e0.elapsed_time(e1) for (n, e0, e1, _) in shapes_pass if n == top]
+        timed_in = "one instrumented warm-up step with host-side lengths (includes host launch gaps)"
+    class_ms = sum(top_ms)
+    flops = sum(algorithmic_flops(top, m) for m in top_meta)
+    achieved = flops / (class_ms / 1e3) / 1e12 if class_ms > 0 else 0.0
     traffic = ncu_traffic(top) if args.config == 2 else None
     roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                 "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                 "traffic_detail": traffic,
                 "peak_source": peaks["source"] + " (sustained bf16, kernel timed inside a long step)",
-                "launches_per_step": rec["launches"] // args.steps, "ms_per_step": rec["ms"] / args.steps,
-                "share_of_step": share, "instrumented_ms_per_step": ms_instr / args.steps,
-                "algorithmic_tflop_per_launch": flops / max(rec["launches"], 1) / 1e12,
-                "timed_in": "a second pass of the same K steps with CUDA events around every launch of this kernel, "
-                            "launched from Python with host-side lengths (the kernels inside the CUDA graph of the "
-                            "`value` pass cannot be bracketed by events; same kernels, bit-identical results)",
-                "note": "algorithmic FLOPs per launch as in DESIGN.md section 5 (error-compensation passes and the "
-                        "second QK^T pass are not credited)"}
-    # the dominant kernel class by launch shape (events of the instrumented pass): where inside the class the time goes
+                "launches_per_step": len(top_ms), "ms_per_step": class_ms,
+                "share_of_step": class_ms / busy_ms if busy_ms > 0 else None,
+                "gpu_busy_ms_per_step": busy_ms, "instrumented_ms_per_step": ms_instr / n_timed,
+                "algorithmic_tflop_per_launch": flops / max(len(top_ms), 1) / 1e12,
+                "timed_in": timed_in,
+                "note": "algorithmic FLOPs per launch as in DESIGN.md section 6 (error-compensation passes and the "
+                        "second QK^T pass are not credited); share_of_step = this class / the sum of all kernels of a step"}
+    # the dominant kernel class by launch shape: where inside the class the time goes
     by_shape = {}
-    for (name, e0, e1, meta) in t_top.records:
+    for meta, tms in zip(top_meta, top_ms):
         d = by_shape.setdefault(tuple(meta), [0, 0.0])
         d[0] += 1
-        d[1] += e0.elapsed_time(e1)
+        d[1] += tms
     shapes = []
-    for meta, (cnt, tms) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:10]:
+    for meta, (cnt, tms) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]:
         fl = algorithmic_flops(top, meta) * cnt
-        shapes.append({"shape": list(meta), "launches_per_step": cnt / args.steps, "us_per_launch": 1e3 * tms / cnt,
+        shapes.append({"shape": list(meta), "launches_per_step": cnt, "us_per_launch": 1e3 * tms / cnt,
                        "tflops": fl / (tms / 1e3) / 1e12 if tms > 0 else 0.0,
-                       "share_of_class": tms / rec["ms"]})
+                       "share_of_class": tms / class_ms if class_ms > 0 else 0.0})
     roofline["by_shape"] = shapes
     step_flops = w.step_flops()                               # oracle trajectory, per rank
     step_roofline = {"algorithmic_tflop_per_step": step_flops / 1e12,

@@ -102,10 +102,26 @@ class Workload:
         raise NotImplementedError
 
     def enable_graphs(self, flag):
+        if self.graphable:
+            self.model.enable_cuda_graphs(flag)
+            return flag
         return False
 
+    def suspend_graphs(self):
+        """Python-issued launches for a while WITHOUT dropping the captured graphs; returns a token for resume_graphs."""
+        if not self.graphable:
+            return None
+        held, self.model._graphs = self.model._graphs, None
+        return held
+
+    def resume_graphs(self, token):
+        if self.graphable:
+            self.model._graphs = token
+
     def graph_launches(self):
-        return 0
+        if not self.graphable:
+            return 0
+        return sum(g.launches * g.replays for g in (self.model._graphs or {}).values())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -146,13 +162,6 @@ class NlvrWorkload(Workload):
 
     def step_flops(self):
         return 2.0 * int(self.cal["macs_pruned"]) * self.PAIRS
-
-    def enable_graphs(self, flag):
-        self.model.enable_cuda_graphs(flag)
-        return flag
-
-    def graph_launches(self):
-        return sum(g.launches * g.replays for g in (self.model._graphs or {}).values())
 
     def config_extra(self):
         return {"pairs_per_gpu": self.PAIRS, "image_size": self.IMAGE, "text_len": self.TEXT_LEN,
@@ -296,6 +305,7 @@ class RetrievalWorkload(Workload):
     workload = ("BLIP retrieval evaluation path (blip_retrieval.py encoders: ViT + text encoder mode 'text' + one multimodal "
                 "ITM pass + itm_head), 384x384, text padded to 35, p=0.75, batch=64/GPU")
     units = 64
+    graphable = True
     CALIB = GOLDEN / "calib_retrieval_p75_b64.npz"
 
     def __init__(self):
@@ -396,6 +406,7 @@ class VqaWorkload(Workload):
     workload = ("BLIP-VQA encoders (blip_vqa.py: ViT at 480x480 = 901 tokens + question encoder with med.py cross-attention "
                 "over the pruned image tokens), p=0.5, batch=64/GPU")
     units = 64
+    graphable = True
     CALIB = GOLDEN / "calib_vqa_p50_b64.npz"
 
     def __init__(self):
@@ -422,7 +433,10 @@ class VqaWorkload(Workload):
         return self._inputs(self.B, 2 + 100 * rank)
 
     def step(self, inputs):
+        from madtp_b200.vit import device_lengths_enabled
         images, ids, mask = inputs
+        if device_lengths_enabled():     # device-resident lengths end to end (a CUDA graph replay when enabled)
+            return self.model.encode_question_packed(images, ids, mask, self.temperature)[2]
         q, _ = self.model.encode_question(images, ids, mask, self.temperature)
         return q[:, 0, :].contiguous()
 

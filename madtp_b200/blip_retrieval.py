@@ -27,7 +27,42 @@ def _med_config(med_config, vision_width, evaluate):
     return cfg
 
 
-class BLIP_Retrieval(nn.Module):
+class _GraphedForward:
+    """CUDA-graph execution of a forward with device-resident lengths (see blip_nlvr.BLIP_NLVR.enable_cuda_graphs):
+    one captured graph, with its own persistent buffers, per entry point, input shapes, temperature and stream."""
+    _graphs = None
+
+    def enable_cuda_graphs(self, enable: bool = True):
+        """Capture the pruned evaluation forward per input shape and replay it on later calls. The graphs bake in the
+        addresses of the weights and of their GEMM-ready copies: call `reset_cuda_graphs()` after changing weights."""
+        self._graphs = {} if enable else None
+        return self
+
+    def reset_cuda_graphs(self):
+        if self._graphs is not None:
+            self._graphs = {}
+
+    def _device_path(self, temperature, *tensors):
+        from .vit import device_lengths_enabled
+        return temperature > 0 and device_lengths_enabled() and all(t.is_cuda for t in tensors)
+
+    def _run_device(self, tag, fn, inputs, temperature):
+        """fn(*inputs) -> (outputs, trajectories) with data-independent launches: inside an arena (persistent buffers,
+        Python-issued launches), or as a replay of the captured graph when enable_cuda_graphs(True)."""
+        inputs = [t.contiguous() for t in inputs]
+        key = (tag,) + tuple(tuple(t.shape) for t in inputs) + (float(temperature),)
+        if self._graphs is None:
+            with L.arena_for(self, key):    # clones: the arena's buffers are reused by the next call with this key
+                return tuple(o.clone() for o in fn(*inputs)[0])
+        from .graphs import GraphedCall
+        key = key + (torch.cuda.current_stream().cuda_stream,)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = GraphedCall(fn, inputs)
+        return g(*inputs)
+
+
+class BLIP_Retrieval(_GraphedForward, nn.Module):
     def __init__(self, med_config='configs/med_config.json', image_size=384, vit='base', vit_grad_ckpt=False,
                  vit_ckpt_layer=0, embed_dim=256, queue_size=57600, momentum=0.995, negative_all_rank=False,
                  evaluate=False, config=None, tokenizer=None):
@@ -119,13 +154,35 @@ class BLIP_Retrieval(nn.Module):
             t = self.tokenizer(caption, padding='max_length', truncation=True, max_length=35,
                                return_tensors="pt").to(image.device)
             ids, mask = t.input_ids, t.attention_mask
+        if self._device_path(temperature, image, ids, mask) and ids.shape[1] <= 64:
+            t = float(temperature)
+            out = self._run_device("retrieval", lambda im, i, m: self._forward_device(im, i, m, t), [image, ids, mask], t)
+            return out[0], out[1]
         image_feat, image_embed = self.encode_image(image, temperature)
         text_embed = self.encode_text(ids, mask, temperature)
         itm = self.itm_score(ids, mask, image_feat, temperature)
         return image_embed @ text_embed.t(), itm
 
+    def _forward_device(self, image, ids, mask, temperature):
+        """The same three passes with device-resident lengths from the first ViT layer to the logits: nothing is read
+        back and every launch argument is data-independent (compress_retrieval_dtp.py:104-122,166-176). Returns
+        ((similarity [B, B], ITM logits [B, 2]), [image, text, multimodal trajectories])."""
+        B = image.shape[0]
+        enc = self.visual_encoder.forward_device(image, self.space_dict, temperature, pack_groups=1, keep_f32=True)
+        img_cls = L.take_token(enc.y, B, enc.cap, 0, n_dev=enc.n_dev)
+        image_embed = torch.nn.functional.normalize(Fn.linear_f32(img_cls, self._lin("vision_proj")), dim=-1)
+        h, _, traj_t, l_dev = self.text_encoder.forward_device(ids, mask, None, self.space_dict, temperature, mode='text')
+        Lcap, d = h.shape[1], h.shape[2]
+        txt_cls = L.take_token(h.view(B * Lcap, d), B, Lcap, 0, n_dev=l_dev)
+        text_embed = torch.nn.functional.normalize(Fn.linear_f32(txt_cls, self._lin("text_proj")), dim=-1)
+        ids2 = ids.clone()
+        ids2[:, 0] = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        h, _, traj_m, l_dev = self.text_encoder.forward_device(ids2, mask, enc, self.space_dict, temperature)
+        itm = Fn.linear_f32(L.take_token(h.view(B * Lcap, d), B, Lcap, 0, n_dev=l_dev), self._lin("itm_head"))
+        return (image_embed @ text_embed.t(), itm), [enc.traj, traj_t, traj_m]
 
-class BLIP_VQA(nn.Module):
+
+class BLIP_VQA(_GraphedForward, nn.Module):
     def __init__(self, med_config='configs/med_config.json', image_size=480, vit='base', vit_grad_ckpt=False,
                  vit_ckpt_layer=0, evaluate=False, config=None, tokenizer=None):
         super().__init__()
@@ -149,6 +206,28 @@ class BLIP_VQA(nn.Module):
                                    encoder_attention_mask=None, return_dict=True, space_dict=self.space_dict,
                                    temperature=temperature)
         return out.last_hidden_state, image_embeds
+
+    @torch.no_grad()
+    def encode_question_packed(self, image, input_ids, attention_mask, temperature):
+        """The two encoders of blip_vqa.py:60,119-125 with device-resident lengths end to end (no read-back; a CUDA
+        graph replay when enable_cuda_graphs(True)). Returns (question states as a capacity-sized buffer [B, L, d] of
+        packed sequences, device scalar with their length, the [ENC] rows [B, d])."""
+        if not self._device_path(temperature, image, input_ids, attention_mask) or input_ids.shape[1] > 64:
+            raise RuntimeError("madtp_b200: encode_question_packed is the pruned device-length path (temperature > 0, "
+                               "question length <= 64)")
+        t = float(temperature)
+        return self._run_device("vqa", lambda im, i, m: self._encode_question_device(im, i, m, t),
+                                [image, input_ids, attention_mask], t)
+
+    def _encode_question_device(self, image, ids, mask, temperature):
+        B = image.shape[0]
+        enc = self.visual_encoder.forward_device(image, self.space_dict, temperature, pack_groups=1)
+        ids = ids.clone()
+        ids[:, 0] = getattr(self.tokenizer, "enc_token_id", ENC_TOKEN_ID)
+        h, _, traj, l_dev = self.text_encoder.forward_device(ids, mask, enc, self.space_dict, temperature)
+        Lcap, d = h.shape[1], h.shape[2]
+        cls = L.take_token(h.view(B * Lcap, d), B, Lcap, 0, n_dev=l_dev)
+        return (h, l_dev, cls), [enc.traj, traj]
 
     @torch.no_grad()
     def rank_answer(self, question_states, question_atts, answer_ids, answer_atts, k):

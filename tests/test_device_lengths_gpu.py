@@ -271,3 +271,75 @@ def test_two_batches_in_flight_match_sequential(dev):
         assert len(model._graphs) == 2       # one captured graph per stream
     finally:
         model.enable_cuda_graphs(False)
+
+
+def test_retrieval_forward_device_and_graph_match_encoder_calls(dev):
+    """BLIP_Retrieval.forward(train=False): the device-length chain (image encoder -> text-only pass -> multimodal ITM
+    pass with nothing read back) and its CUDA-graph replay are bit-identical to the host-length path built from the
+    public encoder calls (compress_retrieval_dtp.py:104-122,166-176)."""
+    from madtp_b200 import vit
+    from madtp_b200.blip_retrieval import BLIP_Retrieval
+    model = BLIP_Retrieval(image_size=224, evaluate=True)
+    msg = model.load_state_dict(weights.retrieval_state_dict(4321, img_size=224), strict=False)
+    assert not msg.unexpected_keys
+    model = model.to(dev).eval()
+    temp = 6.0
+    outs = []
+    try:
+        for seed in (0, 1):
+            images, ids, mask = (t.to(dev) for t in weights.retrieval_inputs(4, 224, 35, seed=seed))
+            vit.device_lengths_enabled(False)
+            ref_sim, ref_itm = model(images, (ids, mask), 0.0, None, temp, train=False)
+            ref_k = [b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1
+                     for b in model.visual_encoder.blocks]
+            vit.device_lengths_enabled(True)
+            sim, itm = model(images, (ids, mask), 0.0, None, temp, train=False)
+            k = [b.last_prune.k if b.last_prune.pruned else -1 for b in model.visual_encoder.blocks]
+            assert k == ref_k and any(v >= 0 for v in k)
+            assert torch.equal(itm, ref_itm), f"ITM logits differ by {(itm - ref_itm).abs().max().item():.3e}"
+            assert torch.allclose(sim, ref_sim, atol=1e-6)
+            outs.append((images, ids, mask, sim.clone(), itm.clone()))
+        model.enable_cuda_graphs(True)
+        for images, ids, mask, sim, itm in outs + outs[:1]:      # capture on the first input, replay on fresh ones
+            g_sim, g_itm = model(images, (ids, mask), 0.0, None, temp, train=False)
+            assert torch.equal(g_itm, itm) and torch.equal(g_sim, sim)
+        assert len(model._graphs) == 1 and next(iter(model._graphs.values())).replays == 3
+    finally:
+        vit.device_lengths_enabled(True)
+        model.enable_cuda_graphs(False)
+
+
+def test_vqa_encode_question_packed_and_graph_match_encode_question(dev):
+    """BLIP_VQA.encode_question_packed (device-resident lengths end to end, optionally a graph replay) against the
+    public encode_question (models/blip_vqa.py:60,119-125): same question states, bit for bit."""
+    from madtp_b200 import vit
+    from madtp_b200.blip_retrieval import BLIP_VQA
+    model = BLIP_VQA(image_size=224, evaluate=True)
+    model.load_state_dict(weights.vqa_state_dict(99, img_size=224), strict=False)
+    model = model.to(dev).eval()
+    temp = 10.0
+    images, ids, mask = (t.to(dev) for t in weights.retrieval_inputs(3, 224, 20, seed=5))
+    try:
+        vit.device_lengths_enabled(False)
+        ref, _ = model.encode_question(images, ids, mask, temp)
+        vit.device_lengths_enabled(True)
+        h, l_dev, cls = model.encode_question_packed(images, ids, mask, temp)
+        n = int(l_dev.item())
+        B, _, d = h.shape
+        assert n == ref.shape[1]
+        assert any(b.last_prune.pruned for b in model.visual_encoder.blocks), "the image encoder was expected to prune"
+        assert torch.equal(h.reshape(-1)[:B * n * d].view(B, n, d), ref)
+        assert torch.equal(cls, ref[:, 0, :])
+        model.enable_cuda_graphs(True)
+        for _ in range(2):
+            _, l2, cls2 = model.encode_question_packed(images, ids, mask, temp)
+            assert int(l2.item()) == n and torch.equal(cls2, ref[:, 0, :])
+        images2, ids2, mask2 = (t.to(dev) for t in weights.retrieval_inputs(3, 224, 20, seed=6))
+        vit.device_lengths_enabled(False)
+        ref2, _ = model.encode_question(images2, ids2, mask2, temp)
+        vit.device_lengths_enabled(True)
+        _, _, cls3 = model.encode_question_packed(images2, ids2, mask2, temp)     # a replay on fresh inputs
+        assert torch.equal(cls3, ref2[:, 0, :])
+    finally:
+        vit.device_lengths_enabled(True)
+        model.enable_cuda_graphs(False)

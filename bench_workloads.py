@@ -511,6 +511,7 @@ class ClipWorkload(Workload):
     workload = ("CLIP ViT-B/16 towers (clip/model.py encode_image + encode_text, retrieval_flickr_clip.yaml image size 336 = 442 "
                 "tokens, context 77), p=0.5, batch=64/GPU")
     units = 64
+    graphable = True
     CALIB = GOLDEN / "calib_clip_p50_b64_r336.npz"
 
     def __init__(self):

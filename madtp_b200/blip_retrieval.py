@@ -16,6 +16,7 @@ from . import _lib as L
 from . import functional as Fn
 from .blip_nlvr import ENC_TOKEN_ID, create_vit
 from .configuration import BertConfig
+from .graphs import GraphedForward as _GraphedForward
 from .med import BertLMHeadModel, BertModel
 
 
@@ -25,41 +26,6 @@ def _med_config(med_config, vision_width, evaluate):
     cfg.encoder_width = vision_width
     cfg.evaluate = evaluate
     return cfg
-
-
-class _GraphedForward:
-    """CUDA-graph execution of a forward with device-resident lengths (see blip_nlvr.BLIP_NLVR.enable_cuda_graphs):
-    one captured graph, with its own persistent buffers, per entry point, input shapes, temperature and stream."""
-    _graphs = None
-
-    def enable_cuda_graphs(self, enable: bool = True):
-        """Capture the pruned evaluation forward per input shape and replay it on later calls. The graphs bake in the
-        addresses of the weights and of their GEMM-ready copies: call `reset_cuda_graphs()` after changing weights."""
-        self._graphs = {} if enable else None
-        return self
-
-    def reset_cuda_graphs(self):
-        if self._graphs is not None:
-            self._graphs = {}
-
-    def _device_path(self, temperature, *tensors):
-        from .vit import device_lengths_enabled
-        return temperature > 0 and device_lengths_enabled() and all(t.is_cuda for t in tensors)
-
-    def _run_device(self, tag, fn, inputs, temperature):
-        """fn(*inputs) -> (outputs, trajectories) with data-independent launches: inside an arena (persistent buffers,
-        Python-issued launches), or as a replay of the captured graph when enable_cuda_graphs(True)."""
-        inputs = [t.contiguous() for t in inputs]
-        key = (tag,) + tuple(tuple(t.shape) for t in inputs) + (float(temperature),)
-        if self._graphs is None:
-            with L.arena_for(self, key):    # clones: the arena's buffers are reused by the next call with this key
-                return tuple(o.clone() for o in fn(*inputs)[0])
-        from .graphs import GraphedCall
-        key = key + (torch.cuda.current_stream().cuda_stream,)
-        g = self._graphs.get(key)
-        if g is None:
-            g = self._graphs[key] = GraphedCall(fn, inputs)
-        return g(*inputs)
 
 
 class BLIP_Retrieval(_GraphedForward, nn.Module):

@@ -19,6 +19,7 @@ from torch import nn
 
 from . import _lib as L
 from . import functional as Fn
+from .graphs import GraphedForward
 from .utils import Query_model, vector_gather  # noqa: F401
 from .vit import _eval_only
 
@@ -74,15 +75,16 @@ class MultiheadAttention(nn.Module):
                               lambda: Fn.PreparedLinear(self.out_proj.weight, self.out_proj.bias, f16=True))
         return qkv, out
 
-    def rows(self, y_hi, y_lo, B, N, residual, want_stats, causal):
+    def rows(self, y_hi, y_lo, B, N, residual, want_stats, causal, n_dev=None):
         qkv_w, out_w = self._prepared()
         C = self.embed_dim
         scale = self.head_dim ** -0.5        # q / sqrt(E) then q.k: exact for head_dim 64 (a power of two)
         # image tower and the causal text tower (clip/mock.py:302-340) both run the tensor-core scoring-lane attention
-        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, scale, want_stats, causal=causal)
+        ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, scale, want_stats, causal=causal,
+                                            n_dev=n_dev)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
-        return Fn.linear_f16(ctx16.view(B * N, C), out_w, residual=residual)
+        return Fn.linear_f16(ctx16.view(B * N, C), out_w, residual=residual, m_dev=n_dev, m_mult=B)
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -105,33 +107,44 @@ class ResidualAttentionBlock(nn.Module):
         b = self._cache.get("pj", [pj.weight, pj.bias], lambda: Fn.PreparedLinear(pj.weight, pj.bias, f16=True))
         return a, b
 
-    def forward_bnc(self, x, space_dict, temperature, sd_ft_all, max_keep):
-        """x [B, N, C] contiguous fp32 -> (x', sd_ft_all)."""
+    def forward_bnc(self, x, space_dict, temperature, sd_ft_all, max_keep, n_dev=None, n_out=None, k_out=None):
+        """x [B, N, C] contiguous fp32 -> (x', sd_ft_all). n_dev / n_out / k_out: device-resident lengths (x is a
+        capacity-sized buffer of packed sequences of *n_dev tokens; the block writes the next length to n_out and its
+        topk_num to k_out -- functional.dtp_finish); needs the pruned path (a codebook and temperature > 0)."""
         B, N, C = x.shape
         with_dict = space_dict is not None
         prune = with_dict and temperature > 0
+        if n_dev is not None and not prune:
+            raise RuntimeError("madtp_b200: device-resident lengths are the PRUNED path")
         ln1 = Fn.layernorm_rows(x.view(B * N, C), self.ln_1.weight, self.ln_1.bias, self.ln_1.eps, split=True,
-                                split_x=with_dict)
+                                split_x=with_dict, n_dev=n_dev, n_mult=B)
         token_attn = None
         if with_dict:                                                                    # :239-245
-            token_attn, sd_ft_all = self.query_model.forward_rows(x, ln1["x_hi"], ln1["x_lo"], space_dict, sd_ft_all)
-        x1 = self.attn.rows(ln1["y_hi"], ln1["y_lo"], B, N, x.view(B * N, C), prune, self.attn_mask is not None)
+            token_attn, sd_ft_all = self.query_model.forward_rows(x, ln1["x_hi"], ln1["x_lo"], space_dict, sd_ft_all,
+                                                                  n_dev=n_dev)
+        x1 = self.attn.rows(ln1["y_hi"], ln1["y_lo"], B, N, x.view(B * N, C), prune, self.attn_mask is not None,
+                            n_dev=n_dev)
         x1 = x1.view(B, N, C)
         self.last_prune = None
+        nd2 = n_dev
         if prune:                                                                        # :254-258
-            res = Fn.dtp_prune(x1, self.attn.get_attention_map(), token_attn, float(temperature),
-                               max_keep=int(max_keep), ln=(self.ln_2.weight, self.ln_2.bias, self.ln_2.eps))
+            pend = Fn.dtp_score_async(self.attn.get_attention_map(), token_attn, float(temperature), N - 1, n_dev=n_dev)
+            res = Fn.dtp_finish(x1, pend, max_keep=int(max_keep), n_dev=n_dev, n_out=n_out, k_out=k_out,
+                                ln=(self.ln_2.weight, self.ln_2.bias, self.ln_2.eps))
             self.last_prune = res
             x1 = res.x
+            if n_dev is not None:
+                nd2 = n_out
         N2 = x1.shape[1]
         x2d = x1.view(B * N2, C)
         fc, pj = self._mlp()
         if prune and res.ln16 is not None:      # ln_2 came out of the fused select + gather kernel
             y16 = res.ln16.view(B * N2, C)
         else:
-            y16 = Fn.layernorm_rows(x2d, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, f16=True)["y16"]
-        h = Fn.linear_f16(y16, fc, out_dtype=torch.float16, act=L.ACT_QUICKGELU)
-        return Fn.linear_f16(h, pj, residual=x2d).view(B, N2, C), sd_ft_all
+            y16 = Fn.layernorm_rows(x2d, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, f16=True, n_dev=nd2,
+                                    n_mult=B)["y16"]
+        h = Fn.linear_f16(y16, fc, out_dtype=torch.float16, act=L.ACT_QUICKGELU, m_dev=nd2, m_mult=B)
+        return Fn.linear_f16(h, pj, residual=x2d, m_dev=nd2, m_mult=B).view(B, N2, C), sd_ft_all
 
     @torch.no_grad()
     def forward(self, inputs):
@@ -141,6 +154,24 @@ class ResidualAttentionBlock(nn.Module):
         _eval_only(self)
         y, sd_ft_all = self.forward_bnc(x.permute(1, 0, 2).contiguous(), space_dict, temperature, sd_ft_all, max_keep)
         return y.permute(1, 0, 2), space_dict, temperature, sd_ft_all, max_keep
+
+
+def _blocks_device(blocks, y, space_dict, temperature, max_keep):
+    """The residual blocks with device-resident lengths: y [B, N, C] stays a capacity-sized buffer of packed sequences,
+    nothing is read back. Returns (y, sd_ft_all, Trajectory, device scalar with the final tokens per sequence)."""
+    B, N, _ = y.shape
+    depth = len(blocks)
+    lens = L.empty((2 * depth + 1,), torch.int32, y.device)
+    dims, ks = lens[:depth + 1], lens[depth + 1:]
+    dims[:1].fill_(N)
+    ks.fill_(-1)
+    traj = Fn.Trajectory(dims, ks)
+    sd_ft_all = None
+    for i, blk in enumerate(blocks):
+        y, sd_ft_all = blk.forward_bnc(y, space_dict, temperature, sd_ft_all, max_keep, n_dev=dims[i:i + 1],
+                                       n_out=dims[i + 1:i + 2], k_out=ks[i:i + 1])
+        blk.last_prune = Fn.LazyPrune(traj, i, blk.last_prune, B)
+    return y, sd_ft_all, traj, dims[depth:depth + 1]
 
 
 class Transformer(nn.Module):
@@ -180,7 +211,7 @@ class VisionTransformer(nn.Module):
         self._cache = Fn.WeightCache()
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, space_dict=None, temperature=0, max_keep=1):
+    def forward(self, x: torch.Tensor, space_dict=None, temperature=0, max_keep=1, _device=False):
         Fn.require_cuda(x, "image")
         _eval_only(self)
         B, _, Hh, Ww = x.shape
@@ -193,6 +224,11 @@ class VisionTransformer(nn.Module):
         C = patches.shape[1]
         tok = L.assemble_tokens(patches, self.class_embedding.detach(), self.positional_embedding.detach(), B, n, C)
         y = self.ln_pre(tok)
+        if _device:     # device-resident lengths: the CLS rows are taken from the packed stream, nothing is read back
+            y, sd_img_ft_all, traj, n_dev = _blocks_device(self.transformer.resblocks, y, space_dict, temperature, max_keep)
+            cls = self.ln_post(L.take_token(y.view(-1, C), B, y.shape[1], 0, n_dev=n_dev))
+            proj = self._cache.get("proj", [self.proj], lambda: Fn.PreparedLinear(self.proj.t(), None, f32=True))
+            return (Fn.linear_f32(cls, proj), sd_img_ft_all), [traj]
         sd_img_ft_all = None
         for blk in self.transformer.resblocks:
             y, sd_img_ft_all = blk.forward_bnc(y, space_dict, temperature if space_dict is not None else 0,
@@ -202,7 +238,7 @@ class VisionTransformer(nn.Module):
         return Fn.linear_f32(cls, proj), sd_img_ft_all
 
 
-class CLIP(nn.Module):
+class CLIP(GraphedForward, nn.Module):
     """The two encoders of clip/model.py:CLIP (ViT towers only) with `encode_image` / `encode_text` (:482-503).
     Constructor arguments and their order are the reference's (:317-332), including the positional `evaluate`; the
     momentum twins, queues and the ResNet towers (:383-437, training only) are out of scope, so their state-dict keys
@@ -263,16 +299,32 @@ class CLIP(nn.Module):
     def dtype(self):
         return self.visual.conv1.weight.dtype
 
+    @torch.no_grad()
     def encode_image(self, image, space_dict=None, temperature=0):
-        return self.visual(image.type(self.dtype), space_dict=space_dict, temperature=temperature)
+        image = image.type(self.dtype)
+        if space_dict is not None and self._device_path(temperature, image):
+            # device-resident lengths end to end (the reference syncs once per block, clip/model.py:219); a CUDA-graph
+            # replay when enable_cuda_graphs(True)
+            t = float(temperature)
+            emb, sd_ft = self._run_device("image", lambda im: self.visual(im, space_dict=space_dict, temperature=t,
+                                                                          _device=True), [image], t,
+                                          extra=(space_dict.data_ptr(),))
+            return emb, sd_ft
+        return self.visual(image, space_dict=space_dict, temperature=temperature)
 
     @torch.no_grad()
     def encode_text(self, text, space_dict=None, temperature=0):
         if not text.is_cuda:
             raise RuntimeError("madtp_b200: text ids must be a CUDA tensor -- this package has no CPU fallback")
+        max_keep = int(text.argmax(dim=-1).max()) + 2                                      # :495
+        if space_dict is not None and self._device_path(temperature, text):
+            # max_keep is a property of the input ids (one read before anything is launched) and part of the graph key
+            t = float(temperature)
+            emb, sd_ft = self._run_device("text", lambda ids: self._encode_text_device(ids, space_dict, t, max_keep),
+                                          [text.to(torch.int64)], t, extra=(max_keep, space_dict.data_ptr()))
+            return emb, sd_ft
         x = L.bert_embed(text.to(torch.int64), self.token_embedding.weight.detach(),
                          self.positional_embedding.detach())                               # :490-492
-        max_keep = int(text.argmax(dim=-1).max()) + 2                                      # :495
         y = x
         sd_txt_ft_all = None
         for blk in self.transformer.resblocks:
@@ -283,6 +335,22 @@ class CLIP(nn.Module):
         proj = self._cache.get("tp", [self.text_projection],
                                lambda: Fn.PreparedLinear(self.text_projection.t(), None, f32=True))
         return Fn.linear_f32(eot, proj), sd_txt_ft_all
+
+    def _encode_text_device(self, text, space_dict, temperature, max_keep):
+        """CLIP.encode_text with device-resident lengths: the blocks run on capacity-sized packed buffers, ln_final on the
+        dynamic row count, and the EOT row of every sequence (clip/model.py:501: index argmax(text) into the PRUNED
+        sequence) is gathered from the packed stream with indices formed on the device."""
+        B, N = text.shape
+        y = L.bert_embed(text, self.token_embedding.weight.detach(), self.positional_embedding.detach())
+        y, sd_ft, traj, n_dev = _blocks_device(self.transformer.resblocks, y, space_dict, temperature, max_keep)
+        C = y.shape[-1]
+        yn = Fn.layernorm_rows(y.view(B * N, C), self.ln_final.weight, self.ln_final.bias, self.ln_final.eps, f32=True,
+                               n_dev=n_dev, n_mult=B)["y"]
+        rows = torch.arange(B, device=y.device, dtype=torch.int64) * n_dev.to(torch.int64) + text.argmax(dim=-1)
+        eot = yn.index_select(0, rows)
+        proj = self._cache.get("tp", [self.text_projection],
+                               lambda: Fn.PreparedLinear(self.text_projection.t(), None, f32=True))
+        return (Fn.linear_f32(eot, proj), sd_ft), [traj]
 
 
 def convert_weights(model: nn.Module):

@@ -343,3 +343,49 @@ def test_vqa_encode_question_packed_and_graph_match_encode_question(dev):
     finally:
         vit.device_lengths_enabled(True)
         model.enable_cuda_graphs(False)
+
+
+def test_clip_towers_device_lengths_and_graph_match_host_lengths(dev):
+    """CLIP.encode_image / encode_text (clip/model.py:482-503): device-resident lengths and the CUDA-graph replay against
+    the host-length path (one read-back per block, the reference's own control flow): embeddings, sd_ft and k
+    trajectories bit for bit -- including the causal text tower with its `max_keep` guard and the EOT gather."""
+    from madtp_b200 import vit
+    from madtp_b200.clip_model import CLIP
+    layers = 4
+    sd = weights.clip_state_dict(777, vision_layers=layers, text_layers=layers)
+    model = CLIP(512, 224, layers, 768, 16, 77, 49408, 512, 8, layers, True, None)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys
+    model = model.to(dev).eval()
+    space = model.space_dict
+
+    def ks(blocks):
+        return [b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1 for b in blocks]
+
+    try:
+        cases = []
+        for seed, t_img, t_txt in ((0, 5.0, 50.0), (1, 5.0, 50.0)):
+            images, text = (t.to(dev) for t in weights.clip_inputs(3, seed=seed))
+            vit.device_lengths_enabled(False)
+            ri, rs = model.encode_image(images, space, t_img)
+            rk = ks(model.visual.transformer.resblocks)
+            rt, rts = model.encode_text(text, space, t_txt)
+            rtk = ks(model.transformer.resblocks)
+            vit.device_lengths_enabled(True)
+            ei, es = model.encode_image(images, space, t_img)
+            assert ks(model.visual.transformer.resblocks) == rk and any(k >= 0 for k in rk)
+            et, ets = model.encode_text(text, space, t_txt)
+            assert ks(model.transformer.resblocks) == rtk
+            assert torch.equal(ei, ri) and torch.equal(es, rs), "vision tower"
+            # sd_ft is a by-product off the scoring lane: below 64 tokens the host-length path aggregates it on the CUDA
+            # cores, the capacity-sized device path always on the tensor cores
+            assert torch.equal(et, rt) and torch.allclose(ets, rts, rtol=2e-5, atol=2e-6), "text tower"
+            cases.append((images, text, t_img, t_txt, ri.clone(), rt.clone()))
+        model.enable_cuda_graphs(True)
+        for images, text, t_img, t_txt, ri, rt in cases + cases[:1]:
+            gi, _ = model.encode_image(images, space, t_img)
+            gt, _ = model.encode_text(text, space, t_txt)
+            assert torch.equal(gi, ri) and torch.equal(gt, rt)
+    finally:
+        vit.device_lengths_enabled(True)
+        model.enable_cuda_graphs(False)

@@ -3,7 +3,7 @@
 // a bmm, two cats and nn.LayerNorm (models/vit.py:148-161,202,205; models/nlvr_encoder.py:434-454; models/med.py:
 // 371-390; models/utils.py:13-33), and what round 1 did with three kernels and a host read-back.
 //
-//   grid (S, B): S CTAs of 1024 threads per sequence (S = ceil(SMs / B), 1..8). Every CTA of a sequence recomputes the
+//   grid (S, B): S CTAs of 1024 threads per sequence (S = floor(SMs / B), 1..8: a single wave). Every CTA of a sequence recomputes the
 //   selection (a few microseconds, no cross-CTA traffic), then the S * 32 warps of the sequence copy its surviving
 //   rows -- one warp per row, the whole row in registers (128-bit loads and stores), so the LayerNorm of the row costs
 //   no extra memory pass.
@@ -310,7 +310,9 @@ int launch_dtp_apply(const DtpApplyArgs& a, cudaStream_t stream) {
   MADTP_CHECK_ARG(a.mask_mode == 0 || a.n <= 256, "dtp_apply: the masked (text) modes are built for short sequences");
   MADTP_CHECK_ARG((a.ln_out == nullptr) || (a.ln_gamma && a.ln_beta), "dtp_apply: LayerNorm needs gamma and beta");
   MADTP_CHECK_ARG(a.n_dev == nullptr || a.n_out != nullptr, "dtp_apply: n_dev needs n_out_dev");
-  int S = (num_sms() + a.B - 1) / a.B;
+  // one CTA per SM (1024 threads, the row in registers): S * B <= SMs keeps the grid a single wave -- 3 x 64 CTAs on
+  // 148 SMs ran as two waves, the second one 30 % full (47 us -> 3x us for block 1 of the bench)
+  int S = num_sms() / a.B;
   if (S < 1) S = 1;
   if (S > 8) S = 8;
   const int d4 = a.d / 4;

@@ -250,7 +250,7 @@ __device__ __forceinline__ void epilogue_chunks_tmem(const GemmEpilogue& ep, uin
 
 // PAIR = true: clusters of two CTAs form a cta_group::2 pair working on two vertically adjacent output tiles (same
 // n-tile): ONE MMA of M = 256 spans both SMs, every CTA stages its own 128 rows of A and only half of B's rows, the
-// leader (cluster rank 0) issues all MMAs and owns the operand-full barriers (see gemm_tf32x3_kernel).
+// leader (cluster rank 0) issues all MMAs and owns the operand-full barriers (see gemm_split3_kernel).
 template <int BLOCK_N, bool TF32X3, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -514,7 +514,7 @@ struct Tf32Cfg {
 // by the L2 -> shared-memory operand traffic), the leader issues all MMAs and owns the operand-full barriers.
 template <int BLOCK_N, int CL, bool F16 = false, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
+gemm_split3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b_lo,
                    GemmEpilogue ep, int M_cap, int N_cap, int K) {
   using Cfg = Tf32Cfg<BLOCK_N, PAIR>;
@@ -969,7 +969,7 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   if ((st = make_tmap(&tb, b, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
   if ((st = make_tmap(&tal, a_lo, !F16, M, K, lda, Cfg::BLOCK_M)) != kOk) return st;
   if ((st = make_tmap(&tbl, b_lo, !F16, N, K, ldb, BLOCK_N / CL)) != kOk) return st;
-  MADTP_SMEM_ATTR_ONCE(Cfg::SMEM_BYTES, gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>);
+  MADTP_SMEM_ATTR_ONCE(Cfg::SMEM_BYTES, gemm_split3_kernel<BLOCK_N, CL, F16, PAIR>);
   GemmEpilogue epc = ep;
   if (epc.chunk_kb <= 0) {
     static const int env_chunk = getenv("MADTP_CHUNK_KB") ? atoi(getenv("MADTP_CHUNK_KB")) : 0;
@@ -991,7 +991,7 @@ static int launch_tf32_cl(const void* a, const void* a_lo, long long lda, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32x3_kernel<BLOCK_N, CL, F16, PAIR>, ta, tal, tb, tbl, epc, M, N, K));
+  MADTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_split3_kernel<BLOCK_N, CL, F16, PAIR>, ta, tal, tb, tbl, epc, M, N, K));
   return kOk;
 }
 

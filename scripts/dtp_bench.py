@@ -56,3 +56,15 @@ for B, n in ((64, 576), (64, 345), (64, 255)):
     a = t(lambda: lib.query_sdft_tc(ta_p, cm, cs, x.view(B * N, d), N, 1, n, T, div, sd, False))
     p = t(lambda: lib.query_sdft_planes(ta_p, cm, cs, hi, lo, N, 1, n, T, div, sd, False))
     print(f"B={B} n={n}: query_sdft_tc {a:.1f} us, query_sdft_planes {p:.1f} us")
+
+# dtp_apply at ViT shapes (select + gather + merged token + LayerNorm)
+for B, n, k in ((64, 576, 410), (64, 411, 345), (64, 346, 319), (64, 260, 257)):
+    g = torch.Generator().manual_seed(2)
+    d = 768
+    x = torch.randn(B, n + 1, d, generator=g).to(dev)
+    score = torch.rand(B, n, generator=g).to(dev)
+    topk = torch.tensor([k], dtype=torch.int32, device=dev)
+    gamma, beta = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    a = t(lambda: lib.dtp_apply(x, score, topk, k, ln=(gamma, beta, 1e-6)))
+    mb = (B * (n + 1) * d * 4 + B * (k + 2) * d * 6) / 1e6
+    print(f"B={B} n={n} k={k}: dtp_apply {a:.1f} us, {mb / a:.2f} TB/s algorithmic")

@@ -34,7 +34,8 @@ torch.cuda.synchronize()
 ViT1 = 1           # block 1
 TARGETS = {
     "madtp_layernorm": {1},                      # LN1 of block 1 (LN1 of block 0 is occurrence 0)
-    "madtp_token_colstats": {ViT1, 12}, "madtp_query_sdft_tc": {ViT1}, "madtp_query_sdft": {0},
+    "madtp_token_colstats": {ViT1, 12}, "madtp_query_sdft_planes": {ViT1}, "madtp_query_sdft_tc": {ViT1},
+    "madtp_query_sdft": {0},
     "madtp_gemm_qkv": {ViT1}, "madtp_attn_tc_fwd": {ViT1}, "madtp_attn_tc_stats": {ViT1},
     "madtp_dtp_score": {ViT1, 12}, "madtp_dtp_apply": {ViT1, 12}, "madtp_layernorm_pack": {0},
     "madtp_attn_small_self": {0}, "madtp_attn_cross_tc": {0},

@@ -391,6 +391,47 @@ def test_blip_vqa_question_encoder_480(dev):
     assert rel(q[:, 0, :], q_o[:, 0, :]) < 5e-3
 
 
+@pytest.mark.parametrize("which,image_size,batch,temp", [("retrieval", 384, 3, 12.0), ("vqa", 480, 2, 6.0)])
+def test_retrieval_vqa_vit_layers_teacher_forced(dev, which, image_size, batch, temp):
+    """The image encoder of BASELINE configurations 3 and 5 layer by layer, both sides consuming the ORACLE's layer input
+    (SURVEY 8-a15): 577 -> ~60 tokens (deep prune, small-M tail) and 901 tokens (480 x 480: eight 128-query tiles, the
+    longest sequences the tensor-core attention / statistics kernels see). Keep-masks, counts and topk_num bit-exact."""
+    from madtp_b200.blip_retrieval import BLIP_Retrieval, BLIP_VQA
+    if which == "retrieval":
+        sd = weights.retrieval_state_dict(4321, img_size=image_size)
+        model = BLIP_Retrieval(image_size=image_size, evaluate=True)
+    else:
+        sd = weights.vqa_state_dict(99, img_size=image_size)
+        model = BLIP_VQA(image_size=image_size, evaluate=True)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    images, _, _ = weights.retrieval_inputs(batch, image_size, 35, seed=3)
+    traces = []
+    with torch.no_grad():
+        O.vit_forward(images, sd, "visual_encoder.", sd["space_dict"], temp, traces=traces)
+    vit = model.visual_encoder
+    space = model.space_dict.detach()
+    worst, pruned_layers = 0.0, 0
+    for i, (blk, t) in enumerate(zip(vit.blocks, traces)):
+        x = t.layer_input.to(dev)
+        with torch.no_grad():
+            token_attn, _, _ = vit.img_query_model(x[:, 1:, :], space, return_token_att=True)
+            y = blk(x, False, 0, temp, token_attn)
+        res = blk.last_prune
+        what = f"{which} ViT layer {i} ({x.shape[1]} tokens, T={temp})"
+        assert_counts_equal(res.count, t.count, t.score, t.threshold, what)
+        assert res.pruned == t.pruned and res.k == t.k, f"{what}: topk_num {res.k} vs oracle {t.k}"
+        assert score_err(res.score, t.score) < SCORE_RTOL, what
+        if t.pruned:
+            pruned_layers += 1
+            assert_masks_equal(res.keep, t.keep, t.score, t.k, what)
+        assert y.shape == t.layer_output.shape
+        worst = max(worst, rel(y, t.layer_output))
+    assert pruned_layers >= 6 and worst < REL_TOL, f"{pruned_layers} pruned layers, hidden-state error {worst:.2e}"
+    if which == "retrieval":
+        assert traces[-1].layer_output.shape[1] < (image_size // 16) ** 2 // 2, "deep prune expected at this temperature"
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # BASELINE configuration 2 at FULL size (32 pairs, 384 x 384, tau calibrated for p = 0.5): the oracle's trajectory is
 # stored in tests/golden/calib_nlvr_p50_b32.npz, so nothing CPU-heavy runs here; plus size-independent properties

@@ -375,6 +375,7 @@ def main():
         torch.cuda.synchronize()
         l0 = _lib.launch_count() + w.graph_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_own = torch.cuda.Event(enable_timing=True)
         _lib.set_launch_timer(t)
         e0.record()
         fork_streams()
@@ -382,12 +383,13 @@ def main():
         for _ in range(steps):
             last = fn()
         join_streams()
+        e_own.record()                       # this rank's own steps are done (diagnostics: ms_per_step_by_rank)
         mdist.all_gather_rows(last)          # the job's one collective: every rank's last results, after the last step
         e1.record()
         _lib.set_launch_timer(None)
         torch.cuda.synchronize()
         mdist.barrier()
-        by_rank.append(mdist.gather_over_ranks(e0.elapsed_time(e1) / steps, dev))
+        by_rank.append(mdist.gather_over_ranks(e0.elapsed_time(e_own) / steps, dev))
         ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
         return ms, _lib.launch_count() + w.graph_launches() - l0, t
 

@@ -1,4 +1,5 @@
 // extern "C" boundary of libmadtp_b200.so -- see include/madtp_b200.h for the contract of every entry point.
+#include <stdlib.h>
 #include "../../include/madtp_b200.h"
 
 #include <stdarg.h>
@@ -31,6 +32,10 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
       sms = 148;
+    // development switch: size the persistent kernels' grids for fewer SMs than the device has, leaving the rest to
+    // kernels of another stream (bench.py --streams 2: the latency-bound text encoder of the other batch)
+    const char* lim = getenv("MADTP_SM_LIMIT");
+    if (lim != nullptr && atoi(lim) > 0 && atoi(lim) < sms) sms = atoi(lim);
   }
   return sms;
 }

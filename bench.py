@@ -262,6 +262,10 @@ def main():
     ap.add_argument("--streams", type=int, default=2, help="batches in flight: consecutive steps alternate between this "
                     "many CUDA streams, each with its own captured graph and buffers (madtp_b200.pipeline.StreamPool); "
                     "1 = every step on the current stream")
+    ap.add_argument("--value-lane", default="f16", choices=["f16", "split"],
+                    help="split: diagnostic -- the ViT's value lane (attention output projection, FFN) also runs on the "
+                         "error-compensated fp16 hi/lo planes with an fp32 context and the exact GELU, to show the "
+                         "free-running keep-mask agreement without the value lane's fp16 rounding (slower)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "madtp_b200" else max(args.warmup, 1)
@@ -286,6 +290,9 @@ def main():
     model = w.build(dev, rank)
     mdist.broadcast_parameters(model, src=0)
     mvit.device_lengths_enabled(not args.host_lengths)
+    if args.value_lane == "split":
+        from madtp_b200 import functional as mfn
+        mfn.value_lane_split(True)
     use_graph = w.graphable and not (args.no_graph or args.host_lengths)
     w.enable_graphs(use_graph)
 
@@ -523,6 +530,8 @@ def main():
                                                    else "device-resident token counts, one read-back per encoder call"))
         cfg = {"workload": w.workload, "baseline_config": w.config, "temperature": w.temperature,
                "parallelism": f"batch-shard x{world}", "execution": execution,
+               "value_lane": "f16 operands (default)" if args.value_lane == "f16" else
+               "DIAGNOSTIC: error-compensated fp16 hi/lo planes + fp32 context + exact GELU in the ViT (--value-lane split)",
                "collectives": "none per step; one all_gather of the last step's results closes the timed region",
                "l2": "per-step working set (weights + activations) exceeds the 126 MB L2; no flush"}
         cfg.update(w.config_extra())

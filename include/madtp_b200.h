@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MADTP_B200_ABI_VERSION 4   /* 3: device-resident token counts (`*_dev` arguments), cross-attention over any Nk; 4: madtp_query_sdft_planes */
+#define MADTP_B200_ABI_VERSION 4   /* 3: device-resident token counts (`*_dev` arguments), cross-attention over any Nk; 4: madtp_query_sdft_planes, out_f32 of madtp_attn_tc_fwd */
 
 /*
  * Device-resident lengths (ABI 3). The number of tokens a layer keeps (topk_num, vit.py:145) decides every later
@@ -264,7 +264,9 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      int causal, const int32_t* n_dev, void* stream);
+                      int causal, const int32_t* n_dev, float* out_f32, void* stream);
+/* out_f32 (may be NULL): fp32 copy of the context with the same ldo / bso (in elements) -- the operand of the opt-in
+ * value lane at scoring precision (madtp_b200.functional.value_lane_split). */
 int madtp_attn_tc_stats(const void* qk_hi, const void* qk_lo, int64_t ld_qk, int B, int H, int N, float scale,
                         const float* key_mask, const float* row_lse, const float* out_norm, float* col_part,
                         int n_parts, float* cls_attn, const float* cls_p, const float* cls_tile_max, int causal,

@@ -70,7 +70,7 @@ SIGNATURES = {
     "madtp_gemm_qkv": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _f32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64,
                        _vp, _vp],
     "madtp_attn_tc_fwd": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp,
-                          _i32, _vp, _vp],
+                          _i32, _vp, _vp, _vp],
     "madtp_attn_tc_stats": [_vp, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp,
                             _vp],
 }
@@ -287,6 +287,14 @@ def set_arena(arena):
     return prev
 
 
+# functional.value_lane_split(): part of every arena / graph key, because the mode changes the launch sequence
+_value_split = [os.environ.get("MADTP_VALUE_LANE", "") == "split"]
+
+
+def mode_key():
+    return ("value_split",) if _value_split[0] else ()
+
+
 class arena_for:
     """`with arena_for(owner, key):` -- run a forward with device-resident lengths inside the persistent Arena that
     `owner` (a module) keeps for `key` (the input shapes). Such a forward NEEDS one: its buffers are capacity-sized and
@@ -295,7 +303,7 @@ class arena_for:
     next call with the same key have to be cloned by the caller."""
 
     def __init__(self, owner, key):
-        self.owner, self.key, self.own, self.prev = owner, key, False, None
+        self.owner, self.key, self.own, self.prev = owner, (key, mode_key()), False, None
 
     def __enter__(self):
         if _arena is not None:
@@ -745,15 +753,19 @@ def gemm_qkv(a_hi, a_lo, w_hi, w_lo, bias, n_tok, heads, alpha=1.0, n_dev=None):
 
 
 def attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, out_f16, row_lse, out_norm, *, key_mask=None, cls_p=None,
-                cls_tile_max=None, n_dev=None, causal=False):
-    """cls_p [B,H,N] / cls_tile_max [B,H,ceil(N/64)] fp32 (both or neither): the CLS query row for attn_tc_stats."""
+                cls_tile_max=None, n_dev=None, causal=False, out_f32=None):
+    """cls_p [B,H,N] / cls_tile_max [B,H,ceil(N/64)] fp32 (both or neither): the CLS query row for attn_tc_stats.
+    out_f32: optional fp32 copy of the context, same shape / strides as out_f16."""
     ldo, bso = _qkv_strides(out_f16, "out_f16")
+    if out_f32 is not None and _qkv_strides(out_f32, "out_f32") != (ldo, bso):
+        raise RuntimeError("madtp_b200.attn_tc_fwd: out_f32 must have the strides of out_f16")
     st = _call("madtp_attn_tc_fwd", _ptr(qk_hi, torch.float16, "qk_hi"), _ptr(qk_lo, torch.float16, "qk_lo"),
                qk_hi.stride(0), _ptr(vt_hi, torch.float16, "vt_hi"), _ptr(vt_lo, torch.float16, "vt_lo"),
                vt_hi.stride(0), B, H, N, float(scale), _ptr(key_mask, torch.float32, "key_mask"),
                _ptr(out_f16, torch.float16, "out_f16"), ldo, bso, _ptr(row_lse, torch.float32, "row_lse"),
                _ptr(out_norm, torch.float32, "out_norm"), _ptr(cls_p, torch.float32, "cls_p"),
-               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), 1 if causal else 0, _dyn(n_dev), _stream())
+               _ptr(cls_tile_max, torch.float32, "cls_tile_max"), 1 if causal else 0, _dyn(n_dev),
+               _ptr(out_f32, torch.float32, "out_f32"), _stream())
     _check(st, "madtp_attn_tc_fwd")
 
 

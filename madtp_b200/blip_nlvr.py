@@ -123,8 +123,8 @@ class BLIP_NLVR(nn.Module):
             Fn.require_cuda(image, "image")
             input_ids, attention_mask = self._tokenize(text, image.device)
             if input_ids.shape[1] <= 64 and image.shape[0] == 2 * input_ids.shape[0]:
+                from . import _lib as L
                 if self._graphs is None:
-                    from . import _lib as L
                     with L.arena_for(self, (tuple(image.shape), tuple(input_ids.shape), self.record_states)):
                         return self._forward_device(image.contiguous(), input_ids, attention_mask,
                                                     float(temperature))[0].clone()
@@ -132,7 +132,7 @@ class BLIP_NLVR(nn.Module):
                 # one captured graph (with its own buffers) per input shape, temperature AND stream: forwards issued on
                 # different streams may overlap on the device (two batches in flight, bench.py --streams 2)
                 key = (tuple(image.shape), tuple(input_ids.shape), float(temperature), self.record_states,
-                       torch.cuda.current_stream().cuda_stream)
+                       torch.cuda.current_stream().cuda_stream) + L.mode_key()
                 g = self._graphs.get(key)
                 if g is None:
                     t = float(temperature)

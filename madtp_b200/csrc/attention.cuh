@@ -34,6 +34,7 @@ struct AttnTcArgs {
   float scale;
   const float* key_mask;                 // additive [B, N] or nullptr
   __half* out_f16; long long ldo, bso;   // context, heads merged
+  float* out_f32;                        // optional fp32 copy of the context (same ldo / bso, in elements)
   float* row_lse;                        // [B, H, N]  log sum_j exp(logit_j)   (max + log of the row sum)
   float* out_norm;                       // [B, H, N]  || context[b, h, i, :] ||_2
   float* col_part; int n_parts;          // [B, ceil(N/128), N]

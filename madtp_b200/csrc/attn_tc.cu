@@ -478,6 +478,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_con
           pk.w = *reinterpret_cast<uint32_t*>(&h3);
           *reinterpret_cast<uint4*>(dst + d) = pk;
         }
+        if (a.out_f32 != nullptr) {   // diagnostic value lane at scoring precision: the context is also kept in fp32
+          float* dst32 = a.out_f32 + b * a.bso + static_cast<long long>(i) * a.ldo + h * 64 + grp * KW;
+#pragma unroll
+          for (int d = 0; d < KW; d += 4)
+            *reinterpret_cast<float4*>(dst32 + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+        }
         if (grp == 0) {
           const long long sidx = (static_cast<long long>(b) * a.H + h) * N + i;
           a.row_lse[sidx] = m + logf(l_tot * (1.0f / kPScale));

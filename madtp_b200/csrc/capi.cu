@@ -298,14 +298,14 @@ int madtp_gemm_qkv(const void* a_hi, const void* a_lo, int64_t lda, const void* 
 int madtp_attn_tc_fwd(const void* qk_hi, const void* qk_lo, int64_t ld_qk, const void* vt_hi, const void* vt_lo,
                       int64_t ld_vt, int B, int H, int N, float scale, const float* key_mask, void* out_f16,
                       int64_t ldo, int64_t bso, float* row_lse, float* out_norm, float* cls_p, float* cls_tile_max,
-                      int causal, const int32_t* n_dev, void* stream) {
+                      int causal, const int32_t* n_dev, float* out_f32, void* stream) {
   AttnTcArgs a = {};
   a.n_dev = n_dev;
   a.causal = causal;
   a.qk_hi = static_cast<const __half*>(qk_hi); a.qk_lo = static_cast<const __half*>(qk_lo); a.ld_qk = ld_qk;
   a.vt_hi = static_cast<const __half*>(vt_hi); a.vt_lo = static_cast<const __half*>(vt_lo); a.ld_vt = ld_vt;
   a.B = B; a.H = H; a.N = N; a.scale = scale; a.key_mask = key_mask;
-  a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso;
+  a.out_f16 = static_cast<__half*>(out_f16); a.ldo = ldo; a.bso = bso; a.out_f32 = out_f32;
   a.row_lse = row_lse; a.out_norm = out_norm;
   a.cls_p = cls_p; a.cls_tile_max = cls_tile_max;
   return counted(launch_attn_fwd_tc(a, as_stream(stream)), B > 0 ? 1 : 0);

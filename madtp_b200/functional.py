@@ -23,6 +23,15 @@ from . import dist as _dist
 Tensor = torch.Tensor
 # MADTP_SDFT_PLANES=0 keeps the round-1 aggregation kernel (fp32 x re-laid out K-major by builder warps)
 SDFT_PLANES = os.environ.get("MADTP_SDFT_PLANES", "1") != "0"
+# Opt-in diagnostic: run the ViT's VALUE lane (attention output projection, FFN) at the scoring lane's precision too --
+# fp32 attention context, error-compensated fp16 hi/lo planes for every operand, exact erf GELU -- to show what the
+# free-running keep-masks do without the fp16 rounding of the value lane (MADTP_VALUE_LANE=split, bench.py --value-lane).
+def value_lane_split(enable=None) -> bool:
+    if enable is not None:
+        L._value_split[0] = bool(enable)
+    return L._value_split[0]
+
+
 TA_LD = 128  # row pitch of token_att buffers (T = 100 codebook entries padded to a 16-byte multiple of columns)
 
 
@@ -265,7 +274,8 @@ def self_attention(q: Tensor, k: Tensor, v: Tensor, H: int, scale: float, key_ma
 
 
 def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N: int, H: int, scale: float,
-                      want_stats: bool, n_dev: Optional[Tensor] = None, causal: bool = False):
+                      want_stats: bool, n_dev: Optional[Tensor] = None, causal: bool = False,
+                      ctx32: Optional[Tensor] = None):
     """Tensor-core scoring-lane self-attention from the fp16 hi/lo planes of the normalised rows [B*N, C]:
     fused q|k|v projection (split / transposed epilogue) -> attention -> (optionally) pruning statistics.
     Returns (ctx16 [B,N,H*64] fp16, AttnStats or None). n_dev: device-resident N (N is then the capacity)."""
@@ -275,11 +285,12 @@ def self_attention_tc(y_hi: Tensor, y_lo: Tensor, qkv: PreparedLinear, B: int, N
     ctx16 = L.empty((B, N, H * 64), torch.float16, dev)
     rows = L.empty((3 if want_stats else 2, B, H, N), torch.float32, dev)
     if not want_stats:
-        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], n_dev=n_dev, causal=causal)
+        L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], n_dev=n_dev, causal=causal,
+                      out_f32=ctx32)
         return ctx16, None
     cls_tile_max = L.empty((B, H, (N + 63) // 64), torch.float32, dev)
     L.attn_tc_fwd(qk_hi, qk_lo, vt_hi, vt_lo, B, H, N, scale, ctx16, rows[0], rows[1], cls_p=rows[2],
-                  cls_tile_max=cls_tile_max, n_dev=n_dev, causal=causal)
+                  cls_tile_max=cls_tile_max, n_dev=n_dev, causal=causal, out_f32=ctx32)
     n_parts = (N + 127) // 128
     col_part = L.empty((B, n_parts, N), torch.float32, dev)
     cls_attn = L.empty((B, N), torch.float32, dev)

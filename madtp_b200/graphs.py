@@ -95,7 +95,7 @@ class GraphedForward:
         if self._graphs is None:
             with L.arena_for(self, key):    # clones: the arena's buffers are reused by the next call with this key
                 return tuple(None if o is None else o.clone() for o in fn(*inputs)[0])
-        key = key + (torch.cuda.current_stream().cuda_stream,)
+        key = key + (torch.cuda.current_stream().cuda_stream,) + L.mode_key()
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = GraphedCall(fn, inputs)

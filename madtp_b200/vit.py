@@ -67,6 +67,22 @@ class Mlp(nn.Module):
         h = Fn.linear_f16(y16, fc1, out_dtype=torch.float16, act=_act_code(self.act), m_dev=m_dev, m_mult=m_mult)
         return Fn.linear_f16(h, fc2, residual=residual, m_dev=m_dev, m_mult=m_mult)
 
+    def forward_rows_split(self, y_hi, y_lo, residual=None, m_dev=None, m_mult=1):
+        """The same FFN at the scoring lane's precision (functional.value_lane_split): hi/lo planes in, exact erf GELU,
+        fp32 hidden activations re-split for fc2."""
+        fc1 = self._cache.get("fc1s", [self.fc1.weight, self.fc1.bias],
+                              lambda: Fn.PreparedLinear(self.fc1.weight, self.fc1.bias, split=True))
+        fc2 = self._cache.get("fc2s", [self.fc2.weight, self.fc2.bias],
+                              lambda: Fn.PreparedLinear(self.fc2.weight, self.fc2.bias, split=True))
+        act = _act_code(self.act)
+        h = Fn.linear_split(y_hi, y_lo, fc1, act=L.ACT_GELU if act == L.FFN_GELU else act, m_dev=m_dev, m_mult=m_mult)
+        # the row kernel takes rows of <= 1024 elements: split the dense [rows, 4 C] activations as [4 rows, C]
+        rows, dh = h.shape
+        parts = dh // y_hi.shape[1]
+        h_hi, h_lo = Fn.split_rows(h.view(rows * parts, dh // parts), n_dev=m_dev, n_mult=m_mult * parts)
+        h_hi, h_lo = h_hi.view(rows, dh), h_lo.view(rows, dh)
+        return Fn.linear_split(h_hi, h_lo, fc2, residual=residual, m_dev=m_dev, m_mult=m_mult)
+
     def forward(self, x):
         Fn.require_cuda(x, "x")
         _eval_only(self)
@@ -128,14 +144,23 @@ class Attention(nn.Module):
     def attend_rows(self, y_hi, y_lo, B, N, want_stats=True, n_dev=None):
         """q|k|v projection, attention and (optionally) the pruning statistics; returns the fp16 context [B,N,C]."""
         qkv_w, _ = self._prepared()
+        # opt-in value lane at scoring precision: the kernel also writes the context in fp32
+        self._ctx32 = L.empty((B, N, self.dim), torch.float32, y_hi.device) if Fn.value_lane_split() else None
         ctx16, stats = Fn.self_attention_tc(y_hi, y_lo, qkv_w, B, N, self.num_heads, self.scale, want_stats,
-                                            n_dev=n_dev)
+                                            n_dev=n_dev, ctx32=self._ctx32)
         self.save_attention_map(stats)
         self.save_cls_attn(None if stats is None else stats.cls_attn[:, 1:])
         return ctx16
 
     def project_rows(self, ctx16, B, N, residual=None, n_dev=None):
         _, proj_w = self._prepared()
+        ctx32 = getattr(self, "_ctx32", None)
+        if ctx32 is not None and Fn.value_lane_split():
+            self._ctx32 = None
+            w = self._cache.get("projs", [self.proj.weight, self.proj.bias],
+                                lambda: Fn.PreparedLinear(self.proj.weight, self.proj.bias, split=True))
+            c_hi, c_lo = Fn.split_rows(ctx32.view(B * N, self.dim), n_dev=n_dev, n_mult=B)
+            return Fn.linear_split(c_hi, c_lo, w, residual=residual, m_dev=n_dev, m_mult=B)
         return Fn.linear_f16(ctx16.view(B * N, self.dim), proj_w, residual=residual, m_dev=n_dev, m_mult=B)
 
     def forward(self, x, register_hook=False):
@@ -207,6 +232,11 @@ class Block(nn.Module):
                 nd2 = n_out
         N2 = x1.shape[1]
         x2d = x1.view(B * N2, C)
+        if Fn.value_lane_split():   # diagnostic: norm2 as hi/lo planes, FFN on the error-compensated lane
+            ln2 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, split=True, n_dev=nd2,
+                                    n_mult=B)
+            return self.mlp.forward_rows_split(ln2["y_hi"], ln2["y_lo"], residual=x2d, m_dev=nd2,
+                                               m_mult=B).view(B, N2, C)
         if y16 is None:     # nothing was pruned (host-side early-out) or pruning is off
             y16 = Fn.layernorm_rows(x2d, self.norm2.weight, self.norm2.bias, self.norm2.eps, f16=True, n_dev=nd2,
                                     n_mult=B)["y16"]

@@ -268,6 +268,32 @@ def test_nlvr_small_end_to_end_against_golden(dev, ti):
     assert rel(model.last["last_hidden_state"], torch.from_numpy(gold[f"t{ti}_last_hidden"])) < 2e-3
 
 
+def test_value_lane_split_tightens_the_free_running_image_encoder(dev):
+    """functional.value_lane_split(True) (diagnostic, bench.py --value-lane split): with the ViT's attention output
+    projection and FFN on the error-compensated lane (fp32 context, hi/lo planes, exact GELU) the FREE-RUNNING image
+    encoder follows the reference an order of magnitude closer than with the fp16 value lane -- which is what the
+    per-layer mask agreement of the bench line then shows at full size."""
+    from madtp_b200 import functional as Fn
+    gold = np.load(GOLDEN / "nlvr_small224.npz")
+    temp = float(gold["temps"][1])
+    model, sd, (images, ids, mask), tr, _ = nlvr_setup(dev, 224, 2, 20, temp)
+    ref = torch.from_numpy(gold["t1_image_embeds_s8"])
+    errs = {}
+    try:
+        for mode in (False, True):
+            Fn.value_lane_split(mode)
+            with torch.no_grad():
+                emb, _ = model.visual_encoder(images.to(dev), space_dict=model.space_dict, temperature=temp)
+            ks = [(b.last_prune.k if b.last_prune is not None and b.last_prune.pruned else -1)
+                  for b in model.visual_encoder.blocks]
+            assert ks == gold["t1_vit_k"].tolist()
+            errs[mode] = rel(emb[:, :, ::8], ref)
+    finally:
+        Fn.value_lane_split(False)
+    print(f"image_embeds relative error: fp16 value lane {errs[False]:.2e}, split value lane {errs[True]:.2e}")
+    assert errs[False] < 2e-3 and errs[True] < 2e-5 and errs[True] < 0.1 * errs[False]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # models/med.py text encoder (BLIP retrieval / VQA): padded text in mode 'text', and mode 'multimodal'
 # ---------------------------------------------------------------------------------------------------------------

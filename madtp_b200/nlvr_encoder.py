@@ -406,12 +406,15 @@ class BertOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
         self._cache = Fn.WeightCache()
 
-    def rows(self, inter16, residual, m_dev=None, m_mult=1):
+    def rows(self, inter16, residual, m_dev=None, m_mult=1, planes=False):
+        """planes=True: the LayerNorm launch also writes the fp16 hi/lo planes of its output -- the operand of the NEXT
+        layer's fused q|k|v + codebook GEMM -- and the dict of outputs is returned instead of the fp32 rows."""
         w = self._cache.get("dense", [self.dense.weight, self.dense.bias],
                             lambda: Fn.PreparedLinear(self.dense.weight, self.dense.bias, f16=True))
         pre = Fn.linear_f16(inter16, w, residual=residual, m_dev=m_dev, m_mult=m_mult)
-        return Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
-                                 n_dev=m_dev, n_mult=m_mult)["y"]
+        o = Fn.layernorm_rows(pre, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, f32=True,
+                              split=planes, n_dev=m_dev, n_mult=m_mult)
+        return o if planes else o["y"]
 
     def forward(self, hidden_states, input_tensor):
         _eval_only(self)
@@ -465,7 +468,7 @@ class BertLayer(nn.Module):
 
     def _forward_impl(self, hidden_states, attention_mask, head_mask, encoder_hidden_states, encoder_attention_mask,
                       past_key_value, output_attentions, mode, token_attn, temperature, _kv, _qkv=None,
-                      _causal=False, _dyn: Optional[LayerLengths] = None):
+                      _causal=False, _dyn: Optional[LayerLengths] = None, _want_planes=False):
         Fn.require_cuda(hidden_states, "hidden_states")
         _eval_only(self)
         _unsupported(head_mask=head_mask, past_key_value=past_key_value, output_attentions=output_attentions)
@@ -518,7 +521,13 @@ class BertLayer(nn.Module):
                                           l_dev=l_dev, nk_dev=None if _dyn is None else _dyn.nk_dev)
 
         inter16 = self.intermediate.rows(att16, m_dev=l_dev, m_mult=B)
-        out = self.output.rows(inter16, att_rows, m_dev=l_dev, m_mult=B).view(B, Ltok, d)
+        self.out_planes = None
+        if _want_planes:
+            o = self.output.rows(inter16, att_rows, m_dev=l_dev, m_mult=B, planes=True)
+            out = o["y"].view(B, Ltok, d)
+            self.out_planes = (o["y_hi"], o["y_lo"], out)
+        else:
+            out = self.output.rows(inter16, att_rows, m_dev=l_dev, m_mult=B).view(B, Ltok, d)
         return (out, None, attention_mask)
 
     def _cross(self, att_rows, att16, B, Ltok, enc, enc_mask, kv, l_dev=None, nk_dev=None):
@@ -730,6 +739,8 @@ class BertEncoder(nn.Module):
             ks.fill_(-1)
             traj = Fn.Trajectory(dims, ks)
         sd_txt_ft_all = None
+        planes = None
+        fuse_planes = space_dict is not None and not self.txt_query_model.map_func
         for i, layer_module in enumerate(self.layer):
             h = hidden_states.contiguous()
             Ltok, d = h.shape[1], h.shape[2]
@@ -737,8 +748,12 @@ class BertEncoder(nn.Module):
             dyn = LayerLengths(dims[i:i + 1], dims[i + 1:i + 2], ks[i:i + 1], nk_dev) if _device else None
             l_dev = None if dyn is None else dyn.l_in
             if space_dict is not None and not self.txt_query_model.map_func:
-                # q|k|v and the codebook dots share the operand h: one split-operand GEMM (see _qkv_book_split)
-                h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d), n_dev=l_dev, n_mult=B)
+                # q|k|v and the codebook dots share the operand h: one split-operand GEMM (see _qkv_book_split). The
+                # planes of h come out of the previous layer's output LayerNorm launch when there is one.
+                if planes is not None and planes[2].data_ptr() == h.data_ptr() and planes[2].shape == h.shape:
+                    h_hi, h_lo = planes[0], planes[1]
+                else:
+                    h_hi, h_lo = Fn.split_rows(h.view(B * Ltok, d), n_dev=l_dev, n_mult=B)
                 qkv, ta_full = layer_module.attention.self.project_qkv_and_token_att(h_hi, h_lo, B, Ltok, space_dict,
                                                                                      l_dev=l_dev)
                 token_attn, sd_txt_ft_all = Fn.query_model_from_token_att(ta_full, h, space_dict.shape[0],
@@ -751,7 +766,9 @@ class BertEncoder(nn.Module):
             layer_outputs = layer_module._forward_impl(h, attention_mask, None, encoder_hidden_states,
                                                        encoder_attention_mask, None, False, mode, token_attn,
                                                        temperature, None if kv is None else kv[i], _qkv=qkv,
-                                                       _causal=_causal, _dyn=dyn)
+                                                       _causal=_causal, _dyn=dyn,
+                                                       _want_planes=(fuse_planes and i + 1 < depth))
+            planes = getattr(layer_module, "out_planes", None)
             if _device:
                 layer_module.last_prune = Fn.LazyPrune(traj, i, layer_module.last_prune, B)
             hidden_states = layer_outputs[0]

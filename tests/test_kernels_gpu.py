@@ -331,6 +331,42 @@ def test_dtp_score_select_gather(lib, dev, B, n, temp):
                 assert torch.equal(mask_out[b, :k + 2], exp)
 
 
+@pytest.mark.parametrize("B,n,T,ld,off", [(3, 1024, 100, 128, 0),     # the longest sequence the slab kernels take
+                                         (2, 333, 97, 128, 0),      # T not a multiple of 4: scalar slab loads
+                                         (2, 50, 128, 128, 0),      # every codebook column in use
+                                         (5, 1, 100, 128, 0),       # a single prunable token
+                                         (2, 77, 33, 131, 1),       # odd row pitch and a view that starts off 16 bytes
+                                         (3, 19, 100, 2432, 2304)])  # the text encoder's fused q|k|v + codebook buffer
+def test_token_statistics_edge_shapes(lib, dev, B, n, T, ld, off):
+    """token_colstats (slab in shared memory) and dtp_score (4-CTA clusters): both load paths (16-byte cp.async and the
+    scalar fallback), the maximum length, odd pitches -- against fp64 (models/vit.py:126-145, models/utils.py:174-178)."""
+    g = torch.Generator(device="cpu").manual_seed(1000 * n + T)
+    N = n + 1
+    buf = (torch.randn(B, N, ld, generator=g) * 8).to(dev)
+    ta = buf[:, 1:, off:off + T] if off + T <= ld else buf[:, 1:, :T]
+    div, temp = math.sqrt(768), 3.0
+    cm, cs = lib.token_colstats(ta, n, T, div)
+    xs = ta.double() / div
+    assert (cm.double() - xs.max(dim=1)[0]).abs().max().item() < 1e-6
+    ref_sum = torch.exp(xs - xs.max(dim=1, keepdim=True)[0]).sum(1)
+    assert ((cs.double() - ref_sum).abs() / ref_sum).max().item() < 2e-6
+    n_parts = (N + 127) // 128
+    col_part = torch.rand(B, n_parts, N, generator=g).to(dev)
+    cls_attn = (torch.rand(B, N, generator=g) / n).to(dev)
+    score, thr, cnt, topk = lib.dtp_score(col_part, cls_attn, ta, n, T, temp)
+    a = col_part.double().sum(1)[:, 1:]
+    a = a / (a.sum(1, keepdim=True) + 1e-8)
+    bm = ta.double().max(2)[0]
+    bm = bm / (bm.sum(1, keepdim=True) + 1e-8)
+    s_ref = (a + bm + cls_attn[:, 1:].double()) / 3.0
+    assert ((score.double() - s_ref).abs() / s_ref.abs().clamp_min(1e-12)).max().item() < 2e-6
+    w = torch.softmax(ta.double() / temp, dim=1)
+    thr_ref = (w * score.double()[..., None]).sum(1).min(1)[0]
+    assert ((thr.double() - thr_ref).abs() / thr_ref.abs().clamp_min(1e-12)).max().item() < 2e-6
+    assert torch.equal(cnt.long(), (score > thr[:, None]).sum(1))
+    assert int(topk.item()) == int(cnt.max())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # tensor-core attention path: fused q|k|v projection with split / transposed epilogue, fwd + statistics
 # ---------------------------------------------------------------------------------------------------------------

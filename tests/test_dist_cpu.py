@@ -31,6 +31,7 @@ def _worker(rank, world, port, q):
     local = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1).repeat(1, 2)      # this rank's "logits"
     gathered = mdist.all_gather_rows(local)
     t = mdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    per_rank = mdist.gather_over_ranks(float(10 * rank + 1), torch.device("cpu"))
     # strict mode: the per-layer survivor count becomes the maximum over all ranks; off by default (reference semantics)
     k_local = torch.tensor([100 + 7 * rank], dtype=torch.int32)
     k_off = int(mdist.allreduce_topk_(k_local.clone()))
@@ -38,7 +39,7 @@ def _worker(rank, world, port, q):
     k_on = int(mdist.allreduce_topk_(k_local.clone()))
     mdist.global_topk(False)
     mdist.barrier()
-    q.put((rank, nbytes, flat.tolist(), gathered.tolist(), t, k_off, k_on))
+    q.put((rank, nbytes, flat.tolist(), gathered.tolist(), t, k_off, k_on, per_rank))
     dist.destroy_process_group()
 
 
@@ -65,7 +66,8 @@ def test_broadcast_and_gather_world2_gloo():
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
-    (r0, n0, w0, g0, t0, koff0, kon0), (r1, n1, w1, g1, t1, koff1, kon1) = res
+    (r0, n0, w0, g0, t0, koff0, kon0, pr0), (r1, n1, w1, g1, t1, koff1, kon1, pr1) = res
+    assert pr0 == pr1 == [1.0, 11.0], "every rank sees every rank's own step time, in rank order"
     assert (koff0, koff1) == (100, 107), "default: every rank keeps its local topk_num"
     assert kon0 == kon1 == 107, "strict mode: the maximum over all ranks"
     assert n0 == n1 == (8 * 8 + 8 + 8 + 8) * 4

@@ -17,7 +17,8 @@
 //       log P_h(i,j) = S_h(i,j) * scale + mask_j - lse_h(i) is formed for every head, the running max over heads is
 //       kept in registers (exp is monotone, so ONE expf per (i,j) after the head loop replaces one per head), then
 //       the tile is column-summed over its query rows in a fixed order.
-//   attn_cls_combine      the CLS query row of every head (kept by the forward pass) weighted by the context norms.
+//       The same kernel first combines the CLS query row of every head (kept by the forward pass) with the context
+//       norms into cls_attn (its consumer warps idle while the operand pipeline fills).
 //
 // Warp roles in both tensor-core kernels: warp 0 = TMA producer, warp 1 = MMA issuer (warp-uniform loops, one elected
 // lane issues), warps 2.. = consumers (TMEM lane quadrant = warp % 4, thread = query row).
@@ -631,6 +632,28 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     // log P = S sc + mask - lse in the natural domain (sc = scale / 64: a power of two for the usual head dim, so the
     // product is exact and the only rounding is the final subtraction); one 2^(t log2e) per (i, j) after the head loop
     const float sc = a.scale * (1.0f / (kQkPlaneScale * kQkPlaneScale));
+    // The CLS row first (it only needs the forward pass' outputs): the consumer warps would otherwise idle while the
+    // operand pipeline fills. cls_attn[b,j] = sum_h P[b,h,0,j] * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8), h ascending.
+    {
+      const int Tk = (N + 63) / 64;
+      for (long long e = static_cast<long long>(blockIdx.x) * 256 + tid; e < static_cast<long long>(a.B) * N;
+           e += static_cast<long long>(gridDim.x) * 256) {
+        const int b = static_cast<int>(e / N), j = static_cast<int>(e - static_cast<long long>(b) * N);
+        const long long base = static_cast<long long>(b) * H * N + j;
+        float hs = 0.f;
+        for (int hh = 0; hh < H; ++hh) hs += a.out_norm[base + static_cast<long long>(hh) * N];
+        hs += 1e-8f;
+        float acc = 0.f;
+        for (int hh = 0; hh < H; ++hh) {
+          const long long bh = static_cast<long long>(b) * H + hh;
+          // P[b,h,0,j] = exp(logit_j - lse) = (256 p_j / 256) * exp(max of its key tile - lse of the CLS row)
+          const float p = a.cls_p[bh * N + j] * (1.0f / kPScale) *
+                          expf(a.cls_tile_max[bh * Tk + (j >> 6)] - a.row_lse[bh * N]);
+          acc += p * (a.out_norm[base + static_cast<long long>(hh) * N] / hs);
+        }
+        a.cls_attn[e] = acc;
+      }
+    }
     int gh = 0, ip = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ip ^= 1) {
       const int jt = item % NT, it = (item / NT) % NT, b = item / (NT * NT);
@@ -708,31 +731,6 @@ attn_stats_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// CLS row: cls_attn[b,j] = sum_h softmax_j(q_0 . k_j)_h * norm[b,h,j] / (sum_h' norm[b,h',j] + 1e-8)
-//   The forward pass leaves the CLS query row of every head as 256 p relative to per-key-tile maxima (cls_p,
-//   cls_tile_max); attn_cls_combine_kernel (grid (ceil(N/256), B)) normalises it with the row's log-sum-exp, applies
-//   the head-importance weighting and sums over heads (h ascending).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-attn_cls_combine_kernel(AttnTcArgs a) {
-  const int N = a.n_dev ? min(a.N, load_len(a.n_dev)) : a.N, H = a.H, T = (N + 63) / 64;
-  const int j = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
-  if (j >= N) return;
-  const long long base = static_cast<long long>(b) * H * N + j;
-  float hs = 0.f;
-  for (int hh = 0; hh < H; ++hh) hs += a.out_norm[base + static_cast<long long>(hh) * N];
-  hs += 1e-8f;
-  float acc = 0.f;
-  for (int hh = 0; hh < H; ++hh) {
-    const long long bh = static_cast<long long>(b) * H + hh;
-    // P[b,h,0,j] = exp(logit_j - lse) = (256 p_j / 256) * exp(max of its key tile - lse of the CLS row)
-    const float p = a.cls_p[bh * N + j] * (1.0f / kPScale) * expf(a.cls_tile_max[bh * T + (j >> 6)] - a.row_lse[bh * N]);
-    acc += p * (a.out_norm[base + static_cast<long long>(hh) * N] / hs);
-  }
-  a.cls_attn[static_cast<long long>(b) * N + j] = acc;
-}
-
-// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int check_tc(const AttnTcArgs& a) {
@@ -798,8 +796,6 @@ int launch_attn_stats_tc(const AttnTcArgs& a, cudaStream_t stream) {
   const long long items = static_cast<long long>(a.n_parts) * a.n_parts * a.B;
   const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
   attn_stats_tc_kernel<<<grid, StatsSmem::THREADS, StatsSmem::TOTAL, stream>>>(t_hi, t_lo, a);
-  MADTP_LAUNCH_CHECK();
-  attn_cls_combine_kernel<<<dim3((a.N + 255) / 256, a.B), 256, 0, stream>>>(a);
   MADTP_LAUNCH_CHECK();
   return kOk;
 }

@@ -42,7 +42,7 @@ PLAN = [
     ("gemm_split3_kernel<256", "q|k|v projection, split fp16 planes (ViT block 1)", *gemm(M1, 3 * d, d, 4, 4, 4)),
     ("attn_fwd_tc_kernel", "attention forward (ViT block 1)", (M1 * 3 * d * 4 + M1 * d * 2) / MB, 4.0 * B * H * N1 * N1 * 64),
     ("attn_stats_tc_kernel", "attention statistics (ViT block 1)", (M1 * 2 * d * 4) / MB, 2.0 * B * H * N1 * N1),
-    ("attn_cls_combine_kernel", "CLS-row combine", B * H * N1 * 4 * 2 / MB, 0),
+    ("attn_cls_combine_kernel", "CLS-row combine (until r2j; since fused into attn_stats_tc_kernel)", B * H * N1 * 4 * 2 / MB, 0),
     ("dtp_score_kernel", "dtp_score: cluster of 4 CTAs per sequence (ViT block 1)", B * (N1 - 1) * (T + 5) * 4 / MB, 0),
     ("gemm_tcgen05_kernel", "attention output projection + residual (ViT block 1)", *gemm(M1, d, d, 2, 2, 4, M1 * d * 4)),
     ("dtp_apply_kernel", "dtp_apply: radix select + gather + merge + norm2 (ViT block 1)", (M1 * d * 4 + M2 * d * 6) / MB, 0),
